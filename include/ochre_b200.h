@@ -1,0 +1,134 @@
+/*
+ * ochre_b200.h -- C ABI of the B200-native replacement for ochre's path rasteriser hot path.
+ *
+ * The reference (glowcoil/ochre, Rust) has no FFI of its own: callers see
+ *   Rasterizer::new()                         src/rasterizer.rs:50
+ *   Rasterizer::fill(&[PathCmd], Transform)   src/rasterizer.rs:161
+ *   Rasterizer::stroke(&[PathCmd], f32, T)    src/rasterizer.rs:169
+ *   Rasterizer::finish(&mut impl TileBuilder) src/rasterizer.rs:180
+ *   trait TileBuilder { tile(x,y,[u8;64]); span(x,y,width) }   src/rasterizer.rs:12-22
+ * These entry points are what a `build.rs`/bindgen FFI crate for that path binds
+ * (INTEGRATION.md shows the Rust side; rust/ochre-b200 holds the facade crate).
+ * One call rasterises a whole batch of independent paths -- each path is what one
+ * reference `Rasterizer` would have accumulated between new() and finish().
+ *
+ * Plain pointers and sizes only.  All functions return 0 on success, a negative
+ * OCHRE_E_* code for invalid input, or a positive cudaError_t.  No function
+ * throws or aborts.  A ctx is bound to one device and is not thread-safe;
+ * distinct ctxs may be used concurrently.  There is no CPU fallback: without a
+ * CUDA device ochre_b200_create fails.
+ */
+#ifndef OCHRE_B200_H
+#define OCHRE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCHRE_TILE_SIZE 8 /* src/rasterizer.rs:4 */
+
+/* PathCmd (src/path.rs:5-12) as a repr(C) record: tag + up to three points.
+ * v = points in declaration order; Conic keeps its weight in v[4]. */
+enum {
+    OCHRE_MOVE = 0,
+    OCHRE_LINE = 1,
+    OCHRE_QUADRATIC = 2,
+    OCHRE_CUBIC = 3,
+    OCHRE_CONIC = 4,
+    OCHRE_CLOSE = 5
+};
+typedef struct OchreCmd {
+    uint32_t tag;
+    float v[6];
+} OchreCmd; /* 28 bytes */
+
+/* Transform (src/geom.rs:204-208): row-major 2x2 matrix then offset. */
+typedef struct OchreTransform {
+    float m[4];
+    float ox, oy;
+} OchreTransform; /* 24 bytes */
+
+/* One TileBuilder::span call (src/rasterizer.rs:21): pixel x, y of its left end, width in pixels; height is 8. */
+typedef struct OchreSpan {
+    int16_t x, y;
+    uint16_t w;
+    uint16_t pad;
+} OchreSpan; /* 8 bytes */
+
+/* error codes (negative) */
+#define OCHRE_E_INVALID_ARG (-1)   /* null pointer, bad flags, non-monotone cmd_off */
+#define OCHRE_E_BAD_COORD (-2)     /* a transformed coordinate is not finite or |v| >= 32760 px */
+#define OCHRE_E_BAD_TAG (-3)       /* unknown command tag */
+#define OCHRE_E_TOO_LARGE (-4)     /* a path or batch exceeds the 32-bit index space of one call */
+#define OCHRE_E_NOT_POLYLINE (-5)  /* stroke input still holds curves (reference panics, src/path.rs:264-266) */
+#define OCHRE_E_NO_DEVICE (-6)     /* no CUDA device / device index out of range */
+
+/* flags of ochre_b200_rasterize */
+#define OCHRE_IN_DEVICE 0x1u   /* cmds / cmd_off / xf are device pointers (cmd_off is also read on the host: pass a host copy in cmd_off_host) */
+#define OCHRE_OUT_DEVICE 0x2u  /* leave results on the device: OchreResult pointers are device pointers */
+#define OCHRE_KEEP_STAGES 0x4u /* keep intermediate buffers of the LAST chunk readable through ochre_b200_debug_* */
+
+/* Result of one call.  Tiles and spans of path p are tile_off[p]..tile_off[p+1]
+ * and span_off[p]..span_off[p+1]; inside a path tiles ascend by (tile_y, tile_x)
+ * -- the order of the reference's TileBuilder::tile calls -- and a span belongs
+ * right after the tile whose right edge it touches (span.x == tile.x + 8, same y).
+ * Buffers are owned by the ctx and stay valid until the next call on it. */
+typedef struct OchreResult {
+    uint32_t n_paths;
+    uint32_t n_tiles;
+    uint32_t n_spans;
+    uint32_t reserved;
+    const uint32_t* tile_off;  /* n_paths + 1 */
+    const int16_t* tile_xy;    /* 2 * n_tiles: pixel x, y of each tile origin (multiples of 8) */
+    const uint8_t* alpha;      /* 64 * n_tiles: row-major 8x8 coverage, TileBuilder::tile's `data` */
+    const uint32_t* span_off;  /* n_paths + 1 */
+    const OchreSpan* spans;    /* n_spans */
+    /* work counters of this call */
+    uint64_t n_cmds, n_lines, n_records, n_chunks;
+    uint64_t kernel_launches;  /* CUDA kernels this call launched */
+    float device_ms;           /* device time of the kernels (first launch to last, CUDA events) */
+    float stage_ms[8];         /* flatten, bin, sort, tile-heads, backdrop/winding scans, coverage, emit, copies */
+} OchreResult;
+
+typedef struct ochre_b200_ctx ochre_b200_ctx;
+
+/* Rasterizer::new() for a whole device: allocates streams and (lazily) workspaces. */
+int ochre_b200_create(int device, ochre_b200_ctx** out);
+int ochre_b200_destroy(ochre_b200_ctx* ctx);
+
+/* fill + finish for n_paths independent paths (src/rasterizer.rs:161-165 and :180-268).
+ * cmds[cmd_off[p] .. cmd_off[p+1]) are path p's commands, xf[p] its transform.
+ * cmd_off_host: host copy of cmd_off when OCHRE_IN_DEVICE is set, else ignored (may be NULL). */
+int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
+                         uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out);
+
+/* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default. */
+int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
+
+/* Human-readable description of the last error on this ctx (never NULL). */
+const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);
+
+/* Host-side pre-pass of Rasterizer::stroke (src/rasterizer.rs:169-171): flatten(path, 0.1)
+ * (src/path.rs:114-144) then stroke(polygon, width) (src/path.rs:152-274).  The result is a
+ * Move/Line/Close path to hand to ochre_b200_rasterize; free it with ochre_b200_free. */
+int ochre_b200_stroke_path(const OchreCmd* path, size_t n, float width, OchreCmd** out, size_t* n_out);
+/* free flatten(path, tolerance) alone (src/path.rs:114-144). */
+int ochre_b200_flatten_path(const OchreCmd* path, size_t n, float tolerance, OchreCmd** out, size_t* n_out);
+void ochre_b200_free(void* p);
+
+/* Stage taps for parity tests (valid after a call made with OCHRE_KEEP_STAGES; last chunk only).
+ * lines: 4 floats (x0, y0, x1, y1) per line slot, in path order, degenerate slots included.
+ * records: sorted (key, val) pairs of stage 2 (layout documented in csrc/raster_core.cuh). */
+int ochre_b200_debug_lines(ochre_b200_ctx* ctx, float* out, uint64_t cap, uint64_t* n);
+int ochre_b200_debug_records(ochre_b200_ctx* ctx, uint64_t* keys, uint64_t* vals, uint64_t cap, uint64_t* n);
+
+/* Version string of the library ("ochre_b200 <semver> sm_100a"). */
+const char* ochre_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCHRE_B200_H */

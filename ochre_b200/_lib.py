@@ -1,0 +1,74 @@
+"""ctypes view of include/ochre_b200.h.  Loading fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(PKG, "libochre_b200.so")
+
+OCHRE_IN_DEVICE = 0x1
+OCHRE_OUT_DEVICE = 0x2
+OCHRE_KEEP_STAGES = 0x4
+
+ERRORS = {
+    -1: "OCHRE_E_INVALID_ARG", -2: "OCHRE_E_BAD_COORD", -3: "OCHRE_E_BAD_TAG", -4: "OCHRE_E_TOO_LARGE",
+    -5: "OCHRE_E_NOT_POLYLINE", -6: "OCHRE_E_NO_DEVICE",
+}
+
+#: every symbol include/ochre_b200.h declares
+SYMBOLS = [
+    "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_last_error",
+    "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
+    "ochre_b200_debug_records", "ochre_b200_version",
+]
+
+
+class OchreResult(C.Structure):
+    _fields_ = [
+        ("n_paths", C.c_uint32), ("n_tiles", C.c_uint32), ("n_spans", C.c_uint32), ("reserved", C.c_uint32),
+        ("tile_off", C.c_void_p), ("tile_xy", C.c_void_p), ("alpha", C.c_void_p), ("span_off", C.c_void_p),
+        ("spans", C.c_void_p),
+        ("n_cmds", C.c_uint64), ("n_lines", C.c_uint64), ("n_records", C.c_uint64), ("n_chunks", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("stage_ms", C.c_float * 8),
+    ]
+
+
+class OchreError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        self.code = code
+        name = ERRORS.get(code, f"cudaError {code}" if code > 0 else str(code))
+        super().__init__(f"{name}: {msg}")
+
+
+_lib = None
+
+
+def load():
+    """Returns the loaded C-ABI library.  Raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise ImportError(
+            f"{SO} is missing: build it with `python -m ochre_b200.build` (needs nvcc). "
+            "ochre_b200 has no CPU fallback.")
+    L = C.CDLL(SO)
+    vp, u32, u64, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t
+    L.ochre_b200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.ochre_b200_destroy.argtypes = [vp]
+    L.ochre_b200_rasterize.argtypes = [vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
+    L.ochre_b200_set_chunk.argtypes = [vp, u32]
+    L.ochre_b200_last_error.argtypes = [vp]
+    L.ochre_b200_last_error.restype = C.c_char_p
+    L.ochre_b200_stroke_path.argtypes = [vp, sz, C.c_float, C.POINTER(vp), C.POINTER(sz)]
+    L.ochre_b200_flatten_path.argtypes = [vp, sz, C.c_float, C.POINTER(vp), C.POINTER(sz)]
+    L.ochre_b200_free.argtypes = [vp]
+    L.ochre_b200_free.restype = None
+    L.ochre_b200_debug_lines.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.ochre_b200_debug_records.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.ochre_b200_version.restype = C.c_char_p
+    for f in SYMBOLS:
+        getattr(L, f)  # AttributeError here = the library does not export what the header declares
+    _lib = L
+    return L

@@ -1,0 +1,277 @@
+"""Host-side mirror of the reference's public API for the rasteriser hot path.
+
+Reference (src/rasterizer.rs): `Rasterizer::{new, move_to, line_to, command, fill, stroke,
+finish}` (:50-180) and `trait TileBuilder { tile, span }` (:12-22).  Same names, same argument
+meaning; `finish` replays the tiles and spans into the TileBuilder in the reference's call
+order (tiles ascending (tile_y, tile_x), each span right after the tile on its left).
+
+`Context.rasterize` is the batch entry point (one reference Rasterizer per path): it is the
+thin wrapper over `ochre_b200_rasterize` that tests and bench.py drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .geom import (CLOSE, CMD_DTYPE, IDENTITY_ROW, LINE, MOVE, SPAN_DTYPE, TILE_SIZE, PathCmd, Transform, Vec2,
+                   cmds_to_array)
+
+F = np.float32
+
+
+class TileBuilder:
+    """Implement `tile` and `span` (rasterizer.rs:12-22)."""
+
+    def tile(self, x: int, y: int, data: bytes) -> None:  # data: 64 bytes, row-major 8x8
+        raise NotImplementedError
+
+    def span(self, x: int, y: int, width: int) -> None:
+        raise NotImplementedError
+
+
+@dataclass
+class BatchResult:
+    tile_off: np.ndarray  # (n_paths+1,) uint32
+    span_off: np.ndarray  # (n_paths+1,) uint32
+    tile_xy: Optional[np.ndarray]  # (n_tiles, 2) int16   (None when left on the device)
+    alpha: Optional[np.ndarray]  # (n_tiles, 64) uint8
+    spans: Optional[np.ndarray]  # (n_spans,) SPAN_DTYPE
+    n_tiles: int
+    n_spans: int
+    n_cmds: int
+    n_lines: int
+    n_records: int
+    n_chunks: int
+    kernel_launches: int
+    device_ms: float
+    stage_ms: tuple
+    device_ptrs: Optional[dict] = None  # OCHRE_OUT_DEVICE: raw device addresses
+
+    def replay(self, path: int, builder: TileBuilder) -> None:
+        """TileBuilder calls of one path, in the reference's order (rasterizer.rs:241, :261-264)."""
+        t0, t1 = int(self.tile_off[path]), int(self.tile_off[path + 1])
+        s0, s1 = int(self.span_off[path]), int(self.span_off[path + 1])
+        s = s0
+        for t in range(t0, t1):
+            x, y = int(self.tile_xy[t, 0]), int(self.tile_xy[t, 1])
+            builder.tile(x, y, self.alpha[t].tobytes())
+            if s < s1 and int(self.spans["y"][s]) == y and int(self.spans["x"][s]) == x + TILE_SIZE:
+                builder.span(int(self.spans["x"][s]), y, int(self.spans["w"][s]))
+                s += 1
+        assert s == s1, "span list out of order"
+
+
+def _check(ctx_handle, rc: int):
+    if rc != 0:
+        L = _lib.load()
+        msg = L.ochre_b200_last_error(ctx_handle).decode() if ctx_handle else ""
+        raise _lib.OchreError(rc, msg)
+
+
+class Context:
+    """One device + its stream and workspaces (`ochre_b200_ctx`).  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        L = _lib.load()
+        h = C.c_void_p()
+        rc = L.ochre_b200_create(device, C.byref(h))
+        if rc != 0:
+            raise _lib.OchreError(rc, "ochre_b200_create failed (is a CUDA device present?)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().ochre_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_chunk(self, max_vcmds: int):
+        _check(self._h, _lib.load().ochre_b200_set_chunk(self._h, max_vcmds))
+
+    def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True) -> BatchResult:
+        """fill + finish of len(cmd_off)-1 independent paths.
+
+        cmds: CMD_DTYPE array; cmd_off: uint32 offsets (n_paths+1); xf: (n_paths, 6) float32 rows
+        (`OchreTransform`).  Host arrays in, host arrays out unless out_device.
+        copy=False returns views of the ctx-owned pinned buffers (valid until the next call).
+        """
+        L = _lib.load()
+        cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
+        cmd_off = np.ascontiguousarray(cmd_off, dtype=np.uint32)
+        n_paths = len(cmd_off) - 1
+        xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n_paths, 6) if n_paths else np.zeros((0, 6), np.float32)
+        res = _lib.OchreResult()
+        flags = _lib.OCHRE_OUT_DEVICE if out_device else 0
+        rc = L.ochre_b200_rasterize(self._h, cmds.ctypes.data, cmd_off.ctypes.data, xf.ctypes.data, n_paths, flags, None,
+                                    C.byref(res))
+        _check(self._h, rc)
+        return self._wrap(res, n_paths, out_device, copy)
+
+    def rasterize_ptrs(self, cmds_ptr: int, cmd_off_ptr: int, xf_ptr: int, n_paths: int, cmd_off_host: np.ndarray,
+                       in_device: bool, out_device: bool, copy: bool = False) -> BatchResult:
+        """Raw-pointer form (pinned host buffers or device buffers), used by bench.py."""
+        L = _lib.load()
+        res = _lib.OchreResult()
+        flags = (_lib.OCHRE_IN_DEVICE if in_device else 0) | (_lib.OCHRE_OUT_DEVICE if out_device else 0)
+        cmd_off_host = np.ascontiguousarray(cmd_off_host, dtype=np.uint32)
+        rc = L.ochre_b200_rasterize(self._h, cmds_ptr, cmd_off_ptr, xf_ptr, n_paths, flags, cmd_off_host.ctypes.data,
+                                    C.byref(res))
+        _check(self._h, rc)
+        return self._wrap(res, n_paths, out_device, copy)
+
+    def _wrap(self, res, n_paths, out_device, copy) -> BatchResult:
+        nt, ns = int(res.n_tiles), int(res.n_spans)
+        common = dict(n_tiles=nt, n_spans=ns, n_cmds=int(res.n_cmds), n_lines=int(res.n_lines),
+                      n_records=int(res.n_records), n_chunks=int(res.n_chunks), kernel_launches=int(res.kernel_launches),
+                      device_ms=float(res.device_ms), stage_ms=tuple(float(x) for x in res.stage_ms))
+        if out_device:
+            ptrs = dict(tile_off=res.tile_off, span_off=res.span_off, tile_xy=res.tile_xy, alpha=res.alpha, spans=res.spans)
+            return BatchResult(None, None, None, None, None, device_ptrs=ptrs, **common)
+
+        def view(ptr, nbytes, dtype, shape):
+            if nbytes == 0:
+                return np.zeros(shape, dtype)
+            buf = (C.c_uint8 * nbytes).from_address(ptr)
+            a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+            return a.copy() if copy else a
+
+        tile_off = view(res.tile_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
+        span_off = view(res.span_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
+        tile_xy = view(res.tile_xy, nt * 4, np.int16, (nt, 2))
+        alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64))
+        spans = view(res.spans, ns * 8, SPAN_DTYPE, (ns,))
+        return BatchResult(tile_off, span_off, tile_xy, alpha, spans, **common)
+
+    def debug_lines(self) -> np.ndarray:
+        L = _lib.load()
+        n = C.c_uint64(0)
+        _check(self._h, L.ochre_b200_debug_lines(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.float32)
+        _check(self._h, L.ochre_b200_debug_lines(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def debug_records(self):
+        L = _lib.load()
+        n = C.c_uint64(0)
+        _check(self._h, L.ochre_b200_debug_records(self._h, None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, np.uint64)
+        vals = np.zeros(n.value, np.uint64)
+        _check(self._h, L.ochre_b200_debug_records(self._h, keys.ctypes.data, vals.ctypes.data, n.value, C.byref(n)))
+        return keys, vals
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _cmd_array_from_c(ptr, n) -> np.ndarray:
+    if n == 0:
+        return np.zeros(0, CMD_DTYPE)
+    buf = (C.c_uint8 * (n * CMD_DTYPE.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=CMD_DTYPE).copy()
+
+
+def flatten(path, tolerance: float) -> np.ndarray:
+    """Free function `flatten(path, tolerance)` (path.rs:114-144)."""
+    L = _lib.load()
+    arr = cmds_to_array(path)
+    out, n = C.c_void_p(), C.c_size_t(0)
+    rc = L.ochre_b200_flatten_path(arr.ctypes.data, len(arr), tolerance, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise _lib.OchreError(rc, "flatten failed")
+    res = _cmd_array_from_c(out.value, n.value)
+    L.ochre_b200_free(out)
+    return res
+
+
+def stroke_to_fill(path, width: float) -> np.ndarray:
+    """`stroke(&flatten(path, TOLERANCE), width)` as Rasterizer::stroke composes it (rasterizer.rs:169-171)."""
+    L = _lib.load()
+    arr = cmds_to_array(path)
+    out, n = C.c_void_p(), C.c_size_t(0)
+    rc = L.ochre_b200_stroke_path(arr.ctypes.data, len(arr), width, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise _lib.OchreError(rc, "stroke failed")
+    res = _cmd_array_from_c(out.value, n.value)
+    L.ochre_b200_free(out)
+    return res
+
+
+def _apply_rows(arr: np.ndarray, t: Transform) -> np.ndarray:
+    """PathCmd::transform (path.rs:16-37) on a CMD_DTYPE array, in float32, unfused, reference order."""
+    m = t.as_row()
+    out = arr.copy()
+    v = arr["v"]
+    npts = np.array([1, 1, 2, 3, 2, 0, 0, 0], np.int32)[np.minimum(arr["tag"], 7)]
+    for i in range(3):
+        sel = npts > i
+        x, y = v[sel, 2 * i], v[sel, 2 * i + 1]
+        out["v"][sel, 2 * i] = (m[0] * x + m[1] * y) + m[4]
+        out["v"][sel, 2 * i + 1] = (m[2] * x + m[3] * y) + m[5]
+    return out
+
+
+class Rasterizer:
+    """Mirror of `ochre::Rasterizer` (rasterizer.rs:40-180) for one path.
+
+    Calls only record commands on the host (already transformed, as `fill` does at
+    rasterizer.rs:163); all rasterisation happens in `finish`, on the GPU.  For throughput
+    use `finish_batch` or `Context.rasterize`, which submit many paths in one call.
+    """
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self._ctx = ctx
+        self._chunks = []
+
+    def move_to(self, point: Vec2):
+        self._chunks.append(cmds_to_array([PathCmd.Move(point)]))
+
+    def line_to(self, point: Vec2):
+        self._chunks.append(cmds_to_array([PathCmd.Line(point)]))
+
+    def command(self, command: PathCmd):
+        self._chunks.append(cmds_to_array([command]))
+
+    def fill(self, path, transform: Transform):
+        self._chunks.append(_apply_rows(cmds_to_array(path), transform))
+
+    def stroke(self, path, width: float, transform: Transform):
+        self.fill(stroke_to_fill(path, width), transform)
+
+    def _cmds(self) -> np.ndarray:
+        return np.concatenate(self._chunks) if self._chunks else np.zeros(0, CMD_DTYPE)
+
+    def finish(self, builder: TileBuilder):
+        finish_batch([self], [builder], self._ctx)
+
+
+def finish_batch(rasterizers: Sequence[Rasterizer], builders: Sequence[TileBuilder], ctx: Optional[Context] = None) -> BatchResult:
+    """`finish` for many rasterisers in one GPU submission; builder i receives path i's calls."""
+    ctx = ctx or default_context()
+    paths = [r._cmds() for r in rasterizers]
+    cmds = np.concatenate(paths) if paths else np.zeros(0, CMD_DTYPE)
+    off = np.zeros(len(paths) + 1, np.uint32)
+    off[1:] = np.cumsum([len(p) for p in paths])
+    xf = np.tile(IDENTITY_ROW, (len(paths), 1))
+    res = ctx.rasterize(cmds, off, xf)
+    for i, b in enumerate(builders):
+        res.replay(i, b)
+    for r in rasterizers:
+        r._chunks = []
+    return res

@@ -1,0 +1,946 @@
+// pipeline.cu -- sm_100a kernels and host orchestration behind include/ochre_b200.h.
+//
+// Batched, multi-path replacement for the reference's single-threaded
+//   Rasterizer::fill  (src/rasterizer.rs:161-165 -> path.rs:16-74 -> rasterizer.rs:61-140)
+//   Rasterizer::finish (src/rasterizer.rs:180-268)
+//
+// Stages (DESIGN.md has the data layout and the per-stage byte counts):
+//   1 flatten      k_flatten_count -> scan -> k_flatten_emit   (lines + per-command record counts)
+//   2 bin          scan -> k_bin_scatter -> radix sort by (path, tile_y, tile_x)
+//   3 tile heads   scan over sorted records -> group_start[]
+//   4 winding      k_group_info -> scans -> k_span_width -> scan (+ span emission)
+//   5 coverage     k_coverage: thread per tile, accumulators in shared memory, row carry
+//                  inside the CTA that owns the tile-row segment, 64-byte alpha rows out
+//
+// No tensor cores: nothing here is a dense contraction.  The work is scans, a sort,
+// a sequential f32 DDA per line and byte-granular output -- HBM and issue bound.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ochre_b200.h"
+#include "radix_sort.cuh"
+#include "raster_core.cuh"
+#include "scan.cuh"
+
+using namespace oc;
+
+// host-side path utilities (host_path.cpp)
+int oc_host_has_conic(const OchreCmd* cmds, uint64_t n);
+int oc_host_preflatten_conics(const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths,
+                              std::vector<OchreCmd>& out_cmds, std::vector<uint32_t>& out_off);
+
+namespace {
+
+constexpr int TPB = 256;  // threads per block of the per-command kernels
+
+enum { ST_OK = 0, ST_BAD_COORD = 1, ST_BAD_TAG = 2, ST_CONIC = 3 };
+
+// ---------------------------------------------------------------------------
+// Stage 1a: lines per virtual command
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t find_path_dev(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_paths,
+                                                  uint32_t v) {
+    uint32_t lo = 0, hi = n_paths;
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (cmd_off[mid] - cmd_base + mid <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base,
+                const float* __restrict__ xf, uint32_t n_paths, uint32_t n_v, uint32_t* __restrict__ vpath,
+                uint32_t* __restrict__ nlines, int* __restrict__ status) {
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= n_v) return;
+    uint32_t p = find_path_dev(cmd_off, cmd_base, n_paths, v);
+    uint32_t c0 = cmd_off[p] - cmd_base, c1 = cmd_off[p + 1] - cmd_base;
+    uint32_t j = v - (c0 + p);
+    const Cmd* pc = cmds + c0;
+    const float* m = xf + 6 * (size_t)p;
+    vpath[v] = p;
+    if (j < c1 - c0) {
+        uint32_t tag = pc[j].tag;
+        if (tag == TAG_CONIC) {
+            atomicMax(status, (int)ST_CONIC);
+        } else if (tag > TAG_LINE_ABS) {
+            atomicMax(status, (int)ST_BAD_TAG);
+        }
+        int np = cmd_npts(tag);
+        bool ok = true;
+        for (int i = 0; i < np; ++i) ok = ok && coord_ok(cmd_point(pc[j], i, m));
+        if (!ok) atomicMax(status, (int)ST_BAD_COORD);
+        if (!ok || tag == TAG_CONIC || tag > TAG_LINE_ABS) {
+            nlines[v] = 0;
+            return;
+        }
+    }
+    VCmd c = decode_vcmd(pc, c1 - c0, j, m);
+    nlines[v] = vcmd_line_count(c);
+}
+
+// ---------------------------------------------------------------------------
+// Stage 1b: emit lines, count bin records per virtual command
+// ---------------------------------------------------------------------------
+template <class Sink>
+struct EmitWalk {
+    float4* lines;
+    uint32_t base;
+    RunTracker<Sink>* trk;
+    __device__ __forceinline__ void operator()(uint32_t k, V2 a, V2 b) {
+        lines[base + k] = make_float4(a.x, a.y, b.x, b.y);
+        trk->walk_line(base + k, a, b);
+    }
+};
+
+__global__ void __launch_bounds__(TPB)
+k_flatten_emit(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base,
+               const float* __restrict__ xf, uint32_t n_v, const uint32_t* __restrict__ vpath,
+               const uint32_t* __restrict__ line_off, float4* __restrict__ lines, uint32_t* __restrict__ nrec,
+               uint32_t* __restrict__ path_has_inc) {
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= n_v) return;
+    uint32_t p = vpath[v];
+    uint32_t c0 = cmd_off[p] - cmd_base, c1 = cmd_off[p + 1] - cmd_base;
+    uint32_t j = v - (c0 + p);
+    uint32_t l0 = line_off[v], l1 = line_off[v + 1];
+    if (l0 == l1) {  // Close, or a command rejected by k_flatten_count
+        nrec[v] = 0;
+        return;
+    }
+    VCmd c = decode_vcmd(cmds + c0, c1 - c0, j, xf + 6 * (size_t)p);
+    RunTracker<CountSink> trk;
+    trk.init();
+    trk.sink.n = 0;
+    EmitWalk<CountSink> f{lines, l0, &trk};
+    vcmd_for_each_line(c, f);
+    trk.finish();
+    nrec[v] = trk.sink.n;
+    if (trk.any_inc) path_has_inc[p] = 1u;
+}
+
+// A path without a single increment still yields one all-zero tile at (0,0)
+// (rasterizer.rs:194, :208 push the initial empty bin).  Its record is owned by
+// the path's FINISH command.
+__global__ void __launch_bounds__(TPB)
+k_phantom_fix(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_paths,
+              const uint32_t* __restrict__ path_has_inc, uint32_t* __restrict__ nrec) {
+    uint32_t p = blockIdx.x * TPB + threadIdx.x;
+    if (p >= n_paths) return;
+    if (!path_has_inc[p]) nrec[cmd_off[p + 1] - cmd_base + p] += 1u;
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2: scatter bin records
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_v, const uint32_t* __restrict__ vpath,
+              const uint32_t* __restrict__ line_off, const float4* __restrict__ lines,
+              const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ path_has_inc,
+              uint64_t* __restrict__ keys, uint64_t* __restrict__ vals) {
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v >= n_v) return;
+    uint32_t r0 = rec_off[v], r1 = rec_off[v + 1];
+    if (r0 == r1) return;
+    uint32_t p = vpath[v];
+    RunTracker<StoreSink> trk;
+    trk.init();
+    trk.sink.keys = keys + r0;
+    trk.sink.vals = vals + r0;
+    trk.sink.path_local = p;
+    trk.sink.n = 0;
+    uint32_t l0 = line_off[v], l1 = line_off[v + 1];
+    for (uint32_t l = l0; l < l1; ++l) {
+        float4 L = __ldg(&lines[l]);
+        trk.walk_line(l, mk(L.x, L.y), mk(L.z, L.w));
+    }
+    trk.finish();
+    bool is_finish = (v == cmd_off[p + 1] - cmd_base + p);
+    if (is_finish && !path_has_inc[p]) trk.sink.emit(0, 0, 0u, 0u, 0, false);  // the empty path's zero tile
+}
+
+// ---------------------------------------------------------------------------
+// Stage 4: per-group (= per sorted key) winding delta / realness, spans
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t group_end(const uint32_t* __restrict__ group_start, uint32_t g, uint32_t n_groups,
+                                              uint32_t n_rec) {
+    return (g + 1 < n_groups) ? group_start[g + 1] : n_rec;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_group_info(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, const uint32_t* __restrict__ group_start,
+             uint32_t n_groups, uint32_t n_rec, uint32_t* __restrict__ g_real, int32_t* __restrict__ g_wd,
+             uint32_t* __restrict__ path_first) {
+    uint32_t g = blockIdx.x * TPB + threadIdx.x;
+    if (g >= n_groups) return;
+    uint32_t r0 = group_start[g], r1 = group_end(group_start, g, n_groups, n_rec);
+    uint32_t real = 0;
+    int wd = 0;
+    for (uint32_t r = r0; r < r1; ++r) {
+        uint64_t v = vals[r];
+        wd += val_wdelta(v);
+        if (!val_wonly(v)) real = 1;
+    }
+    g_real[g] = real;
+    g_wd[g] = wd;
+    uint32_t p = key_path(keys[r0]);
+    if (g == 0 || key_path(keys[group_start[g - 1]]) != p) path_first[p] = g;
+}
+
+// Width (in tiles) of the span that follows tile group g, 0 if none.  rasterizer.rs:252-265:
+// the next real tile lies on the same tile row, at least two tiles to the right, and the
+// path's running winding (all TileIncrements with key <= this tile) is non-zero.
+__global__ void __launch_bounds__(TPB)
+k_span_width(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ group_start, uint32_t n_groups,
+             const uint32_t* __restrict__ g_real, const int32_t* __restrict__ g_wincl /* inclusive scan of g_wd */,
+             const uint32_t* __restrict__ path_first, uint32_t* __restrict__ span_w) {
+    uint32_t g = blockIdx.x * TPB + threadIdx.x;
+    if (g >= n_groups) return;
+    uint32_t w = 0;
+    if (g_real[g]) {
+        uint64_t k = keys[group_start[g]];
+        uint32_t g2 = g + 1;
+        while (g2 < n_groups && !g_real[g2]) ++g2;
+        if (g2 < n_groups) {
+            uint64_t k2 = keys[group_start[g2]];
+            if (key_row(k2) == key_row(k) && key_tx(k2) > key_tx(k) + 1) {
+                uint32_t pf = path_first[key_path(k)];
+                int winding = g_wincl[g] - (pf > 0 ? g_wincl[pf - 1] : 0);
+                if (winding != 0) w = (uint32_t)(key_tx(k2) - key_tx(k) - 1);
+            }
+        }
+    }
+    span_w[g] = w;
+}
+
+// span records: x = (tile_x + 1) * 8, y = tile_y * 8, w = gap * 8   (rasterizer.rs:261-264)
+__global__ void __launch_bounds__(TPB)
+k_emit_spans(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ group_start, uint32_t n_groups,
+             const uint32_t* __restrict__ span_w, const uint32_t* __restrict__ span_idx, uint32_t span_base,
+             OchreSpan* __restrict__ spans) {
+    uint32_t g = blockIdx.x * TPB + threadIdx.x;
+    if (g >= n_groups) return;
+    uint32_t w = span_w[g];
+    if (!w) return;
+    uint64_t k = keys[group_start[g]];
+    OchreSpan s;
+    s.x = (int16_t)((key_tx(k) + 1) * 8);
+    s.y = (int16_t)(key_ty(k) * 8);
+    s.w = (uint16_t)(w * 8u);
+    s.pad = 0;
+    spans[span_base + span_idx[g]] = s;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_path_offsets(uint32_t n_paths, const uint32_t* __restrict__ path_first, const uint32_t* __restrict__ tile_idx,
+               const uint32_t* __restrict__ span_idx, uint32_t tile_base, uint32_t span_base,
+               uint32_t* __restrict__ tile_off, uint32_t* __restrict__ span_off) {
+    uint32_t p = blockIdx.x * TPB + threadIdx.x;
+    if (p >= n_paths) return;
+    uint32_t g = path_first[p];
+    tile_off[p] = tile_base + tile_idx[g];
+    span_off[p] = span_base + span_idx[g];
+}
+
+// ---------------------------------------------------------------------------
+// Stage 5: coverage.  One thread per tile; its 64 area + 64 height accumulators
+// live in shared memory, interleaved so that lane i always hits bank i.  A CTA owns
+// every tile-row segment (path, tile_y) that STARTS inside its 128-group range and
+// follows the last one past the range end, so the left-to-right row carry
+// (`prev`/`next`, rasterizer.rs:233-250) never crosses CTAs.
+// ---------------------------------------------------------------------------
+constexpr int CV_THREADS = 128;
+constexpr size_t CV_SMEM = (size_t)CV_THREADS * 128 * sizeof(float);
+
+struct SmemAcc {
+    float* base;  // &acc[tid]; element e of this thread lives at base[e * CV_THREADS]
+    __device__ __forceinline__ void add(int pix, float area, float height) {
+        base[(2 * pix) * CV_THREADS] += area;
+        base[(2 * pix + 1) * CV_THREADS] += height;
+    }
+};
+struct LineFetch {
+    const float4* lines;
+    __device__ __forceinline__ void operator()(uint32_t i, V2& a, V2& b) const {
+        float4 L = __ldg(&lines[i]);
+        a = mk(L.x, L.y);
+        b = mk(L.z, L.w);
+    }
+};
+
+__global__ void __launch_bounds__(CV_THREADS)
+k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, const uint32_t* __restrict__ group_start,
+           uint32_t n_groups, uint32_t n_rec, const float4* __restrict__ lines, const uint32_t* __restrict__ g_real,
+           const uint32_t* __restrict__ tile_idx, uint32_t tile_base, int16_t* __restrict__ tile_xy,
+           uint8_t* __restrict__ alpha) {
+    extern __shared__ float cv_acc[];
+    __shared__ float s_row[8][CV_THREADS];
+    __shared__ float s_carry[8];
+    __shared__ uint32_t s_flag[CV_THREADS];
+    __shared__ uint32_t s_first, s_stop;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lo = blockIdx.x * CV_THREADS;
+    const uint32_t hi = (lo + CV_THREADS < n_groups) ? lo + CV_THREADS : n_groups;
+
+    if (tid == 0) s_first = 0xffffffffu;
+    if (tid < 8) s_carry[tid] = 0.0f;
+    __syncthreads();
+    {
+        uint32_t g = lo + tid;
+        if (g < hi) {
+            bool start = (g == 0) || key_row(keys[group_start[g]]) != key_row(keys[group_start[g - 1]]);
+            if (start) atomicMin(&s_first, g);
+        }
+    }
+    __syncthreads();
+    const uint32_t first = s_first;
+    if (first == 0xffffffffu) return;  // every group of this range belongs to an earlier CTA's segment
+
+    float* my = cv_acc + tid;
+    SmemAcc acc{my};
+    LineFetch fetch{lines};
+
+    for (uint32_t base = first;; base += CV_THREADS) {
+        if (tid == 0) s_stop = 0xffffffffu;
+        __syncthreads();
+        const uint32_t g = base + tid;
+        const bool in_range = g < n_groups;
+        uint64_t key = 0;
+        uint32_t r0 = 0, r1 = 0;
+        bool seg_start = false;
+        if (in_range) {
+            r0 = group_start[g];
+            r1 = group_end(group_start, g, n_groups, n_rec);
+            key = keys[r0];
+            seg_start = (g == 0) || key_row(key) != key_row(keys[group_start[g - 1]]);
+            if (g >= hi && seg_start) atomicMin(&s_stop, g);
+        }
+        s_flag[tid] = seg_start ? 1u : 0u;
+        __syncthreads();
+        const uint32_t stop = s_stop;  // first group owned by a later CTA (if it falls in this round)
+        const bool real = in_range && g < stop && g_real[g] != 0;
+        const int tx = key_tx(key), ty = key_ty(key);
+
+        if (real) {
+#pragma unroll 8
+            for (int e = 0; e < 128; ++e) my[e * CV_THREADS] = 0.0f;
+            for (uint32_t r = r0; r < r1; ++r) {
+                uint64_t v = vals[r];
+                if (!val_wonly(v)) cover_record(acc, fetch, val_line0(v), val_nlines(v), tx, ty);
+            }
+        }
+        // heights summed per pixel row: what this tile adds to the carry of the tiles on its right
+#pragma unroll
+        for (int y = 0; y < 8; ++y) {
+            float s = 0.0f;
+            if (real) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) s += my[(2 * (y * 8 + x) + 1) * CV_THREADS];
+            }
+            s_row[y][tid] = s;
+        }
+        __syncthreads();
+        if (tid < 8) {  // exclusive, segment-restarting running sum along the row, left to right
+            float c = s_carry[tid];
+            for (int t = 0; t < CV_THREADS; ++t) {
+                if (s_flag[t]) c = 0.0f;
+                float rs = s_row[tid][t];
+                s_row[tid][t] = c;
+                c += rs;
+            }
+            s_carry[tid] = c;
+        }
+        __syncthreads();
+        if (real) {
+            const uint32_t ti = tile_base + tile_idx[g];
+            uint32_t xy = (uint32_t)(uint16_t)(int16_t)(tx * 8) | ((uint32_t)(uint16_t)(int16_t)(ty * 8) << 16);
+            reinterpret_cast<uint32_t*>(tile_xy)[ti] = xy;
+            uint4* out = reinterpret_cast<uint4*>(alpha + (size_t)ti * 64);
+#pragma unroll
+            for (int yy = 0; yy < 8; yy += 2) {
+                uint32_t w[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int y = yy + h;
+                    float a = s_row[y][tid];  // `prev[y]`
+                    uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        const int pix = y * 8 + x;
+                        uint32_t q = alpha_u8(a + my[(2 * pix) * CV_THREADS]);
+                        a += my[(2 * pix + 1) * CV_THREADS];
+                        if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
+                    }
+                    w[2 * h] = lo32;
+                    w[2 * h + 1] = hi32;
+                }
+                out[yy >> 1] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        const bool last_round = (stop != 0xffffffffu) || (base + CV_THREADS >= n_groups);
+        __syncthreads();
+        if (last_round) break;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = 0) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (p) {
+            if (keep && cap) {
+                e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) { cudaFree(np); return e; }
+            }
+            cudaFree(p);
+        }
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t ncap = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, ncap, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        cap = ncap;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr uint32_t DEFAULT_CHUNK_VCMDS = 4u << 20;
+constexpr int N_STAGE = 8;
+
+}  // namespace
+
+struct ochre_b200_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    uint32_t chunk_vcmds = DEFAULT_CHUNK_VCMDS;
+    // inputs
+    DevBuf d_cmds, d_cmd_off, d_xf;
+    // per virtual command
+    DevBuf d_vpath, d_line_off, d_rec_off, d_path_has_inc, d_scalars, d_scan_ws;
+    // lines and records
+    DevBuf d_lines, d_keys[2], d_vals[2], d_hist;
+    // per group
+    DevBuf d_group_start, d_g_real, d_g_wd, d_tile_idx, d_span_w, d_span_idx, d_path_first;
+    // outputs
+    DevBuf o_tile_off, o_span_off, o_tile_xy, o_alpha, o_spans;
+    HostBuf h_tile_off, h_span_off, h_tile_xy, h_alpha, h_spans, h_scalars;
+    // stage taps of the last chunk
+    uint64_t dbg_n_lines = 0, dbg_n_rec = 0;
+    int dbg_sorted = 0;
+    bool dbg_valid = false;
+    cudaEvent_t ev[N_STAGE + 1] = {};
+    bool attrs_set = false;
+};
+
+namespace {
+
+#define CK(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            char buf_[256];                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = buf_;                                                       \
+            return (int)e_;                                                        \
+        }                                                                          \
+    } while (0)
+
+inline uint32_t nblk(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
+inline int bits_for(uint32_t n) {  // bits needed to hold values 0..n-1
+    int b = 0;
+    while (b < 32 && (1ull << b) < (uint64_t)n) ++b;
+    return b;
+}
+
+// scalars block (device words; mirrored into pinned host memory after each readback)
+enum { SC_STATUS = 0, SC_NLINES = 1, SC_NREC = 2, SC_NGROUPS = 3, SC_NTILES = 4, SC_NSPANS = 5, SC_COUNT = 8 };
+
+struct ChunkOut {
+    uint32_t n_tiles = 0, n_spans = 0;
+    uint64_t n_lines = 0, n_rec = 0, launches = 0;
+    float ms[N_STAGE] = {0};
+};
+
+int read_scalars(ochre_b200_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_scalars.p, ctx->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return 0;
+}
+
+// One pipeline pass over paths [p0, p1) whose inputs are already on the device.
+int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all, uint32_t p0,
+              uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base, ChunkOut* co) {
+    cudaStream_t st = ctx->st;
+    const uint32_t n_paths = p1 - p0;
+    const uint32_t n_cmds = cmd_hi - cmd_lo;
+    const uint64_t n_v64 = (uint64_t)n_cmds + n_paths;
+    if (n_v64 >= 0xfffffff0ull) {
+        ctx->err = "chunk exceeds the 32-bit virtual command space";
+        return OCHRE_E_TOO_LARGE;
+    }
+    const uint32_t n_v = (uint32_t)n_v64;
+    const Cmd* cmds = d_cmds_all + cmd_lo;
+    const uint32_t* cmd_off = d_cmd_off_all + p0;
+    const float* xf = d_xf_all + 6 * (size_t)p0;
+    uint32_t* h_sc = ctx->h_scalars.as<uint32_t>();
+    uint32_t* d_sc = ctx->d_scalars.as<uint32_t>();
+    uint64_t launches = 0;
+
+    CK(ctx->d_vpath.ensure((size_t)n_v * 4));
+    CK(ctx->d_line_off.ensure(((size_t)n_v + 1) * 4));
+    CK(ctx->d_rec_off.ensure(((size_t)n_v + 1) * 4));
+    CK(ctx->d_path_has_inc.ensure((size_t)n_paths * 4));
+    CK(ctx->d_path_first.ensure((size_t)n_paths * 4));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(n_v) * 4));
+    uint32_t* vpath = ctx->d_vpath.as<uint32_t>();
+    uint32_t* line_off = ctx->d_line_off.as<uint32_t>();
+    uint32_t* rec_off = ctx->d_rec_off.as<uint32_t>();
+    uint32_t* path_has_inc = ctx->d_path_has_inc.as<uint32_t>();
+    uint32_t* path_first = ctx->d_path_first.as<uint32_t>();
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    // ---- stage 1: flatten ------------------------------------------------------
+    CK(cudaMemsetAsync(d_sc, 0, SC_COUNT * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(path_has_inc, 0, (size_t)n_paths * 4, st));
+    k_flatten_count<<<nblk(n_v, TPB), TPB, 0, st>>>(cmds, cmd_off, cmd_lo, xf, n_paths, n_v, vpath, line_off,
+                                                      reinterpret_cast<int*>(d_sc + SC_STATUS));
+    launches += 1;
+    {
+        uint32_t* lo_ = line_off;
+        launches += device_scan(
+            st, n_v, [lo_] __device__(uint32_t i) { return lo_[i]; },
+            [lo_] __device__(uint32_t i, uint32_t excl, uint32_t) { lo_[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+            d_sc + SC_NLINES);
+    }
+    if (int rc = read_scalars(ctx)) return rc;
+    if (h_sc[SC_STATUS] != ST_OK) {
+        switch (h_sc[SC_STATUS]) {
+            case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
+            case ST_CONIC: ctx->err = "conic"; return 1000;  // handled by the caller (host pre-flatten)
+            default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
+        }
+    }
+    const uint32_t n_lines = h_sc[SC_NLINES];
+    CK(cudaMemcpyAsync(line_off + n_v, d_sc + SC_NLINES, 4, cudaMemcpyDeviceToDevice, st));
+    CK(ctx->d_lines.ensure(((size_t)n_lines + 1) * sizeof(float4)));
+    float4* lines = ctx->d_lines.as<float4>();
+    k_flatten_emit<<<nblk(n_v, TPB), TPB, 0, st>>>(cmds, cmd_off, cmd_lo, xf, n_v, vpath, line_off, lines, rec_off,
+                                                     path_has_inc);
+    k_phantom_fix<<<nblk(n_paths, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_paths, path_has_inc, rec_off);
+    launches += 2;
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // ---- stage 2: bin + sort ---------------------------------------------------
+    {
+        uint32_t* ro_ = rec_off;
+        launches += device_scan(
+            st, n_v, [ro_] __device__(uint32_t i) { return ro_[i]; },
+            [ro_] __device__(uint32_t i, uint32_t excl, uint32_t) { ro_[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+            d_sc + SC_NREC);
+    }
+    if (int rc = read_scalars(ctx)) return rc;
+    const uint32_t n_rec = h_sc[SC_NREC];
+    CK(cudaMemcpyAsync(rec_off + n_v, d_sc + SC_NREC, 4, cudaMemcpyDeviceToDevice, st));
+    RadixSortPlan rp = radix_plan(n_rec);
+    for (int b = 0; b < 2; ++b) {
+        CK(ctx->d_keys[b].ensure(((size_t)n_rec + 1) * 8));
+        CK(ctx->d_vals[b].ensure(((size_t)n_rec + 1) * 8));
+    }
+    CK(ctx->d_hist.ensure((rp.hist_words + 1) * 4));
+    CK(ctx->d_scan_ws.ensure((rp.scan_words + scan_ws_words(n_rec) + scan_ws_words(n_v)) * 4));
+    uint64_t* keys2[2] = {ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>()};
+    uint64_t* vals2[2] = {ctx->d_vals[0].as<uint64_t>(), ctx->d_vals[1].as<uint64_t>()};
+    k_bin_scatter<<<nblk(n_v, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_v, vpath, line_off, lines, rec_off, path_has_inc,
+                                                    keys2[0], vals2[0]);
+    launches += 1;
+    CK(cudaEventRecord(ctx->ev[2], st));
+    int lc = 0;
+    const int sort_bits = OC_KEY_TILE_BITS + bits_for(n_paths);
+    int cur = radix_sort_pairs(st, keys2, vals2, n_rec, sort_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan_ws.as<uint32_t>(), &lc);
+    launches += lc;
+    const uint64_t* keys = keys2[cur];
+    const uint64_t* vals = vals2[cur];
+    CK(cudaEventRecord(ctx->ev[3], st));
+    // ---- stage 3: tile heads ---------------------------------------------------
+    CK(ctx->d_group_start.ensure(((size_t)n_rec + 1) * 4));
+    uint32_t* group_start = ctx->d_group_start.as<uint32_t>();
+    launches += device_scan(
+        st, n_rec, [keys] __device__(uint32_t i) { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; },
+        [group_start] __device__(uint32_t i, uint32_t excl, uint32_t v) {
+            if (v) group_start[excl] = i;
+        },
+        ctx->d_scan_ws.as<uint32_t>(), d_sc + SC_NGROUPS);
+    if (int rc = read_scalars(ctx)) return rc;
+    const uint32_t n_groups = h_sc[SC_NGROUPS];
+    CK(cudaEventRecord(ctx->ev[4], st));
+    // ---- stage 4: winding / realness / spans -----------------------------------
+    CK(ctx->d_g_real.ensure((size_t)n_groups * 4 + 4));
+    CK(ctx->d_g_wd.ensure((size_t)n_groups * 4 + 4));
+    CK(ctx->d_tile_idx.ensure((size_t)n_groups * 4 + 4));
+    CK(ctx->d_span_w.ensure((size_t)n_groups * 4 + 4));
+    CK(ctx->d_span_idx.ensure((size_t)n_groups * 4 + 4));
+    uint32_t* g_real = ctx->d_g_real.as<uint32_t>();
+    int32_t* g_wd = ctx->d_g_wd.as<int32_t>();
+    uint32_t* tile_idx = ctx->d_tile_idx.as<uint32_t>();
+    uint32_t* span_w = ctx->d_span_w.as<uint32_t>();
+    uint32_t* span_idx = ctx->d_span_idx.as<uint32_t>();
+    k_group_info<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, vals, group_start, n_groups, n_rec, g_real, g_wd, path_first);
+    launches += 1;
+    launches += device_scan(
+        st, n_groups, [g_real] __device__(uint32_t i) { return g_real[i]; },
+        [tile_idx] __device__(uint32_t i, uint32_t excl, uint32_t) { tile_idx[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+        d_sc + SC_NTILES);
+    launches += device_scan(
+        st, n_groups, [g_wd] __device__(uint32_t i) { return (uint32_t)g_wd[i]; },
+        [g_wd] __device__(uint32_t i, uint32_t excl, uint32_t v) { g_wd[i] = (int32_t)(excl + v); },  // inclusive, in place
+        ctx->d_scan_ws.as<uint32_t>(), nullptr);
+    k_span_width<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, group_start, n_groups, g_real, g_wd, path_first, span_w);
+    launches += 1;
+    // spans are emitted from inside the scan that numbers them; the output arena may have to grow first
+    launches += device_scan(
+        st, n_groups, [span_w] __device__(uint32_t i) { return span_w[i] ? 1u : 0u; },
+        [span_idx] __device__(uint32_t i, uint32_t excl, uint32_t) { span_idx[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+        d_sc + SC_NSPANS);
+    if (int rc = read_scalars(ctx)) return rc;
+    const uint32_t n_tiles = h_sc[SC_NTILES], n_spans = h_sc[SC_NSPANS];
+    if ((uint64_t)tile_base + n_tiles >= 0xffffffffull || (uint64_t)span_base + n_spans >= 0xffffffffull) {
+        ctx->err = "more than 2^32 tiles or spans in one call";
+        return OCHRE_E_TOO_LARGE;
+    }
+    CK(cudaEventRecord(ctx->ev[5], st));
+    // ---- stage 5: coverage + emission ------------------------------------------
+    CK(ctx->o_tile_xy.ensure(((size_t)tile_base + n_tiles + 1) * 4, true, st));
+    CK(ctx->o_alpha.ensure(((size_t)tile_base + n_tiles + 1) * 64, true, st));
+    CK(ctx->o_spans.ensure(((size_t)span_base + n_spans + 1) * sizeof(OchreSpan), true, st));
+    int16_t* o_xy = ctx->o_tile_xy.as<int16_t>();
+    uint8_t* o_alpha = ctx->o_alpha.as<uint8_t>();
+    OchreSpan* o_spans = ctx->o_spans.as<OchreSpan>();
+    if (n_groups) {
+        k_coverage<<<nblk(n_groups, CV_THREADS), CV_THREADS, CV_SMEM, st>>>(keys, vals, group_start, n_groups, n_rec, lines,
+                                                                            g_real, tile_idx, tile_base, o_xy, o_alpha);
+        launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    k_emit_spans<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, group_start, n_groups, span_w, span_idx, span_base, o_spans);
+    launches += 1;
+    k_path_offsets<<<nblk(n_paths, TPB), TPB, 0, st>>>(n_paths, path_first, tile_idx, span_idx, tile_base, span_base,
+                                                         ctx->o_tile_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0);
+    launches += 1;
+    CK(cudaEventRecord(ctx->ev[7], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int s = 0; s < 7; ++s) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]));
+        co->ms[s] += ms;
+    }
+    co->n_tiles = n_tiles;
+    co->n_spans = n_spans;
+    co->n_lines = n_lines;
+    co->n_rec = n_rec;
+    co->launches = launches;
+    ctx->dbg_n_lines = n_lines;
+    ctx->dbg_n_rec = n_rec;
+    ctx->dbg_sorted = cur;
+    ctx->dbg_valid = true;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ochre_b200_version(void) { return "ochre_b200 0.1.0 sm_100a"; }
+
+int ochre_b200_create(int device, ochre_b200_ctx** out) {
+    if (!out) return OCHRE_E_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) return OCHRE_E_NO_DEVICE;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    ochre_b200_ctx* ctx = new (std::nothrow) ochre_b200_ctx();
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return (int)e; }
+    for (int i = 0; i <= N_STAGE; ++i) {
+        e = cudaEventCreate(&ctx->ev[i]);
+        if (e != cudaSuccess) { delete ctx; return (int)e; }
+    }
+    e = cudaFuncSetAttribute(k_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+    if (e == cudaSuccess) e = ctx->d_scalars.ensure(SC_COUNT * sizeof(uint32_t));
+    if (e == cudaSuccess) e = ctx->h_scalars.ensure(SC_COUNT * sizeof(uint32_t));
+    if (e != cudaSuccess) { ochre_b200_destroy(ctx); return (int)e; }
+    *out = ctx;
+    return 0;
+}
+
+int ochre_b200_destroy(ochre_b200_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->st) cudaStreamSynchronize(ctx->st);
+    DevBuf* db[] = {&ctx->d_cmds, &ctx->d_cmd_off, &ctx->d_xf, &ctx->d_vpath, &ctx->d_line_off, &ctx->d_rec_off,
+                    &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
+                    &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
+                    &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans};
+    for (DevBuf* b : db) b->release();
+    HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars};
+    for (HostBuf* b : hb) b->release();
+    for (int i = 0; i <= N_STAGE; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+    return 0;
+}
+
+int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    ctx->chunk_vcmds = max_vcmds ? max_vcmds : DEFAULT_CHUNK_VCMDS;
+    return 0;
+}
+
+const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
+                          uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out, bool allow_conic_retry) {
+    ctx->err.clear();
+    ctx->dbg_valid = false;
+    memset(out, 0, sizeof *out);
+    out->n_paths = n_paths;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const bool in_dev = (flags & OCHRE_IN_DEVICE) != 0;
+    const uint32_t* h_off = in_dev ? cmd_off_host : cmd_off;
+    if (n_paths && (!cmd_off || !xf || !h_off)) {
+        ctx->err = "null input pointer";
+        return OCHRE_E_INVALID_ARG;
+    }
+    static const uint32_t zero_off[1] = {0};
+    if (n_paths == 0) h_off = zero_off;
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        if (h_off[p + 1] < h_off[p]) {
+            ctx->err = "cmd_off is not monotone";
+            return OCHRE_E_INVALID_ARG;
+        }
+    }
+    const uint32_t n_cmds = h_off[n_paths] - h_off[0];
+    if (n_cmds && !cmds) {
+        ctx->err = "null cmds";
+        return OCHRE_E_INVALID_ARG;
+    }
+    out->n_cmds = n_cmds;
+
+    cudaEvent_t ev_begin = ctx->ev[N_STAGE];
+    float copy_ms = 0;
+    // ---- inputs ---------------------------------------------------------------
+    const Cmd* d_cmds;
+    const uint32_t* d_off;
+    const float* d_xf;
+    if (in_dev) {
+        d_cmds = reinterpret_cast<const Cmd*>(cmds) - 0;
+        d_off = cmd_off;
+        d_xf = reinterpret_cast<const float*>(xf);
+    } else {
+        CK(ctx->d_cmds.ensure((size_t)n_cmds * sizeof(OchreCmd) + 16));
+        CK(ctx->d_cmd_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->d_xf.ensure((size_t)n_paths * sizeof(OchreTransform) + 16));
+        CK(cudaEventRecord(ev_begin, st));
+        if (n_cmds) CK(cudaMemcpyAsync(ctx->d_cmds.p, cmds + h_off[0], (size_t)n_cmds * sizeof(OchreCmd), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_cmd_off.p, h_off, ((size_t)n_paths + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (n_paths) CK(cudaMemcpyAsync(ctx->d_xf.p, xf, (size_t)n_paths * sizeof(OchreTransform), cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&copy_ms, ev_begin, ctx->ev[0]));
+        // d_cmds holds cmds[h_off[0]..]; kernels index it with (cmd_off - h_off[0])
+        d_cmds = ctx->d_cmds.as<Cmd>() - h_off[0];
+        d_off = ctx->d_cmd_off.as<uint32_t>();
+        d_xf = ctx->d_xf.as<float>();
+    }
+    CK(ctx->o_tile_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->o_span_off.ensure(((size_t)n_paths + 1) * 4));
+
+    // ---- chunks ---------------------------------------------------------------
+    uint32_t tile_base = 0, span_base = 0;
+    uint32_t p0 = 0;
+    ChunkOut total;
+    while (p0 < n_paths) {
+        uint32_t p1 = p0;
+        uint64_t nv = 0;
+        while (p1 < n_paths) {
+            uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
+            if (p1 > p0 && nv + add > ctx->chunk_vcmds) break;
+            nv += add;
+            ++p1;
+        }
+        ChunkOut co;
+        int rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+        if (rc == 1000) {
+            // A Conic reached the device.  Flatten conics on the host (reference path.rs:75-104,
+            // recursive; device recursion is a later row of SURVEY.md section 8f) and run again.
+            if (!allow_conic_retry || in_dev) {
+                ctx->err = "Conic commands need host-resident inputs (they are flattened on the host)";
+                return OCHRE_E_BAD_TAG;
+            }
+            std::vector<OchreCmd> ncmds;
+            std::vector<uint32_t> noff;
+            if (oc_host_preflatten_conics(cmds, h_off, xf, n_paths, ncmds, noff) != 0) {
+                ctx->err = "conic pre-flatten failed (path too large)";
+                return OCHRE_E_TOO_LARGE;
+            }
+            return rasterize_impl(ctx, ncmds.data(), noff.data(), xf, n_paths, flags, nullptr, out, false);
+        }
+        if (rc != 0) return rc;
+        tile_base += co.n_tiles;
+        span_base += co.n_spans;
+        total.n_lines += co.n_lines;
+        total.n_rec += co.n_rec;
+        total.launches += co.launches;
+        for (int s = 0; s < N_STAGE; ++s) total.ms[s] += co.ms[s];
+        out->n_chunks += 1;
+        p0 = p1;
+    }
+    // closing entries of the offset arrays
+    {
+        uint32_t tail[2] = {tile_base, span_base};
+        uint32_t* hs = ctx->h_scalars.as<uint32_t>();
+        hs[0] = tail[0];
+        hs[1] = tail[1];
+        CK(cudaMemcpyAsync(ctx->o_tile_off.as<uint32_t>() + n_paths, hs, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->o_span_off.as<uint32_t>() + n_paths, hs + 1, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    out->n_tiles = tile_base;
+    out->n_spans = span_base;
+    out->n_lines = total.n_lines;
+    out->n_records = total.n_rec;
+    out->kernel_launches = total.launches;
+    float dev_ms = 0;
+    for (int s = 0; s < 7; ++s) {
+        out->stage_ms[s] = total.ms[s];
+        dev_ms += total.ms[s];
+    }
+    out->device_ms = dev_ms;
+
+    // ---- outputs ---------------------------------------------------------------
+    if (flags & OCHRE_OUT_DEVICE) {
+        out->tile_off = ctx->o_tile_off.as<uint32_t>();
+        out->span_off = ctx->o_span_off.as<uint32_t>();
+        out->tile_xy = ctx->o_tile_xy.as<int16_t>();
+        out->alpha = ctx->o_alpha.as<uint8_t>();
+        out->spans = ctx->o_spans.as<OchreSpan>();
+    } else {
+        CK(ctx->h_tile_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->h_span_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->h_tile_xy.ensure((size_t)tile_base * 4 + 4));
+        CK(ctx->h_alpha.ensure((size_t)tile_base * 64 + 64));
+        CK(ctx->h_spans.ensure((size_t)span_base * sizeof(OchreSpan) + 8));
+        CK(cudaEventRecord(ev_begin, st));
+        CK(cudaMemcpyAsync(ctx->h_tile_off.p, ctx->o_tile_off.p, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_span_off.p, ctx->o_span_off.p, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (tile_base) {
+            CK(cudaMemcpyAsync(ctx->h_tile_xy.p, ctx->o_tile_xy.p, (size_t)tile_base * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->o_alpha.p, (size_t)tile_base * 64, cudaMemcpyDeviceToHost, st));
+        }
+        if (span_base) CK(cudaMemcpyAsync(ctx->h_spans.p, ctx->o_spans.p, (size_t)span_base * sizeof(OchreSpan), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev_begin, ctx->ev[0]));
+        copy_ms += ms;
+        out->tile_off = ctx->h_tile_off.as<uint32_t>();
+        out->span_off = ctx->h_span_off.as<uint32_t>();
+        out->tile_xy = ctx->h_tile_xy.as<int16_t>();
+        out->alpha = ctx->h_alpha.as<uint8_t>();
+        out->spans = ctx->h_spans.as<OchreSpan>();
+    }
+    out->stage_ms[7] = copy_ms;
+    return 0;
+}
+
+int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
+                         uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    if (!out) {
+        ctx->err = "null result pointer";
+        return OCHRE_E_INVALID_ARG;
+    }
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES)) {
+        ctx->err = "unknown flag bits";
+        return OCHRE_E_INVALID_ARG;
+    }
+    return rasterize_impl(ctx, cmds, cmd_off, xf, n_paths, flags, cmd_off_host, out, true);
+}
+
+int ochre_b200_debug_lines(ochre_b200_ctx* ctx, float* outp, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return OCHRE_E_INVALID_ARG;
+    if (!ctx->dbg_valid) {
+        ctx->err = "no stage data: call ochre_b200_rasterize first";
+        return OCHRE_E_INVALID_ARG;
+    }
+    *n = ctx->dbg_n_lines;
+    if (outp) {
+        uint64_t m = cap < ctx->dbg_n_lines ? cap : ctx->dbg_n_lines;
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpy(outp, ctx->d_lines.p, m * 16, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int ochre_b200_debug_records(ochre_b200_ctx* ctx, uint64_t* keys, uint64_t* vals, uint64_t cap, uint64_t* n) {
+    if (!ctx || !n) return OCHRE_E_INVALID_ARG;
+    if (!ctx->dbg_valid) {
+        ctx->err = "no stage data: call ochre_b200_rasterize first";
+        return OCHRE_E_INVALID_ARG;
+    }
+    *n = ctx->dbg_n_rec;
+    uint64_t m = cap < ctx->dbg_n_rec ? cap : ctx->dbg_n_rec;
+    CK(cudaSetDevice(ctx->device));
+    if (keys) CK(cudaMemcpy(keys, ctx->d_keys[ctx->dbg_sorted].p, m * 8, cudaMemcpyDeviceToHost));
+    if (vals) CK(cudaMemcpy(vals, ctx->d_vals[ctx->dbg_sorted].p, m * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

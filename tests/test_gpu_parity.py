@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA pipeline (through the C ABI) vs the CPU oracle.
+
+Bar: tile coordinates and spans bit-exact, alpha within +-1/255 (tolerance stated by
+BASELINE.json north_star).  Run on the B200 box with `pytest -m gpu`.
+"""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+import emu as E
+import oracle as O
+import ochre_b200 as ob
+from ochre_b200 import workloads as W
+from ochre_b200.geom import CLOSE, CONIC, CUBIC, LINE, MOVE, QUADRATIC, make_cmds
+from parity import assert_batch_parity, lines_match
+from test_emu_parity import KATS
+from test_oracle_kat import BASIC, _random_path
+
+pytestmark = pytest.mark.gpu
+
+ID = O.IDENTITY
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)  # raises loudly without a device / without the built extension
+    yield c
+    c.close()
+
+
+def pack(paths, xfs=None):
+    cmds = np.concatenate(paths) if paths else np.zeros(0, O.CMD_DTYPE)
+    off = np.cumsum([0] + [len(p) for p in paths]).astype(np.uint32)
+    xf = np.tile(ID, (len(paths), 1)) if xfs is None else np.asarray(xfs, np.float32)
+    return cmds, off, xf
+
+
+def oracle_batch(cmds, off, xf):
+    return O.rasterize_batch(cmds, off.astype(np.uint64), xf, threads=0)
+
+
+def test_config1_basic_rs_bit_exact(ctx):
+    cmds, off, xf = W.basic()
+    g = ctx.rasterize(cmds, off, xf)
+    o = oracle_batch(cmds, off, xf)
+    assert_batch_parity(g, o, alpha_tol=0, what="basic.rs")
+    h = hashlib.sha256()
+    for (x, y), a in zip(g.tile_xy, g.alpha):
+        h.update(struct.pack("<hh", int(x), int(y)) + a.tobytes())
+    for s in g.spans:
+        h.update(struct.pack("<iii", int(s["x"]), int(s["y"]), int(s["w"])))
+    assert h.hexdigest() == "5ada168c9d3a5382b5c4d8b3fc9a90e085d38fe0a0a551ef32908e296de0f917"
+    assert g.n_tiles == 100 and g.n_spans == 23 and g.kernel_launches > 0
+
+
+def test_kats_as_one_batch(ctx):
+    cmds, off, xf = pack(KATS)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what="KATs")
+
+
+def test_stage1_lines_bit_exact(ctx):
+    for path in KATS + [W.blobs(3)[0]]:
+        cmds, off, xf = pack([path])
+        ctx.rasterize(cmds, off, xf)
+        lines_match(ctx.debug_lines(), O.rasterize_path(path).lines)
+
+
+def test_gpu_equals_cpu_emulation_byte_for_byte(ctx):
+    cmds, off, xf = W.blobs(200, first=77)
+    g = ctx.rasterize(cmds, off, xf)
+    e = E.rasterize(cmds, off, xf)
+    assert np.array_equal(g.tile_off, e.tile_off) and np.array_equal(g.span_off, e.span_off)
+    assert np.array_equal(g.tile_xy, e.tile_xy) and g.spans.tobytes() == e.spans.tobytes()
+    assert np.array_equal(g.alpha, e.alpha)
+    keys, vals = ctx.debug_records()
+    assert np.array_equal(keys, e.keys) and np.array_equal(vals, e.vals)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_paths(ctx, seed):
+    rng = np.random.default_rng(5000 + seed)
+    paths = [_random_path(rng, int(rng.integers(0, 10)), float(rng.choice([6.0, 30.0, 120.0, 700.0]))) for _ in range(200)]
+    xfs = []
+    for _ in paths:
+        th, s = rng.uniform(0, 6.28), rng.uniform(0.3, 2.0)
+        xfs.append([s * np.cos(th), s * np.sin(th), -s * np.sin(th), s * np.cos(th), rng.uniform(-40, 40), rng.uniform(-40, 40)])
+    cmds, off, xf = pack(paths, xfs)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what=f"seed {seed}")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_integer_grid_polygons(ctx, seed):
+    rng = np.random.default_rng(9000 + seed)
+    paths = []
+    for _ in range(300):
+        n = int(rng.integers(3, 9))
+        pts = rng.integers(-20, 60, (n, 2)).astype(np.float64) * float(rng.choice([1.0, 0.5, 8.0, 4.0]))
+        rows = [(MOVE, *pts[0])] + [(LINE, *p) for p in pts[1:]] + ([(CLOSE,)] if rng.random() < 0.5 else [])
+        paths.append(make_cmds(rows))
+    cmds, off, xf = pack(paths)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what=f"seed {seed}")
+
+
+def test_config3_glyph_sample(ctx):
+    cmds, off, xf = W.glyphs(20000)
+    g = ctx.rasterize(cmds, off, xf)
+    stats = assert_batch_parity(g, oracle_batch(cmds, off, xf), what="G3 x 20k")
+    assert stats["alpha_mismatch_frac"] < 1e-3
+
+
+def test_config4_blob_sample(ctx):
+    cmds, off, xf = W.blobs(5000)
+    g = ctx.rasterize(cmds, off, xf)
+    stats = assert_batch_parity(g, oracle_batch(cmds, off, xf), what="G4 x 5k")
+    assert stats["alpha_mismatch_frac"] < 1e-3
+
+
+def test_config5a_rings_single_giant_path(ctx):
+    cmds, off, xf = W.rings(96, 16.0, 256)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what="G5a rings x 96")
+
+
+def test_chunking_and_rerun_do_not_change_a_byte(ctx):
+    cmds, off, xf = W.blobs(1500, first=4242)
+    a = ctx.rasterize(cmds, off, xf)
+    b = ctx.rasterize(cmds, off, xf)
+    ctx.set_chunk(4096)  # forces many chunks
+    try:
+        c = ctx.rasterize(cmds, off, xf)
+    finally:
+        ctx.set_chunk(0)
+    assert c.n_chunks > 4 and a.n_chunks == 1
+    for r in (b, c):
+        assert np.array_equal(a.tile_off, r.tile_off) and np.array_equal(a.span_off, r.span_off)
+        assert np.array_equal(a.tile_xy, r.tile_xy) and np.array_equal(a.alpha, r.alpha)
+        assert a.spans.tobytes() == r.spans.tobytes()
+
+
+def test_conics_are_flattened_on_the_host(ctx):
+    rng = np.random.default_rng(11)
+    paths = [_random_path(rng, int(rng.integers(2, 8)), 80.0, conic=True) for _ in range(60)]
+    assert any((p["tag"] == CONIC).any() for p in paths)
+    xfs = [[1.25, 0.1, -0.2, 0.9, 3.5, -2.25]] * len(paths)
+    cmds, off, xf = pack(paths, xfs)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what="conics")
+
+
+def test_strokes_match_reference_stroke(ctx):
+    rng = np.random.default_rng(21)
+    src = [_random_path(rng, int(rng.integers(2, 7)), 60.0) for _ in range(40)]
+    widths = rng.uniform(0.5, 4.0, len(src)).astype(np.float32)
+    polys = [ob.stroke_to_fill(p, float(w)) for p, w in zip(src, widths)]
+    xf = np.tile(np.array([0.8, 0.0, 0.0, 0.8, 2.0, 1.0], np.float32), (len(src), 1))
+    cmds, off, _ = pack(polys)
+    g = ctx.rasterize(cmds, off, xf)
+    scmds, soff, _ = pack(src)
+    o = O.rasterize_batch(scmds, soff.astype(np.uint64), xf, stroke_width=widths)
+    assert_batch_parity(g, o, what="strokes")
+
+
+def test_rasterizer_facade_replays_in_reference_order(ctx):
+    class Rec(ob.TileBuilder):
+        def __init__(self):
+            self.calls = []
+
+        def tile(self, x, y, data):
+            self.calls.append(("tile", x, y, data))
+
+        def span(self, x, y, w):
+            self.calls.append(("span", x, y, w))
+
+    r = ob.Rasterizer(ctx)
+    V = ob.Vec2
+    r.fill([ob.PathCmd.Move(V(400, 300)), ob.PathCmd.Quadratic(V(500, 200), V(400, 100)),
+            ob.PathCmd.Cubic(V(350, 150), V(100, 250), V(400, 300)), ob.PathCmd.Close], ob.Transform.id())
+    b = Rec()
+    r.finish(b)
+    ref = O.rasterize_path(BASIC)
+    want, ti, si = [], 0, 0
+    for kind in ref.order:
+        if kind == 0:
+            want.append(("tile", int(ref.tile_xy[ti, 0]), int(ref.tile_xy[ti, 1]), ref.alpha[ti].tobytes()))
+            ti += 1
+        else:
+            s = ref.spans[si]
+            want.append(("span", int(s["x"]), int(s["y"]), int(s["w"])))
+            si += 1
+    assert b.calls == want
+
+
+def test_fill_twice_then_finish_is_the_union(ctx):
+    sq = [ob.PathCmd.Move(ob.Vec2(2, 2)), ob.PathCmd.Line(ob.Vec2(6, 2)), ob.PathCmd.Line(ob.Vec2(6, 6)),
+          ob.PathCmd.Line(ob.Vec2(2, 6)), ob.PathCmd.Close]
+    r = ob.Rasterizer(ctx)
+    r.fill(sq, ob.Transform.id())
+    r.fill(sq, ob.Transform.translate(0.5, 0.25))
+    res = ob.finish_batch([r], [], ctx)
+    o = O.Rasterizer()
+    arr = ob.cmds_to_array(sq)
+    o.fill(arr)
+    o.fill(arr, np.array([1, 0, 0, 1, 0.5, 0.25], np.float32))
+    ref = o.finish()
+    assert np.array_equal(res.tile_xy, ref.tile_xy) and np.abs(res.alpha.astype(int) - ref.alpha.astype(int)).max() <= 1
+
+
+def test_errors(ctx):
+    with pytest.raises(ob._lib.OchreError) as e:
+        ctx.rasterize(make_cmds([(MOVE, 0, 0), (LINE, 50000.0, 1.0)]), np.array([0, 2], np.uint32), ID[None])
+    assert e.value.code == -2
+    with pytest.raises(ob._lib.OchreError) as e:
+        ctx.rasterize(make_cmds([(MOVE, 0, 0), (LINE, float("inf"), 1.0)]), np.array([0, 2], np.uint32), ID[None])
+    assert e.value.code == -2
+    with pytest.raises(ob._lib.OchreError) as e:
+        ctx.rasterize(make_cmds([(9, 0, 0)]), np.array([0, 1], np.uint32), ID[None])
+    assert e.value.code == -3
+    # the ctx stays usable after an error, and an empty batch is legal
+    g = ctx.rasterize(np.zeros(0, O.CMD_DTYPE), np.array([0], np.uint32), np.zeros((0, 6), np.float32))
+    assert g.n_tiles == 0 and g.tile_off.tolist() == [0]
+    g = ctx.rasterize(np.zeros(0, O.CMD_DTYPE), np.array([0, 0, 0], np.uint32), np.tile(ID, (2, 1)))
+    assert g.n_tiles == 2 and g.tile_xy.tolist() == [[0, 0], [0, 0]] and not g.alpha.any()
