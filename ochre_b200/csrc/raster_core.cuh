@@ -98,7 +98,10 @@ OC_HD V2 cmd_point(const Cmd& c, int i, const float* xf) {
 }
 // End point of a command = what `self.last` equals after Rasterizer::command ran it.
 // (A flattened curve's final lerp at t == 1.0 returns `point` itself.)
-OC_HD V2 cmd_endpoint(const Cmd& c, const float* xf) { return cmd_point(c, cmd_npts(c.tag) - 1, xf); }
+OC_HD V2 cmd_endpoint(const Cmd& c, const float* xf) {
+    int np = cmd_npts(c.tag);
+    return np > 0 ? cmd_point(c, np - 1, xf) : mk(0.0f, 0.0f);  // np == 0: rejected tag, result unused
+}
 
 // ---------------------------------------------------------------------------
 // Curve flattening, path.rs:49-74.  The parameter sequence is the *rounded*
