@@ -80,7 +80,7 @@ typedef struct OchreResult {
     uint32_t n_paths;
     uint32_t n_tiles;
     uint32_t n_spans;
-    uint32_t reserved;
+    uint32_t reserved;         /* bit 0: fused per-path kernel ran, bit 1: general pipeline ran */
     const uint32_t* tile_off;  /* n_paths + 1 */
     const int16_t* tile_xy;    /* 2 * n_tiles: pixel x, y of each tile origin (multiples of 8) */
     const uint8_t* alpha;      /* 64 * n_tiles: row-major 8x8 coverage, TileBuilder::tile's `data` */
@@ -107,6 +107,16 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
 
 /* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default. */
 int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
+
+/* Which implementation ochre_b200_rasterize uses.  AUTO (default): the fused per-path kernel
+ * (csrc/path_kernel.cuh), with the general global-memory pipeline (csrc/pipeline.cu) for chunks
+ * holding a path that exceeds the fused kernel's on-chip budgets.  GENERAL / FUSED force one of
+ * the two (FUSED fails with OCHRE_E_TOO_LARGE instead of falling back).  Both satisfy the same
+ * parity bar; they differ in accumulation arithmetic (f32 sums vs 2^-22 fixed point). */
+#define OCHRE_MODE_AUTO 0
+#define OCHRE_MODE_GENERAL 1
+#define OCHRE_MODE_FUSED 2
+int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode);
 
 /* Human-readable description of the last error on this ctx (never NULL). */
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);

@@ -5,11 +5,12 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(PKG, "libochre_b200.so")
+SO = os.environ.get("OCHRE_B200_LIB") or os.path.join(PKG, "libochre_b200.so")  # override: tuning builds only
 
 OCHRE_IN_DEVICE = 0x1
 OCHRE_OUT_DEVICE = 0x2
 OCHRE_KEEP_STAGES = 0x4
+MODE_AUTO, MODE_GENERAL, MODE_FUSED = 0, 1, 2
 
 ERRORS = {
     -1: "OCHRE_E_INVALID_ARG", -2: "OCHRE_E_BAD_COORD", -3: "OCHRE_E_BAD_TAG", -4: "OCHRE_E_TOO_LARGE",
@@ -18,7 +19,8 @@ ERRORS = {
 
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
-    "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_last_error",
+    "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_set_mode",
+    "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_version",
 ]
@@ -59,6 +61,7 @@ def load():
     L.ochre_b200_destroy.argtypes = [vp]
     L.ochre_b200_rasterize.argtypes = [vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
+    L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
     L.ochre_b200_last_error.argtypes = [vp]
     L.ochre_b200_last_error.restype = C.c_char_p
     L.ochre_b200_stroke_path.argtypes = [vp, sz, C.c_float, C.POINTER(vp), C.POINTER(sz)]

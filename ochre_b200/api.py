@@ -50,6 +50,7 @@ class BatchResult:
     device_ms: float
     stage_ms: tuple
     device_ptrs: Optional[dict] = None  # OCHRE_OUT_DEVICE: raw device addresses
+    used: int = 0  # bit 0: fused per-path kernel ran, bit 1: general pipeline ran
 
     def replay(self, path: int, builder: TileBuilder) -> None:
         """TileBuilder calls of one path, in the reference's order (rasterizer.rs:241, :261-264)."""
@@ -98,6 +99,11 @@ class Context:
     def set_chunk(self, max_vcmds: int):
         _check(self._h, _lib.load().ochre_b200_set_chunk(self._h, max_vcmds))
 
+    def set_mode(self, mode):
+        """'auto' (fused per-path kernel, general pipeline as fallback), 'general' or 'fused'."""
+        m = {"auto": 0, "general": 1, "fused": 2}.get(mode, mode)
+        _check(self._h, _lib.load().ochre_b200_set_mode(self._h, int(m)))
+
     def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.
 
@@ -133,7 +139,7 @@ class Context:
         nt, ns = int(res.n_tiles), int(res.n_spans)
         common = dict(n_tiles=nt, n_spans=ns, n_cmds=int(res.n_cmds), n_lines=int(res.n_lines),
                       n_records=int(res.n_records), n_chunks=int(res.n_chunks), kernel_launches=int(res.kernel_launches),
-                      device_ms=float(res.device_ms), stage_ms=tuple(float(x) for x in res.stage_ms))
+                      device_ms=float(res.device_ms), stage_ms=tuple(float(x) for x in res.stage_ms), used=int(res.reserved))
         if out_device:
             ptrs = dict(tile_off=res.tile_off, span_off=res.span_off, tile_xy=res.tile_xy, alpha=res.alpha, spans=res.spans)
             return BatchResult(None, None, None, None, None, device_ptrs=ptrs, **common)

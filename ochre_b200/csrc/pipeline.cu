@@ -19,10 +19,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/ochre_b200.h"
+#include "path_kernel.cuh"
 #include "radix_sort.cuh"
 #include "raster_core.cuh"
 #include "scan.cuh"
@@ -391,6 +393,24 @@ k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals,
 }
 
 // ---------------------------------------------------------------------------
+// Fused path, stage 5b: copy each path's tiles / spans from the staging arena (completion order)
+// into the result arena in path order.  One warp per path, 16-byte words.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_gather_paths(const uint4* __restrict__ rec, uint32_t n_paths, const uint32_t* __restrict__ tile_off,
+               const uint32_t* __restrict__ span_off, const uint4* __restrict__ st_alpha, const uint32_t* __restrict__ st_xy,
+               const uint2* __restrict__ st_spans, uint4* __restrict__ alpha, uint32_t* __restrict__ xy,
+               uint2* __restrict__ spans) {
+    const uint32_t p = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (p >= n_paths) return;
+    const uint4 r = rec[p];
+    const size_t src_t = r.x, dst_t = tile_off[p], src_s = r.z, dst_s = span_off[p];
+    for (uint32_t i = lane; i < r.y * 4; i += 32) alpha[dst_t * 4 + i] = st_alpha[src_t * 4 + i];
+    for (uint32_t i = lane; i < r.y; i += 32) xy[dst_t + i] = st_xy[src_t + i];
+    for (uint32_t i = lane; i < r.w; i += 32) spans[dst_s + i] = st_spans[src_s + i];
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct DevBuf {
@@ -470,6 +490,14 @@ struct ochre_b200_ctx {
     bool dbg_valid = false;
     cudaEvent_t ev[N_STAGE + 1] = {};
     bool attrs_set = false;
+    // fused per-path kernel
+    int mode = OCHRE_MODE_AUTO;
+    int sm_count = 148;
+    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl;  // ctl: ticket(1) cursor(2) status(3) words
+    DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
+    HostBuf h_pk_ctl;
+    uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
+    double tiles_per_cmd = 4.0, spans_per_cmd = 0.75;  // arena growth estimates, refined every call
 };
 
 namespace {
@@ -556,7 +584,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     if (h_sc[SC_STATUS] != ST_OK) {
         switch (h_sc[SC_STATUS]) {
             case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
-            case ST_CONIC: ctx->err = "conic"; return 1000;  // handled by the caller (host pre-flatten)
+            case ST_CONIC: ctx->err = "conic"; return 1000;  // RC_CONIC: handled by the caller (host pre-flatten)
             default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
         }
     }
@@ -685,6 +713,117 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused path: one k_path launch rasterises paths [p0, p1).  Returns 0, an error code, or
+// RC_NEED_GENERAL when some path does not fit the kernel's on-chip budgets (the caller then
+// runs the general pipeline for this chunk).
+// ---------------------------------------------------------------------------
+enum { RC_CONIC = 1000, RC_NEED_GENERAL = 1001 };
+enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_WORDS = 8 };
+
+int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
+                    uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base,
+                    ChunkOut* co) {
+    cudaStream_t st = ctx->st;
+    const uint32_t n_paths = p1 - p0;
+    const uint32_t n_cmds = cmd_hi - cmd_lo;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM);
+    CK(ctx->d_pk_scratch.ensure((size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_MAXLINES * sizeof(float4)));
+    CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4)));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
+    uint32_t* ctl = ctx->d_pk_ctl.as<uint32_t>();
+    uint32_t* h_ctl = ctx->h_pk_ctl.as<uint32_t>();
+    uint4* rec = ctx->d_pk_rec.as<uint4>();
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        // staging arena: estimate from the running tiles-per-command ratio, grow and retry on overflow
+        uint64_t want_t = (uint64_t)((double)(n_cmds + n_paths) * ctx->tiles_per_cmd * 1.15) + 1024;
+        uint64_t want_s = (uint64_t)((double)(n_cmds + n_paths) * ctx->spans_per_cmd * 1.15) + 1024;
+        if (want_t > 0xfffffff0ull) want_t = 0xfffffff0ull;
+        if (want_s > 0xfffffff0ull) want_s = 0xfffffff0ull;
+        CK(ctx->s_tile_xy.ensure(want_t * 4));
+        CK(ctx->s_alpha.ensure(want_t * 64));
+        CK(ctx->s_spans.ensure(want_s * sizeof(OchreSpan)));
+        const uint32_t cap_t = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::min<uint64_t>(ctx->s_alpha.cap / 64, ctx->s_tile_xy.cap / 4));
+        const uint32_t cap_s = (uint32_t)std::min<uint64_t>(0xfffffff0ull, ctx->s_spans.cap / sizeof(OchreSpan));
+        CK(cudaMemsetAsync(ctl, 0, PKC_WORDS * 4, st));
+        PathKernelArgs A;
+        A.cmds = d_cmds_all + cmd_lo;
+        A.cmd_off = d_cmd_off_all + p0;
+        A.cmd_base = cmd_lo;
+        A.xf = d_xf_all + 6 * (size_t)p0;
+        A.n_paths = n_paths;
+        A.ticket = ctl + PKC_TICKET;
+        A.cursor = ctl + PKC_CURSOR;
+        A.rec = rec;
+        A.cap_tiles = cap_t;
+        A.cap_spans = cap_s;
+        A.tile_xy = ctx->s_tile_xy.as<int16_t>();
+        A.alpha = ctx->s_alpha.as<uint8_t>();
+        A.spans = ctx->s_spans.as<OchreSpan>();
+        A.scratch = ctx->d_pk_scratch.as<float4>();
+        A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
+        CK(cudaEventRecord(ctx->ev[0], st));
+        k_path<<<grid, PK_THREADS, PK_SMEM, st>>>(A);
+        CK(cudaEventRecord(ctx->ev[1], st));
+        CK(cudaMemcpyAsync(h_ctl, ctl, PKC_WORDS * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        co->ms[0] += ms;
+        co->launches += 1;
+        const int* stt = reinterpret_cast<const int*>(h_ctl + PKC_STATUS);
+        if (stt[0] != ST_OK) {
+            switch (stt[0]) {
+                case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
+                case ST_CONIC: ctx->err = "conic"; return RC_CONIC;
+                default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
+            }
+        }
+        if (stt[1] > 0) return RC_NEED_GENERAL;
+        const uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];
+        if ((uint64_t)tile_base + nt >= 0xffffffffull || (uint64_t)span_base + ns >= 0xffffffffull) {
+            ctx->err = "more than 2^32 tiles or spans in one call";
+            return OCHRE_E_TOO_LARGE;
+        }
+        // refine the growth estimates (the totals are exact even when the run overflowed)
+        double denom = (double)(n_cmds + n_paths);
+        ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)nt / denom);
+        ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)ns / denom);
+        if (stt[2]) continue;  // staging arena too small: grown at the top of the loop, run again
+        // path order: offsets by exclusive scan of the per-path counts, then the gather copy
+        CK(ctx->o_tile_xy.ensure(((size_t)tile_base + nt + 1) * 4, true, st));
+        CK(ctx->o_alpha.ensure(((size_t)tile_base + nt + 1) * 64, true, st));
+        CK(ctx->o_spans.ensure(((size_t)span_base + ns + 1) * sizeof(OchreSpan), true, st));
+        uint32_t* toff = ctx->o_tile_off.as<uint32_t>() + p0;
+        uint32_t* soff = ctx->o_span_off.as<uint32_t>() + p0;
+        co->launches += device_scan(
+            st, n_paths, [rec] __device__(uint32_t i) { return rec[i].y; },
+            [toff, tile_base] __device__(uint32_t i, uint32_t excl, uint32_t) { toff[i] = tile_base + excl; },
+            ctx->d_scan_ws.as<uint32_t>(), nullptr);
+        co->launches += device_scan(
+            st, n_paths, [rec] __device__(uint32_t i) { return rec[i].w; },
+            [soff, span_base] __device__(uint32_t i, uint32_t excl, uint32_t) { soff[i] = span_base + excl; },
+            ctx->d_scan_ws.as<uint32_t>(), nullptr);
+        k_gather_paths<<<nblk((uint64_t)n_paths * 32, TPB), TPB, 0, st>>>(
+            rec, n_paths, toff, soff, ctx->s_alpha.as<uint4>(), ctx->s_tile_xy.as<uint32_t>(), ctx->s_spans.as<uint2>(),
+            ctx->o_alpha.as<uint4>(), ctx->o_tile_xy.as<uint32_t>(), ctx->o_spans.as<uint2>());
+        co->launches += 1;
+        CK(cudaEventRecord(ctx->ev[2], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+        co->ms[6] += ms;
+        co->n_tiles = nt;
+        co->n_spans = ns;
+        ctx->dbg_valid = false;
+        return 0;
+    }
+    ctx->err = "internal: output arenas did not converge";
+    return OCHRE_E_TOO_LARGE;
+}
+
 }  // namespace
 
 extern "C" {
@@ -710,6 +849,10 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     }
     e = cudaFuncSetAttribute(k_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = ctx->d_pk_ctl.ensure(64);
+    if (e == cudaSuccess) e = ctx->h_pk_ctl.ensure(64);
     if (e == cudaSuccess) e = ctx->d_scalars.ensure(SC_COUNT * sizeof(uint32_t));
     if (e == cudaSuccess) e = ctx->h_scalars.ensure(SC_COUNT * sizeof(uint32_t));
     if (e != cudaSuccess) { ochre_b200_destroy(ctx); return (int)e; }
@@ -725,9 +868,9 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars};
+    HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -742,12 +885,19 @@ int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds) {
     return 0;
 }
 
+int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode) {
+    if (!ctx || mode < OCHRE_MODE_AUTO || mode > OCHRE_MODE_FUSED) return OCHRE_E_INVALID_ARG;
+    ctx->mode = mode;
+    return 0;
+}
+
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
 static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
                           uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out, bool allow_conic_retry) {
     ctx->err.clear();
     ctx->dbg_valid = false;
+    ctx->used_paths = 0;
     memset(out, 0, sizeof *out);
     out->n_paths = n_paths;
     CK(cudaSetDevice(ctx->device));
@@ -816,8 +966,20 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             ++p1;
         }
         ChunkOut co;
-        int rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
-        if (rc == 1000) {
+        int rc = RC_NEED_GENERAL;
+        if (ctx->mode != OCHRE_MODE_GENERAL) {
+            rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+            if (rc == 0) ctx->used_paths |= 1u;
+            if (rc == RC_NEED_GENERAL && ctx->mode == OCHRE_MODE_FUSED) {
+                ctx->err = "a path exceeds the fused kernel's on-chip budgets (mode = fused only)";
+                return OCHRE_E_TOO_LARGE;
+            }
+        }
+        if (rc == RC_NEED_GENERAL) {
+            rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+            if (rc == 0) ctx->used_paths |= 2u;
+        }
+        if (rc == RC_CONIC) {
             // A Conic reached the device.  Flatten conics on the host (reference path.rs:75-104,
             // recursive; device recursion is a later row of SURVEY.md section 8f) and run again.
             if (!allow_conic_retry || in_dev) {
@@ -854,6 +1016,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
     out->n_tiles = tile_base;
     out->n_spans = span_base;
+    out->reserved = ctx->used_paths;
     out->n_lines = total.n_lines;
     out->n_records = total.n_rec;
     out->kernel_launches = total.launches;

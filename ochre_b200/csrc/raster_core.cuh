@@ -81,6 +81,25 @@ OC_HD int f2i16(float f) {
 OC_HD int wrap16(int v) { return (int)(int16_t)v; }
 OC_HD float signum(float f) { return (f == f) ? copysignf(1.0f, f) : f; }
 
+// The two conversions of the DDA, specialised for VALIDATED coordinates (finite, |v| < 32760,
+// enforced by coord_ok before any walk): there the reference's saturating `floor() as i16`,
+// `signum() as i16` and wrapping i16 `x + 1` are plain floor / sign bit / integer add, so the
+// NaN / saturation / wrap branches are dropped on the device.
+OC_HD int floor_px(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rd(f);
+#else
+    return f2i16(floorf(f));
+#endif
+}
+OC_HD int sign_dir(float d) {  // signum(d) as i16 for non-NaN d: -1 for negative (incl. -0.0), else +1
+#if defined(__CUDA_ARCH__)
+    return (__float_as_int(d) < 0) ? -1 : 1;
+#else
+    return f2i16(signum(d));
+#endif
+}
+
 // Number of points a command carries / index of its end point.
 OC_HD int cmd_npts(uint32_t tag) {
     switch (tag) {
@@ -162,32 +181,32 @@ struct Walker {
         last = a;
         point = b;
         float dx = b.x - a.x, dy = b.y - a.y;
-        x_dir = f2i16(signum(dx));
-        y_dir = f2i16(signum(dy));
+        x_dir = sign_dir(dx);
+        y_dir = sign_dir(dy);
         float dtdx = 1.0f / dx;
         float dtdy = 1.0f / dy;
-        x = f2i16(floorf(a.x));
-        y = f2i16(floorf(a.y));
+        x = floor_px(a.x);
+        y = floor_px(a.y);
         row_t0 = 0.0f;
         col_t0 = 0.0f;
         if (a.y == b.y) {
             row_t1 = INFINITY;
         } else {
-            float next_y = (b.y > a.y) ? (float)wrap16(y + 1) : (float)y;
+            float next_y = (b.y > a.y) ? (float)(y + 1) : (float)y;
             row_t1 = fminf(dtdy * (next_y - a.y), 1.0f);
         }
         if (a.x == b.x) {
             col_t1 = INFINITY;
         } else {
-            float next_x = (b.x > a.x) ? (float)wrap16(x + 1) : (float)x;
+            float next_x = (b.x > a.x) ? (float)(x + 1) : (float)x;
             col_t1 = fminf(dtdx * (next_x - a.x), 1.0f);
         }
         x_step = fabsf(dtdx);
         y_step = fabsf(dtdy);
         // p0 of the first increment: t0 = max(0, 0) = 0
         p0 = add(scale(1.0f - 0.0f, a), scale(0.0f, b));
-        end_x = f2i16(floorf(b.x));
-        end_y = f2i16(floorf(b.y));
+        end_x = floor_px(b.x);
+        end_y = floor_px(b.y);
         tile_y_prev = y >> 3;
         ti_sign = 0;
     }
@@ -199,18 +218,18 @@ struct Walker {
         float t1 = fminf(row_t1, col_t1);
         V2 p1 = add(scale(1.0f - t1, last), scale(t1, point));
         height = p1.y - p0.y;
-        float right = (float)wrap16(x + 1);
+        float right = (float)(x + 1);
         area = 0.5f * height * ((right - p0.x) + (right - p1.x));
         ix = x;
         iy = y;
         if (row_t1 < col_t1) {
             row_t0 = row_t1;
             row_t1 = fminf(row_t1 + y_step, 1.0f);
-            y = wrap16(y + y_dir);
+            y = y + y_dir;
         } else {
             col_t0 = col_t1;
             col_t1 = fminf(col_t1 + x_step, 1.0f);
-            x = wrap16(x + x_dir);
+            x = x + x_dir;
         }
         p0 = p1;
         bool done = (row_t0 == 1.0f) || (col_t0 == 1.0f);
@@ -236,11 +255,11 @@ struct Walker {
         if (row_t1 < col_t1) {
             row_t0 = row_t1;
             row_t1 = fminf(row_t1 + y_step, 1.0f);
-            y = wrap16(y + y_dir);
+            y = y + y_dir;
         } else {
             col_t0 = col_t1;
             col_t1 = fminf(col_t1 + x_step, 1.0f);
-            x = wrap16(x + x_dir);
+            x = x + x_dir;
         }
         bool done = (row_t0 == 1.0f) || (col_t0 == 1.0f);
         if (done) {

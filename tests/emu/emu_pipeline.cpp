@@ -6,6 +6,7 @@
 // sums in place of the device scans.  It lets the `-m "not gpu"` suite check the record
 // scheme, winding/span logic and row-carry association against the oracle without a GPU;
 // on the GPU box the kernels are expected to reproduce it byte for byte.
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,6 +43,14 @@ struct ArrAcc {
     float a[64], h[64];
     void add(int pix, float area, float height) { a[pix] += area; h[pix] += height; }
 };
+// the fused kernel's arithmetic (csrc/path_kernel.cuh): 2^-22 fixed-point integer sums
+struct FxAcc {
+    int a[64], h[64];
+    void add(int pix, float area, float height) {
+        a[pix] += (int)lrintf(area * 4194304.0f);
+        h[pix] += (int)lrintf(height * 4194304.0f);
+    }
+};
 struct Fetch {
     const float* lines;
     void operator()(uint32_t i, V2& a, V2& b) const {
@@ -63,7 +72,7 @@ struct EmuResult {
 
 extern "C" {
 
-EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths) {
+EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths, int fixed) {
     EmuResult* R = new EmuResult();
     R->status = 0;
     const Cmd* cmds = reinterpret_cast<const Cmd*>(cmds_);
@@ -165,14 +174,31 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
             R->spans[span_idx[g]] = s;
         }
         if (!real[g]) continue;
-        ArrAcc acc;
-        memset(&acc, 0, sizeof acc);
         int tx = key_tx(k), ty = key_ty(k);
-        for (uint32_t i = gs[g]; i < gend(g); ++i)
-            if (!val_wonly(V[i])) cover_record(acc, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
         uint32_t ti = tile_idx[g];
         R->tile_xy[2 * (size_t)ti] = (int16_t)(tx * 8);
         R->tile_xy[2 * (size_t)ti + 1] = (int16_t)(ty * 8);
+        if (fixed) {
+            FxAcc fx;
+            memset(&fx, 0, sizeof fx);
+            for (uint32_t i = gs[g]; i < gend(g); ++i)
+                if (!val_wonly(V[i])) cover_record(fx, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
+            const float inv = 1.0f / 4194304.0f;
+            for (int y = 0; y < 8; ++y) {
+                int rs = 0, run = 0;
+                for (int x = 0; x < 8; ++x) rs += fx.h[y * 8 + x];
+                for (int x = 0; x < 8; ++x) {
+                    R->alpha[64 * (size_t)ti + y * 8 + x] = (uint8_t)alpha_u8(carry[y] + (float)(run + fx.a[y * 8 + x]) * inv);
+                    run += fx.h[y * 8 + x];
+                }
+                carry[y] += (float)rs * inv;
+            }
+            continue;
+        }
+        ArrAcc acc;
+        memset(&acc, 0, sizeof acc);
+        for (uint32_t i = gs[g]; i < gend(g); ++i)
+            if (!val_wonly(V[i])) cover_record(acc, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
         for (int y = 0; y < 8; ++y) {
             float rs = 0.0f;
             for (int x = 0; x < 8; ++x) rs += acc.h[y * 8 + x];

@@ -23,9 +23,21 @@ pytestmark = pytest.mark.gpu
 ID = O.IDENTITY
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["general", "auto"])
+def ctx(request):
+    """Both implementations behind ochre_b200_rasterize: the general global-memory pipeline and
+    (mode auto) the fused per-path kernel with the general pipeline as its fallback."""
     c = ob.Context(0)  # raises loudly without a device / without the built extension
+    c.set_mode(request.param)
+    c.mode_name = request.param
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def gctx():
+    c = ob.Context(0)
+    c.set_mode("general")
     yield c
     c.close()
 
@@ -53,6 +65,7 @@ def test_config1_basic_rs_bit_exact(ctx):
         h.update(struct.pack("<iii", int(s["x"]), int(s["y"]), int(s["w"])))
     assert h.hexdigest() == "5ada168c9d3a5382b5c4d8b3fc9a90e085d38fe0a0a551ef32908e296de0f917"
     assert g.n_tiles == 100 and g.n_spans == 23 and g.kernel_launches > 0
+    assert g.used == (1 if ctx.mode_name == "auto" else 2)
 
 
 def test_kats_as_one_batch(ctx):
@@ -61,22 +74,51 @@ def test_kats_as_one_batch(ctx):
     assert_batch_parity(g, oracle_batch(cmds, off, xf), what="KATs")
 
 
-def test_stage1_lines_bit_exact(ctx):
+def test_stage1_lines_bit_exact(gctx):
     for path in KATS + [W.blobs(3)[0]]:
         cmds, off, xf = pack([path])
-        ctx.rasterize(cmds, off, xf)
-        lines_match(ctx.debug_lines(), O.rasterize_path(path).lines)
+        gctx.rasterize(cmds, off, xf)
+        lines_match(gctx.debug_lines(), O.rasterize_path(path).lines)
 
 
 def test_gpu_equals_cpu_emulation_byte_for_byte(ctx):
-    cmds, off, xf = W.blobs(200, first=77)
+    """general pipeline == emulation with f32 sums; fused kernel == emulation with 2^-22 fixed point."""
+    cmds, off, xf = W.blobs(400, first=77)
     g = ctx.rasterize(cmds, off, xf)
-    e = E.rasterize(cmds, off, xf)
+    fused = ctx.mode_name == "auto"
+    assert g.used == (1 if fused else 2)
+    e = E.rasterize(cmds, off, xf, fixed=fused)
     assert np.array_equal(g.tile_off, e.tile_off) and np.array_equal(g.span_off, e.span_off)
     assert np.array_equal(g.tile_xy, e.tile_xy) and g.spans.tobytes() == e.spans.tobytes()
     assert np.array_equal(g.alpha, e.alpha)
-    keys, vals = ctx.debug_records()
-    assert np.array_equal(keys, e.keys) and np.array_equal(vals, e.vals)
+    if not fused:
+        keys, vals = ctx.debug_records()
+        assert np.array_equal(keys, e.keys) and np.array_equal(vals, e.vals)
+
+
+def test_fused_kernel_falls_back_for_oversized_paths():
+    c = ob.Context(0)
+    try:
+        cmds, off, xf = W.rings(96, 16.0, 256)  # one path, 24k commands: beyond the fused kernel's command table
+        c.set_mode("fused")
+        with pytest.raises(ob._lib.OchreError) as e:
+            c.rasterize(cmds, off, xf)
+        assert e.value.code == -4
+        c.set_mode("auto")
+        g = c.rasterize(cmds, off, xf)
+        assert g.used == 2
+        # a mixed batch: small paths + one wide path; chunks without the big path stay on the fused kernel
+        b_cmds, b_off, b_xf = W.blobs(300)
+        wide = make_cmds([(MOVE, 10, 10), (LINE, 30000, 14), (LINE, 30000, 40), (LINE, 10, 30), (CLOSE,)])
+        cmds = np.concatenate([b_cmds, wide])
+        off2 = np.concatenate([b_off, [b_off[-1] + len(wide)]]).astype(np.uint32)
+        xf2 = np.concatenate([b_xf, ID[None]])
+        c.set_chunk(2048)
+        g = c.rasterize(cmds, off2, xf2)
+        assert g.used == 3 and g.n_chunks > 2
+        assert_batch_parity(g, oracle_batch(cmds, off2, xf2), what="mixed batch")
+    finally:
+        c.close()
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -136,6 +178,7 @@ def test_chunking_and_rerun_do_not_change_a_byte(ctx):
     finally:
         ctx.set_chunk(0)
     assert c.n_chunks > 4 and a.n_chunks == 1
+    assert a.used == (1 if ctx.mode_name == "auto" else 2) and c.used == a.used
     for r in (b, c):
         assert np.array_equal(a.tile_off, r.tile_off) and np.array_equal(a.span_off, r.span_off)
         assert np.array_equal(a.tile_xy, r.tile_xy) and np.array_equal(a.alpha, r.alpha)
