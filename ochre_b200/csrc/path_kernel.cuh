@@ -1,26 +1,29 @@
-// path_kernel.cuh -- the fused per-path rasteriser: one CTA rasterises one whole path
-// (flatten -> bin -> coverage -> backdrop/winding -> emission) out of shared memory.
+// path_kernel.cuh -- the fused per-path rasteriser: one CTA takes one path from its PathCmd
+// array to its finished alpha tiles and spans without leaving the SM.
 //
-// This is the fast path of the pipeline for paths that fit its on-chip budgets (every path of
-// BASELINE configs 1-4); pipeline.cu's global-memory pipeline stays the general path (giant
-// paths, config 5a) and the fallback.  The five north_star stages are all here, per path:
+// This is the hot kernel for batches of ordinary paths (glyphs, SVG shapes, the synthetic blobs
+// of BASELINE configs 1-4); pipeline.cu's global-memory pipeline handles the paths that exceed
+// the on-chip budgets below (giant paths, config 5a).  The five north_star stages, per path:
 //
-//   1 flatten   thread per command counts lines (rounded t recurrence), CTA scan, thread per
-//               line evaluates its end points                   ref path.rs:16-74, rasterizer.rs:61-69
-//   2 bin       "pass A": thread per line walks the DDA control flow and marks the tiles of the
-//               path's bounding grid it touches (+ TileIncrement winding deltas); an ordered CTA
-//               scan of the grid plays the role of the (tile_y, tile_x) sort  ref rasterizer.rs:72-140, :185-211
-//   3 coverage  "pass B": thread per line walks the full DDA and adds area/height into the
-//               tile's accumulators with native shared-memory integer atomics (fixed point 2^-22)
-//                                                                ref rasterizer.rs:97-116, :221-228
-//   4 backdrop  per tile row: left-to-right carry of the row heights (f32), inclusive scan of
-//               winding deltas over the grid in (tile_y, tile_x) order   ref rasterizer.rs:233-260
-//   5 emission  alpha rows as 8-byte stores, spans, per-path offsets; output positions come from
-//               a decoupled look-back over per-path (tiles, spans) counts in path order
+//   1 flatten   thread per command: transform, dt, line count, the rounded t sequence
+//               (path.rs:49-74); CTA scan; thread per line: curve evaluation
+//                                                        ref path.rs:16-74, rasterizer.rs:61-69, :145-165
+//   2 bin       "mark": thread per line runs the DDA's control flow and counts the increments on
+//               every tile of the path's bounding grid (+ TileIncrement winding deltas); an
+//               ordered scan of the grid plays the role of the (tile_y, tile_x) sort
+//                                                        ref rasterizer.rs:72-140, :185-211
+//   3 coverage  "accumulate": thread per line walks the DDA again and adds area/height into the
+//               tile's 8x9 accumulator block with native shared-memory integer atomics
+//               (2^-22 fixed point; column x holds area, column x+1 receives height - area, so a
+//               row prefix sum yields accum + area directly)     ref rasterizer.rs:97-116, :221-228
+//   4 backdrop  per tile row: left-to-right carry of the row sums; inclusive scan of the winding
+//               deltas over the grid in (tile_y, tile_x) order       ref rasterizer.rs:233-260
+//   5 emission  alpha rows as coalesced 8-byte stores, tile origins, spans; each path reserves
+//               its output range in the arena with one atomicAdd
 //
-// HBM traffic is the compulsory B_alg (commands in, tiles/spans out) plus an L2-resident
-// per-CTA line scratch.  Accumulation is order-independent (integer adds), so results do not
-// depend on scheduling; tests/emu reproduces the arithmetic byte for byte.
+// HBM traffic is the compulsory B_alg (commands in, tiles/spans out) plus an L2-resident per-CTA
+// line scratch.  Accumulation is order-independent (integer adds), so results do not depend on
+// scheduling; tests/emu reproduces the arithmetic byte for byte.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,207 +38,392 @@ namespace oc {
 #define OC_PK_THREADS 256
 #endif
 #ifndef OC_PK_SLOTS
-#define OC_PK_SLOTS 136
+#define OC_PK_SLOTS 126
 #endif
 #ifndef OC_PK_CELLS
-#define OC_PK_CELLS 2048
+#define OC_PK_CELLS 4608
 #endif
 #ifndef OC_PK_CTAS
-#define OC_PK_CTAS 2
+#define OC_PK_CTAS 4
 #endif
 constexpr int PK_THREADS = OC_PK_THREADS;
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
 constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the bounding grid resident at once (a band of tile rows)
 constexpr int PK_CTAS_PER_SM = OC_PK_CTAS;
-constexpr int PK_MAXV = 96;         // virtual commands per path
-constexpr int PK_MAXLINES = 8192;   // line slots per path (per-CTA scratch in global memory, L2 resident)
-constexpr int PK_MAXROWS = 4096;    // tile rows of the bounding grid
+constexpr int PK_MAXLINES = 4095;   // line slots per path: keeps a cell's 16-bit increment count exact (<= 16 per line)
+constexpr int PK_LINECAP = 4096;    // scratch stride
+constexpr int PK_MAXROWS = 16384;   // grid height in tile rows (16-bit row fields)
 constexpr int PK_MAXCNT = 511;      // increments per tile: keeps the fixed-point sums inside int32
+constexpr int PK_ACCW = 72;         // accumulator words per tile: 8 pixel rows x (8 columns + 1 carry-out column)
 #define OC_FX_SCALE 4194304.0f      /* 2^22 */
-#define OC_FX_INV (1.0f / 4194304.0f)
+#define OC_FX_TO_256 (1.0f / 16384.0f) /* 2^-22 * 256 */
+#define PK_CELL_INIT 0x80000000u    /* increments 0, winding delta 0 (biased by 0x8000) */
+#define PK_ROWS_NONE 0xffffffffu
+#define PK_OWNER_NONE 0xffffffffu
 
-// per-path status codes written to pk_flags[path]
-enum : uint32_t { PK_OK = 0, PK_FALLBACK = 1 };
+// Per-CTA scratch in global memory (stays in L2): lines, (t, owner) of every line, tile-row range of every line.
+constexpr size_t PK_SCR_LINES = 0;                                             // float4[LINECAP]
+constexpr size_t PK_SCR_REC = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;      // uint2[LINECAP]
+constexpr size_t PK_SCR_ROWS = PK_SCR_REC + sizeof(uint2) * PK_LINECAP;        // uint32[LINECAP]
+constexpr size_t PK_SCR_BYTES = PK_SCR_ROWS + 4 * (size_t)PK_LINECAP;
 
 struct PathKernelArgs {
     const Cmd* cmds;            // chunk base (index with cmd_off[p] - cmd_base)
-    const uint32_t* cmd_off;    // chunk base, n_paths + 1 entries
+    const uint32_t* cmd_off;    // cmd_off[0 .. n_paths] of this chunk
     uint32_t cmd_base;
-    const float* xf;            // chunk base, 6 floats per path
+    const float* xf;            // 6 floats per path
     uint32_t n_paths;
-    // work distribution: paths are handed out in index order by an atomic ticket
-    uint32_t* ticket;           // zeroed before launch
-    // Outputs go to a staging arena in COMPLETION order: each path reserves its tile / span range
-    // with one atomicAdd on `cursor` (no CTA ever waits for another one) and records where it
-    // landed in rec[p] = {tile_start, n_tiles, span_start, n_spans}.  k_gather_paths then copies
-    // the ranges into path order (pipeline.cu), which is what keeps the result deterministic.
-    uint32_t* cursor;           // [0] tiles, [1] spans; zeroed before launch; totals after it
-    uint4* rec;                 // n_paths
-    uint32_t cap_tiles, cap_spans;        // staging capacities
+    uint32_t* ticket;           // work counter (dynamic path assignment)
+    uint32_t* cursor;           // [0] tiles, [1] spans handed out so far in the arena
+    uint4* rec;                 // per path: (tile start, n_tiles, span start, n_spans) in the arena
+    uint32_t cap_tiles, cap_spans;
     int16_t* tile_xy;
     uint8_t* alpha;
     OchreSpan* spans;
-    // scratch + status
-    float4* scratch;            // gridDim.x * PK_MAXLINES
-    int* status;                // [0] input error (ST_*), [1] #fallback paths, [2] output overflow
+    unsigned char* scratch;     // gridDim.x * PK_SCR_BYTES
+    int* status;                // [0] input error (ST_*), [1] #paths left to the general pipeline, [2] arena overflow
+    uint32_t* fb_list;          // paths left to the general pipeline (chunk-local ids), status[1] entries
 };
+
+struct PkCurves {  // decoded curve commands of the current command chunk (slot = thread id)
+    V2 last[PK_THREADS], a[PK_THREADS], b[PK_THREADS], c[PK_THREADS];
+    uint32_t loff[PK_THREADS];  // first line of the command
+    uint32_t tag[PK_THREADS];
+};
+struct PkGrid {
+    uint32_t cell[PK_CELLS];   // mark pass: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: flags
+    uint16_t tcell[PK_CELLS];  // touched cells in (tile_y, tile_x) order
+};
+enum : uint32_t { CF_TOUCHED = 1, CF_WIND = 2, CF_SPAN = 4 };
 
 struct PkShared {
-    int acc[PK_SLOTS * 128];
-    uint32_t cnt[PK_CELLS];        // increments per cell (pass A)
-    int wind[PK_CELLS];            // winding delta per cell -> inclusive prefix (path order) after the scan
-    uint16_t rank[PK_CELLS + 2];   // exclusive count of touched cells before this cell (band local)
-    uint16_t tcell[PK_CELLS];      // touched cells in order: tcell[rank] = cell
-    uint16_t spanx[PK_CELLS];      // exclusive count of spans before this cell (band local)
-    float carry[PK_SLOTS * 8];     // `prev[y]` of each resident tile
-    // command table
-    uint32_t v_tag[PK_MAXV];
-    float v_dt[PK_MAXV];
-    V2 v_last[PK_MAXV], v_a[PK_MAXV], v_b[PK_MAXV], v_c[PK_MAXV];
-    uint32_t v_loff[PK_MAXV + 1];
-    uint32_t ws[33];
-    int bbox[4];                   // min tx, min ty, max tx, max ty over every line end point
-    uint32_t path, n_lines, flag, r1, any_inc;
-    uint32_t tot_tiles, tot_spans, base_tiles, base_spans;
+    union {  // phase-aliased: flatten | mark + scan + span/origin emission | accumulate + quantise
+        int acc[PK_SLOTS * PK_ACCW];
+        PkGrid g;
+        PkCurves v;
+    } u;
+    uint16_t rank[PK_CELLS + 2];   // touched cells before this cell (band local); kept across the slot bands
+    uint32_t ws[72];
+    int bbox[4];                   // min tx, min ty, max tx, max ty over every non-degenerate line
+    uint32_t path, r1, base_tiles, base_spans;
 };
 
-// CTA-wide exclusive scan over n items held in shared memory, 256 at a time.
-// get(i) -> value, put(i, excl, v).  Returns the total (same in every thread).
-template <class Get, class Put>
-__device__ __forceinline__ uint32_t pk_scan(uint32_t n, uint32_t* ws, Get get, Put put) {
-    uint32_t run = 0;
-    for (uint32_t base = 0; base < n; base += PK_THREADS) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = (i < n) ? get(i) : 0u;
-        uint32_t total;
-        uint32_t excl = block_excl_scan(v, ws, total);
-        if (i < n) put(i, run + excl, v);
-        run += total;
+// Exclusive scan of two values per thread across the CTA in one pass.  `ws` must hold 72 words.
+__device__ __forceinline__ void block_excl_scan_pair(uint32_t a, uint32_t b, uint32_t* ws, uint32_t& ex_a, uint32_t& ex_b,
+                                                     uint32_t& tot_a, uint32_t& tot_b) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t na = __shfl_up_sync(0xffffffffu, ia, d);
+        uint32_t nb = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= (unsigned)d) {
+            ia += na;
+            ib += nb;
+        }
     }
-    return run;
-}
-
-// tile rows a line can touch, padded by one pixel for the DDA's overshoot / end snap
-__device__ __forceinline__ void line_rows(const float4& L, int& lo, int& hi) {
-    float ylo = fminf(L.y, L.w), yhi = fmaxf(L.y, L.w);
-    lo = (floor_px(ylo) - 1) >> 3;
-    hi = (floor_px(yhi) + 1) >> 3;
-}
-
-// Pass A over the cell band [row0, row0 + nrows): marks cells, counts increments, adds winding deltas.
-__device__ __forceinline__ void pk_pass_a(PkShared& S, const float4* lines, uint32_t n_lines, int gx0, int gy0,
-                                          int W, int row0, int nrows, uint32_t& err) {
-    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
-        float4 L = __ldcg(&lines[i]);  // L2: the scratch is rewritten for every path this CTA takes
-        if (L.x == L.z && L.y == L.w) continue;
-        int lo, hi;
-        line_rows(L, lo, hi);
-        if (hi < gy0 + row0 || lo >= gy0 + row0 + nrows) continue;
-        Walker w;
-        w.init(mk(L.x, L.y), mk(L.z, L.w));
-        for (;;) {
-            int ix, iy;
-            bool done = w.step_cells(ix, iy);
-            int cy = (iy >> 3) - gy0 - row0, cx = (ix >> 3) - gx0;
-            if (cy >= 0 && cy < nrows) {
-                if (cx < 0 || cx >= W) err = 1; else atomicAdd(&S.cnt[cy * W + cx], 1u);
+    if (lane == 31) {
+        ws[warp] = ia;
+        ws[36 + warp] = ib;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned nw = blockDim.x >> 5;
+        uint32_t wa = (lane < nw) ? ws[lane] : 0u, wb = (lane < nw) ? ws[36 + lane] : 0u;
+        uint32_t sa = wa, sb = wb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t na = __shfl_up_sync(0xffffffffu, sa, d);
+            uint32_t nb = __shfl_up_sync(0xffffffffu, sb, d);
+            if (lane >= (unsigned)d) {
+                sa += na;
+                sb += nb;
             }
-            if (w.ti_sign != 0) {
-                int ty = w.ti_ty - gy0 - row0, tx = w.ti_tx - gx0;
-                if (ty >= 0 && ty < nrows) {
-                    if (tx < 0 || tx >= W) err = 1; else atomicAdd(&S.wind[ty * W + tx], w.ti_sign);
+        }
+        ws[lane] = sa - wa;
+        ws[36 + lane] = sb - wb;
+        if (lane == 31) {
+            ws[32] = sa;
+            ws[68] = sb;
+        }
+    }
+    __syncthreads();
+    ex_a = ia - a + ws[warp];
+    ex_b = ib - b + ws[36 + warp];
+    tot_a = ws[32];
+    tot_b = ws[68];
+    __syncthreads();
+}
+
+// The DDA of Rasterizer::line_to (rasterizer.rs:74-136), device form.  Same operations in the
+// same order as raster_core.cuh's Walker; the loop exit `row_t0 == 1 || col_t0 == 1` is tested
+// as `t1 == 1`: the t0 a trip stores is the t1 it consumed, and an earlier one would have ended
+// the loop already.
+struct LineWalk {
+    float lx, ly, px, py;
+    float row_t1, col_t1, x_step, y_step;
+    int x, y, x_dir, y_dir, end_x, end_y;
+    __device__ __forceinline__ void init(const float4 L) {
+        lx = L.x;
+        ly = L.y;
+        px = L.z;
+        py = L.w;
+        const float dx = px - lx, dy = py - ly;
+        x_dir = sign_dir(dx);
+        y_dir = sign_dir(dy);
+        const float dtdx = 1.0f / dx, dtdy = 1.0f / dy;
+        x = floor_px(lx);
+        y = floor_px(ly);
+        row_t1 = INFINITY;
+        col_t1 = INFINITY;
+        if (ly != py) row_t1 = fminf(dtdy * (((py > ly) ? (float)(y + 1) : (float)y) - ly), 1.0f);
+        if (lx != px) col_t1 = fminf(dtdx * (((px > lx) ? (float)(x + 1) : (float)x) - lx), 1.0f);
+        x_step = fabsf(dtdx);
+        y_step = fabsf(dtdy);
+        end_x = floor_px(px);
+        end_y = floor_px(py);
+    }
+    // one loop trip's control flow: returns the trip's t1, moves to the next pixel (or the end snap)
+    __device__ __forceinline__ bool advance(float& t1) {
+        t1 = fminf(row_t1, col_t1);
+        if (row_t1 < col_t1) {
+            row_t1 = fminf(row_t1 + y_step, 1.0f);
+            y += y_dir;
+        } else {
+            col_t1 = fminf(col_t1 + x_step, 1.0f);
+            x += x_dir;
+        }
+        const bool done = (t1 == 1.0f);
+        if (done) {
+            x = end_x;
+            y = end_y;
+        }
+        return done;
+    }
+};
+
+struct PkScratch {
+    float4* lines;
+    uint2* rec;
+    uint32_t* rows;
+    __device__ __forceinline__ explicit PkScratch(unsigned char* b)
+        : lines(reinterpret_cast<float4*>(b + PK_SCR_LINES)), rec(reinterpret_cast<uint2*>(b + PK_SCR_REC)),
+          rows(reinterpret_cast<uint32_t*>(b + PK_SCR_ROWS)) {}
+};
+
+struct PkBBox {
+    int x0, y0, x1, y1;
+    __device__ __forceinline__ void add(V2 a, V2 b) {
+        const int ax = floor_px(a.x) >> 3, ay = floor_px(a.y) >> 3, ex = floor_px(b.x) >> 3, ey = floor_px(b.y) >> 3;
+        x0 = min(x0, min(ax, ex));
+        x1 = max(x1, max(ax, ex));
+        y0 = min(y0, min(ay, ey));
+        y1 = max(y1, max(ay, ey));
+    }
+};
+
+// Mark pass over the cell band [row0, row0 + nrows) of the grid (rasterizer.rs:97-136, control
+// flow only): counts the increments per cell and adds the TileIncrement signs.  With `first`
+// every line is walked and its tile-row range recorded; later bands use the range to skip.
+__device__ __forceinline__ uint32_t pk_mark(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W, int row0,
+                                            int nrows, bool first) {
+    uint32_t err = 0;
+    uint32_t* cell = S.u.g.cell;
+    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
+        if (!first) {
+            const uint32_t rr = __ldcg(&G.rows[i]);
+            if (rr == PK_ROWS_NONE || (int)(rr >> 16) < row0 || (int)(rr & 0xffffu) >= row0 + nrows) continue;
+        }
+        const float4 L = __ldcg(&G.lines[i]);
+        if (L.x == L.z && L.y == L.w) {  // rasterizer.rs:73
+            if (first) __stcg(&G.rows[i], PK_ROWS_NONE);
+            continue;
+        }
+        LineWalk w;
+        w.init(L);
+        int prev_ty = w.y >> 3;
+        int tmin = prev_ty, tmax = prev_ty;
+        for (;;) {
+            const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0 - row0;
+            if ((unsigned)cy < (unsigned)nrows) {
+                if ((unsigned)cx < (unsigned)W) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
+            }
+            float t1;
+            const bool done = w.advance(t1);
+            const int ty = w.y >> 3;
+            if (ty != prev_ty) {  // rasterizer.rs:123-131
+                const int tiy = min(ty, prev_ty) - gy0 - row0, tix = (w.x >> 3) - gx0;
+                if ((unsigned)tiy < (unsigned)nrows) {
+                    if ((unsigned)tix < (unsigned)W) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16); else err = 1;
+                }
+                tmin = min(tmin, ty);
+                tmax = max(tmax, ty);
+                prev_ty = ty;
+            }
+            if (done) break;
+        }
+        if (first) __stcg(&G.rows[i], (uint32_t)(tmin - gy0) | ((uint32_t)(tmax - gy0) << 16));
+    }
+    return err;
+}
+
+// Accumulate pass over the slot band: grid rows [R0, R1) (relative to gy0); `cell_row0` is the first
+// row of the resident cell band, slot = rank - rank0.
+__device__ __forceinline__ void pk_accumulate(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W,
+                                              int cell_row0, int R0, int R1, uint32_t rank0) {
+    int* acc = S.u.acc;
+    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
+        const uint32_t rr = __ldcg(&G.rows[i]);
+        if (rr == PK_ROWS_NONE || (int)(rr >> 16) < R0 || (int)(rr & 0xffffu) >= R1) continue;
+        const float4 L = __ldcg(&G.lines[i]);
+        LineWalk w;
+        w.init(L);
+        // p0 of the first increment: t0 = max(0, 0) = 0 (rasterizer.rs:99-101)
+        float p0x = (1.0f - 0.0f) * w.lx + 0.0f * w.px, p0y = (1.0f - 0.0f) * w.ly + 0.0f * w.py;
+        for (;;) {
+            const int x0 = w.x, y0 = w.y;
+            float t1;
+            const bool done = w.advance(t1);
+            const float omt = 1.0f - t1;
+            const float p1x = omt * w.lx + t1 * w.px, p1y = omt * w.ly + t1 * w.py;
+            const float height = p1y - p0y;
+            const float right = (float)(x0 + 1);
+            const float area = 0.5f * height * ((right - p0x) + (right - p1x));
+            const int ry = (y0 >> 3) - gy0;
+            if (ry >= R0 && ry < R1) {
+                const uint32_t slot = (uint32_t)S.rank[(ry - cell_row0) * W + ((x0 >> 3) - gx0)] - rank0;
+                int* d = &acc[slot * PK_ACCW + (y0 & 7) * 9 + (x0 & 7)];
+                const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
+                atomicAdd(d, qa);
+                atomicAdd(d + 1, qh - qa);
+            } else if ((w.y_dir > 0) ? (ry >= R1) : (ry < R0)) {
+                break;  // the walk is monotone in y: it has left the band for good
+            }
+            p0x = p1x;
+            p0y = p1y;
+            if (done) break;
+        }
+    }
+}
+
+// Per-thread state of the grid scan that the emission pass needs again.
+struct PkScan {
+    uint32_t c0, c1;      // this thread's contiguous run of cells
+    uint32_t span_excl;   // spans of the band before this thread's run
+};
+
+// Mark + ordered scan of one cell band.  On return: S.rank (touched cells before each cell, band
+// local, S.rank[ncells] = n_touched), S.u.g.tcell (ordered touched cells), S.u.g.cell = CF_* flags.
+__device__ __forceinline__ void pk_band_setup(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W,
+                                              int row0, int nrows, bool first, int wcarry, PkScan& sc, uint32_t& n_touched,
+                                              uint32_t& n_spans, int& wtotal, uint32_t& bad) {
+    const uint32_t ncells = (uint32_t)(W * nrows);
+    uint32_t* cell = S.u.g.cell;
+    for (uint32_t i = threadIdx.x; i < ncells; i += PK_THREADS) cell[i] = PK_CELL_INIT;
+    __syncthreads();
+    uint32_t err = pk_mark(S, G, n_lines, gx0, gy0, W, row0, nrows, first);
+    __syncthreads();
+    // every thread owns a contiguous run of cells: local sums, one CTA scan, local prefix
+    const uint32_t per = (ncells + PK_THREADS - 1) / PK_THREADS;
+    sc.c0 = min(ncells, threadIdx.x * per);
+    sc.c1 = min(ncells, sc.c0 + per);
+    uint32_t lt = 0, lw = 0;
+    for (uint32_t c = sc.c0; c < sc.c1; ++c) {
+        const uint32_t w = cell[c];
+        const uint32_t cnt = w & 0xffffu;
+        if (cnt > PK_MAXCNT) err = 1;  // keeps the fixed-point sums inside int32
+        lt += cnt ? 1u : 0u;
+        lw += (w >> 16) - 0x8000u;
+    }
+    uint32_t ex_t, ex_w, tot_t, tot_w;
+    block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
+    {
+        uint32_t r = ex_t;
+        int wp = wcarry + (int)ex_w;
+        for (uint32_t c = sc.c0; c < sc.c1; ++c) {
+            const uint32_t w = cell[c];
+            const uint32_t cnt = w & 0xffffu;
+            wp += (int)((w >> 16) - 0x8000u);
+            S.rank[c] = (uint16_t)r;
+            uint32_t f = 0;
+            if (cnt) {
+                S.u.g.tcell[r] = (uint16_t)c;
+                ++r;
+                f = CF_TOUCHED | (wp != 0 ? CF_WIND : 0u);
+            }
+            cell[c] = f;
+        }
+    }
+    n_touched = tot_t;
+    wtotal = wcarry + (int)tot_w;
+    if (threadIdx.x == 0) S.rank[ncells] = (uint16_t)tot_t;
+    __syncthreads();
+    // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
+    uint32_t ls = 0;
+    if (sc.c0 < sc.c1) {
+        uint32_t row_end = (sc.c0 / (uint32_t)W + 1u) * (uint32_t)W;
+        for (uint32_t c = sc.c0; c < sc.c1; ++c) {
+            if (c == row_end) row_end += (uint32_t)W;
+            const uint32_t f = cell[c];
+            if ((f & (CF_TOUCHED | CF_WIND)) == (CF_TOUCHED | CF_WIND)) {
+                const uint32_t r = S.rank[c];
+                if (r + 1 < tot_t) {
+                    const uint32_t nx = S.u.g.tcell[r + 1];
+                    if (nx > c + 1 && nx < row_end) {
+                        cell[c] = f | CF_SPAN;
+                        ++ls;
+                    }
                 }
             }
-            if (done) break;
         }
     }
-}
-
-// Pass B over the slot band: rows [row0 + r0, row0 + r1) of the cell band, slot = rank - rank0.
-__device__ __forceinline__ void pk_pass_b(PkShared& S, const float4* lines, uint32_t n_lines, int gx0, int gy0,
-                                          int W, int row0, int r0, int r1, uint32_t rank0) {
-    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
-        float4 L = __ldcg(&lines[i]);
-        if (L.x == L.z && L.y == L.w) continue;
-        int lo, hi;
-        line_rows(L, lo, hi);
-        if (hi < gy0 + row0 + r0 || lo >= gy0 + row0 + r1) continue;
-        Walker w;
-        w.init(mk(L.x, L.y), mk(L.z, L.w));
-        for (;;) {
-            int ix, iy;
-            float area, height;
-            bool done = w.step(ix, iy, area, height);
-            int cy = (iy >> 3) - gy0 - row0, cx = (ix >> 3) - gx0;
-            if (cy >= r0 && cy < r1) {
-                uint32_t slot = (uint32_t)S.rank[cy * W + cx] - rank0;
-                int* a = &S.acc[slot * 128 + ((((iy & 7) << 3) | (ix & 7)) << 1)];
-                atomicAdd(a, __float2int_rn(area * OC_FX_SCALE));
-                atomicAdd(a + 1, __float2int_rn(height * OC_FX_SCALE));
-            }
-            if (done) break;
-        }
-    }
-}
-
-// Mark + scan one cell band.  On return: S.cnt (increments), S.wind (inclusive winding prefix in
-// path order, including `wcarry`), S.rank / S.tcell (ordered touched cells), S.spanx (exclusive
-// span index).  Returns touched / span counts of the band through the references.
-__device__ __forceinline__ void pk_band_setup(PkShared& S, const float4* lines, uint32_t n_lines, int gx0, int gy0,
-                                              int W, int row0, int nrows, int wcarry, uint32_t& n_touched, uint32_t& n_spans,
-                                              int& wtotal, uint32_t& bad) {
-    const uint32_t ncells = (uint32_t)(W * nrows);
-    for (uint32_t i = threadIdx.x; i < ncells; i += PK_THREADS) {
-        S.cnt[i] = 0;
-        S.wind[i] = 0;
-    }
-    __syncthreads();
-    uint32_t err = 0;
-    pk_pass_a(S, lines, n_lines, gx0, gy0, W, row0, nrows, err);
-    __syncthreads();
-    // per-cell limits (keeps fixed-point sums inside int32)
-    for (uint32_t i = threadIdx.x; i < ncells; i += PK_THREADS)
-        if (S.cnt[i] > PK_MAXCNT) err = 1;
-    // ranks of touched cells, in (tile_y, tile_x) order
-    n_touched = pk_scan(
-        ncells, S.ws, [&](uint32_t i) { return S.cnt[i] ? 1u : 0u; },
-        [&](uint32_t i, uint32_t excl, uint32_t v) {
-            S.rank[i] = (uint16_t)excl;
-            if (v) S.tcell[excl] = (uint16_t)i;
-        });
-    if (threadIdx.x == 0) S.rank[ncells] = (uint16_t)n_touched;
-    // inclusive winding prefix (two's complement wrap-around sums)
-    uint32_t wt = pk_scan(
-        ncells, S.ws, [&](uint32_t i) { return (uint32_t)S.wind[i]; },
-        [&](uint32_t i, uint32_t excl, uint32_t v) { S.wind[i] = (int)(excl + v) + wcarry; });
-    wtotal = (int)wt + wcarry;
-    __syncthreads();
-    // spans: touched cell, next touched cell on the same row at distance > 1, winding != 0
-    n_spans = pk_scan(
-        ncells, S.ws,
-        [&](uint32_t i) {
-            if (!S.cnt[i]) return 0u;
-            uint32_t r = S.rank[i];
-            if (r + 1 >= n_touched) return 0u;
-            uint32_t nx = S.tcell[r + 1];
-            return (nx / (uint32_t)W == i / (uint32_t)W && nx > i + 1 && S.wind[i] != 0) ? 1u : 0u;
-        },
-        [&](uint32_t i, uint32_t excl, uint32_t) { S.spanx[i] = (uint16_t)excl; });
+    uint32_t tot_s;
+    sc.span_excl = block_excl_scan(ls, S.ws, tot_s);
+    n_spans = tot_s;
     bad = __syncthreads_or((int)err);
+}
+
+// Tile origins and spans of the resident cell band (needs the CF_* flags and tcell, i.e. runs before
+// the accumulators reuse that shared memory).
+__device__ __forceinline__ void pk_emit_band_index(const PkShared& S, const PathKernelArgs& A, const PkScan& sc, int gx0, int gy0,
+                                                   int W, int row0, uint32_t tile_at, uint32_t span_at) {
+    if (sc.c0 >= sc.c1) return;
+    const uint32_t* cell = S.u.g.cell;
+    int cy = (int)(sc.c0 / (uint32_t)W), cx = (int)(sc.c0 - (uint32_t)cy * (uint32_t)W);
+    uint32_t sidx = span_at + sc.span_excl;
+    for (uint32_t c = sc.c0; c < sc.c1; ++c) {
+        const uint32_t f = cell[c];
+        if (f & CF_TOUCHED) {
+            const uint32_t r = S.rank[c];
+            const int px = (gx0 + cx) * 8, py = (gy0 + row0 + cy) * 8;
+            reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at + r] = (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16);
+            if (f & CF_SPAN) {
+                const uint32_t nx = S.u.g.tcell[r + 1];
+                OchreSpan sp;
+                sp.x = (int16_t)(px + 8);
+                sp.y = (int16_t)py;
+                sp.w = (uint16_t)((nx - c - 1) * 8u);
+                sp.pad = 0;
+                A.spans[sidx++] = sp;
+            }
+        }
+        if (++cx == W) {
+            cx = 0;
+            ++cy;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelArgs A) {
     extern __shared__ __align__(16) unsigned char pk_smem_raw[];
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
     const uint32_t tid = threadIdx.x;
-    float4* lines = A.scratch + (size_t)blockIdx.x * PK_MAXLINES;
+    const PkScratch G(A.scratch + (size_t)blockIdx.x * PK_SCR_BYTES);
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             S.path = atomicAdd(A.ticket, 1u);
-            S.flag = PK_OK;
-            S.any_inc = 0;
             S.bbox[0] = S.bbox[1] = 0x7fffffff;
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
         }
@@ -243,144 +431,158 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         const uint32_t p = S.path;
         if (p >= A.n_paths) return;
 
-        // ---- 1. command table, line counts -------------------------------------------------
         const uint32_t c0 = A.cmd_off[p] - A.cmd_base, c1 = A.cmd_off[p + 1] - A.cmd_base;
-        const uint32_t nc = c1 - c0, nv = nc + 1;
+        const uint32_t nc = c1 - c0, nv = nc + 1;  // + the virtual FINISH command (finish()'s auto-close)
         const Cmd* pc = A.cmds + c0;
         const float* m = A.xf + 6 * (size_t)p;
-        uint32_t my_n = 0;
-        bool ok = true;
-        if (nv <= PK_MAXV && tid < nc) {
-            uint32_t tag = pc[tid].tag;
-            if (tag == TAG_CONIC) { atomicMax(A.status, 3); ok = false; }
-            else if (tag > TAG_LINE_ABS) { atomicMax(A.status, 2); ok = false; }
-            int np = cmd_npts(tag);
-            for (int i = 0; i < np && ok; ++i)
-                if (!coord_ok(cmd_point(pc[tid], i, m))) { atomicMax(A.status, 1); ok = false; }
-        }
-        // one bad command poisons `last` of its successors: a path with any rejected command is
-        // not walked at all (the call fails with the status code anyway)
-        const bool bad_path = __syncthreads_or(ok ? 0 : 1) != 0;
-        if (!bad_path && nv <= PK_MAXV && tid < nv) {
-            VCmd c = decode_vcmd(pc, nc, tid, m);
-            float dt = 0.0f;
-            if (c.tag == TAG_QUAD) dt = quad_dt(c.last, c.a, c.b);
-            else if (c.tag == TAG_CUBIC) dt = cubic_dt(c.last, c.a, c.b, c.c);
-            switch (c.tag) {
-                case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
-                case TAG_QUAD: case TAG_CUBIC: my_n = curve_count(dt); break;
-                default: my_n = 0; break;
-            }
-            S.v_tag[tid] = c.tag;
-            S.v_dt[tid] = dt;
-            S.v_last[tid] = c.last;
-            S.v_a[tid] = c.a;
-            S.v_b[tid] = c.b;
-            S.v_c[tid] = c.c;
-        }
-        uint32_t n_lines;
-        {
-            uint32_t total;
-            uint32_t excl = block_excl_scan(my_n, S.ws, total);
-            if (nv <= PK_MAXV && tid < nv) S.v_loff[tid] = excl;
-            if (tid == 0 && nv <= PK_MAXV) S.v_loff[nv] = total;
-            n_lines = total;
-        }
-        bool fallback = (nv > PK_MAXV) || (n_lines > PK_MAXLINES);
-        __syncthreads();
 
-        // ---- 2. evaluate the lines into the per-CTA scratch, bounding grid -----------------
-        if (!fallback) {
-            int bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
-            for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                uint32_t lo = 0, hi = nv;  // largest v with v_loff[v] <= i
-                while (hi - lo > 1) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (S.v_loff[mid] <= i) lo = mid; else hi = mid;
+        // ---- 0. validation: tags and transformed coordinates -----------------------------------
+        {
+            int bad = 0;
+            for (uint32_t j = tid; j < nc; j += PK_THREADS) {
+                const uint32_t tag = pc[j].tag;
+                if (tag == TAG_CONIC) bad = max(bad, 3);
+                else if (tag > TAG_LINE_ABS) bad = max(bad, 2);
+                else {
+                    const int np = cmd_npts(tag);
+                    for (int i = 0; i < np; ++i)
+                        if (!coord_ok(cmd_point(pc[j], i, m))) bad = max(bad, 1);
                 }
-                const uint32_t v = lo, k = i - S.v_loff[v];
-                const uint32_t tag = S.v_tag[v];
-                V2 a = S.v_last[v], b;
-                if (tag == TAG_QUAD || tag == TAG_CUBIC) {
-                    const float dt = S.v_dt[v];
-                    float t = 0.0f, tp = 0.0f;
-                    for (uint32_t s = 0; s <= k; ++s) {
-                        tp = t;
-                        t = fminf(t + dt, 1.0f);
-                    }
-                    if (tag == TAG_QUAD) {
-                        if (k) a = quad_eval(tp, S.v_last[v], S.v_a[v], S.v_b[v]);
-                        b = quad_eval(t, S.v_last[v], S.v_a[v], S.v_b[v]);
-                    } else {
-                        if (k) a = cubic_eval(tp, S.v_last[v], S.v_a[v], S.v_b[v], S.v_c[v]);
-                        b = cubic_eval(t, S.v_last[v], S.v_a[v], S.v_b[v], S.v_c[v]);
+            }
+            if (bad) atomicMax(A.status, bad);
+            // one bad command poisons `last` of its successors: the path is not walked at all
+            // (the call fails with the status code anyway)
+            if (__syncthreads_or(bad)) continue;
+        }
+
+        // ---- 1. flatten: command chunks of PK_THREADS -> lines in the scratch --------------------
+        PkBBox bb;
+        bb.x0 = bb.y0 = 0x7fffffff;
+        bb.x1 = bb.y1 = -0x7fffffff;
+        uint32_t n_lines = 0;
+        bool fallback = false;
+        for (uint32_t jb = 0; jb < nv; jb += PK_THREADS) {
+            const uint32_t j = jb + tid;
+            uint32_t my_n = 0, my_tag = TAG_CLOSE;
+            float my_dt = 0.0f;
+            VCmd c;
+            c.last = c.a = c.b = c.c = mk(0.0f, 0.0f);
+            if (j < nv) {
+                c = decode_vcmd(pc, nc, j, m);
+                my_tag = c.tag;
+                switch (c.tag) {
+                    case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
+                    case TAG_QUAD: my_dt = quad_dt(c.last, c.a, c.b); my_n = curve_count(my_dt); break;
+                    case TAG_CUBIC: my_dt = cubic_dt(c.last, c.a, c.b, c.c); my_n = curve_count(my_dt); break;
+                    default: break;  // Close: rasterizer.rs:154
+                }
+            }
+            uint32_t total;
+            const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);
+            if (n_lines + total > PK_MAXLINES) {
+                fallback = true;
+                break;
+            }
+            if (my_n) {
+                if (my_tag == TAG_QUAD || my_tag == TAG_CUBIC) {
+                    S.u.v.last[tid] = c.last;
+                    S.u.v.a[tid] = c.a;
+                    S.u.v.b[tid] = c.b;
+                    S.u.v.c[tid] = c.c;
+                    S.u.v.loff[tid] = first;
+                    S.u.v.tag[tid] = my_tag;
+                    float t = 0.0f;  // the rounded recurrence of path.rs:52-53 / :65-66
+                    for (uint32_t k = 0; k < my_n; ++k) {
+                        t = fminf(t + my_dt, 1.0f);
+                        __stcg(&G.rec[first + k], make_uint2(__float_as_uint(t), tid));
                     }
                 } else {
-                    b = S.v_a[v];
-                }
-                __stcg(&lines[i], make_float4(a.x, a.y, b.x, b.y));
-                if (!same(a, b)) {
-                    int ax = floor_px(a.x) >> 3, ay = floor_px(a.y) >> 3;
-                    int ex = floor_px(b.x) >> 3, ey = floor_px(b.y) >> 3;
-                    bx0 = min(bx0, min(ax, ex));
-                    bx1 = max(bx1, max(ax, ex));
-                    by0 = min(by0, min(ay, ey));
-                    by1 = max(by1, max(ay, ey));
+                    __stcg(&G.rec[first], make_uint2(0u, PK_OWNER_NONE));
+                    __stcg(&G.lines[first], make_float4(c.last.x, c.last.y, c.a.x, c.a.y));
+                    if (!same(c.last, c.a)) bb.add(c.last, c.a);
                 }
             }
-            if (bx0 <= bx1) {
-                atomicMin(&S.bbox[0], bx0);
-                atomicMin(&S.bbox[1], by0);
-                atomicMax(&S.bbox[2], bx1);
-                atomicMax(&S.bbox[3], by1);
+            __syncthreads();
+            for (uint32_t i = n_lines + tid; i < n_lines + total; i += PK_THREADS) {
+                const uint2 r = __ldcg(&G.rec[i]);
+                if (r.y == PK_OWNER_NONE) continue;
+                const uint32_t o = r.y;
+                const float t = __uint_as_float(r.x);
+                const V2 l = S.u.v.last[o], ca = S.u.v.a[o], cb = S.u.v.b[o];
+                V2 a = l, b;
+                if (S.u.v.tag[o] == TAG_QUAD) {
+                    if (i != S.u.v.loff[o]) a = quad_eval(__uint_as_float(__ldcg(&G.rec[i - 1]).x), l, ca, cb);
+                    b = quad_eval(t, l, ca, cb);
+                } else {
+                    const V2 cc = S.u.v.c[o];
+                    if (i != S.u.v.loff[o]) a = cubic_eval(__uint_as_float(__ldcg(&G.rec[i - 1]).x), l, ca, cb, cc);
+                    b = cubic_eval(t, l, ca, cb, cc);
+                }
+                __stcg(&G.lines[i], make_float4(a.x, a.y, b.x, b.y));
+                if (!same(a, b)) bb.add(a, b);
+            }
+            n_lines += total;
+            __syncthreads();
+        }
+        if (!fallback) {
+            const int x0 = __reduce_min_sync(0xffffffffu, bb.x0), y0 = __reduce_min_sync(0xffffffffu, bb.y0);
+            const int x1 = __reduce_max_sync(0xffffffffu, bb.x1), y1 = __reduce_max_sync(0xffffffffu, bb.y1);
+            if ((tid & 31) == 0 && x0 <= x1) {
+                atomicMin(&S.bbox[0], x0);
+                atomicMin(&S.bbox[1], y0);
+                atomicMax(&S.bbox[2], x1);
+                atomicMax(&S.bbox[3], y1);
             }
         }
         __syncthreads();
+
+        // ---- 2. the bounding grid ------------------------------------------------------------------
         const bool empty = !fallback && (S.bbox[0] > S.bbox[2]);  // no line with two distinct end points
         // one tile of margin: the DDA may overshoot its end pixel by one before the end snap
         const int gx0 = S.bbox[0] - 1, gy0 = S.bbox[1] - 1;
         const int W = empty ? 1 : S.bbox[2] - S.bbox[0] + 3, H = empty ? 1 : S.bbox[3] - S.bbox[1] + 3;
         if (!fallback && !empty && (W > PK_CELLS || H > PK_MAXROWS)) fallback = true;
-        const int rows_per_band = fallback || empty ? 1 : min(H, PK_CELLS / W);
+        const int rows_per_band = (fallback || empty) ? 1 : min(H, PK_CELLS / W);
         const int nbands = (H + rows_per_band - 1) / rows_per_band;
 
-        // ---- 3. count pass: tiles and spans of the whole path ------------------------------
+        // ---- 3. mark + scan: tiles and spans of the whole path --------------------------------------
         uint32_t tot_tiles = 0, tot_spans = 0;
+        PkScan sc;
+        sc.c0 = sc.c1 = sc.span_excl = 0;
         if (!fallback && !empty) {
             int wcarry = 0;
             for (int b = 0; b < nbands && !fallback; ++b) {
                 const int row0 = b * rows_per_band, nrows = min(rows_per_band, H - row0);
                 uint32_t nt, ns, bad;
                 int wtot;
-                pk_band_setup(S, lines, n_lines, gx0, gy0, W, row0, nrows, wcarry, nt, ns, wtot, bad);
-                // a tile row must fit the resident accumulators
-                uint32_t over = 0;
+                pk_band_setup(S, G, n_lines, gx0, gy0, W, row0, nrows, b == 0, wcarry, sc, nt, ns, wtot, bad);
+                uint32_t over = 0;  // a tile row must fit the resident accumulators
                 for (int r = tid; r < nrows; r += PK_THREADS)
                     if ((uint32_t)(S.rank[(r + 1) * W] - S.rank[r * W]) > PK_SLOTS) over = 1;
-                if (bad || __syncthreads_or((int)over)) fallback = true;
+                if (__syncthreads_or((int)(over | bad))) fallback = true;
                 tot_tiles += nt;
                 tot_spans += ns;
                 wcarry = wtot;
             }
         }
-        if (empty) tot_tiles = 1;  // the empty path's all-zero tile at (0,0)
+        if (empty) tot_tiles = 1;  // the empty path's all-zero tile at (0,0), rasterizer.rs:194, :208
         if (fallback) {
             tot_tiles = 0;
             tot_spans = 0;
         }
 
-        // ---- 4. reserve the output range (staging arena, completion order) -----------------
+        // ---- 4. reserve the output range ---------------------------------------------------------------
         if (tid == 0) {
-            uint32_t ts = atomicAdd(A.cursor, tot_tiles);
-            uint32_t ss = atomicAdd(A.cursor + 1, tot_spans);
+            const uint32_t ts = atomicAdd(A.cursor, tot_tiles);
+            const uint32_t ss = atomicAdd(A.cursor + 1, tot_spans);
             S.base_tiles = ts;
             S.base_spans = ss;
             A.rec[p] = make_uint4(ts, tot_tiles, ss, tot_spans);
-            if (fallback) atomicAdd(A.status + 1, 1);
+            if (fallback) A.fb_list[atomicAdd(A.status + 1, 1)] = p;
         }
         __syncthreads();
         if (fallback) continue;
-        uint32_t tile_at = S.base_tiles;  // staging index of this path's next tile
+        uint32_t tile_at = S.base_tiles;  // arena index of this path's next tile
         uint32_t span_at = S.base_spans;
         const bool fits = (uint64_t)tile_at + tot_tiles <= A.cap_tiles && (uint64_t)span_at + tot_spans <= A.cap_spans;
         if (!fits) {
@@ -393,40 +595,19 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             continue;
         }
 
-        // ---- 5. per band: accumulate, carry, quantise, emit ---------------------------------
+        // ---- 5. per band: origins + spans, then accumulate, carry, quantise, emit --------------------
         int wcarry = 0;
         for (int b = 0; b < nbands; ++b) {
             const int row0 = b * rows_per_band, nrows = min(rows_per_band, H - row0);
-            uint32_t nt = 0, ns = 0, bad;
+            uint32_t nt = tot_tiles, ns = tot_spans, bad;
             int wtot = 0;
-            if (nbands > 1) {
-                pk_band_setup(S, lines, n_lines, gx0, gy0, W, row0, nrows, wcarry, nt, ns, wtot, bad);
-            } else {
-                nt = tot_tiles;
-                ns = tot_spans;
-            }
+            if (nbands > 1) pk_band_setup(S, G, n_lines, gx0, gy0, W, row0, nrows, false, wcarry, sc, nt, ns, wtot, bad);
             wcarry = wtot;
-            // spans of the band
-            const uint32_t ncells = (uint32_t)(W * nrows);
-            for (uint32_t i = tid; i < ncells; i += PK_THREADS) {
-                if (!S.cnt[i]) continue;
-                uint32_t r = S.rank[i];
-                if (r + 1 >= nt) continue;
-                uint32_t nx = S.tcell[r + 1];
-                if (nx / (uint32_t)W == i / (uint32_t)W && nx > i + 1 && S.wind[i] != 0) {
-                    OchreSpan sp;
-                    int cx = (int)(i % (uint32_t)W), cy = (int)(i / (uint32_t)W);
-                    sp.x = (int16_t)((gx0 + cx + 1) * 8);
-                    sp.y = (int16_t)((gy0 + row0 + cy) * 8);
-                    sp.w = (uint16_t)((nx - i - 1) * 8u);
-                    sp.pad = 0;
-                    A.spans[span_at + S.spanx[i]] = sp;
-                }
-            }
+            pk_emit_band_index(S, A, sc, gx0, gy0, W, row0, tile_at, span_at);
             // slot bands: as many whole tile rows as fit PK_SLOTS resident tiles
             int r0 = 0;
             while (r0 < nrows) {
-                __syncthreads();
+                __syncthreads();  // also: the flags / tcell are dead from here on (the accumulators reuse them)
                 if (tid == 0) {
                     int r1 = r0 + 1;
                     const uint32_t rk0 = S.rank[r0 * W];
@@ -438,45 +619,45 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 const uint32_t rank0 = S.rank[r0 * W];
                 const uint32_t nslots = (uint32_t)S.rank[r1 * W] - rank0;
                 if (nslots) {
-                    for (uint32_t i = tid; i < nslots * 128; i += PK_THREADS) S.acc[i] = 0;
+                    {
+                        uint4* z = reinterpret_cast<uint4*>(S.u.acc);
+                        for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
                     __syncthreads();
-                    pk_pass_b(S, lines, n_lines, gx0, gy0, W, row0, r0, r1, rank0);
+                    pk_accumulate(S, G, n_lines, gx0, gy0, W, row0, row0 + r0, row0 + r1, rank0);
                     __syncthreads();
-                    // row carry: one thread per (tile row, pixel row), left to right over the row's tiles
+                    // row carry (x256): one thread per (tile row, pixel row), left to right over the row's tiles;
+                    // the carry into a tile replaces its carry-out column
                     for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
                         const int r = r0 + (it >> 3), y = it & 7;
                         const uint32_t s0 = S.rank[r * W] - rank0, s1 = S.rank[(r + 1) * W] - rank0;
                         float c = 0.0f;
                         for (uint32_t s = s0; s < s1; ++s) {
-                            S.carry[s * 8 + y] = c;
+                            int* d = &S.u.acc[s * PK_ACCW + y * 9];
                             int rs = 0;
 #pragma unroll
-                            for (int x = 0; x < 8; ++x) rs += S.acc[s * 128 + ((y * 8 + x) << 1) + 1];
-                            c += (float)rs * OC_FX_INV;
+                            for (int x = 0; x < 9; ++x) rs += d[x];
+                            d[8] = __float_as_int(c);
+                            c += (float)rs * OC_FX_TO_256;
                         }
                     }
                     __syncthreads();
                     // quantise + emit: one thread per (tile, pixel row) -> one 8-byte store
                     for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
                         const uint32_t s = it >> 3, y = it & 7;
-                        const float c = S.carry[s * 8 + y];
+                        const int* d = &S.u.acc[s * PK_ACCW + y * 9];
+                        const float c = __int_as_float(d[8]);
                         int run = 0;
                         uint32_t lo32 = 0, hi32 = 0;
 #pragma unroll
                         for (int x = 0; x < 8; ++x) {
-                            const int* a = &S.acc[s * 128 + ((y * 8 + x) << 1)];
-                            uint32_t q = alpha_u8(c + (float)(run + a[0]) * OC_FX_INV);
-                            run += a[1];
+                            run += d[x];
+                            // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
+                            const uint32_t q = (uint32_t)(int)fminf(fabsf(c + (float)run * OC_FX_TO_256), 255.0f);
                             if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                         }
-                        const uint32_t ti = tile_at + (rank0 + s);
+                        const uint32_t ti = tile_at + rank0 + s;
                         reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64)[y] = make_uint2(lo32, hi32);
-                        if (y == 0) {
-                            const uint32_t cell = S.tcell[rank0 + s];
-                            const int cx = (int)(cell % (uint32_t)W), cy = (int)(cell / (uint32_t)W);
-                            reinterpret_cast<uint32_t*>(A.tile_xy)[ti] = (uint32_t)(uint16_t)(int16_t)((gx0 + cx) * 8) |
-                                                                        ((uint32_t)(uint16_t)(int16_t)((gy0 + row0 + cy) * 8) << 16);
-                        }
                     }
                 }
                 r0 = r1;

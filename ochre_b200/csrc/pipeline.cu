@@ -493,7 +493,7 @@ struct ochre_b200_ctx {
     // fused per-path kernel
     int mode = OCHRE_MODE_AUTO;
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl;  // ctl: ticket(1) cursor(2) status(3) words
+    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
     HostBuf h_pk_ctl;
     uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
@@ -729,7 +729,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
     const uint32_t n_paths = p1 - p0;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM);
-    CK(ctx->d_pk_scratch.ensure((size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_MAXLINES * sizeof(float4)));
+    CK(ctx->d_pk_scratch.ensure((size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_SCR_BYTES));
+    CK(ctx->d_pk_fb.ensure((size_t)n_paths * 4 + 4));
     CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4)));
     CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
     uint32_t* ctl = ctx->d_pk_ctl.as<uint32_t>();
@@ -761,7 +762,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.tile_xy = ctx->s_tile_xy.as<int16_t>();
         A.alpha = ctx->s_alpha.as<uint8_t>();
         A.spans = ctx->s_spans.as<OchreSpan>();
-        A.scratch = ctx->d_pk_scratch.as<float4>();
+        A.scratch = ctx->d_pk_scratch.as<unsigned char>();
+        A.fb_list = ctx->d_pk_fb.as<uint32_t>();
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
         CK(cudaEventRecord(ctx->ev[0], st));
         k_path<<<grid, PK_THREADS, PK_SMEM, st>>>(A);
@@ -868,7 +870,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
