@@ -8,18 +8,22 @@
 //   1 flatten   thread per command: transform, dt, line count, the rounded t sequence
 //               (path.rs:49-74); CTA scan; thread per line: curve evaluation
 //                                                        ref path.rs:16-74, rasterizer.rs:61-69, :145-165
-//   2 bin       "mark": thread per line runs the DDA's control flow and counts the increments on
-//               every tile of the path's bounding grid (+ TileIncrement winding deltas); an
-//               ordered scan of the grid plays the role of the (tile_y, tile_x) sort
-//                                                        ref rasterizer.rs:72-140, :185-211
+//   2 bin       lines are bucketed by their pixel-step count so that the lanes of a warp walk
+//               lines of equal length; "mark": thread per line runs the DDA's control flow and
+//               counts the increments on every tile of the path's bounding grid (+ TileIncrement
+//               winding deltas); an ordered scan of the grid plays the role of the
+//               (tile_y, tile_x) sort                     ref rasterizer.rs:72-140, :185-211
 //   3 coverage  "accumulate": thread per line walks the DDA again and adds area/height into the
 //               tile's 8x9 accumulator block with native shared-memory integer atomics
 //               (2^-22 fixed point; column x holds area, column x+1 receives height - area, so a
 //               row prefix sum yields accum + area directly)     ref rasterizer.rs:97-116, :221-228
-//   4 backdrop  per tile row: left-to-right carry of the row sums; inclusive scan of the winding
-//               deltas over the grid in (tile_y, tile_x) order       ref rasterizer.rs:233-260
+//   4 backdrop  per tile row: left-to-right integer carry of the row sums; inclusive scan of the
+//               winding deltas over the grid in (tile_y, tile_x) order  ref rasterizer.rs:233-260
 //   5 emission  alpha rows as coalesced 8-byte stores, tile origins, spans; each path reserves
 //               its output range in the arena with one atomicAdd
+//
+// Paths with more tiles than accumulator slots are processed in bands of whole tile rows; their
+// lines are re-bucketed by (band, step count) so that every band walks only its own lines.
 //
 // HBM traffic is the compulsory B_alg (commands in, tiles/spans out) plus an L2-resident per-CTA
 // line scratch.  Accumulation is order-independent (integer adds), so results do not depend on
@@ -38,34 +42,37 @@ namespace oc {
 #define OC_PK_THREADS 256
 #endif
 #ifndef OC_PK_SLOTS
-#define OC_PK_SLOTS 126
+#define OC_PK_SLOTS 133
 #endif
 #ifndef OC_PK_CELLS
-#define OC_PK_CELLS 4608
+#define OC_PK_CELLS 6400
 #endif
 #ifndef OC_PK_CTAS
 #define OC_PK_CTAS 4
 #endif
 constexpr int PK_THREADS = OC_PK_THREADS;
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
-constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the bounding grid resident at once (a band of tile rows)
+constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the path's bounding grid (tiles)
 constexpr int PK_CTAS_PER_SM = OC_PK_CTAS;
 constexpr int PK_MAXLINES = 4095;   // line slots per path: keeps a cell's 16-bit increment count exact (<= 16 per line)
 constexpr int PK_LINECAP = 4096;    // scratch stride
-constexpr int PK_MAXROWS = 16384;   // grid height in tile rows (16-bit row fields)
+constexpr int PK_SLINECAP = 2 * PK_LINECAP;  // bucketed copies (one per slot band a line touches)
 constexpr int PK_MAXCNT = 511;      // increments per tile: keeps the fixed-point sums inside int32
 constexpr int PK_ACCW = 72;         // accumulator words per tile: 8 pixel rows x (8 columns + 1 carry-out column)
+constexpr int PK_NCLS = 8;          // step-count classes: 1, 2, 3, 4, 5-6, 7-9, 10-15, 16+
+constexpr int PK_MAXB = 32;         // slot bands per path
 #define OC_FX_SCALE 4194304.0f      /* 2^22 */
 #define OC_FX_TO_256 (1.0f / 16384.0f) /* 2^-22 * 256 */
 #define PK_CELL_INIT 0x80000000u    /* increments 0, winding delta 0 (biased by 0x8000) */
-#define PK_ROWS_NONE 0xffffffffu
+#define PK_INFO_NONE 0xffffffffu
 #define PK_OWNER_NONE 0xffffffffu
 
-// Per-CTA scratch in global memory (stays in L2): lines, (t, owner) of every line, tile-row range of every line.
-constexpr size_t PK_SCR_LINES = 0;                                             // float4[LINECAP]
-constexpr size_t PK_SCR_REC = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;      // uint2[LINECAP]
-constexpr size_t PK_SCR_ROWS = PK_SCR_REC + sizeof(uint2) * PK_LINECAP;        // uint32[LINECAP]
-constexpr size_t PK_SCR_BYTES = PK_SCR_ROWS + 4 * (size_t)PK_LINECAP;
+// Per-CTA scratch in global memory (stays in L2).
+constexpr size_t PK_SCR_LINES = 0;                                             // float4[LINECAP]   lines in path order
+constexpr size_t PK_SCR_SLINES = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;   // float4[SLINECAP]  lines in bucket order
+constexpr size_t PK_SCR_REC = PK_SCR_SLINES + sizeof(float4) * PK_SLINECAP;    // uint2[LINECAP]    (t, owner) of every line
+constexpr size_t PK_SCR_INFO = PK_SCR_REC + sizeof(uint2) * PK_LINECAP;        // uint32[LINECAP]   tile rows + class
+constexpr size_t PK_SCR_BYTES = PK_SCR_INFO + 4 * (size_t)PK_LINECAP;
 
 struct PathKernelArgs {
     const Cmd* cmds;            // chunk base (index with cmd_off[p] - cmd_base)
@@ -102,10 +109,13 @@ struct PkShared {
         PkGrid g;
         PkCurves v;
     } u;
-    uint16_t rank[PK_CELLS + 2];   // touched cells before this cell (band local); kept across the slot bands
+    uint16_t rank[PK_CELLS + 2];            // touched cells before this cell; kept across the slot bands
+    uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
+    uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
+    uint16_t brow[PK_MAXB + 2];             // first grid row of every slot band
     uint32_t ws[72];
-    int bbox[4];                   // min tx, min ty, max tx, max ty over every non-degenerate line
-    uint32_t path, r1, base_tiles, base_spans;
+    int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
+    uint32_t path, next_path, nbands, base_tiles, base_spans, flag;
 };
 
 // Exclusive scan of two values per thread across the CTA in one pass.  `ws` must hold 72 words.
@@ -204,78 +214,82 @@ struct LineWalk {
 
 struct PkScratch {
     float4* lines;
+    float4* slines;
     uint2* rec;
-    uint32_t* rows;
+    uint32_t* info;
     __device__ __forceinline__ explicit PkScratch(unsigned char* b)
-        : lines(reinterpret_cast<float4*>(b + PK_SCR_LINES)), rec(reinterpret_cast<uint2*>(b + PK_SCR_REC)),
-          rows(reinterpret_cast<uint32_t*>(b + PK_SCR_ROWS)) {}
+        : lines(reinterpret_cast<float4*>(b + PK_SCR_LINES)), slines(reinterpret_cast<float4*>(b + PK_SCR_SLINES)),
+          rec(reinterpret_cast<uint2*>(b + PK_SCR_REC)), info(reinterpret_cast<uint32_t*>(b + PK_SCR_INFO)) {}
 };
 
 struct PkBBox {
     int x0, y0, x1, y1;
-    __device__ __forceinline__ void add(V2 a, V2 b) {
-        const int ax = floor_px(a.x) >> 3, ay = floor_px(a.y) >> 3, ex = floor_px(b.x) >> 3, ey = floor_px(b.y) >> 3;
-        x0 = min(x0, min(ax, ex));
-        x1 = max(x1, max(ax, ex));
-        y0 = min(y0, min(ay, ey));
-        y1 = max(y1, max(ay, ey));
-    }
 };
 
-// Mark pass over the cell band [row0, row0 + nrows) of the grid (rasterizer.rs:97-136, control
-// flow only): counts the increments per cell and adds the TileIncrement signs.  With `first`
-// every line is walked and its tile-row range recorded; later bands use the range to skip.
-__device__ __forceinline__ uint32_t pk_mark(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W, int row0,
-                                            int nrows, bool first) {
+// Per-line record for bucketing: [12:0] first tile row + 4096, [25:13] last tile row + 4096 (both
+// padded by one pixel for the DDA's overshoot before the end snap), [28:26] step-count class.
+// Also grows the bounding box (tile units).  Only called for lines with two distinct end points.
+__device__ __forceinline__ uint32_t pk_line_info(V2 a, V2 b, PkBBox& bb) {
+    const int ax = floor_px(a.x), ay = floor_px(a.y), ex = floor_px(b.x), ey = floor_px(b.y);
+    bb.x0 = min(bb.x0, min(ax, ex) >> 3);
+    bb.x1 = max(bb.x1, max(ax, ex) >> 3);
+    bb.y0 = min(bb.y0, min(ay, ey) >> 3);
+    bb.y1 = max(bb.y1, max(ay, ey) >> 3);
+    const int lo = ((min(ay, ey) - 1) >> 3) + 4096, hi = ((max(ay, ey) + 1) >> 3) + 4096;
+    const int n = abs(ex - ax) + abs(ey - ay) + 1;  // DDA trips of the line, up to rounding overshoot
+    const int cls = n <= 4 ? n - 1 : 4 + (n > 6) + (n > 9) + (n > 15);
+    return (uint32_t)lo | ((uint32_t)hi << 13) | ((uint32_t)cls << 26);
+}
+__device__ __forceinline__ int pk_info_lo(uint32_t f) { return (int)(f & 0x1fffu) - 4096; }
+__device__ __forceinline__ int pk_info_hi(uint32_t f) { return (int)((f >> 13) & 0x1fffu) - 4096; }
+__device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return (f >> 26) & 7u; }
+
+// Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
+// increments per cell of the W x H grid and adds the TileIncrement signs.
+__device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H) {
     uint32_t err = 0;
-    uint32_t* cell = S.u.g.cell;
-    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
-        if (!first) {
-            const uint32_t rr = __ldcg(&G.rows[i]);
-            if (rr == PK_ROWS_NONE || (int)(rr >> 16) < row0 || (int)(rr & 0xffffu) >= row0 + nrows) continue;
-        }
-        const float4 L = __ldcg(&G.lines[i]);
-        if (L.x == L.z && L.y == L.w) {  // rasterizer.rs:73
-            if (first) __stcg(&G.rows[i], PK_ROWS_NONE);
-            continue;
-        }
+    uint32_t pos = threadIdx.x;
+    float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos < n) Ln = __ldcg(&sl[pos]);
+    // (the trip count is warp-uniform: bounded by the warp's first lane)
+    for (uint32_t wpos = threadIdx.x & ~31u; wpos < n; wpos += PK_THREADS, pos += PK_THREADS) {
+        __syncwarp();  // lanes of a warp hold lines of (nearly) equal step count: keep them in lockstep
+        if (pos >= n) continue;
+        const float4 L = Ln;
+        if (pos + PK_THREADS < n) Ln = __ldcg(&sl[pos + PK_THREADS]);
         LineWalk w;
         w.init(L);
         int prev_ty = w.y >> 3;
-        int tmin = prev_ty, tmax = prev_ty;
         for (;;) {
-            const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0 - row0;
-            if ((unsigned)cy < (unsigned)nrows) {
-                if ((unsigned)cx < (unsigned)W) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
-            }
+            const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0;
+            if ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
             float t1;
             const bool done = w.advance(t1);
             const int ty = w.y >> 3;
             if (ty != prev_ty) {  // rasterizer.rs:123-131
-                const int tiy = min(ty, prev_ty) - gy0 - row0, tix = (w.x >> 3) - gx0;
-                if ((unsigned)tiy < (unsigned)nrows) {
-                    if ((unsigned)tix < (unsigned)W) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16); else err = 1;
-                }
-                tmin = min(tmin, ty);
-                tmax = max(tmax, ty);
+                const int tiy = min(ty, prev_ty) - gy0, tix = (w.x >> 3) - gx0;
+                if ((unsigned)tix < (unsigned)W && (unsigned)tiy < (unsigned)H) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16);
+                else err = 1;
                 prev_ty = ty;
             }
             if (done) break;
         }
-        if (first) __stcg(&G.rows[i], (uint32_t)(tmin - gy0) | ((uint32_t)(tmax - gy0) << 16));
     }
     return err;
 }
 
-// Accumulate pass over the slot band: grid rows [R0, R1) (relative to gy0); `cell_row0` is the first
-// row of the resident cell band, slot = rank - rank0.
-__device__ __forceinline__ void pk_accumulate(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W,
-                                              int cell_row0, int R0, int R1, uint32_t rank0) {
-    int* acc = S.u.acc;
-    for (uint32_t i = threadIdx.x; i < n_lines; i += PK_THREADS) {
-        const uint32_t rr = __ldcg(&G.rows[i]);
-        if (rr == PK_ROWS_NONE || (int)(rr >> 16) < R0 || (int)(rr & 0xffffu) >= R1) continue;
-        const float4 L = __ldcg(&G.lines[i]);
+// Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
+// tile rows; slot = rank - rank0.
+__device__ __forceinline__ void pk_accumulate(int* acc, const uint16_t* rank, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
+                                              int gx0, int gy0, int W, int R0, int R1, uint32_t rank0) {
+    uint32_t pos = p0 + threadIdx.x;
+    float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos < p1) Ln = __ldcg(&sl[pos]);
+    for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
+        __syncwarp();
+        if (pos >= p1) continue;
+        const float4 L = Ln;
+        if (pos + PK_THREADS < p1) Ln = __ldcg(&sl[pos + PK_THREADS]);
         LineWalk w;
         w.init(L);
         // p0 of the first increment: t0 = max(0, 0) = 0 (rasterizer.rs:99-101)
@@ -289,9 +303,9 @@ __device__ __forceinline__ void pk_accumulate(PkShared& S, const PkScratch& G, u
             const float height = p1y - p0y;
             const float right = (float)(x0 + 1);
             const float area = 0.5f * height * ((right - p0x) + (right - p1x));
-            const int ry = (y0 >> 3) - gy0;
+            const int ry = y0 >> 3;
             if (ry >= R0 && ry < R1) {
-                const uint32_t slot = (uint32_t)S.rank[(ry - cell_row0) * W + ((x0 >> 3) - gx0)] - rank0;
+                const uint32_t slot = (uint32_t)rank[(ry - gy0) * W + ((x0 >> 3) - gx0)] - rank0;
                 int* d = &acc[slot * PK_ACCW + (y0 & 7) * 9 + (x0 & 7)];
                 const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
                 atomicAdd(d, qa);
@@ -309,20 +323,15 @@ __device__ __forceinline__ void pk_accumulate(PkShared& S, const PkScratch& G, u
 // Per-thread state of the grid scan that the emission pass needs again.
 struct PkScan {
     uint32_t c0, c1;      // this thread's contiguous run of cells
-    uint32_t span_excl;   // spans of the band before this thread's run
+    uint32_t span_excl;   // spans of the path before this thread's run
 };
 
-// Mark + ordered scan of one cell band.  On return: S.rank (touched cells before each cell, band
-// local, S.rank[ncells] = n_touched), S.u.g.tcell (ordered touched cells), S.u.g.cell = CF_* flags.
-__device__ __forceinline__ void pk_band_setup(PkShared& S, const PkScratch& G, uint32_t n_lines, int gx0, int gy0, int W,
-                                              int row0, int nrows, bool first, int wcarry, PkScan& sc, uint32_t& n_touched,
-                                              uint32_t& n_spans, int& wtotal, uint32_t& bad) {
-    const uint32_t ncells = (uint32_t)(W * nrows);
+// Ordered scan of the marked grid.  On return: S.rank (touched cells before each cell,
+// S.rank[ncells] = n_touched), S.u.g.tcell (ordered touched cells), S.u.g.cell = CF_* flags.
+__device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, PkScan& sc, uint32_t& n_touched,
+                                             uint32_t& n_spans, uint32_t& bad) {
+    const uint32_t ncells = (uint32_t)(W * H);
     uint32_t* cell = S.u.g.cell;
-    for (uint32_t i = threadIdx.x; i < ncells; i += PK_THREADS) cell[i] = PK_CELL_INIT;
-    __syncthreads();
-    uint32_t err = pk_mark(S, G, n_lines, gx0, gy0, W, row0, nrows, first);
-    __syncthreads();
     // every thread owns a contiguous run of cells: local sums, one CTA scan, local prefix
     const uint32_t per = (ncells + PK_THREADS - 1) / PK_THREADS;
     sc.c0 = min(ncells, threadIdx.x * per);
@@ -339,7 +348,7 @@ __device__ __forceinline__ void pk_band_setup(PkShared& S, const PkScratch& G, u
     block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
     {
         uint32_t r = ex_t;
-        int wp = wcarry + (int)ex_w;
+        int wp = (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
         for (uint32_t c = sc.c0; c < sc.c1; ++c) {
             const uint32_t w = cell[c];
             const uint32_t cnt = w & 0xffffu;
@@ -355,7 +364,6 @@ __device__ __forceinline__ void pk_band_setup(PkShared& S, const PkScratch& G, u
         }
     }
     n_touched = tot_t;
-    wtotal = wcarry + (int)tot_w;
     if (threadIdx.x == 0) S.rank[ncells] = (uint16_t)tot_t;
     __syncthreads();
     // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
@@ -383,10 +391,10 @@ __device__ __forceinline__ void pk_band_setup(PkShared& S, const PkScratch& G, u
     bad = __syncthreads_or((int)err);
 }
 
-// Tile origins and spans of the resident cell band (needs the CF_* flags and tcell, i.e. runs before
-// the accumulators reuse that shared memory).
-__device__ __forceinline__ void pk_emit_band_index(const PkShared& S, const PathKernelArgs& A, const PkScan& sc, int gx0, int gy0,
-                                                   int W, int row0, uint32_t tile_at, uint32_t span_at) {
+// Tile origins and spans (needs the CF_* flags and tcell, i.e. runs before the accumulators reuse
+// that shared memory).
+__device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKernelArgs& A, const PkScan& sc, int gx0, int gy0,
+                                              int W, uint32_t tile_at, uint32_t span_at) {
     if (sc.c0 >= sc.c1) return;
     const uint32_t* cell = S.u.g.cell;
     int cy = (int)(sc.c0 / (uint32_t)W), cx = (int)(sc.c0 - (uint32_t)cy * (uint32_t)W);
@@ -395,7 +403,7 @@ __device__ __forceinline__ void pk_emit_band_index(const PkShared& S, const Path
         const uint32_t f = cell[c];
         if (f & CF_TOUCHED) {
             const uint32_t r = S.rank[c];
-            const int px = (gx0 + cx) * 8, py = (gy0 + row0 + cy) * 8;
+            const int px = (gx0 + cx) * 8, py = (gy0 + cy) * 8;
             reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at + r] = (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16);
             if (f & CF_SPAN) {
                 const uint32_t nx = S.u.g.tcell[r + 1];
@@ -414,19 +422,34 @@ __device__ __forceinline__ void pk_emit_band_index(const PkShared& S, const Path
     }
 }
 
+// slot band of grid row r (S.brow[b] <= r < S.brow[b + 1])
+__device__ __forceinline__ int pk_band_of(const PkShared& S, int nb, int r) {
+    int lo = 0, hi = nb;  // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)S.brow[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelArgs A) {
     extern __shared__ __align__(16) unsigned char pk_smem_raw[];
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
     const uint32_t tid = threadIdx.x;
     const PkScratch G(A.scratch + (size_t)blockIdx.x * PK_SCR_BYTES);
 
+    if (tid == 0) S.next_path = atomicAdd(A.ticket, 1u);
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            S.path = atomicAdd(A.ticket, 1u);
+            const uint32_t np = S.next_path;
+            S.path = np;
+            // the next ticket is fetched while this path is processed (hides the L2 round trip)
+            if (np < A.n_paths) S.next_path = atomicAdd(A.ticket, 1u);
             S.bbox[0] = S.bbox[1] = 0x7fffffff;
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
         }
+        if (tid < PK_NCLS) S.bcur[tid] = 0;  // lines per step-count class
         __syncthreads();
         const uint32_t p = S.path;
         if (p >= A.n_paths) return;
@@ -436,54 +459,45 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         const Cmd* pc = A.cmds + c0;
         const float* m = A.xf + 6 * (size_t)p;
 
-        // ---- 0. validation: tags and transformed coordinates -----------------------------------
-        {
-            int bad = 0;
-            for (uint32_t j = tid; j < nc; j += PK_THREADS) {
-                const uint32_t tag = pc[j].tag;
-                if (tag == TAG_CONIC) bad = max(bad, 3);
-                else if (tag > TAG_LINE_ABS) bad = max(bad, 2);
-                else {
-                    const int np = cmd_npts(tag);
-                    for (int i = 0; i < np; ++i)
-                        if (!coord_ok(cmd_point(pc[j], i, m))) bad = max(bad, 1);
-                }
-            }
-            if (bad) atomicMax(A.status, bad);
-            // one bad command poisons `last` of its successors: the path is not walked at all
-            // (the call fails with the status code anyway)
-            if (__syncthreads_or(bad)) continue;
-        }
-
         // ---- 1. flatten: command chunks of PK_THREADS -> lines in the scratch --------------------
         PkBBox bb;
         bb.x0 = bb.y0 = 0x7fffffff;
         bb.x1 = bb.y1 = -0x7fffffff;
         uint32_t n_lines = 0;
-        bool fallback = false;
+        bool fallback = false, bad_path = false;
         for (uint32_t jb = 0; jb < nv; jb += PK_THREADS) {
             const uint32_t j = jb + tid;
             uint32_t my_n = 0, my_tag = TAG_CLOSE;
             float my_dt = 0.0f;
+            int bad = 0;
             VCmd c;
             c.last = c.a = c.b = c.c = mk(0.0f, 0.0f);
             if (j < nv) {
-                c = decode_vcmd(pc, nc, j, m);
-                my_tag = c.tag;
-                switch (c.tag) {
-                    case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
-                    case TAG_QUAD: my_dt = quad_dt(c.last, c.a, c.b); my_n = curve_count(my_dt); break;
-                    case TAG_CUBIC: my_dt = cubic_dt(c.last, c.a, c.b, c.c); my_n = curve_count(my_dt); break;
-                    default: break;  // Close: rasterizer.rs:154
+                // validation: tag, and every transformed coordinate the command reads (its own points
+                // and `last`): finite, |v| < 32760
+                const uint32_t tag = (j < nc) ? pc[j].tag : (uint32_t)TAG_FINISH;
+                if (tag == TAG_CONIC) bad = 3;
+                else if (j < nc && tag > TAG_LINE_ABS) bad = 2;
+                else {
+                    c = decode_vcmd(pc, nc, j, m);
+                    if (!(coord_ok(c.last) && coord_ok(c.a) && coord_ok(c.b) && coord_ok(c.c))) bad = 1;
+                }
+                if (!bad) {
+                    my_tag = c.tag;
+                    switch (c.tag) {
+                        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
+                        case TAG_QUAD: my_dt = quad_dt(c.last, c.a, c.b); my_n = curve_count(my_dt); break;
+                        case TAG_CUBIC: my_dt = cubic_dt(c.last, c.a, c.b, c.c); my_n = curve_count(my_dt); break;
+                        default: break;  // Close: rasterizer.rs:154
+                    }
+                } else {
+                    atomicMax(A.status, bad);
                 }
             }
             uint32_t total;
             const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);
-            if (n_lines + total > PK_MAXLINES) {
-                fallback = true;
-                break;
-            }
-            if (my_n) {
+            if (n_lines + total > PK_MAXLINES) fallback = true;
+            if (my_n && !fallback) {
                 if (my_tag == TAG_QUAD || my_tag == TAG_CUBIC) {
                     S.u.v.last[tid] = c.last;
                     S.u.v.a[tid] = c.a;
@@ -497,12 +511,20 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         __stcg(&G.rec[first + k], make_uint2(__float_as_uint(t), tid));
                     }
                 } else {
+                    uint32_t info = PK_INFO_NONE;  // degenerate lines are skipped by line_to, rasterizer.rs:73
+                    if (!same(c.last, c.a)) {
+                        info = pk_line_info(c.last, c.a, bb);
+                        atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
+                    }
                     __stcg(&G.rec[first], make_uint2(0u, PK_OWNER_NONE));
                     __stcg(&G.lines[first], make_float4(c.last.x, c.last.y, c.a.x, c.a.y));
-                    if (!same(c.last, c.a)) bb.add(c.last, c.a);
+                    __stcg(&G.info[first], info);
                 }
             }
-            __syncthreads();
+            // one bad command poisons `last` of its successors: the path is not walked at all (the
+            // call fails with the status code anyway)
+            if (__syncthreads_or(bad)) bad_path = true;
+            if (bad_path || fallback) break;
             for (uint32_t i = n_lines + tid; i < n_lines + total; i += PK_THREADS) {
                 const uint2 r = __ldcg(&G.rec[i]);
                 if (r.y == PK_OWNER_NONE) continue;
@@ -518,12 +540,18 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     if (i != S.u.v.loff[o]) a = cubic_eval(__uint_as_float(__ldcg(&G.rec[i - 1]).x), l, ca, cb, cc);
                     b = cubic_eval(t, l, ca, cb, cc);
                 }
+                uint32_t info = PK_INFO_NONE;
+                if (!same(a, b)) {
+                    info = pk_line_info(a, b, bb);
+                    atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
+                }
                 __stcg(&G.lines[i], make_float4(a.x, a.y, b.x, b.y));
-                if (!same(a, b)) bb.add(a, b);
+                __stcg(&G.info[i], info);
             }
             n_lines += total;
             __syncthreads();
         }
+        if (bad_path) continue;
         if (!fallback) {
             const int x0 = __reduce_min_sync(0xffffffffu, bb.x0), y0 = __reduce_min_sync(0xffffffffu, bb.y0);
             const int x1 = __reduce_max_sync(0xffffffffu, bb.x1), y1 = __reduce_max_sync(0xffffffffu, bb.y1);
@@ -536,33 +564,111 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         }
         __syncthreads();
 
-        // ---- 2. the bounding grid ------------------------------------------------------------------
+        // ---- 2. the bounding grid; lines bucketed by step-count class --------------------------------
         const bool empty = !fallback && (S.bbox[0] > S.bbox[2]);  // no line with two distinct end points
         // one tile of margin: the DDA may overshoot its end pixel by one before the end snap
         const int gx0 = S.bbox[0] - 1, gy0 = S.bbox[1] - 1;
         const int W = empty ? 1 : S.bbox[2] - S.bbox[0] + 3, H = empty ? 1 : S.bbox[3] - S.bbox[1] + 3;
-        if (!fallback && !empty && (W > PK_CELLS || H > PK_MAXROWS)) fallback = true;
-        const int rows_per_band = (fallback || empty) ? 1 : min(H, PK_CELLS / W);
-        const int nbands = (H + rows_per_band - 1) / rows_per_band;
+        if (!fallback && !empty && (long long)W * H > PK_CELLS) fallback = true;
+        const bool walk = !fallback && !empty;
+        uint32_t n_sorted = 0;
+        if (walk) {
+            uint32_t cbase[PK_NCLS];
+#pragma unroll
+            for (int k = 0; k < PK_NCLS; ++k) {
+                cbase[k] = n_sorted;
+                n_sorted += S.bcur[k];
+            }
+            __syncthreads();  // everybody has read the class counts
+            if (tid <= PK_NCLS) {
+                uint32_t o = 0;
+                for (uint32_t k = 0; k < tid; ++k) o += S.bcur[k];
+                S.boff[tid] = o;
+            }
+            for (uint32_t i = tid; i < (uint32_t)(W * H); i += PK_THREADS) S.u.g.cell[i] = PK_CELL_INIT;
+            __syncthreads();
+            if (tid < PK_NCLS) S.bcur[tid] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                const uint32_t info = __ldcg(&G.info[i]);
+                if (info == PK_INFO_NONE) continue;
+                const uint32_t k = pk_info_cls(info);
+                uint32_t base = 0;
+#pragma unroll
+                for (int q = 0; q < PK_NCLS; ++q) base = (k == (uint32_t)q) ? cbase[q] : base;
+                const uint32_t pos = base + atomicAdd(&S.bcur[k], 1u);
+                __stcg(&G.slines[pos], __ldcg(&G.lines[i]));
+            }
+            __syncthreads();
+        }
 
-        // ---- 3. mark + scan: tiles and spans of the whole path --------------------------------------
+        // ---- 3. mark + scan: tiles and spans of the path; slot bands -----------------------------------
         uint32_t tot_tiles = 0, tot_spans = 0;
         PkScan sc;
         sc.c0 = sc.c1 = sc.span_excl = 0;
-        if (!fallback && !empty) {
-            int wcarry = 0;
-            for (int b = 0; b < nbands && !fallback; ++b) {
-                const int row0 = b * rows_per_band, nrows = min(rows_per_band, H - row0);
-                uint32_t nt, ns, bad;
-                int wtot;
-                pk_band_setup(S, G, n_lines, gx0, gy0, W, row0, nrows, b == 0, wcarry, sc, nt, ns, wtot, bad);
-                uint32_t over = 0;  // a tile row must fit the resident accumulators
-                for (int r = tid; r < nrows; r += PK_THREADS)
-                    if ((uint32_t)(S.rank[(r + 1) * W] - S.rank[r * W]) > PK_SLOTS) over = 1;
-                if (__syncthreads_or((int)(over | bad))) fallback = true;
-                tot_tiles += nt;
-                tot_spans += ns;
-                wcarry = wtot;
+        uint32_t nbands = 1;
+        if (walk) {
+            const uint32_t err = pk_mark(S.u.g.cell, G.slines, n_sorted, gx0, gy0, W, H);
+            __syncthreads();
+            uint32_t bad;
+            pk_grid_scan(S, W, H, err, sc, tot_tiles, tot_spans, bad);
+            // slot bands: as many whole tile rows as fit PK_SLOTS resident tiles
+            if (tid == 0) {
+                uint32_t nb = 0, f = 0;
+                int r = 0;
+                while (r < H) {
+                    if (nb == PK_MAXB) { f = 1; break; }
+                    S.brow[nb++] = (uint16_t)r;
+                    const uint32_t rk0 = S.rank[r * W];
+                    if ((uint32_t)S.rank[(r + 1) * W] - rk0 > PK_SLOTS) { f = 1; break; }  // a tile row must fit
+                    ++r;
+                    while (r < H && (uint32_t)S.rank[(r + 1) * W] - rk0 <= PK_SLOTS) ++r;
+                }
+                S.brow[nb] = (uint16_t)H;
+                S.nbands = nb;
+                S.flag = f;
+            }
+            __syncthreads();
+            nbands = S.nbands;
+            if (bad || S.flag) fallback = true;
+            // more than one band: bucket the lines again, by (band, class), one copy per band a line touches
+            if (!fallback && nbands > 1) {
+                const uint32_t nkeys = nbands * PK_NCLS;
+                for (uint32_t k = tid; k < nkeys; k += PK_THREADS) S.bcur[k] = 0;
+                __syncthreads();
+                for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                    const uint32_t info = __ldcg(&G.info[i]);
+                    if (info == PK_INFO_NONE) continue;
+                    const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
+                    const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
+                    for (int b = b0; b <= b1; ++b) atomicAdd(&S.bcur[b * PK_NCLS + pk_info_cls(info)], 1u);
+                }
+                __syncthreads();
+                uint32_t total;
+                const uint32_t v = (tid < nkeys) ? S.bcur[tid] : 0u;  // PK_MAXB * PK_NCLS <= PK_THREADS
+                const uint32_t ex = block_excl_scan(v, S.ws, total);
+                if (tid < nkeys) {
+                    S.boff[tid] = ex;
+                    S.bcur[tid] = 0;
+                }
+                if (tid == 0) S.boff[nkeys] = total;
+                __syncthreads();
+                if (total > PK_SLINECAP) {
+                    fallback = true;
+                } else {
+                    for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                        const uint32_t info = __ldcg(&G.info[i]);
+                        if (info == PK_INFO_NONE) continue;
+                        const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
+                        const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
+                        const float4 L = __ldcg(&G.lines[i]);
+                        for (int b = b0; b <= b1; ++b) {
+                            const uint32_t k = b * PK_NCLS + pk_info_cls(info);
+                            __stcg(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L);
+                        }
+                    }
+                }
+                // (the barrier before the first band's accumulate pass orders these stores)
             }
         }
         if (empty) tot_tiles = 1;  // the empty path's all-zero tile at (0,0), rasterizer.rs:194, :208
@@ -582,8 +688,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         }
         __syncthreads();
         if (fallback) continue;
-        uint32_t tile_at = S.base_tiles;  // arena index of this path's next tile
-        uint32_t span_at = S.base_spans;
+        const uint32_t tile_at = S.base_tiles;  // arena index of this path's first tile
+        const uint32_t span_at = S.base_spans;
         const bool fits = (uint64_t)tile_at + tot_tiles <= A.cap_tiles && (uint64_t)span_at + tot_spans <= A.cap_spans;
         if (!fits) {
             if (tid == 0) atomicMax(A.status + 2, 1);
@@ -595,80 +701,67 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             continue;
         }
 
-        // ---- 5. per band: origins + spans, then accumulate, carry, quantise, emit --------------------
-        int wcarry = 0;
-        for (int b = 0; b < nbands; ++b) {
-            const int row0 = b * rows_per_band, nrows = min(rows_per_band, H - row0);
-            uint32_t nt = tot_tiles, ns = tot_spans, bad;
-            int wtot = 0;
-            if (nbands > 1) pk_band_setup(S, G, n_lines, gx0, gy0, W, row0, nrows, false, wcarry, sc, nt, ns, wtot, bad);
-            wcarry = wtot;
-            pk_emit_band_index(S, A, sc, gx0, gy0, W, row0, tile_at, span_at);
-            // slot bands: as many whole tile rows as fit PK_SLOTS resident tiles
-            int r0 = 0;
-            while (r0 < nrows) {
-                __syncthreads();  // also: the flags / tcell are dead from here on (the accumulators reuse them)
-                if (tid == 0) {
-                    int r1 = r0 + 1;
-                    const uint32_t rk0 = S.rank[r0 * W];
-                    while (r1 < nrows && (uint32_t)S.rank[(r1 + 1) * W] - rk0 <= PK_SLOTS) ++r1;
-                    S.r1 = (uint32_t)r1;
-                }
-                __syncthreads();
-                const int r1 = (int)S.r1;
-                const uint32_t rank0 = S.rank[r0 * W];
-                const uint32_t nslots = (uint32_t)S.rank[r1 * W] - rank0;
-                if (nslots) {
-                    {
-                        uint4* z = reinterpret_cast<uint4*>(S.u.acc);
-                        for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                    __syncthreads();
-                    pk_accumulate(S, G, n_lines, gx0, gy0, W, row0, row0 + r0, row0 + r1, rank0);
-                    __syncthreads();
-                    // row carry (x256): one thread per (tile row, pixel row), left to right over the row's tiles;
-                    // the carry into a tile replaces its carry-out column
-                    for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
-                        const int r = r0 + (it >> 3), y = it & 7;
-                        const uint32_t s0 = S.rank[r * W] - rank0, s1 = S.rank[(r + 1) * W] - rank0;
-                        float c = 0.0f;
-                        for (uint32_t s = s0; s < s1; ++s) {
-                            int* d = &S.u.acc[s * PK_ACCW + y * 9];
-                            int rs = 0;
-#pragma unroll
-                            for (int x = 0; x < 9; ++x) rs += d[x];
-                            d[8] = __float_as_int(c);
-                            c += (float)rs * OC_FX_TO_256;
-                        }
-                    }
-                    __syncthreads();
-                    // quantise + emit: one thread per (tile, pixel row) -> one 8-byte store
-                    for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
-                        const uint32_t s = it >> 3, y = it & 7;
-                        const int* d = &S.u.acc[s * PK_ACCW + y * 9];
-                        const float c = __int_as_float(d[8]);
-                        int run = 0;
-                        uint32_t lo32 = 0, hi32 = 0;
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) {
-                            run += d[x];
-                            // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
-                            const uint32_t q = (uint32_t)(int)fminf(fabsf(c + (float)run * OC_FX_TO_256), 255.0f);
-                            if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
-                        }
-                        const uint32_t ti = tile_at + rank0 + s;
-                        reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64)[y] = make_uint2(lo32, hi32);
-                    }
-                }
-                r0 = r1;
+        // ---- 5. origins + spans, then per slot band: accumulate, carry, quantise, emit ---------------
+        pk_emit_index(S, A, sc, gx0, gy0, W, tile_at, span_at);
+        for (uint32_t b = 0; b < nbands; ++b) {
+            __syncthreads();  // also: the flags / tcell are dead from here on (the accumulators reuse them)
+            const int r0 = S.brow[b], r1 = S.brow[b + 1];
+            const uint32_t rank0 = S.rank[r0 * W];
+            const uint32_t nslots = (uint32_t)S.rank[r1 * W] - rank0;
+            if (!nslots) continue;
+            {
+                uint4* z = reinterpret_cast<uint4*>(S.u.acc);
+                for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
             }
-            tile_at += nt;
-            span_at += ns;
             __syncthreads();
+            pk_accumulate(S.u.acc, S.rank, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, gy0, W, gy0 + r0, gy0 + r1,
+                          rank0);
+            __syncthreads();
+            // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
+            for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
+                int* d = &S.u.acc[(it >> 3) * PK_ACCW + (it & 7) * 9];
+                int rs = 0;
+#pragma unroll
+                for (int x = 0; x < 9; ++x) rs += d[x];
+                d[8] = rs;
+            }
+            __syncthreads();
+            // row carry: one thread per (tile row, pixel row), left to right over the row's tiles, as an exact
+            // integer sum; the carry into a tile (x256, as f32) replaces its row sum
+            for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
+                const int r = r0 + (it >> 3), y = it & 7;
+                const uint32_t s0 = S.rank[r * W] - rank0, s1 = S.rank[(r + 1) * W] - rank0;
+                long long c = 0;
+                for (uint32_t s = s0; s < s1; ++s) {
+                    int* d = &S.u.acc[s * PK_ACCW + y * 9 + 8];
+                    const int rs = *d;
+                    *d = __float_as_int((float)c * OC_FX_TO_256);
+                    c += rs;
+                }
+            }
+            __syncthreads();
+            // quantise + emit: one thread per (tile, pixel row) -> one 8-byte store
+            for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
+                const uint32_t s = it >> 3, y = it & 7;
+                const int* d = &S.u.acc[s * PK_ACCW + y * 9];
+                const float c = __int_as_float(d[8]);
+                int run = 0;
+                uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    run += d[x];
+                    // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
+                    const uint32_t q = (uint32_t)(int)fminf(fabsf(c + (float)run * OC_FX_TO_256), 255.0f);
+                    if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
+                }
+                const uint32_t ti = tile_at + rank0 + s;
+                reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64)[y] = make_uint2(lo32, hi32);
+            }
         }
     }
 }
 
 constexpr size_t PK_SMEM = sizeof(PkShared);
+static_assert(PK_MAXB * PK_NCLS <= PK_THREADS, "one CTA scan covers every (band, class) bucket");
 
 }  // namespace oc

@@ -410,6 +410,37 @@ k_gather_paths(const uint4* __restrict__ rec, uint32_t n_paths, const uint32_t* 
     for (uint32_t i = lane; i < r.w; i += 32) spans[dst_s + i] = st_spans[src_s + i];
 }
 
+
+// ---------------------------------------------------------------------------
+// Fused path, hand-over: the paths the fused kernel left to the general pipeline are compacted
+// into a side batch (one warp per path copies its commands and transform), and after the
+// pipeline ran, their (start, count) records point into the staging arena they were appended to.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_fb_gather_cmds(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base,
+                 const float* __restrict__ xf, const uint32_t* __restrict__ fb, const uint32_t* __restrict__ sub_off,
+                 uint32_t n_fb, uint32_t* __restrict__ out_cmds /* 7 words per command */, float* __restrict__ out_xf) {
+    const uint32_t q = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= n_fb) return;
+    const uint32_t p = fb[q];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(cmds + (cmd_off[p] - cmd_base));
+    const uint32_t nw = (cmd_off[p + 1] - cmd_off[p]) * 7u;
+    uint32_t* dst = out_cmds + (size_t)sub_off[q] * 7u;
+    for (uint32_t i = lane; i < nw; i += 32) dst[i] = src[i];
+    if (lane < 6) out_xf[6 * (size_t)q + lane] = xf[6 * (size_t)p + lane];
+}
+
+__global__ void __launch_bounds__(TPB)
+k_fb_records(const uint32_t* __restrict__ fb, uint32_t n_fb, const uint32_t* __restrict__ tile_off,
+             const uint32_t* __restrict__ span_off, uint32_t n_tiles, uint32_t n_spans, uint32_t tile_at, uint32_t span_at,
+             uint4* __restrict__ rec) {
+    const uint32_t q = blockIdx.x * TPB + threadIdx.x;
+    if (q >= n_fb) return;
+    const uint32_t t0 = tile_off[q], t1 = (q + 1 < n_fb) ? tile_off[q + 1] : n_tiles;
+    const uint32_t s0 = span_off[q], s1 = (q + 1 < n_fb) ? span_off[q + 1] : n_spans;
+    rec[fb[q]] = make_uint4(tile_at + t0, t1 - t0, span_at + s0, s1 - s0);
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -493,7 +524,9 @@ struct ochre_b200_ctx {
     // fused per-path kernel
     int mode = OCHRE_MODE_AUTO;
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;  // ctl: ticket(1) cursor(2) status(3) words
+    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;
+    DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
+    uint64_t fb_paths = 0;  // paths the fused kernel left to the general pipeline in the last call  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
     HostBuf h_pk_ctl;
     uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
@@ -536,8 +569,19 @@ int read_scalars(ochre_b200_ctx* ctx) {
 }
 
 // One pipeline pass over paths [p0, p1) whose inputs are already on the device.
+// Where a pipeline pass leaves its tiles and spans: the result arena (default) or, for the paths
+// the fused kernel hands over, a side arena that is then appended to the fused kernel's staging arena.
+struct OutTarget {
+    DevBuf* tile_xy;
+    DevBuf* alpha;
+    DevBuf* spans;
+    uint32_t* tile_off;  // [p1 - p0] (device)
+    uint32_t* span_off;
+};
+
 int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all, uint32_t p0,
-              uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base, ChunkOut* co) {
+              uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base, ChunkOut* co,
+              const OutTarget& ot) {
     cudaStream_t st = ctx->st;
     const uint32_t n_paths = p1 - p0;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
@@ -676,12 +720,12 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     }
     CK(cudaEventRecord(ctx->ev[5], st));
     // ---- stage 5: coverage + emission ------------------------------------------
-    CK(ctx->o_tile_xy.ensure(((size_t)tile_base + n_tiles + 1) * 4, true, st));
-    CK(ctx->o_alpha.ensure(((size_t)tile_base + n_tiles + 1) * 64, true, st));
-    CK(ctx->o_spans.ensure(((size_t)span_base + n_spans + 1) * sizeof(OchreSpan), true, st));
-    int16_t* o_xy = ctx->o_tile_xy.as<int16_t>();
-    uint8_t* o_alpha = ctx->o_alpha.as<uint8_t>();
-    OchreSpan* o_spans = ctx->o_spans.as<OchreSpan>();
+    CK(ot.tile_xy->ensure(((size_t)tile_base + n_tiles + 1) * 4, true, st));
+    CK(ot.alpha->ensure(((size_t)tile_base + n_tiles + 1) * 64, true, st));
+    CK(ot.spans->ensure(((size_t)span_base + n_spans + 1) * sizeof(OchreSpan), true, st));
+    int16_t* o_xy = ot.tile_xy->as<int16_t>();
+    uint8_t* o_alpha = ot.alpha->as<uint8_t>();
+    OchreSpan* o_spans = ot.spans->as<OchreSpan>();
     if (n_groups) {
         k_coverage<<<nblk(n_groups, CV_THREADS), CV_THREADS, CV_SMEM, st>>>(keys, vals, group_start, n_groups, n_rec, lines,
                                                                             g_real, tile_idx, tile_base, o_xy, o_alpha);
@@ -691,7 +735,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     k_emit_spans<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, group_start, n_groups, span_w, span_idx, span_base, o_spans);
     launches += 1;
     k_path_offsets<<<nblk(n_paths, TPB), TPB, 0, st>>>(n_paths, path_first, tile_idx, span_idx, tile_base, span_base,
-                                                         ctx->o_tile_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0);
+                                                         ot.tile_off, ot.span_off);
     launches += 1;
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(cudaStreamSynchronize(st));
@@ -723,8 +767,8 @@ enum { RC_CONIC = 1000, RC_NEED_GENERAL = 1001 };
 enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_WORDS = 8 };
 
 int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
-                    uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base,
-                    ChunkOut* co) {
+                    const uint32_t* h_off, uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base,
+                    uint32_t span_base, ChunkOut* co) {
     cudaStream_t st = ctx->st;
     const uint32_t n_paths = p1 - p0;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
@@ -783,8 +827,9 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
                 default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
             }
         }
-        if (stt[1] > 0) return RC_NEED_GENERAL;
-        const uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];
+        uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];
+        const uint32_t n_fb = (uint32_t)stt[1];
+        if (n_fb && ctx->mode == OCHRE_MODE_FUSED) return RC_NEED_GENERAL;
         if ((uint64_t)tile_base + nt >= 0xffffffffull || (uint64_t)span_base + ns >= 0xffffffffull) {
             ctx->err = "more than 2^32 tiles or spans in one call";
             return OCHRE_E_TOO_LARGE;
@@ -794,6 +839,62 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)nt / denom);
         ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)ns / denom);
         if (stt[2]) continue;  // staging arena too small: grown at the top of the loop, run again
+        if (n_fb) {
+            // ---- hand-over: the general pipeline rasterises the paths that exceed the on-chip budgets ----
+            std::vector<uint32_t> fb(n_fb), sub_off((size_t)n_fb + 1);
+            CK(cudaMemcpyAsync(fb.data(), ctx->d_pk_fb.p, (size_t)n_fb * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            std::sort(fb.begin(), fb.end());
+            uint64_t acc = 0;
+            for (uint32_t q = 0; q < n_fb; ++q) {
+                sub_off[q] = (uint32_t)acc;
+                acc += h_off[p0 + fb[q] + 1] - h_off[p0 + fb[q]];
+            }
+            sub_off[n_fb] = (uint32_t)acc;
+            const uint32_t n_sub = (uint32_t)acc;
+            CK(ctx->f_cmds.ensure((size_t)n_sub * sizeof(Cmd) + 16));
+            CK(ctx->f_off.ensure(((size_t)n_fb + 1) * 4));
+            CK(ctx->f_xf.ensure((size_t)n_fb * 24 + 16));
+            CK(ctx->f_fb.ensure((size_t)n_fb * 4));
+            CK(ctx->f_tile_off.ensure(((size_t)n_fb + 1) * 4));
+            CK(ctx->f_span_off.ensure(((size_t)n_fb + 1) * 4));
+            CK(cudaMemcpyAsync(ctx->f_fb.p, fb.data(), (size_t)n_fb * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->f_off.p, sub_off.data(), ((size_t)n_fb + 1) * 4, cudaMemcpyHostToDevice, st));
+            k_fb_gather_cmds<<<nblk((uint64_t)n_fb * 32, TPB), TPB, 0, st>>>(A.cmds, A.cmd_off, A.cmd_base, A.xf, ctx->f_fb.as<uint32_t>(),
+                                                                           ctx->f_off.as<uint32_t>(), n_fb, ctx->f_cmds.as<uint32_t>(),
+                                                                           ctx->f_xf.as<float>());
+            co->launches += 1;
+            CK(cudaStreamSynchronize(st));  // fb / sub_off are host temporaries
+            ChunkOut co2;
+            OutTarget ot{&ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, ctx->f_tile_off.as<uint32_t>(), ctx->f_span_off.as<uint32_t>()};
+            int rc = run_chunk(ctx, ctx->f_cmds.as<Cmd>(), ctx->f_off.as<uint32_t>(), ctx->f_xf.as<float>(), 0, n_fb, 0, n_sub, 0, 0, &co2, ot);
+            if (rc != 0) return rc;
+            if ((uint64_t)tile_base + nt + co2.n_tiles >= 0xffffffffull || (uint64_t)span_base + ns + co2.n_spans >= 0xffffffffull) {
+                ctx->err = "more than 2^32 tiles or spans in one call";
+                return OCHRE_E_TOO_LARGE;
+            }
+            // append to the staging arena and point the paths' records at it
+            CK(ctx->s_tile_xy.ensure(((size_t)nt + co2.n_tiles + 1) * 4, true, st));
+            CK(ctx->s_alpha.ensure(((size_t)nt + co2.n_tiles + 1) * 64, true, st));
+            CK(ctx->s_spans.ensure(((size_t)ns + co2.n_spans + 1) * sizeof(OchreSpan), true, st));
+            if (co2.n_tiles) {
+                CK(cudaMemcpyAsync(ctx->s_tile_xy.as<uint32_t>() + nt, ctx->f_tile_xy.p, (size_t)co2.n_tiles * 4, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(ctx->s_alpha.as<uint8_t>() + (size_t)nt * 64, ctx->f_alpha.p, (size_t)co2.n_tiles * 64, cudaMemcpyDeviceToDevice, st));
+            }
+            if (co2.n_spans)
+                CK(cudaMemcpyAsync(ctx->s_spans.as<OchreSpan>() + ns, ctx->f_spans.p, (size_t)co2.n_spans * sizeof(OchreSpan), cudaMemcpyDeviceToDevice, st));
+            k_fb_records<<<nblk(n_fb, TPB), TPB, 0, st>>>(ctx->f_fb.as<uint32_t>(), n_fb, ctx->f_tile_off.as<uint32_t>(),
+                                                         ctx->f_span_off.as<uint32_t>(), co2.n_tiles, co2.n_spans, nt, ns, rec);
+            co->launches += co2.launches + 1;
+            for (int k = 1; k < 7; ++k) co->ms[k] += co2.ms[k];  // (stage 0 keeps the fused kernel's own time)
+            co->ms[1] += co2.ms[0];
+            co->n_lines += co2.n_lines;
+            co->n_rec += co2.n_rec;
+            nt += co2.n_tiles;
+            ns += co2.n_spans;
+            ctx->used_paths |= 2u;
+            ctx->fb_paths += n_fb;
+        }
         // path order: offsets by exclusive scan of the per-path counts, then the gather copy
         CK(ctx->o_tile_xy.ensure(((size_t)tile_base + nt + 1) * 4, true, st));
         CK(ctx->o_alpha.ensure(((size_t)tile_base + nt + 1) * 64, true, st));
@@ -870,7 +971,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
@@ -900,6 +1001,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     ctx->err.clear();
     ctx->dbg_valid = false;
     ctx->used_paths = 0;
+    ctx->fb_paths = 0;
     memset(out, 0, sizeof *out);
     out->n_paths = n_paths;
     CK(cudaSetDevice(ctx->device));
@@ -970,7 +1072,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         ChunkOut co;
         int rc = RC_NEED_GENERAL;
         if (ctx->mode != OCHRE_MODE_GENERAL) {
-            rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+            rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
             if (rc == 0) ctx->used_paths |= 1u;
             if (rc == RC_NEED_GENERAL && ctx->mode == OCHRE_MODE_FUSED) {
                 ctx->err = "a path exceeds the fused kernel's on-chip budgets (mode = fused only)";
@@ -978,7 +1080,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             }
         }
         if (rc == RC_NEED_GENERAL) {
-            rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+            OutTarget ot{&ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, ctx->o_tile_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0};
+            rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, ot);
             if (rc == 0) ctx->used_paths |= 2u;
         }
         if (rc == RC_CONIC) {

@@ -160,11 +160,12 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
     R->span_off.assign((size_t)n_paths + 1, 0);
     // coverage with the row carry of k_coverage (rowsum per tile, then sequential carry)
     float carry[8] = {0};
+    long long fcarry[8] = {0};
     Fetch fetch{lines.data()};
     for (uint32_t g = 0; g < ng; ++g) {
         uint64_t k = K[gs[g]];
         bool seg_start = (g == 0) || key_row(k) != key_row(K[gs[g - 1]]);
-        if (seg_start) for (int y = 0; y < 8; ++y) carry[y] = 0.0f;
+        if (seg_start) for (int y = 0; y < 8; ++y) { carry[y] = 0.0f; fcarry[y] = 0; }
         if (span_w[g]) {
             OchreSpan s;
             s.x = (int16_t)((key_tx(k) + 1) * 8);
@@ -183,15 +184,18 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
             memset(&fx, 0, sizeof fx);
             for (uint32_t i = gs[g]; i < gend(g); ++i)
                 if (!val_wonly(V[i])) cover_record(fx, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
-            const float inv = 1.0f / 4194304.0f;
+            // csrc/path_kernel.cuh: exact integer row carry, both terms of rasterizer.rs:235 scaled by 256
+            const float k256 = 1.0f / 16384.0f;  // 2^-22 * 256
             for (int y = 0; y < 8; ++y) {
                 int rs = 0, run = 0;
                 for (int x = 0; x < 8; ++x) rs += fx.h[y * 8 + x];
+                const float cf = (float)fcarry[y] * k256;
                 for (int x = 0; x < 8; ++x) {
-                    R->alpha[64 * (size_t)ti + y * 8 + x] = (uint8_t)alpha_u8(carry[y] + (float)(run + fx.a[y * 8 + x]) * inv);
+                    float w = fminf(fabsf(cf + (float)(run + fx.a[y * 8 + x]) * k256), 255.0f);
+                    R->alpha[64 * (size_t)ti + y * 8 + x] = (uint8_t)(int)w;
                     run += fx.h[y * 8 + x];
                 }
-                carry[y] += (float)rs * inv;
+                fcarry[y] += rs;
             }
             continue;
         }

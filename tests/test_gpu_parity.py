@@ -106,13 +106,17 @@ def test_fused_kernel_falls_back_for_oversized_paths():
         assert e.value.code == -4
         c.set_mode("auto")
         g = c.rasterize(cmds, off, xf)
-        assert g.used == 2
-        # a mixed batch: small paths + one wide path; chunks without the big path stay on the fused kernel
+        assert g.used & 2  # the general pipeline took the path over
+        assert_batch_parity(g, oracle_batch(cmds, off, xf), what="rings, handed over")
+        # a mixed batch: small paths + one wide path; only the wide path is handed to the general pipeline
         b_cmds, b_off, b_xf = W.blobs(300)
         wide = make_cmds([(MOVE, 10, 10), (LINE, 30000, 14), (LINE, 30000, 40), (LINE, 10, 30), (CLOSE,)])
         cmds = np.concatenate([b_cmds, wide])
         off2 = np.concatenate([b_off, [b_off[-1] + len(wide)]]).astype(np.uint32)
         xf2 = np.concatenate([b_xf, ID[None]])
+        g = c.rasterize(cmds, off2, xf2)
+        assert g.used == 3 and g.n_chunks == 1
+        assert_batch_parity(g, oracle_batch(cmds, off2, xf2), what="mixed batch, one chunk")
         c.set_chunk(2048)
         g = c.rasterize(cmds, off2, xf2)
         assert g.used == 3 and g.n_chunks > 2
