@@ -39,16 +39,16 @@
 namespace oc {
 
 #ifndef OC_PK_THREADS
-#define OC_PK_THREADS 256
+#define OC_PK_THREADS 128
 #endif
 #ifndef OC_PK_SLOTS
-#define OC_PK_SLOTS 133
+#define OC_PK_SLOTS 80
 #endif
 #ifndef OC_PK_CELLS
-#define OC_PK_CELLS 6400
+#define OC_PK_CELLS 5888
 #endif
 #ifndef OC_PK_CTAS
-#define OC_PK_CTAS 4
+#define OC_PK_CTAS 8
 #endif
 constexpr int PK_THREADS = OC_PK_THREADS;
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
@@ -97,19 +97,19 @@ struct PkCurves {  // decoded curve commands of the current command chunk (slot 
     uint32_t loff[PK_THREADS];  // first line of the command
     uint32_t tag[PK_THREADS];
 };
-struct PkGrid {
-    uint32_t cell[PK_CELLS];   // mark pass: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: flags
-    uint16_t tcell[PK_CELLS];  // touched cells in (tile_y, tile_x) order
-};
 enum : uint32_t { CF_TOUCHED = 1, CF_WIND = 2, CF_SPAN = 4 };
+constexpr int PK_WORDS = (PK_CELLS + 31) / 32;
 
 struct PkShared {
     union {  // phase-aliased: flatten | mark + scan + span/origin emission | accumulate + quantise
         int acc[PK_SLOTS * PK_ACCW];
-        PkGrid g;
+        uint32_t cell[PK_CELLS];  // mark pass: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: CF_* flags
         PkCurves v;
     } u;
-    uint16_t rank[PK_CELLS + 2];            // touched cells before this cell; kept across the slot bands
+    // touched cells of the grid in (tile_y, tile_x) order, kept across the slot bands:
+    // rank(c) = wbase[c >> 5] + popc(bits[c >> 5] & below(c & 31))
+    uint32_t bits[PK_WORDS + 1];
+    uint16_t wbase[PK_WORDS + 2];
     uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
     uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
     uint16_t brow[PK_MAXB + 2];             // first grid row of every slot band
@@ -117,6 +117,20 @@ struct PkShared {
     int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
     uint32_t path, next_path, nbands, base_tiles, base_spans, flag;
 };
+
+// touched cells before cell c (c may be one past the last cell)
+__device__ __forceinline__ uint32_t pk_rank(const PkShared& S, uint32_t c) {
+    return (uint32_t)S.wbase[c >> 5] + (uint32_t)__popc(S.bits[c >> 5] & ((1u << (c & 31u)) - 1u));
+}
+// first touched cell in [c, end), or `end`
+__device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t c, uint32_t end) {
+    while (c < end) {
+        const uint32_t w = S.bits[c >> 5] >> (c & 31u);
+        if (w) return min(end, c + (uint32_t)__ffs((int)w) - 1u);
+        c = (c | 31u) + 1u;
+    }
+    return end;
+}
 
 // Exclusive scan of two values per thread across the CTA in one pass.  `ws` must hold 72 words.
 __device__ __forceinline__ void block_excl_scan_pair(uint32_t a, uint32_t b, uint32_t* ws, uint32_t& ex_a, uint32_t& ex_b,
@@ -280,7 +294,7 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
 
 // Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
 // tile rows; slot = rank - rank0.
-__device__ __forceinline__ void pk_accumulate(int* acc, const uint16_t* rank, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
+__device__ __forceinline__ void pk_accumulate(int* acc, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
                                               int gx0, int gy0, int W, int R0, int R1, uint32_t rank0) {
     uint32_t pos = p0 + threadIdx.x;
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -305,7 +319,7 @@ __device__ __forceinline__ void pk_accumulate(int* acc, const uint16_t* rank, co
             const float area = 0.5f * height * ((right - p0x) + (right - p1x));
             const int ry = y0 >> 3;
             if (ry >= R0 && ry < R1) {
-                const uint32_t slot = (uint32_t)rank[(ry - gy0) * W + ((x0 >> 3) - gx0)] - rank0;
+                const uint32_t slot = pk_rank(S, (uint32_t)((ry - gy0) * W + ((x0 >> 3) - gx0))) - rank0;
                 int* d = &acc[slot * PK_ACCW + (y0 & 7) * 9 + (x0 & 7)];
                 const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
                 atomicAdd(d, qa);
@@ -326,14 +340,16 @@ struct PkScan {
     uint32_t span_excl;   // spans of the path before this thread's run
 };
 
-// Ordered scan of the marked grid.  On return: S.rank (touched cells before each cell,
-// S.rank[ncells] = n_touched), S.u.g.tcell (ordered touched cells), S.u.g.cell = CF_* flags.
+// Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells),
+// S.u.cell = CF_* flags of every cell.
 __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, PkScan& sc, uint32_t& n_touched,
                                              uint32_t& n_spans, uint32_t& bad) {
     const uint32_t ncells = (uint32_t)(W * H);
-    uint32_t* cell = S.u.g.cell;
-    // every thread owns a contiguous run of cells: local sums, one CTA scan, local prefix
-    const uint32_t per = (ncells + PK_THREADS - 1) / PK_THREADS;
+    uint32_t* cell = S.u.cell;
+    // every thread owns a contiguous run of cells -- whole 32-cell words, or a power-of-two fraction of
+    // one on small grids: local sums, one CTA scan, local prefix
+    uint32_t per = (ncells + PK_THREADS - 1) / PK_THREADS;
+    per = per >= 32u ? ((per + 31u) & ~31u) : (per <= 1u ? 1u : 1u << (32 - __clz((int)per - 1)));
     sc.c0 = min(ncells, threadIdx.x * per);
     sc.c1 = min(ncells, sc.c0 + per);
     uint32_t lt = 0, lw = 0;
@@ -347,24 +363,28 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
     uint32_t ex_t, ex_w, tot_t, tot_w;
     block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
     {
-        uint32_t r = ex_t;
+        uint32_t r = ex_t, word = 0;
         int wp = (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
         for (uint32_t c = sc.c0; c < sc.c1; ++c) {
+            if ((c & 31u) == 0) S.wbase[c >> 5] = (uint16_t)r;
             const uint32_t w = cell[c];
             const uint32_t cnt = w & 0xffffu;
             wp += (int)((w >> 16) - 0x8000u);
-            S.rank[c] = (uint16_t)r;
             uint32_t f = 0;
             if (cnt) {
-                S.u.g.tcell[r] = (uint16_t)c;
+                word |= 1u << (c & 31u);
                 ++r;
                 f = CF_TOUCHED | (wp != 0 ? CF_WIND : 0u);
             }
             cell[c] = f;
+            if ((c & 31u) == 31u || c + 1 == sc.c1) {
+                if (word) atomicOr(&S.bits[c >> 5], word);  // (runs shorter than a word share it)
+                word = 0;
+            }
         }
     }
     n_touched = tot_t;
-    if (threadIdx.x == 0) S.rank[ncells] = (uint16_t)tot_t;
+    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.wbase[ncells >> 5] = (uint16_t)tot_t;  // rank(ncells) reads one word past the last cell
     __syncthreads();
     // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
     uint32_t ls = 0;
@@ -374,13 +394,10 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
             if (c == row_end) row_end += (uint32_t)W;
             const uint32_t f = cell[c];
             if ((f & (CF_TOUCHED | CF_WIND)) == (CF_TOUCHED | CF_WIND)) {
-                const uint32_t r = S.rank[c];
-                if (r + 1 < tot_t) {
-                    const uint32_t nx = S.u.g.tcell[r + 1];
-                    if (nx > c + 1 && nx < row_end) {
-                        cell[c] = f | CF_SPAN;
-                        ++ls;
-                    }
+                const uint32_t nx = pk_next_touched(S, c + 1, row_end);
+                if (nx > c + 1 && nx < row_end) {
+                    cell[c] = f | CF_SPAN;
+                    ++ls;
                 }
             }
         }
@@ -391,22 +408,23 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
     bad = __syncthreads_or((int)err);
 }
 
-// Tile origins and spans (needs the CF_* flags and tcell, i.e. runs before the accumulators reuse
-// that shared memory).
+// Tile origins and spans (needs the CF_* flags, i.e. runs before the accumulators reuse that
+// shared memory).
 __device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKernelArgs& A, const PkScan& sc, int gx0, int gy0,
                                               int W, uint32_t tile_at, uint32_t span_at) {
     if (sc.c0 >= sc.c1) return;
-    const uint32_t* cell = S.u.g.cell;
+    const uint32_t* cell = S.u.cell;
     int cy = (int)(sc.c0 / (uint32_t)W), cx = (int)(sc.c0 - (uint32_t)cy * (uint32_t)W);
     uint32_t sidx = span_at + sc.span_excl;
+    uint32_t r = pk_rank(S, sc.c0);
     for (uint32_t c = sc.c0; c < sc.c1; ++c) {
         const uint32_t f = cell[c];
         if (f & CF_TOUCHED) {
-            const uint32_t r = S.rank[c];
             const int px = (gx0 + cx) * 8, py = (gy0 + cy) * 8;
             reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at + r] = (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16);
+            ++r;
             if (f & CF_SPAN) {
-                const uint32_t nx = S.u.g.tcell[r + 1];
+                const uint32_t nx = pk_next_touched(S, c + 1, c + (uint32_t)(W - cx));
                 OchreSpan sp;
                 sp.x = (int16_t)(px + 8);
                 sp.y = (int16_t)py;
@@ -585,7 +603,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 for (uint32_t k = 0; k < tid; ++k) o += S.bcur[k];
                 S.boff[tid] = o;
             }
-            for (uint32_t i = tid; i < (uint32_t)(W * H); i += PK_THREADS) S.u.g.cell[i] = PK_CELL_INIT;
+            for (uint32_t i = tid; i < (uint32_t)(W * H); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
+            for (uint32_t i = tid; i <= (uint32_t)(W * H) >> 5; i += PK_THREADS) S.bits[i] = 0;
             __syncthreads();
             if (tid < PK_NCLS) S.bcur[tid] = 0;
             __syncthreads();
@@ -608,7 +627,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         sc.c0 = sc.c1 = sc.span_excl = 0;
         uint32_t nbands = 1;
         if (walk) {
-            const uint32_t err = pk_mark(S.u.g.cell, G.slines, n_sorted, gx0, gy0, W, H);
+            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, gy0, W, H);
             __syncthreads();
             uint32_t bad;
             pk_grid_scan(S, W, H, err, sc, tot_tiles, tot_spans, bad);
@@ -619,10 +638,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 while (r < H) {
                     if (nb == PK_MAXB) { f = 1; break; }
                     S.brow[nb++] = (uint16_t)r;
-                    const uint32_t rk0 = S.rank[r * W];
-                    if ((uint32_t)S.rank[(r + 1) * W] - rk0 > PK_SLOTS) { f = 1; break; }  // a tile row must fit
+                    const uint32_t rk0 = pk_rank(S, (uint32_t)(r * W));
+                    if (pk_rank(S, (uint32_t)((r + 1) * W)) - rk0 > PK_SLOTS) { f = 1; break; }  // a tile row must fit
                     ++r;
-                    while (r < H && (uint32_t)S.rank[(r + 1) * W] - rk0 <= PK_SLOTS) ++r;
+                    while (r < H && pk_rank(S, (uint32_t)((r + 1) * W)) - rk0 <= PK_SLOTS) ++r;
                 }
                 S.brow[nb] = (uint16_t)H;
                 S.nbands = nb;
@@ -644,12 +663,17 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     for (int b = b0; b <= b1; ++b) atomicAdd(&S.bcur[b * PK_NCLS + pk_info_cls(info)], 1u);
                 }
                 __syncthreads();
-                uint32_t total;
-                const uint32_t v = (tid < nkeys) ? S.bcur[tid] : 0u;  // PK_MAXB * PK_NCLS <= PK_THREADS
-                const uint32_t ex = block_excl_scan(v, S.ws, total);
-                if (tid < nkeys) {
-                    S.boff[tid] = ex;
-                    S.bcur[tid] = 0;
+                uint32_t total = 0;
+                for (uint32_t kb = 0; kb < nkeys; kb += PK_THREADS) {  // exclusive scan of the bucket counts
+                    const uint32_t k = kb + tid;
+                    const uint32_t v = (k < nkeys) ? S.bcur[k] : 0u;
+                    uint32_t part;
+                    const uint32_t ex = total + block_excl_scan(v, S.ws, part);
+                    if (k < nkeys) {
+                        S.boff[k] = ex;
+                        S.bcur[k] = 0;
+                    }
+                    total += part;
                 }
                 if (tid == 0) S.boff[nkeys] = total;
                 __syncthreads();
@@ -706,15 +730,15 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         for (uint32_t b = 0; b < nbands; ++b) {
             __syncthreads();  // also: the flags / tcell are dead from here on (the accumulators reuse them)
             const int r0 = S.brow[b], r1 = S.brow[b + 1];
-            const uint32_t rank0 = S.rank[r0 * W];
-            const uint32_t nslots = (uint32_t)S.rank[r1 * W] - rank0;
+            const uint32_t rank0 = pk_rank(S, (uint32_t)(r0 * W));
+            const uint32_t nslots = pk_rank(S, (uint32_t)(r1 * W)) - rank0;
             if (!nslots) continue;
             {
                 uint4* z = reinterpret_cast<uint4*>(S.u.acc);
                 for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
             }
             __syncthreads();
-            pk_accumulate(S.u.acc, S.rank, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, gy0, W, gy0 + r0, gy0 + r1,
+            pk_accumulate(S.u.acc, S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, gy0, W, gy0 + r0, gy0 + r1,
                           rank0);
             __syncthreads();
             // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
@@ -730,7 +754,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             // integer sum; the carry into a tile (x256, as f32) replaces its row sum
             for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
                 const int r = r0 + (it >> 3), y = it & 7;
-                const uint32_t s0 = S.rank[r * W] - rank0, s1 = S.rank[(r + 1) * W] - rank0;
+                const uint32_t s0 = pk_rank(S, (uint32_t)(r * W)) - rank0, s1 = pk_rank(S, (uint32_t)((r + 1) * W)) - rank0;
                 long long c = 0;
                 for (uint32_t s = s0; s < s1; ++s) {
                     int* d = &S.u.acc[s * PK_ACCW + y * 9 + 8];
@@ -762,6 +786,5 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
 }
 
 constexpr size_t PK_SMEM = sizeof(PkShared);
-static_assert(PK_MAXB * PK_NCLS <= PK_THREADS, "one CTA scan covers every (band, class) bucket");
 
 }  // namespace oc
