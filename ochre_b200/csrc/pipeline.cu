@@ -447,12 +447,17 @@ k_fb_records(const uint32_t* __restrict__ fb, uint32_t n_fb, const uint32_t* __r
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    cudaStream_t guard = nullptr;  // a stream that may still be reading the buffer (result download): drained before a reallocation
     cudaError_t ensure(size_t bytes, bool keep = false, cudaStream_t st = 0) {
         if (bytes <= cap) return cudaSuccess;
         size_t ncap = bytes + bytes / 4 + 256;
         void* np = nullptr;
         cudaError_t e = cudaMalloc(&np, ncap);
         if (e != cudaSuccess) return e;
+        if (p && guard) {
+            e = cudaStreamSynchronize(guard);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
         if (p) {
             if (keep && cap) {
                 e = cudaMemcpyAsync(np, p, cap, cudaMemcpyDeviceToDevice, st);
@@ -475,6 +480,23 @@ struct DevBuf {
 struct HostBuf {  // pinned
     void* p = nullptr;
     size_t cap = 0;
+    // grow while a download stream is filling the buffer: drains the stream, keeps the first `used` bytes
+    cudaError_t ensure_keep(size_t bytes, size_t used, cudaStream_t guard) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(guard);
+        if (e != cudaSuccess) return e;
+        size_t ncap = bytes + bytes / 4 + 256;
+        void* np = nullptr;
+        e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (p) {
+            if (used) memcpy(np, p, used < cap ? used : cap);
+            cudaFreeHost(p);
+        }
+        p = np;
+        cap = ncap;
+        return cudaSuccess;
+    }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
@@ -501,7 +523,11 @@ constexpr int N_STAGE = 8;
 
 struct ochre_b200_ctx {
     int device = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;       // kernels
+    cudaStream_t st_in = nullptr;    // host -> device input upload, one event per chunk
+    cudaStream_t st_out = nullptr;   // device -> host result download, chunk by chunk behind the kernels
+    std::vector<cudaEvent_t> ev_in;
+    cudaEvent_t ev_out[2] = {};
     std::string err;
     uint32_t chunk_vcmds = DEFAULT_CHUNK_VCMDS;
     // inputs
@@ -945,7 +971,12 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (!ctx) return OCHRE_E_INVALID_ARG;
     ctx->device = device;
     e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[1]);
     if (e != cudaSuccess) { delete ctx; return (int)e; }
+    ctx->o_tile_xy.guard = ctx->o_alpha.guard = ctx->o_spans.guard = ctx->o_tile_off.guard = ctx->o_span_off.guard = ctx->st_out;
     for (int i = 0; i <= N_STAGE; ++i) {
         e = cudaEventCreate(&ctx->ev[i]);
         if (e != cudaSuccess) { delete ctx; return (int)e; }
@@ -967,6 +998,13 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     if (ctx->st) cudaStreamSynchronize(ctx->st);
+    if (ctx->st_in) cudaStreamSynchronize(ctx->st_in);
+    if (ctx->st_out) cudaStreamSynchronize(ctx->st_out);
+    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_out)
+        if (e) cudaEventDestroy(e);
+    if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
+    if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
     DevBuf* db[] = {&ctx->d_cmds, &ctx->d_cmd_off, &ctx->d_xf, &ctx->d_vpath, &ctx->d_line_off, &ctx->d_rec_off,
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
@@ -1027,9 +1065,25 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
     out->n_cmds = n_cmds;
 
-    cudaEvent_t ev_begin = ctx->ev[N_STAGE];
+    const bool out_dev = (flags & OCHRE_OUT_DEVICE) != 0;
     float copy_ms = 0;
-    // ---- inputs ---------------------------------------------------------------
+    // ---- chunk plan -------------------------------------------------------------
+    std::vector<uint32_t> cuts;  // chunk i = paths [cuts[i], cuts[i + 1])
+    cuts.push_back(0);
+    for (uint32_t p0 = 0; p0 < n_paths;) {
+        uint32_t p1 = p0;
+        uint64_t nv = 0;
+        while (p1 < n_paths) {
+            uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
+            if (p1 > p0 && nv + add > ctx->chunk_vcmds) break;
+            nv += add;
+            ++p1;
+        }
+        cuts.push_back(p1);
+        p0 = p1;
+    }
+    const size_t n_chunks = cuts.size() - 1;
+    // ---- inputs: uploaded chunk by chunk on their own stream, ahead of the kernels ---------------
     const Cmd* d_cmds;
     const uint32_t* d_off;
     const float* d_xf;
@@ -1041,13 +1095,20 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(ctx->d_cmds.ensure((size_t)n_cmds * sizeof(OchreCmd) + 16));
         CK(ctx->d_cmd_off.ensure(((size_t)n_paths + 1) * 4));
         CK(ctx->d_xf.ensure((size_t)n_paths * sizeof(OchreTransform) + 16));
-        CK(cudaEventRecord(ev_begin, st));
-        if (n_cmds) CK(cudaMemcpyAsync(ctx->d_cmds.p, cmds + h_off[0], (size_t)n_cmds * sizeof(OchreCmd), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_cmd_off.p, h_off, ((size_t)n_paths + 1) * 4, cudaMemcpyHostToDevice, st));
-        if (n_paths) CK(cudaMemcpyAsync(ctx->d_xf.p, xf, (size_t)n_paths * sizeof(OchreTransform), cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(ctx->ev[0], st));
-        CK(cudaStreamSynchronize(st));
-        CK(cudaEventElapsedTime(&copy_ms, ev_begin, ctx->ev[0]));
+        while (ctx->ev_in.size() < n_chunks) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_in.push_back(e);
+        }
+        CK(cudaMemcpyAsync(ctx->d_cmd_off.p, h_off, ((size_t)n_paths + 1) * 4, cudaMemcpyHostToDevice, ctx->st_in));
+        if (n_paths) CK(cudaMemcpyAsync(ctx->d_xf.p, xf, (size_t)n_paths * sizeof(OchreTransform), cudaMemcpyHostToDevice, ctx->st_in));
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const uint32_t lo = h_off[cuts[c]], hi = h_off[cuts[c + 1]];
+            if (hi > lo)
+                CK(cudaMemcpyAsync(ctx->d_cmds.as<OchreCmd>() + (lo - h_off[0]), cmds + lo, (size_t)(hi - lo) * sizeof(OchreCmd),
+                                   cudaMemcpyHostToDevice, ctx->st_in));
+            CK(cudaEventRecord(ctx->ev_in[c], ctx->st_in));
+        }
         // d_cmds holds cmds[h_off[0]..]; kernels index it with (cmd_off - h_off[0])
         d_cmds = ctx->d_cmds.as<Cmd>() - h_off[0];
         d_off = ctx->d_cmd_off.as<uint32_t>();
@@ -1055,20 +1116,28 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
     CK(ctx->o_tile_off.ensure(((size_t)n_paths + 1) * 4));
     CK(ctx->o_span_off.ensure(((size_t)n_paths + 1) * 4));
+    if (!out_dev) {
+        // result arenas sized from the running tiles-per-command estimate, so that a warm ctx does not
+        // reallocate while the download stream is busy
+        const double denom = (double)n_cmds + n_paths;
+        const size_t est_t = (size_t)(denom * ctx->tiles_per_cmd * 1.05) + 1024, est_s = (size_t)(denom * ctx->spans_per_cmd * 1.05) + 1024;
+        CK(ctx->h_tile_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->h_span_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->h_tile_xy.ensure_keep(est_t * 4, 0, ctx->st_out));
+        CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
+        CK(ctx->h_spans.ensure_keep(est_s * sizeof(OchreSpan), 0, ctx->st_out));
+        CK(ctx->o_tile_xy.ensure(est_t * 4));
+        CK(ctx->o_alpha.ensure(est_t * 64));
+        CK(ctx->o_spans.ensure(est_s * sizeof(OchreSpan)));
+        CK(cudaEventRecord(ctx->ev_out[0], ctx->st_out));
+    }
 
     // ---- chunks ---------------------------------------------------------------
     uint32_t tile_base = 0, span_base = 0;
-    uint32_t p0 = 0;
     ChunkOut total;
-    while (p0 < n_paths) {
-        uint32_t p1 = p0;
-        uint64_t nv = 0;
-        while (p1 < n_paths) {
-            uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
-            if (p1 > p0 && nv + add > ctx->chunk_vcmds) break;
-            nv += add;
-            ++p1;
-        }
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const uint32_t p0 = cuts[c], p1 = cuts[c + 1];
+        if (!in_dev) CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
         ChunkOut co;
         int rc = RC_NEED_GENERAL;
         if (ctx->mode != OCHRE_MODE_GENERAL) {
@@ -1087,6 +1156,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         if (rc == RC_CONIC) {
             // A Conic reached the device.  Flatten conics on the host (reference path.rs:75-104,
             // recursive; device recursion is a later row of SURVEY.md section 8f) and run again.
+            CK(cudaStreamSynchronize(ctx->st_in));
+            CK(cudaStreamSynchronize(ctx->st_out));
             if (!allow_conic_retry || in_dev) {
                 ctx->err = "Conic commands need host-resident inputs (they are flattened on the host)";
                 return OCHRE_E_BAD_TAG;
@@ -1099,7 +1170,27 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             }
             return rasterize_impl(ctx, ncmds.data(), noff.data(), xf, n_paths, flags, nullptr, out, false);
         }
-        if (rc != 0) return rc;
+        if (rc != 0) {
+            cudaStreamSynchronize(ctx->st_in);
+            cudaStreamSynchronize(ctx->st_out);
+            return rc;
+        }
+        if (!out_dev) {
+            // the chunk is complete on the device (run_chunk* drained the kernel stream): its slice of the
+            // result goes to the host while the next chunk is being rasterised
+            const size_t t0 = tile_base, nt = co.n_tiles, s0 = span_base, ns = co.n_spans;
+            CK(ctx->h_tile_xy.ensure_keep((t0 + nt) * 4 + 4, t0 * 4, ctx->st_out));
+            CK(ctx->h_alpha.ensure_keep((t0 + nt) * 64 + 64, t0 * 64, ctx->st_out));
+            CK(ctx->h_spans.ensure_keep((s0 + ns) * sizeof(OchreSpan) + 8, s0 * sizeof(OchreSpan), ctx->st_out));
+            if (nt) {
+                CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + t0 * 4, ctx->o_tile_xy.as<uint8_t>() + t0 * 4, nt * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + t0 * 64, ctx->o_alpha.as<uint8_t>() + t0 * 64, nt * 64, cudaMemcpyDeviceToHost, ctx->st_out));
+            }
+            if (ns)
+                CK(cudaMemcpyAsync(ctx->h_spans.as<OchreSpan>() + s0, ctx->o_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToHost, ctx->st_out));
+            CK(cudaMemcpyAsync(ctx->h_tile_off.as<uint32_t>() + p0, ctx->o_tile_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+            CK(cudaMemcpyAsync(ctx->h_span_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+        }
         tile_base += co.n_tiles;
         span_base += co.n_spans;
         total.n_lines += co.n_lines;
@@ -1107,14 +1198,13 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         total.launches += co.launches;
         for (int s = 0; s < N_STAGE; ++s) total.ms[s] += co.ms[s];
         out->n_chunks += 1;
-        p0 = p1;
     }
+    if (!in_dev) CK(cudaStreamSynchronize(ctx->st_in));
     // closing entries of the offset arrays
     {
-        uint32_t tail[2] = {tile_base, span_base};
         uint32_t* hs = ctx->h_scalars.as<uint32_t>();
-        hs[0] = tail[0];
-        hs[1] = tail[1];
+        hs[0] = tile_base;
+        hs[1] = span_base;
         CK(cudaMemcpyAsync(ctx->o_tile_off.as<uint32_t>() + n_paths, hs, 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(ctx->o_span_off.as<uint32_t>() + n_paths, hs + 1, 4, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
@@ -1131,33 +1221,24 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         dev_ms += total.ms[s];
     }
     out->device_ms = dev_ms;
+    if (n_cmds + n_paths) {  // refine the arena estimates
+        ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)tile_base / ((double)n_cmds + n_paths));
+        ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)span_base / ((double)n_cmds + n_paths));
+    }
 
     // ---- outputs ---------------------------------------------------------------
-    if (flags & OCHRE_OUT_DEVICE) {
+    if (out_dev) {
         out->tile_off = ctx->o_tile_off.as<uint32_t>();
         out->span_off = ctx->o_span_off.as<uint32_t>();
         out->tile_xy = ctx->o_tile_xy.as<int16_t>();
         out->alpha = ctx->o_alpha.as<uint8_t>();
         out->spans = ctx->o_spans.as<OchreSpan>();
     } else {
-        CK(ctx->h_tile_off.ensure(((size_t)n_paths + 1) * 4));
-        CK(ctx->h_span_off.ensure(((size_t)n_paths + 1) * 4));
-        CK(ctx->h_tile_xy.ensure((size_t)tile_base * 4 + 4));
-        CK(ctx->h_alpha.ensure((size_t)tile_base * 64 + 64));
-        CK(ctx->h_spans.ensure((size_t)span_base * sizeof(OchreSpan) + 8));
-        CK(cudaEventRecord(ev_begin, st));
-        CK(cudaMemcpyAsync(ctx->h_tile_off.p, ctx->o_tile_off.p, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->h_span_off.p, ctx->o_span_off.p, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
-        if (tile_base) {
-            CK(cudaMemcpyAsync(ctx->h_tile_xy.p, ctx->o_tile_xy.p, (size_t)tile_base * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->o_alpha.p, (size_t)tile_base * 64, cudaMemcpyDeviceToHost, st));
-        }
-        if (span_base) CK(cudaMemcpyAsync(ctx->h_spans.p, ctx->o_spans.p, (size_t)span_base * sizeof(OchreSpan), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(ctx->ev[0], st));
-        CK(cudaStreamSynchronize(st));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ev_begin, ctx->ev[0]));
-        copy_ms += ms;
+        ctx->h_tile_off.as<uint32_t>()[n_paths] = tile_base;  // (ordered after the downloads by the synchronize below)
+        ctx->h_span_off.as<uint32_t>()[n_paths] = span_base;
+        CK(cudaEventRecord(ctx->ev_out[1], ctx->st_out));
+        CK(cudaStreamSynchronize(ctx->st_out));
+        CK(cudaEventElapsedTime(&copy_ms, ctx->ev_out[0], ctx->ev_out[1]));
         out->tile_off = ctx->h_tile_off.as<uint32_t>();
         out->span_off = ctx->h_span_off.as<uint32_t>();
         out->tile_xy = ctx->h_tile_xy.as<int16_t>();
