@@ -234,42 +234,17 @@ def main():
 
     def gather_to_rank0(res):
         """Concatenate every rank's compacted alpha / tile_xy / span lists on GPU 0 (NCCL send/recv over NVLink)."""
-        counts = torch.tensor([res.n_tiles, res.n_spans], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(allc, counts)
-        allc = torch.stack(allc).cpu().numpy()
-        nt_tot, ns_tot = int(allc[:, 0].sum()), int(allc[:, 1].sum())
-        if rank == 0:
-            for name, per, tot in (("alpha", 64, nt_tot), ("xy", 4, nt_tot), ("spans", 8, ns_tot)):
-                if name not in gbuf or gbuf[name].numel() < per * tot:
-                    gbuf[name] = torch.empty(int(per * tot * 1.05) + 64, dtype=torch.uint8, device="cuda")
+        from ochre_b200 import sharding
+
         ptrs = res.device_ptrs
         mine = {
             "alpha": torch.as_tensor(CudaArray(ptrs["alpha"], max(res.n_tiles * 64, 1)), device="cuda")[: res.n_tiles * 64],
             "xy": torch.as_tensor(CudaArray(ptrs["tile_xy"], max(res.n_tiles * 4, 1)), device="cuda")[: res.n_tiles * 4],
             "spans": torch.as_tensor(CudaArray(ptrs["spans"], max(res.n_spans * 8, 1)), device="cuda")[: res.n_spans * 8],
         }
-        ops = []
-        if rank == 0:
-            for name, per, col in (("alpha", 64, 0), ("xy", 4, 0), ("spans", 8, 1)):
-                o = 0
-                for r in range(world):
-                    nb = int(allc[r, col]) * per
-                    dst = gbuf[name][o:o + nb]
-                    if r == 0:
-                        dst.copy_(mine[name])
-                    elif nb:
-                        ops.append(dist.P2POp(dist.irecv, dst, r))
-                    o += nb
-        else:
-            for name in ("alpha", "xy", "spans"):
-                if mine[name].numel():
-                    ops.append(dist.P2POp(dist.isend, mine[name], 0))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        sizes, _ = sharding.gather_bytes(mine, rank, world, bufs=gbuf)
         torch.cuda.synchronize()
-        return nt_tot, ns_tot
+        return int(sizes["alpha"].sum()) // 64, int(sizes["spans"].sum()) // 8
 
     def step_device():
         res = ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,

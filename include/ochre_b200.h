@@ -118,6 +118,15 @@ int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
 #define OCHRE_MODE_FUSED 2
 int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode);
 
+/* Row-band sharding of one huge path across GPUs (BASELINE config 5): only
+ * tiles and spans whose tile row ty = y / 8 lies in [tile_row_lo, tile_row_hi) are produced.  Every
+ * tile row of the reference's output depends only on the increments of that row
+ * (src/rasterizer.rs:221-265: `prev`/`next` and `winding` never cross a row of a closed contour),
+ * so the concatenation of the bands' results in band order is the whole result.  A band with
+ * lo >= hi resets to "all rows".  The filter lives in the general pipeline: with a band set the
+ * fused per-path kernel is not used. */
+int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t tile_row_hi);
+
 /* Human-readable description of the last error on this ctx (never NULL). */
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);
 

@@ -20,7 +20,7 @@ ERRORS = {
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
     "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_set_mode",
-    "ochre_b200_last_error",
+    "ochre_b200_set_row_band", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_version",
 ]
@@ -62,6 +62,7 @@ def load():
     L.ochre_b200_rasterize.argtypes = [vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
     L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
+    L.ochre_b200_set_row_band.argtypes = [vp, C.c_int32, C.c_int32]
     L.ochre_b200_last_error.argtypes = [vp]
     L.ochre_b200_last_error.restype = C.c_char_p
     L.ochre_b200_stroke_path.argtypes = [vp, sz, C.c_float, C.POINTER(vp), C.POINTER(sz)]

@@ -104,6 +104,10 @@ class Context:
         m = {"auto": 0, "general": 1, "fused": 2}.get(mode, mode)
         _check(self._h, _lib.load().ochre_b200_set_mode(self._h, int(m)))
 
+    def set_row_band(self, tile_row_lo: int = 0, tile_row_hi: int = 0):
+        """Rasterise only tile rows [lo, hi) (row-band sharding of one huge path); lo >= hi resets."""
+        _check(self._h, _lib.load().ochre_b200_set_row_band(self._h, int(tile_row_lo), int(tile_row_hi)))
+
     def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(TPB)
 k_flatten_emit(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base,
                const float* __restrict__ xf, uint32_t n_v, const uint32_t* __restrict__ vpath,
                const uint32_t* __restrict__ line_off, float4* __restrict__ lines, uint32_t* __restrict__ nrec,
-               uint32_t* __restrict__ path_has_inc) {
+               uint32_t* __restrict__ path_has_inc, int band_lo, int band_hi) {
     uint32_t v = blockIdx.x * TPB + threadIdx.x;
     if (v >= n_v) return;
     uint32_t p = vpath[v];
@@ -120,6 +120,8 @@ k_flatten_emit(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_of
     RunTracker<CountSink> trk;
     trk.init();
     trk.sink.n = 0;
+    trk.sink.band_lo = band_lo;
+    trk.sink.band_hi = band_hi;
     EmitWalk<CountSink> f{lines, l0, &trk};
     vcmd_for_each_line(c, f);
     trk.finish();
@@ -132,10 +134,10 @@ k_flatten_emit(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_of
 // the path's FINISH command.
 __global__ void __launch_bounds__(TPB)
 k_phantom_fix(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_paths,
-              const uint32_t* __restrict__ path_has_inc, uint32_t* __restrict__ nrec) {
+              const uint32_t* __restrict__ path_has_inc, uint32_t* __restrict__ nrec, int band_lo, int band_hi) {
     uint32_t p = blockIdx.x * TPB + threadIdx.x;
     if (p >= n_paths) return;
-    if (!path_has_inc[p]) nrec[cmd_off[p + 1] - cmd_base + p] += 1u;
+    if (!path_has_inc[p] && band_lo <= 0 && 0 < band_hi) nrec[cmd_off[p + 1] - cmd_base + p] += 1u;
 }
 
 // ---------------------------------------------------------------------------
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(TPB)
 k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_v, const uint32_t* __restrict__ vpath,
               const uint32_t* __restrict__ line_off, const float4* __restrict__ lines,
               const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ path_has_inc,
-              uint64_t* __restrict__ keys, uint64_t* __restrict__ vals) {
+              uint64_t* __restrict__ keys, uint64_t* __restrict__ vals, int band_lo, int band_hi) {
     uint32_t v = blockIdx.x * TPB + threadIdx.x;
     if (v >= n_v) return;
     uint32_t r0 = rec_off[v], r1 = rec_off[v + 1];
@@ -157,6 +159,8 @@ k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t 
     trk.sink.vals = vals + r0;
     trk.sink.path_local = p;
     trk.sink.n = 0;
+    trk.sink.band_lo = band_lo;
+    trk.sink.band_hi = band_hi;
     uint32_t l0 = line_off[v], l1 = line_off[v + 1];
     for (uint32_t l = l0; l < l1; ++l) {
         float4 L = __ldg(&lines[l]);
@@ -164,7 +168,7 @@ k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t 
     }
     trk.finish();
     bool is_finish = (v == cmd_off[p + 1] - cmd_base + p);
-    if (is_finish && !path_has_inc[p]) trk.sink.emit(0, 0, 0u, 0u, 0, false);  // the empty path's zero tile
+    if (is_finish && !path_has_inc[p]) trk.sink.emit(0, 0, 0u, 0u, 0, false);  // the empty path's zero tile (if row 0 is in the band)
 }
 
 // ---------------------------------------------------------------------------
@@ -240,14 +244,33 @@ k_emit_spans(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ gro
 }
 
 __global__ void __launch_bounds__(TPB)
-k_path_offsets(uint32_t n_paths, const uint32_t* __restrict__ path_first, const uint32_t* __restrict__ tile_idx,
-               const uint32_t* __restrict__ span_idx, uint32_t tile_base, uint32_t span_base,
-               uint32_t* __restrict__ tile_off, uint32_t* __restrict__ span_off) {
+k_fill_offsets(uint32_t n_paths, uint32_t tile_base, uint32_t span_base, uint32_t* __restrict__ tile_off, uint32_t* __restrict__ span_off) {
     uint32_t p = blockIdx.x * TPB + threadIdx.x;
     if (p >= n_paths) return;
-    uint32_t g = path_first[p];
-    tile_off[p] = tile_base + tile_idx[g];
-    span_off[p] = span_base + span_idx[g];
+    tile_off[p] = tile_base;
+    span_off[p] = span_base;
+}
+
+// path_first[p] = first tile group of path p.  With a row band set a path may own no group at all:
+// its entry keeps the sentinel and it takes the offsets of the next path that has one.
+#define OC_NO_GROUP 0xffffffffu
+__global__ void __launch_bounds__(TPB)
+k_path_offsets(uint32_t n_paths, const uint32_t* __restrict__ path_first, const uint32_t* __restrict__ tile_idx,
+               const uint32_t* __restrict__ span_idx, uint32_t tile_base, uint32_t span_base,
+               const uint32_t* __restrict__ totals /* n_tiles, n_spans */, uint32_t* __restrict__ tile_off,
+               uint32_t* __restrict__ span_off) {
+    uint32_t p = blockIdx.x * TPB + threadIdx.x;
+    if (p >= n_paths) return;
+    uint32_t q = p;
+    while (q < n_paths && path_first[q] == OC_NO_GROUP) ++q;
+    if (q < n_paths) {
+        uint32_t g = path_first[q];
+        tile_off[p] = tile_base + tile_idx[g];
+        span_off[p] = span_base + span_idx[g];
+    } else {
+        tile_off[p] = tile_base + totals[0];
+        span_off[p] = span_base + totals[1];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -549,6 +572,7 @@ struct ochre_b200_ctx {
     bool attrs_set = false;
     // fused per-path kernel
     int mode = OCHRE_MODE_AUTO;
+    int band_lo = OC_BAND_MIN, band_hi = OC_BAND_MAX;  // tile rows rasterised (row-band sharding)
     int sm_count = 148;
     DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
@@ -663,8 +687,8 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     CK(ctx->d_lines.ensure(((size_t)n_lines + 1) * sizeof(float4)));
     float4* lines = ctx->d_lines.as<float4>();
     k_flatten_emit<<<nblk(n_v, TPB), TPB, 0, st>>>(cmds, cmd_off, cmd_lo, xf, n_v, vpath, line_off, lines, rec_off,
-                                                     path_has_inc);
-    k_phantom_fix<<<nblk(n_paths, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_paths, path_has_inc, rec_off);
+                                                     path_has_inc, ctx->band_lo, ctx->band_hi);
+    k_phantom_fix<<<nblk(n_paths, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_paths, path_has_inc, rec_off, ctx->band_lo, ctx->band_hi);
     launches += 2;
     CK(cudaEventRecord(ctx->ev[1], st));
     // ---- stage 2: bin + sort ---------------------------------------------------
@@ -677,6 +701,15 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     }
     if (int rc = read_scalars(ctx)) return rc;
     const uint32_t n_rec = h_sc[SC_NREC];
+    if (n_rec == 0) {  // only with a row band: nothing of this chunk falls inside it
+        k_fill_offsets<<<nblk(n_paths, TPB), TPB, 0, st>>>(n_paths, tile_base, span_base, ot.tile_off, ot.span_off);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        co->n_lines = n_lines;
+        co->launches = launches + 1;
+        ctx->dbg_valid = false;
+        return 0;
+    }
     CK(cudaMemcpyAsync(rec_off + n_v, d_sc + SC_NREC, 4, cudaMemcpyDeviceToDevice, st));
     RadixSortPlan rp = radix_plan(n_rec);
     for (int b = 0; b < 2; ++b) {
@@ -688,7 +721,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     uint64_t* keys2[2] = {ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>()};
     uint64_t* vals2[2] = {ctx->d_vals[0].as<uint64_t>(), ctx->d_vals[1].as<uint64_t>()};
     k_bin_scatter<<<nblk(n_v, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_v, vpath, line_off, lines, rec_off, path_has_inc,
-                                                    keys2[0], vals2[0]);
+                                                    keys2[0], vals2[0], ctx->band_lo, ctx->band_hi);
     launches += 1;
     CK(cudaEventRecord(ctx->ev[2], st));
     int lc = 0;
@@ -721,6 +754,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     uint32_t* tile_idx = ctx->d_tile_idx.as<uint32_t>();
     uint32_t* span_w = ctx->d_span_w.as<uint32_t>();
     uint32_t* span_idx = ctx->d_span_idx.as<uint32_t>();
+    CK(cudaMemsetAsync(path_first, 0xff, (size_t)n_paths * 4, st));  // OC_NO_GROUP
     k_group_info<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, vals, group_start, n_groups, n_rec, g_real, g_wd, path_first);
     launches += 1;
     launches += device_scan(
@@ -761,7 +795,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     k_emit_spans<<<nblk(n_groups, TPB), TPB, 0, st>>>(keys, group_start, n_groups, span_w, span_idx, span_base, o_spans);
     launches += 1;
     k_path_offsets<<<nblk(n_paths, TPB), TPB, 0, st>>>(n_paths, path_first, tile_idx, span_idx, tile_base, span_base,
-                                                         ot.tile_off, ot.span_off);
+                                                         d_sc + SC_NTILES, ot.tile_off, ot.span_off);
     launches += 1;
     CK(cudaEventRecord(ctx->ev[7], st));
     CK(cudaStreamSynchronize(st));
@@ -1032,6 +1066,18 @@ int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode) {
     return 0;
 }
 
+int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t tile_row_hi) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    if (tile_row_lo >= tile_row_hi) {  // reset
+        ctx->band_lo = OC_BAND_MIN;
+        ctx->band_hi = OC_BAND_MAX;
+        return 0;
+    }
+    ctx->band_lo = tile_row_lo < OC_BAND_MIN ? OC_BAND_MIN : tile_row_lo;
+    ctx->band_hi = tile_row_hi > OC_BAND_MAX ? OC_BAND_MAX : tile_row_hi;
+    return 0;
+}
+
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
 static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
@@ -1140,7 +1186,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         if (!in_dev) CK(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
         ChunkOut co;
         int rc = RC_NEED_GENERAL;
-        if (ctx->mode != OCHRE_MODE_GENERAL) {
+        const bool banded = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;  // the row filter lives in the general pipeline
+        if (ctx->mode != OCHRE_MODE_GENERAL && !banded) {
             rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
             if (rc == 0) ctx->used_paths |= 1u;
             if (rc == RC_NEED_GENERAL && ctx->mode == OCHRE_MODE_FUSED) {

@@ -321,17 +321,26 @@ OC_HD int val_wdelta(uint64_t v) {
 }
 OC_HD bool val_wonly(uint64_t v) { return (v >> 63) != 0; }
 
-// Sinks: CountSink counts records, StoreSink writes them.
+// Sinks: CountSink counts records, StoreSink writes them.  Both drop records whose tile row lies
+// outside [band_lo, band_hi): the row-band sharding of one huge path across GPUs (every tile row's
+// tiles and spans depend only on the records of that row).
+#define OC_BAND_MIN (-32768)
+#define OC_BAND_MAX 32767
 struct CountSink {
     uint32_t n;
-    OC_HD void emit(int, int, uint32_t, uint32_t, int, bool) { n++; }
+    int band_lo, band_hi;
+    OC_HD void emit(int, int ty, uint32_t, uint32_t, int, bool) {
+        if (ty >= band_lo && ty < band_hi) n++;
+    }
 };
 struct StoreSink {
     uint64_t* keys;
     uint64_t* vals;
     uint32_t path_local;
     uint32_t n;
+    int band_lo, band_hi;
     OC_HD void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly) {
+        if (ty < band_lo || ty >= band_hi) return;
         keys[n] = make_key(path_local, tx, ty);
         vals[n] = make_val(line0, nlines, wdelta, wonly);
         n++;

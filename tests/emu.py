@@ -35,6 +35,8 @@ def lib():
         vp = C.c_void_p
         L.emu_rasterize.restype = vp
         L.emu_rasterize.argtypes = [vp, vp, vp, C.c_uint32, C.c_int]
+        L.emu_rasterize_band.restype = vp
+        L.emu_rasterize_band.argtypes = [vp, vp, vp, C.c_uint32, C.c_int, C.c_int, C.c_int]
         L.emu_status.argtypes = [vp]
         L.emu_n_tiles.restype = C.c_uint32
         L.emu_n_tiles.argtypes = [vp]
@@ -62,7 +64,7 @@ class EmuResult:
     vals: np.ndarray
 
 
-def rasterize(cmds, cmd_off, xf, fixed: bool = False) -> EmuResult:
+def rasterize(cmds, cmd_off, xf, fixed: bool = False, band=None) -> EmuResult:
     """fixed=False: the general pipeline's f32 accumulation; fixed=True: the fused kernel's 2^-22 fixed point."""
     cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
     cmd_off = np.ascontiguousarray(cmd_off, dtype=np.uint32)
@@ -70,7 +72,8 @@ def rasterize(cmds, cmd_off, xf, fixed: bool = False) -> EmuResult:
     xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n, 6)
     L = lib()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    r = L.emu_rasterize(p(cmds), p(cmd_off), p(xf), n, 1 if fixed else 0)
+    lo, hi = band if band is not None else (-32768, 32767)
+    r = L.emu_rasterize_band(p(cmds), p(cmd_off), p(xf), n, 1 if fixed else 0, int(lo), int(hi))
     st = L.emu_status(r)
     if st != 0:
         L.emu_free(r)

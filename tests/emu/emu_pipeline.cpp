@@ -24,7 +24,9 @@ struct VecSink {
     std::vector<uint64_t>* keys;
     std::vector<uint64_t>* vals;
     uint32_t path_local;
+    int band_lo, band_hi;
     void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly) {
+        if (ty < band_lo || ty >= band_hi) return;
         keys->push_back(make_key(path_local, tx, ty));
         vals->push_back(make_val(line0, nlines, wdelta, wonly));
     }
@@ -72,7 +74,8 @@ struct EmuResult {
 
 extern "C" {
 
-EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths, int fixed) {
+EmuResult* emu_rasterize_band(const OchreCmd* cmds_, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths, int fixed,
+                              int band_lo, int band_hi) {
     EmuResult* R = new EmuResult();
     R->status = 0;
     const Cmd* cmds = reinterpret_cast<const Cmd*>(cmds_);
@@ -99,6 +102,8 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
             trk.sink.keys = &keys;
             trk.sink.vals = &vals;
             trk.sink.path_local = p;
+            trk.sink.band_lo = band_lo;
+            trk.sink.band_hi = band_hi;
             EmitWalk f{&lines, base, &trk};
             vcmd_for_each_line(c, f);
             trk.finish();
@@ -122,7 +127,7 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
         if (i == 0 || K[i] != K[i - 1]) gs.push_back((uint32_t)i);
     uint32_t ng = (uint32_t)gs.size();
     auto gend = [&](uint32_t g) { return g + 1 < ng ? gs[g + 1] : (uint32_t)n_rec; };
-    std::vector<uint32_t> real(ng), tile_idx(ng), span_w(ng, 0), span_idx(ng), path_first(n_paths, 0);
+    std::vector<uint32_t> real(ng), tile_idx(ng), span_w(ng, 0), span_idx(ng), path_first(n_paths, 0xffffffffu);
     std::vector<int32_t> wincl(ng);
     int32_t wrun = 0;
     uint32_t nt = 0;
@@ -215,12 +220,18 @@ EmuResult* emu_rasterize(const OchreCmd* cmds_, const uint32_t* cmd_off, const O
         }
     }
     for (uint32_t p = 0; p < n_paths; ++p) {
-        R->tile_off[p] = tile_idx[path_first[p]];
-        R->span_off[p] = span_idx[path_first[p]];
+        uint32_t q = p;  // with a row band a path may own no tile group: it takes the next path's offsets
+        while (q < n_paths && path_first[q] == 0xffffffffu) ++q;
+        R->tile_off[p] = q < n_paths ? tile_idx[path_first[q]] : nt;
+        R->span_off[p] = q < n_paths ? span_idx[path_first[q]] : ns;
     }
     R->tile_off[n_paths] = nt;
     R->span_off[n_paths] = ns;
     return R;
+}
+
+EmuResult* emu_rasterize(const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths, int fixed) {
+    return emu_rasterize_band(cmds, cmd_off, xf, n_paths, fixed, OC_BAND_MIN, OC_BAND_MAX);
 }
 
 int emu_status(const EmuResult* r) { return r->status; }

@@ -172,6 +172,46 @@ def test_config5a_rings_single_giant_path(ctx):
     assert_batch_parity(g, oracle_batch(cmds, off, xf), what="G5a rings x 96")
 
 
+def test_row_bands_on_the_gpu_concatenate_to_the_whole_path(gctx):
+    """BASELINE config 5a's sharding: each band is what one GPU would rasterise; here one GPU runs them in turn."""
+    from ochre_b200 import sharding as S
+
+    cmds, off, xf = W.rings(64, 16.0, 128)
+    whole = gctx.rasterize(cmds, off, xf)
+    assert_batch_parity(whole, oracle_batch(cmds, off, xf), what="rings x 64")
+    rows = whole.tile_xy[:, 1] // 8
+    lo, hi = int(rows.min()), int(rows.max()) + 1
+    c = ob.Context(0)  # default mode: the band switches the fused kernel off
+    try:
+        for world in (2, 8):
+            bands = S.plan_row_bands(lo, hi, world, S.band_weights_from_bbox(cmds, xf, lo, hi))
+            parts = []
+            for b in bands:
+                c.set_row_band(*b)
+                r = c.rasterize(cmds, off, xf)
+                assert r.used == 2
+                parts.append(S.Shard.of(r))
+            m = S.concat_row_bands(parts)
+            w = S.Shard.of(whole)
+            assert np.array_equal(m.tile_off, w.tile_off) and np.array_equal(m.tile_xy, w.tile_xy)
+            assert np.array_equal(m.alpha, w.alpha) and m.spans.tobytes() == w.spans.tobytes()
+            assert max(p.n_tiles for p in parts) < 0.35 * w.n_tiles if world == 8 else True
+        # several paths, bands that hold nothing for some of them, and a band that holds nothing at all
+        cmds2, off2, xf2 = W.blobs(60, first=5)
+        w = S.Shard.of(gctx.rasterize(cmds2, off2, xf2))  # same arithmetic: banded runs use the general pipeline (f32 sums)
+        parts = []
+        for b in [(-100, 100), (100, 101), (101, 300), (300, 9000)]:
+            c.set_row_band(*b)
+            parts.append(S.Shard.of(c.rasterize(cmds2, off2, xf2)))
+        m = S.concat_row_bands(parts)
+        assert np.array_equal(m.tile_off, w.tile_off) and np.array_equal(m.alpha, w.alpha) and m.spans.tobytes() == w.spans.tobytes()
+        c.set_row_band(20000, 20010)
+        r = c.rasterize(cmds2, off2, xf2)
+        assert r.n_tiles == 0 and r.n_spans == 0 and not r.tile_off.any()
+    finally:
+        c.close()
+
+
 def test_chunking_and_rerun_do_not_change_a_byte(ctx):
     cmds, off, xf = W.blobs(1500, first=4242)
     a = ctx.rasterize(cmds, off, xf)
