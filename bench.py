@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: sub-batches per step whose tiles travel to GPU 0 behind the kernels")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -232,26 +233,87 @@ def main():
     gather = world > 1 and not args.no_gather
     gbuf = {}
 
-    def gather_to_rank0(res):
-        """Concatenate every rank's compacted alpha / tile_xy / span lists on GPU 0 (NCCL send/recv over NVLink)."""
+    # N > 1: the gather is pipelined behind the kernels.  The rank's batch is cut into sub-batches that alternate
+    # between two contexts (each owns its result arenas); while sub-batch j + 1 is rasterised, sub-batch j's tiles
+    # travel to GPU 0.  Blocks land in arrival order (sub-batch major, rank minor); `gather_blocks` is the table.
+    K = max(1, args.gather_chunks)
+    subs = [(P * j // K, P * (j + 1) // K) for j in range(K)]
+    ctxs = [ctx]
+    gather_blocks = []
+    if gather:
+        # GPU 0 keeps its own sub-batches where they were produced (one context per sub-batch, no copy);
+        # the other ranks alternate between two contexts while the previous sub-batch is on the wire
+        for _ in range((K if rank == 0 else 2) - 1):
+            c2 = ob.Context(local_rank)
+            if args.chunk:
+                c2.set_chunk(args.chunk)
+            ctxs.append(c2)
+    NC = len(ctxs)
+
+    def raster_sub(c, a, b):
+        return c.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr() + 4 * a, d_xf_t.data_ptr() + 24 * a, b - a, h_off[a:b + 1],
+                                in_device=True, out_device=True)
+
+    def step_pipelined():
         from ochre_b200 import sharding
 
-        ptrs = res.device_ptrs
-        mine = {
-            "alpha": torch.as_tensor(CudaArray(ptrs["alpha"], max(res.n_tiles * 64, 1)), device="cuda")[: res.n_tiles * 64],
-            "xy": torch.as_tensor(CudaArray(ptrs["tile_xy"], max(res.n_tiles * 4, 1)), device="cuda")[: res.n_tiles * 4],
-            "spans": torch.as_tensor(CudaArray(ptrs["spans"], max(res.n_spans * 8, 1)), device="cuda")[: res.n_spans * 8],
-        }
-        sizes, _ = sharding.gather_bytes(mine, rank, world, bufs=gbuf)
+        pending = [None] * NC
+        offs = {"alpha": 0, "xy": 0, "spans": 0}
+        agg = None
+        gather_blocks.clear()
+        for j, (a, b) in enumerate(subs):
+            c = ctxs[j % NC]
+            if pending[j % NC] is not None:  # the arenas of this context are still being read by the previous send
+                pending[j % NC].synchronize()
+                pending[j % NC] = None
+            res = raster_sub(c, a, b)
+            agg = res if agg is None else _merge_counts(agg, res)
+            ptrs = res.device_ptrs
+            mine = {
+                "alpha": torch.as_tensor(CudaArray(ptrs["alpha"], max(res.n_tiles * 64, 1)), device="cuda")[: res.n_tiles * 64],
+                "xy": torch.as_tensor(CudaArray(ptrs["tile_xy"], max(res.n_tiles * 4, 1)), device="cuda")[: res.n_tiles * 4],
+                "spans": torch.as_tensor(CudaArray(ptrs["spans"], max(res.n_spans * 8, 1)), device="cuda")[: res.n_spans * 8],
+            }
+            sizes = sharding.post_gather(mine, rank, world, gbuf, offs, own_in_place=True)
+            gather_blocks.append({n: sizes[n].tolist() for n in sizes})
+            ev = torch.cuda.Event()
+            ev.record()  # NCCL work of this sub-batch is ordered before the event on the current stream
+            pending[j % NC] = ev
         torch.cuda.synchronize()
-        return int(sizes["alpha"].sum()) // 64, int(sizes["spans"].sum()) // 8
+        return agg
+
+    def _merge_counts(x, y):
+        x.n_tiles += y.n_tiles
+        x.n_spans += y.n_spans
+        x.n_cmds += y.n_cmds
+        x.n_chunks += y.n_chunks
+        x.kernel_launches += y.kernel_launches
+        x.device_ms += y.device_ms
+        x.stage_ms = tuple(p + q for p, q in zip(x.stage_ms, y.stage_ms))
+        x.used |= y.used
+        return x
 
     def step_device():
-        res = ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,
-                                 out_device=True)
         if gather:
-            gather_to_rank0(res)
-        return res
+            return step_pipelined()
+        return ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,
+                                  out_device=True)
+
+    if gather:
+        # size every arena before anything is in flight: both contexts see every sub-batch once, and GPU 0's
+        # gather buffers are sized from the all-rank totals
+        nt = ns = 0
+        for j, (a, b) in enumerate(subs):
+            for c in (ctxs[j % NC:j % NC + 1] if rank == 0 else ctxs):
+                r = raster_sub(c, a, b)
+            nt += r.n_tiles
+            ns += r.n_spans
+        tot = torch.tensor([nt if rank else 0, ns if rank else 0], dtype=torch.int64, device="cuda")  # GPU 0's own tiles stay in place
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            gbuf["alpha"] = torch.empty(int(tot[0]) * 64 + 4096, dtype=torch.uint8, device="cuda")
+            gbuf["xy"] = torch.empty(int(tot[0]) * 4 + 4096, dtype=torch.uint8, device="cuda")
+            gbuf["spans"] = torch.empty(int(tot[1]) * 8 + 4096, dtype=torch.uint8, device="cuda")
 
     def step_e2e():
         return ctx.rasterize_ptrs(h_cmds_t.data_ptr(), h_off_t.data_ptr(), h_xf_t.data_ptr(), P, h_off, in_device=False,
@@ -290,6 +352,7 @@ def main():
     # ungathered figure for N > 1 (what a renderer that draws per GPU would see)
     ungathered = None
     if gather:
+        ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True)  # sizes the arenas
         barrier()
         e0.record()
         for _ in range(args.steps):
@@ -376,7 +439,7 @@ def main():
                 "workload": WORKLOAD, "paths_per_gpu": P, "paths_total": paths_total, "cmds_per_gpu": int(res.n_cmds),
                 "lines_per_gpu": int(res.n_lines), "bin_records_per_gpu": int(res.n_records), "tiles_total": int(tiles_total),
                 "spans_total": int(spans_total), "tiles_per_s": tps, "alpha_MB_per_s": tps * 64e-6, "chunks": int(res.n_chunks),
-                "parallelism": f"path-batch x{world}" + (", tiles gathered to GPU 0 (NCCL send/recv)" if gather else ""),
+                "parallelism": f"path-batch x{world}" + (f", tiles gathered to GPU 0 (NCCL send/recv, pipelined in {K} sub-batches)" if gather else ""),
                 "l2": "inputs (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (n_cmds * 28 / 1e9),
                 "timing": "CUDA events bracketing the K steps, max over ranks; library-reported device ms/step = %.3f, wall = %.3f"
                           % (dev_ms / args.steps, wall_ms / args.steps),

@@ -539,7 +539,7 @@ struct HostBuf {  // pinned
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr uint32_t DEFAULT_CHUNK_VCMDS = 4u << 20;
+constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
 constexpr int N_STAGE = 8;
 
 }  // namespace

@@ -198,6 +198,48 @@ def gather_bytes(mine: dict, rank: int, world: int, bufs: Optional[dict] = None,
     return sizes, gathered
 
 
+def post_gather(mine: dict, rank: int, world: int, bufs: dict, offs: dict, group=None, own_in_place: bool = False) -> dict:
+    """Pipelined form of `gather_bytes`: exchanges the sizes, posts the sends / receives of this block into
+    `bufs[name][offs[name]:]` on rank 0 (pre-sized by the caller) and returns WITHOUT waiting for them; the
+    NCCL work is ordered on the current CUDA stream (record an event there to know when it is done).
+    `offs` is advanced by the block's total size on every rank.  With `own_in_place` rank 0's own slice is
+    not copied (it stays where rank 0 produced it) and takes no room in `bufs`.
+    Returns per-rank byte counts per name."""
+    import torch
+    import torch.distributed as dist
+
+    names = sorted(mine)
+    dev = mine[names[0]].device
+    counts = torch.tensor([int(mine[n].numel()) for n in names], dtype=torch.int64, device=dev)
+    allc = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(allc, counts, group=group)
+    allc = torch.stack(allc).cpu().numpy()
+    sizes = {n: allc[:, i].astype(np.int64) for i, n in enumerate(names)}
+    ops = []
+    for n in names:
+        o = int(offs[n])
+        for r in range(world):
+            nb = int(sizes[n][r])
+            if rank == 0:
+                if not (own_in_place and r == 0) and o + nb > bufs[n].numel():
+                    raise RuntimeError(f"gather buffer '{n}' too small")
+                dst = bufs[n][o:o + nb]
+                if r == 0:
+                    if not own_in_place:
+                        dst.copy_(mine[n], non_blocking=True)
+                elif nb:
+                    ops.append(dist.P2POp(dist.irecv, dst, r, group=group))
+            elif r == rank and nb:
+                ops.append(dist.P2POp(dist.isend, mine[n], 0, group=group))
+            if not (own_in_place and r == 0):
+                o += nb
+        offs[n] = o
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()  # stream-level wait (NCCL): does not block the host
+    return sizes
+
+
 def gather_to_rank0(local: Shard, rank: int, world: int, mode: str = "paths", group=None) -> Optional[Shard]:
     """Host-array convenience wrapper (tests, small jobs): gathers a Shard to rank 0 and merges it."""
     import torch

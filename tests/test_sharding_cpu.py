@@ -109,6 +109,27 @@ def _worker(rank, world, port, mode, q):
             band = (cuts[rank], cuts[rank + 1])
             local = S.Shard.of(E.rasterize(cmds, off, xf, band=band))
         merged = S.gather_to_rank0(local, rank, world, mode=mode)
+        if mode == "paths":
+            # the pipelined form bench.py uses: two blocks posted back to back into pre-sized buffers
+            import torch
+
+            al = torch.from_numpy(local.alpha.reshape(-1).copy())
+            half = (local.n_tiles // 2) * 64
+            tot = torch.tensor([al.numel()], dtype=torch.int64)
+            dist.all_reduce(tot)
+            bufs = {"alpha": torch.zeros(int(tot[0]) + 64, dtype=torch.uint8)}
+            offs = {"alpha": 0}
+            s1 = S.post_gather({"alpha": al[:half]}, rank, world, bufs, offs)
+            s2 = S.post_gather({"alpha": al[half:]}, rank, world, bufs, offs)
+            assert offs["alpha"] == int(tot[0])
+            if rank == 0:
+                # block-major, rank-minor: [r0 first half][r1 first half][r0 second half][r1 second half]
+                whole_alpha = S.Shard.of(E.rasterize(cmds, off, xf)).alpha.reshape(-1)
+                n0 = local.n_tiles * 64
+                a0, a1 = whole_alpha[:n0], whole_alpha[n0:]
+                h1 = int(s1["alpha"][1])
+                want = np.concatenate([a0[:half], a1[:h1], a0[half:], a1[h1:]])
+                assert np.array_equal(bufs["alpha"][: int(tot[0])].numpy(), want)
         if rank == 0:
             whole = S.Shard.of(E.rasterize(cmds, off, xf))
             ok = (np.array_equal(merged.tile_off, whole.tile_off) and np.array_equal(merged.span_off, whole.span_off)
