@@ -226,6 +226,48 @@ struct LineWalk {
     }
 };
 
+// Scratch accesses carry an L2 evict_last policy (OC_PK_EVICT_LAST=1): the per-CTA line scratch is
+// rewritten for every path and should not be flushed to HBM by the streaming results.
+#ifndef OC_PK_EVICT_LAST
+#define OC_PK_EVICT_LAST 0
+#endif
+#if OC_PK_EVICT_LAST
+__device__ __forceinline__ uint64_t pk_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#define PK_POLICY_DECL const uint64_t pk_pol = pk_policy();
+__device__ __forceinline__ void pk_st(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void pk_st(uint2* p, uint2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void pk_st(uint32_t* p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 pk_ld(const float4* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint2 pk_ld(const uint2* p, uint64_t pol) {
+    uint2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t pk_ld(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+#else
+#define PK_POLICY_DECL const uint64_t pk_pol = 0;
+template <class T> __device__ __forceinline__ void pk_st(T* p, T v, uint64_t) { __stcg(p, v); }
+template <class T> __device__ __forceinline__ T pk_ld(const T* p, uint64_t) { return __ldcg(p); }
+#endif
+
 struct PkScratch {
     float4* lines;
     float4* slines;
@@ -260,17 +302,18 @@ __device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return (f >> 26) &
 
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
-__device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H) {
+__device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
+                                            uint64_t pk_pol) {
     uint32_t err = 0;
     uint32_t pos = threadIdx.x;
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pos < n) Ln = __ldcg(&sl[pos]);
+    if (pos < n) Ln = pk_ld(&sl[pos], pk_pol);
     // (the trip count is warp-uniform: bounded by the warp's first lane)
     for (uint32_t wpos = threadIdx.x & ~31u; wpos < n; wpos += PK_THREADS, pos += PK_THREADS) {
         __syncwarp();  // lanes of a warp hold lines of (nearly) equal step count: keep them in lockstep
         if (pos >= n) continue;
         const float4 L = Ln;
-        if (pos + PK_THREADS < n) Ln = __ldcg(&sl[pos + PK_THREADS]);
+        if (pos + PK_THREADS < n) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
         LineWalk w;
         w.init(L);
         int prev_ty = w.y >> 3;
@@ -295,15 +338,15 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
 // Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
 // tile rows; slot = rank - rank0.
 __device__ __forceinline__ void pk_accumulate(int* acc, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
-                                              int gx0, int gy0, int W, int R0, int R1, uint32_t rank0) {
+                                              int gx0, int gy0, int W, int R0, int R1, uint32_t rank0, uint64_t pk_pol) {
     uint32_t pos = p0 + threadIdx.x;
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pos < p1) Ln = __ldcg(&sl[pos]);
+    if (pos < p1) Ln = pk_ld(&sl[pos], pk_pol);
     for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
         __syncwarp();
         if (pos >= p1) continue;
         const float4 L = Ln;
-        if (pos + PK_THREADS < p1) Ln = __ldcg(&sl[pos + PK_THREADS]);
+        if (pos + PK_THREADS < p1) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
         LineWalk w;
         w.init(L);
         // p0 of the first increment: t0 = max(0, 0) = 0 (rasterizer.rs:99-101)
@@ -421,16 +464,13 @@ __device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKerne
         const uint32_t f = cell[c];
         if (f & CF_TOUCHED) {
             const int px = (gx0 + cx) * 8, py = (gy0 + cy) * 8;
-            reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at + r] = (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16);
+            __stcs(reinterpret_cast<uint32_t*>(A.tile_xy) + tile_at + r, (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16));
             ++r;
             if (f & CF_SPAN) {
                 const uint32_t nx = pk_next_touched(S, c + 1, c + (uint32_t)(W - cx));
-                OchreSpan sp;
-                sp.x = (int16_t)(px + 8);
-                sp.y = (int16_t)py;
-                sp.w = (uint16_t)((nx - c - 1) * 8u);
-                sp.pad = 0;
-                A.spans[sidx++] = sp;
+                // OchreSpan {x, y, w, pad}; streaming store: results must not push the line scratch out of L2
+                __stcs(reinterpret_cast<uint2*>(A.spans) + sidx++,
+                       make_uint2((uint32_t)(uint16_t)(int16_t)(px + 8) | ((uint32_t)(uint16_t)(int16_t)py << 16), (nx - c - 1) * 8u));
             }
         }
         if (++cx == W) {
@@ -455,6 +495,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
     const uint32_t tid = threadIdx.x;
     const PkScratch G(A.scratch + (size_t)blockIdx.x * PK_SCR_BYTES);
+    PK_POLICY_DECL
 
     if (tid == 0) S.next_path = atomicAdd(A.ticket, 1u);
     for (;;) {
@@ -526,7 +567,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     float t = 0.0f;  // the rounded recurrence of path.rs:52-53 / :65-66
                     for (uint32_t k = 0; k < my_n; ++k) {
                         t = fminf(t + my_dt, 1.0f);
-                        __stcg(&G.rec[first + k], make_uint2(__float_as_uint(t), tid));
+                        pk_st(&G.rec[first + k], make_uint2(__float_as_uint(t), tid), pk_pol);
                     }
                 } else {
                     uint32_t info = PK_INFO_NONE;  // degenerate lines are skipped by line_to, rasterizer.rs:73
@@ -534,9 +575,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         info = pk_line_info(c.last, c.a, bb);
                         atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
                     }
-                    __stcg(&G.rec[first], make_uint2(0u, PK_OWNER_NONE));
-                    __stcg(&G.lines[first], make_float4(c.last.x, c.last.y, c.a.x, c.a.y));
-                    __stcg(&G.info[first], info);
+                    pk_st(&G.rec[first], make_uint2(0u, PK_OWNER_NONE), pk_pol);
+                    pk_st(&G.lines[first], make_float4(c.last.x, c.last.y, c.a.x, c.a.y), pk_pol);
+                    pk_st(&G.info[first], info, pk_pol);
                 }
             }
             // one bad command poisons `last` of its successors: the path is not walked at all (the
@@ -544,18 +585,18 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             if (__syncthreads_or(bad)) bad_path = true;
             if (bad_path || fallback) break;
             for (uint32_t i = n_lines + tid; i < n_lines + total; i += PK_THREADS) {
-                const uint2 r = __ldcg(&G.rec[i]);
+                const uint2 r = pk_ld(&G.rec[i], pk_pol);
                 if (r.y == PK_OWNER_NONE) continue;
                 const uint32_t o = r.y;
                 const float t = __uint_as_float(r.x);
                 const V2 l = S.u.v.last[o], ca = S.u.v.a[o], cb = S.u.v.b[o];
                 V2 a = l, b;
                 if (S.u.v.tag[o] == TAG_QUAD) {
-                    if (i != S.u.v.loff[o]) a = quad_eval(__uint_as_float(__ldcg(&G.rec[i - 1]).x), l, ca, cb);
+                    if (i != S.u.v.loff[o]) a = quad_eval(__uint_as_float(pk_ld(&G.rec[i - 1], pk_pol).x), l, ca, cb);
                     b = quad_eval(t, l, ca, cb);
                 } else {
                     const V2 cc = S.u.v.c[o];
-                    if (i != S.u.v.loff[o]) a = cubic_eval(__uint_as_float(__ldcg(&G.rec[i - 1]).x), l, ca, cb, cc);
+                    if (i != S.u.v.loff[o]) a = cubic_eval(__uint_as_float(pk_ld(&G.rec[i - 1], pk_pol).x), l, ca, cb, cc);
                     b = cubic_eval(t, l, ca, cb, cc);
                 }
                 uint32_t info = PK_INFO_NONE;
@@ -563,8 +604,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     info = pk_line_info(a, b, bb);
                     atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
                 }
-                __stcg(&G.lines[i], make_float4(a.x, a.y, b.x, b.y));
-                __stcg(&G.info[i], info);
+                pk_st(&G.lines[i], make_float4(a.x, a.y, b.x, b.y), pk_pol);
+                pk_st(&G.info[i], info, pk_pol);
             }
             n_lines += total;
             __syncthreads();
@@ -609,14 +650,14 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             if (tid < PK_NCLS) S.bcur[tid] = 0;
             __syncthreads();
             for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                const uint32_t info = __ldcg(&G.info[i]);
+                const uint32_t info = pk_ld(&G.info[i], pk_pol);
                 if (info == PK_INFO_NONE) continue;
                 const uint32_t k = pk_info_cls(info);
                 uint32_t base = 0;
 #pragma unroll
                 for (int q = 0; q < PK_NCLS; ++q) base = (k == (uint32_t)q) ? cbase[q] : base;
                 const uint32_t pos = base + atomicAdd(&S.bcur[k], 1u);
-                __stcg(&G.slines[pos], __ldcg(&G.lines[i]));
+                pk_st(&G.slines[pos], pk_ld(&G.lines[i], pk_pol), pk_pol);
             }
             __syncthreads();
         }
@@ -627,7 +668,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         sc.c0 = sc.c1 = sc.span_excl = 0;
         uint32_t nbands = 1;
         if (walk) {
-            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, gy0, W, H);
+            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, gy0, W, H, pk_pol);
             __syncthreads();
             uint32_t bad;
             pk_grid_scan(S, W, H, err, sc, tot_tiles, tot_spans, bad);
@@ -656,7 +697,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 for (uint32_t k = tid; k < nkeys; k += PK_THREADS) S.bcur[k] = 0;
                 __syncthreads();
                 for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                    const uint32_t info = __ldcg(&G.info[i]);
+                    const uint32_t info = pk_ld(&G.info[i], pk_pol);
                     if (info == PK_INFO_NONE) continue;
                     const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
                     const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
@@ -681,14 +722,14 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     fallback = true;
                 } else {
                     for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                        const uint32_t info = __ldcg(&G.info[i]);
+                        const uint32_t info = pk_ld(&G.info[i], pk_pol);
                         if (info == PK_INFO_NONE) continue;
                         const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
                         const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
-                        const float4 L = __ldcg(&G.lines[i]);
+                        const float4 L = pk_ld(&G.lines[i], pk_pol);
                         for (int b = b0; b <= b1; ++b) {
                             const uint32_t k = b * PK_NCLS + pk_info_cls(info);
-                            __stcg(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L);
+                            pk_st(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L, pk_pol);
                         }
                     }
                 }
@@ -739,7 +780,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             }
             __syncthreads();
             pk_accumulate(S.u.acc, S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, gy0, W, gy0 + r0, gy0 + r1,
-                          rank0);
+                          rank0, pk_pol);
             __syncthreads();
             // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
             for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
@@ -779,7 +820,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                 }
                 const uint32_t ti = tile_at + rank0 + s;
-                reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64)[y] = make_uint2(lo32, hi32);
+                __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
             }
         }
     }

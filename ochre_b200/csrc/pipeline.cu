@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -539,6 +540,9 @@ struct HostBuf {  // pinned
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+#ifndef OC_L2_SETASIDE_MB
+#define OC_L2_SETASIDE_MB 0
+#endif
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
 constexpr int N_STAGE = 8;
 
@@ -576,6 +580,7 @@ struct ochre_b200_ctx {
     int sm_count = 148;
     DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
+    long l2_setaside_mb = -1;
     uint64_t fb_paths = 0;  // paths the fused kernel left to the general pipeline in the last call  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
     HostBuf h_pk_ctl;
@@ -833,7 +838,21 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
     const uint32_t n_paths = p1 - p0;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM);
-    CK(ctx->d_pk_scratch.ensure((size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_SCR_BYTES));
+    {
+        const size_t scr_bytes = (size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_SCR_BYTES;
+        CK(ctx->d_pk_scratch.ensure(scr_bytes));
+        // L2 set-aside for the kernel's evict_last accesses to its line scratch (path_kernel.cuh)
+        const char* env = getenv("OCHRE_B200_L2_PERSIST_MB");
+        const long mb = env ? atol(env) : OC_L2_SETASIDE_MB;
+        if (mb != ctx->l2_setaside_mb) {
+            int max_persist = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            size_t want = std::min((size_t)(mb > 0 ? mb : 0) << 20, (size_t)max_persist);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaGetLastError();  // best effort
+            ctx->l2_setaside_mb = mb;
+        }
+    }
     CK(ctx->d_pk_fb.ensure((size_t)n_paths * 4 + 4));
     CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4)));
     CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
