@@ -81,3 +81,39 @@ def basic():
         (CLOSE,),
     ])
     return cmds, np.array([0, 4], np.uint32), IDENTITY_ROW[None].copy()
+
+
+def svg_paints(name: str):
+    """Config 2: the paints (fills and strokes) of one bundled SVG as the reference's examples/svg.rs
+    would hand them to `Rasterizer::fill` / `Rasterizer::stroke` (fixture written by tools/svg_fixtures.py).
+    Returns (cmds, cmd_off, xf, kind, width): kind 0 = fill, 1 = stroke (source path, not yet stroked)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"svg_{name}.npz"))
+    cmds = np.zeros(len(d["tag"]), CMD_DTYPE)
+    cmds["tag"] = d["tag"]
+    cmds["v"] = d["v"]
+    return cmds, d["cmd_off"].astype(np.uint32), d["xf"].astype(np.float32), d["kind"], d["width"]
+
+
+def svg(name: str, scale: float = 1.0, stroker=None):
+    """Config 2 as a batch for `Context.rasterize`: one path per paint; stroke paints are expanded on the
+    host by `stroker(cmds, width)` (default: the library's `Rasterizer::stroke` pre-pass,
+    rasterizer.rs:169-171) and every transform is `t.then(Transform::scale(scale))` (geom.rs:252-257)."""
+    from .geom import Mat2x2, Transform, Vec2
+
+    if stroker is None:
+        from .api import stroke_to_fill as stroker
+    cmds, off, xf, kind, width = svg_paints(name)
+    parts, xfs = [], []
+    for i in range(len(off) - 1):
+        c = cmds[off[i]:off[i + 1]]
+        if kind[i] == 1:
+            c = stroker(c, float(width[i]))
+        parts.append(c)
+        t = Transform(Mat2x2.new(*xf[i, :4]), Vec2.new(xf[i, 4], xf[i, 5]))
+        if scale != 1.0:
+            t = t.then(Transform.scale(scale))
+        xfs.append(t.as_row())
+    out = np.concatenate(parts) if parts else np.zeros(0, CMD_DTYPE)
+    o = np.zeros(len(parts) + 1, np.uint32)
+    o[1:] = np.cumsum([len(p) for p in parts])
+    return out, o, np.asarray(xfs, np.float32).reshape(-1, 6)
