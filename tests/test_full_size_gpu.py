@@ -1,0 +1,109 @@
+"""Full-size runs of BASELINE configs 3 and 4 on the GPU (pytest -m gpu).
+
+Config 3 (100k glyphs) is compared with the oracle tile by tile.  Config 4 (1M blobs, 157M tiles,
+10 GB of alpha) is checked through size-independent properties: per-path tile / span counts equal
+to the oracle's, an order-independent checksum of per-tile checksums (the oracle's timing sink
+computes the same hash on the CPU), sortedness of every path's tile list, idempotence, and
+invariance under the order of the paths in the batch."""
+import numpy as np
+import pytest
+
+import oracle as O
+import ochre_b200 as ob
+from ochre_b200 import workloads as W
+from parity import assert_batch_parity
+
+pytestmark = pytest.mark.gpu
+
+K1 = np.uint64(0x9E3779B97F4A7C15)
+FNV = np.uint64(0x100000001B3)
+
+
+def sink_checksum(tile_xy, alpha, spans, block=4_000_000):
+    """oracle/ochre_oracle.c cnt_tile / cnt_span, vectorised (uint64 wrap-around)."""
+    total = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for a in range(0, len(tile_xy), block):
+            xy = tile_xy[a:a + block]
+            s = xy[:, 0].astype(np.uint16).astype(np.uint64) * K1 + xy[:, 1].astype(np.uint16).astype(np.uint64)
+            w = np.ascontiguousarray(alpha[a:a + block]).view(np.uint64).reshape(-1, 8)
+            for i in range(8):
+                s = (s ^ w[:, i]) * FNV
+            total = total + s.sum(dtype=np.uint64)
+        if len(spans):
+            t = (spans["x"].astype(np.uint16).astype(np.uint64) << np.uint64(32)) ^ (spans["y"].astype(np.uint16).astype(np.uint64) << np.uint64(16)) ^ spans["w"].astype(np.uint64)
+            total = total + t.sum(dtype=np.uint64)
+    return int(total)
+
+
+def test_config3_full_100k_glyphs_tile_by_tile():
+    cmds, off, xf = W.glyphs(100_000)
+    ctx = ob.Context(0)
+    try:
+        g = ctx.rasterize(cmds, off, xf)
+        o = O.rasterize_batch(cmds, off.astype(np.uint64), xf, threads=0)
+        stats = assert_batch_parity(g, o, what="G3 x 100k")
+        assert g.used == 1 and stats["alpha_mismatch_frac"] < 1e-4
+    finally:
+        ctx.close()
+
+
+def test_config4_full_1m_blobs_properties():
+    n = 1_000_000
+    cmds, off, xf = W.blobs(n)
+    ctx = ob.Context(0)
+    try:
+        g = ctx.rasterize(cmds, off, xf, copy=False)
+        o = O.rasterize_batch(cmds, off.astype(np.uint64), xf, threads=0, count_only=True)
+        # counts per path: exact
+        assert np.array_equal(g.tile_off.astype(np.uint64), o.tile_off) and np.array_equal(g.span_off.astype(np.uint64), o.span_off)
+        assert g.n_tiles == o.n_tiles > 150_000_000 and g.n_spans == o.n_spans
+        # every path's tiles ascend by (tile_y, tile_x); tile origins are multiples of 8
+        key = (g.tile_xy[:, 1].astype(np.int64) << 20) + g.tile_xy[:, 0].astype(np.int64)
+        not_first = np.ones(g.n_tiles, bool)
+        not_first[g.tile_off[:-1][g.tile_off[:-1] < g.n_tiles]] = False
+        assert np.all(np.diff(key)[not_first[1:]] > 0)
+        assert not np.any(g.tile_xy & 7)
+        # checksum of checksums against the oracle's sink
+        cs = sink_checksum(g.tile_xy, g.alpha, g.spans)
+        if cs != o.checksum:
+            # the parity bar allows alpha +-1: find out whether that is all that differs
+            bad = 0
+            for a in range(0, n, 50_000):
+                b = min(n, a + 50_000)
+                oo = O.rasterize_batch(cmds[off[a]:off[b]], (off[a:b + 1] - off[a]).astype(np.uint64), xf[a:b], threads=0)
+                ga = g.alpha[g.tile_off[a]:g.tile_off[b]]
+                d = np.abs(ga.astype(np.int16) - oo.alpha.astype(np.int16))
+                assert d.max() <= 1, "alpha differs by more than 1/255"
+                assert np.array_equal(g.tile_xy[g.tile_off[a]:g.tile_off[b]], oo.tile_xy)
+                bad += int((d != 0).sum())
+            print(f"config 4 x 1M: {bad} of {64 * g.n_tiles} alpha bytes differ from the oracle by 1/255 (fraction {bad / (64.0 * g.n_tiles):.3g})")
+            assert bad / (64.0 * g.n_tiles) < 1e-4, f"{bad} alpha bytes differ by 1"
+        first_cs = cs
+        tile_off0 = g.tile_off.copy()
+        # idempotence: a second run over the same inputs is byte-identical
+        g2 = ctx.rasterize(cmds, off, xf, copy=False)
+        assert np.array_equal(g2.tile_off, tile_off0) and sink_checksum(g2.tile_xy, g2.alpha, g2.spans) == first_cs
+    finally:
+        ctx.close()
+
+
+def test_batch_order_does_not_change_a_path():
+    """Paths are independent (rasterizer.rs:40-46): reversing the batch reverses the result, nothing else."""
+    n = 20_000
+    cmds, off, xf = W.blobs(n, first=123_456)
+    order = np.arange(n)[::-1]
+    parts = [cmds[off[p]:off[p + 1]] for p in order]
+    rcmds = np.concatenate(parts)
+    roff = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint32)
+    ctx = ob.Context(0)
+    try:
+        a = ctx.rasterize(cmds, off, xf)
+        b = ctx.rasterize(rcmds, roff, xf[order])
+        for p in (0, 1, 777, n // 2, n - 1):
+            q = n - 1 - p
+            ta, tb = slice(a.tile_off[p], a.tile_off[p + 1]), slice(b.tile_off[q], b.tile_off[q + 1])
+            assert np.array_equal(a.tile_xy[ta], b.tile_xy[tb]) and np.array_equal(a.alpha[ta], b.alpha[tb])
+        assert sink_checksum(a.tile_xy, a.alpha, a.spans) == sink_checksum(b.tile_xy, b.alpha, b.spans)
+    finally:
+        ctx.close()
