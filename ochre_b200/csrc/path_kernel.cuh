@@ -584,28 +584,37 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             // call fails with the status code anyway)
             if (__syncthreads_or(bad)) bad_path = true;
             if (bad_path || fallback) break;
-            for (uint32_t i = n_lines + tid; i < n_lines + total; i += PK_THREADS) {
-                const uint2 r = pk_ld(&G.rec[i], pk_pol);
-                if (r.y == PK_OWNER_NONE) continue;
-                const uint32_t o = r.y;
-                const float t = __uint_as_float(r.x);
-                const V2 l = S.u.v.last[o], ca = S.u.v.a[o], cb = S.u.v.b[o];
-                V2 a = l, b;
-                if (S.u.v.tag[o] == TAG_QUAD) {
-                    if (i != S.u.v.loff[o]) a = quad_eval(__uint_as_float(pk_ld(&G.rec[i - 1], pk_pol).x), l, ca, cb);
-                    b = quad_eval(t, l, ca, cb);
-                } else {
-                    const V2 cc = S.u.v.c[o];
-                    if (i != S.u.v.loff[o]) a = cubic_eval(__uint_as_float(pk_ld(&G.rec[i - 1], pk_pol).x), l, ca, cb, cc);
-                    b = cubic_eval(t, l, ca, cb, cc);
+            // thread per line: one curve evaluation each.  A line's start point is its predecessor's end point,
+            // taken from the neighbouring lane: every warp pass covers 31 lines, lane 0 only evaluates the
+            // predecessor of the pass's first line.
+            {
+                const uint32_t lane = tid & 31u, warp = tid >> 5;
+                const uint32_t end = n_lines + total;
+                for (uint32_t base = n_lines + warp * 31u; base < end; base += (PK_THREADS / 32) * 31u) {
+                    const uint32_t i = base + lane - 1u;  // (lane 0 of the very first pass: n_lines - 1, out of range)
+                    const bool inr = (lane != 0 || base > n_lines) && i < end;
+                    uint2 r = make_uint2(0u, PK_OWNER_NONE);
+                    if (inr) r = pk_ld(&G.rec[i], pk_pol);
+                    const bool curve = r.y != PK_OWNER_NONE;
+                    const uint32_t o = curve ? r.y : 0u;
+                    V2 b = mk(0.0f, 0.0f);
+                    if (curve) {
+                        const float t = __uint_as_float(r.x);
+                        if (S.u.v.tag[o] == TAG_QUAD) b = quad_eval(t, S.u.v.last[o], S.u.v.a[o], S.u.v.b[o]);
+                        else b = cubic_eval(t, S.u.v.last[o], S.u.v.a[o], S.u.v.b[o], S.u.v.c[o]);
+                    }
+                    const float pbx = __shfl_up_sync(0xffffffffu, b.x, 1), pby = __shfl_up_sync(0xffffffffu, b.y, 1);
+                    if (curve && lane != 0) {
+                        const V2 a = (i == S.u.v.loff[o]) ? S.u.v.last[o] : mk(pbx, pby);
+                        uint32_t info = PK_INFO_NONE;
+                        if (!same(a, b)) {
+                            info = pk_line_info(a, b, bb);
+                            atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
+                        }
+                        pk_st(&G.lines[i], make_float4(a.x, a.y, b.x, b.y), pk_pol);
+                        pk_st(&G.info[i], info, pk_pol);
+                    }
                 }
-                uint32_t info = PK_INFO_NONE;
-                if (!same(a, b)) {
-                    info = pk_line_info(a, b, bb);
-                    atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
-                }
-                pk_st(&G.lines[i], make_float4(a.x, a.y, b.x, b.y), pk_pol);
-                pk_st(&G.info[i], info, pk_pol);
             }
             n_lines += total;
             __syncthreads();
@@ -700,7 +709,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     const uint32_t info = pk_ld(&G.info[i], pk_pol);
                     if (info == PK_INFO_NONE) continue;
                     const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
-                    const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
+                    int b1 = b0;  // lines are short: the last band is the first one or a neighbour
+                    const int rhi = min(pk_info_hi(info) - gy0, H - 1);
+                    while (b1 + 1 < (int)nbands && (int)S.brow[b1 + 1] <= rhi) ++b1;
+                    pk_st(&G.rec[i], make_uint2((uint32_t)b0 | ((uint32_t)b1 << 8), 0u), pk_pol);  // (rec is dead after flattening)
                     for (int b = b0; b <= b1; ++b) atomicAdd(&S.bcur[b * PK_NCLS + pk_info_cls(info)], 1u);
                 }
                 __syncthreads();
@@ -724,8 +736,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
                         const uint32_t info = pk_ld(&G.info[i], pk_pol);
                         if (info == PK_INFO_NONE) continue;
-                        const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
-                        const int b1 = pk_band_of(S, (int)nbands, min(pk_info_hi(info) - gy0, H - 1));
+                        const uint32_t bb01 = pk_ld(&G.rec[i], pk_pol).x;
+                        const int b0 = (int)(bb01 & 0xffu), b1 = (int)(bb01 >> 8);
                         const float4 L = pk_ld(&G.lines[i], pk_pol);
                         for (int b = b0; b <= b1; ++b) {
                             const uint32_t k = b * PK_NCLS + pk_info_cls(info);
@@ -816,7 +828,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 for (int x = 0; x < 8; ++x) {
                     run += d[x];
                     // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
-                    const uint32_t q = (uint32_t)(int)fminf(fabsf(c + (float)run * OC_FX_TO_256), 255.0f);
+                    const uint32_t q = (uint32_t)(int)fminf(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c)), 255.0f);  // (exact product: == mul, add)
                     if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                 }
                 const uint32_t ti = tile_at + rank0 + s;
