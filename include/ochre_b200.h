@@ -127,6 +127,36 @@ int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode);
  * fused per-path kernel is not used. */
 int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t tile_row_hi);
 
+/* ---- device-side consumer of the tile list: atlas packer + quad builder ----------------------
+ * What the reference's examples/svg.rs does on the CPU inside its TileBuilder (svg.rs:22-88):
+ * every tile's 64 alpha bytes go to the next 8x8 slot of a 4096x4096 R8 atlas (slot 0 = an
+ * all-255 tile, slots fill row-major from slot 1) plus a textured quad; every span becomes a
+ * solid quad sampling texel (0,0).  Quads come in TileBuilder call order (per path: tiles
+ * ascending, each span right after the tile on its left), coloured with the path's paint. */
+typedef struct OchreVertex { /* svg.rs:15-20 */
+    int16_t pos[2];
+    uint16_t uv[2];
+    uint8_t col[4];
+} OchreVertex; /* 12 bytes */
+
+typedef struct OchreAtlas {
+    uint32_t n_quads;    /* n_tiles + n_spans; 4 vertices and 6 indices each */
+    uint32_t n_pages;    /* atlas pages of 4096 x 4096 bytes; the reference has one (<= 262143 tiles) */
+    const OchreVertex* vertices; /* 4 * n_quads */
+    const uint32_t* indices;     /* 6 * n_quads: base, base+1, base+2, base, base+2, base+3 */
+    const uint8_t* atlas;        /* n_pages * 4096 * 4096, row-major */
+    const uint32_t* page_quad_off; /* n_pages + 1 (HOST memory): quads [off[k], off[k+1]) sample page k */
+    float device_ms;
+    uint64_t kernel_launches;
+} OchreAtlas;
+
+/* Builds the atlas and the quad buffers from the result of the LAST ochre_b200_rasterize call on
+ * this ctx (its device copy; valid whatever flags that call used).  colors: 4 bytes (r, g, b, a)
+ * per path of that call, host memory.  flags: OCHRE_OUT_DEVICE leaves vertices / indices / atlas
+ * on the device, otherwise they are copied to ctx-owned pinned host memory.  Buffers stay valid
+ * until the next call on the ctx. */
+int ochre_b200_build_atlas(ochre_b200_ctx* ctx, const uint8_t* colors, uint32_t flags, OchreAtlas* out);
+
 /* Human-readable description of the last error on this ctx (never NULL). */
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);
 

@@ -20,7 +20,7 @@ ERRORS = {
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
     "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_set_mode",
-    "ochre_b200_set_row_band", "ochre_b200_last_error",
+    "ochre_b200_set_row_band", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_version",
 ]
@@ -33,6 +33,13 @@ class OchreResult(C.Structure):
         ("spans", C.c_void_p),
         ("n_cmds", C.c_uint64), ("n_lines", C.c_uint64), ("n_records", C.c_uint64), ("n_chunks", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("stage_ms", C.c_float * 8),
+    ]
+
+
+class OchreAtlas(C.Structure):
+    _fields_ = [
+        ("n_quads", C.c_uint32), ("n_pages", C.c_uint32), ("vertices", C.c_void_p), ("indices", C.c_void_p),
+        ("atlas", C.c_void_p), ("page_quad_off", C.c_void_p), ("device_ms", C.c_float), ("kernel_launches", C.c_uint64),
     ]
 
 
@@ -63,6 +70,7 @@ def load():
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
     L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
     L.ochre_b200_set_row_band.argtypes = [vp, C.c_int32, C.c_int32]
+    L.ochre_b200_build_atlas.argtypes = [vp, vp, u32, C.POINTER(OchreAtlas)]
     L.ochre_b200_last_error.argtypes = [vp]
     L.ochre_b200_last_error.restype = C.c_char_p
     L.ochre_b200_stroke_path.argtypes = [vp, sz, C.c_float, C.POINTER(vp), C.POINTER(sz)]

@@ -66,6 +66,23 @@ class BatchResult:
         assert s == s1, "span list out of order"
 
 
+#: numpy view of `OchreVertex` (examples/svg.rs:15-20)
+VERTEX_DTYPE = np.dtype([("pos", "<i2", (2,)), ("uv", "<u2", (2,)), ("col", "u1", (4,))])
+
+
+@dataclass
+class AtlasResult:
+    vertices: Optional[np.ndarray]  # (4 * n_quads,) VERTEX_DTYPE
+    indices: Optional[np.ndarray]   # (6 * n_quads,) uint32
+    atlas: Optional[np.ndarray]     # (n_pages, 4096, 4096) uint8
+    n_quads: int
+    n_pages: int
+    page_quad_off: np.ndarray       # (n_pages + 1,) quads [off[k], off[k+1]) sample atlas page k
+    device_ms: float
+    kernel_launches: int
+    device_ptrs: Optional[dict] = None
+
+
 def _check(ctx_handle, rc: int):
     if rc != 0:
         L = _lib.load()
@@ -107,6 +124,29 @@ class Context:
     def set_row_band(self, tile_row_lo: int = 0, tile_row_hi: int = 0):
         """Rasterise only tile rows [lo, hi) (row-band sharding of one huge path); lo >= hi resets."""
         _check(self._h, _lib.load().ochre_b200_set_row_band(self._h, int(tile_row_lo), int(tile_row_hi)))
+
+    def build_atlas(self, colors, out_device: bool = False, copy: bool = True) -> "AtlasResult":
+        """Device-side atlas packer + quad builder (the reference's examples/svg.rs `Builder`, svg.rs:22-88)
+        over the result of the last `rasterize` call.  colors: (n_paths, 4) uint8 rgba."""
+        L = _lib.load()
+        colors = np.ascontiguousarray(colors, dtype=np.uint8).reshape(-1, 4)
+        res = _lib.OchreAtlas()
+        rc = L.ochre_b200_build_atlas(self._h, colors.ctypes.data, _lib.OCHRE_OUT_DEVICE if out_device else 0, C.byref(res))
+        _check(self._h, rc)
+        nq, npg = int(res.n_quads), int(res.n_pages)
+        page = np.frombuffer((C.c_uint8 * ((npg + 1) * 4)).from_address(res.page_quad_off), dtype=np.uint32).copy()
+        common = dict(n_quads=nq, n_pages=npg, page_quad_off=page, device_ms=float(res.device_ms), kernel_launches=int(res.kernel_launches))
+        if out_device:
+            return AtlasResult(None, None, None, device_ptrs=dict(vertices=res.vertices, indices=res.indices, atlas=res.atlas), **common)
+
+        def view(ptr, nbytes, dtype, shape):
+            if nbytes == 0:
+                return np.zeros(shape, dtype)
+            a = np.frombuffer((C.c_uint8 * nbytes).from_address(ptr), dtype=dtype).reshape(shape)
+            return a.copy() if copy else a
+
+        return AtlasResult(view(res.vertices, nq * 48, VERTEX_DTYPE, (nq * 4,)), view(res.indices, nq * 24, np.uint32, (nq * 6,)),
+                           view(res.atlas, npg * 4096 * 4096, np.uint8, (npg, 4096, 4096)), **common)
 
     def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/ochre_b200.h"
+#include "atlas.cuh"
 #include "path_kernel.cuh"
 #include "radix_sort.cuh"
 #include "raster_core.cuh"
@@ -580,6 +581,11 @@ struct ochre_b200_ctx {
     int sm_count = 148;
     DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
+    // atlas / quad builder (csrc/atlas.cuh)
+    DevBuf a_vtx, a_idx, a_atlas, a_span_tile, a_flag, a_sb, a_colors;
+    HostBuf ha_vtx, ha_idx, ha_atlas, ha_page;
+    uint32_t last_n_paths = 0, last_n_tiles = 0, last_n_spans = 0;
+    bool last_valid = false;
     long l2_setaside_mb = -1;
     uint64_t fb_paths = 0;  // paths the fused kernel left to the general pipeline in the last call  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
@@ -1062,9 +1068,9 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
+    HostBuf* hb[] = {&ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1105,6 +1111,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     ctx->dbg_valid = false;
     ctx->used_paths = 0;
     ctx->fb_paths = 0;
+    ctx->last_valid = false;
     memset(out, 0, sizeof *out);
     out->n_paths = n_paths;
     CK(cudaSetDevice(ctx->device));
@@ -1312,6 +1319,10 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         out->spans = ctx->h_spans.as<OchreSpan>();
     }
     out->stage_ms[7] = copy_ms;
+    ctx->last_n_paths = n_paths;
+    ctx->last_n_tiles = tile_base;
+    ctx->last_n_spans = span_base;
+    ctx->last_valid = true;
     return 0;
 }
 
@@ -1327,6 +1338,114 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
         return OCHRE_E_INVALID_ARG;
     }
     return rasterize_impl(ctx, cmds, cmd_off, xf, n_paths, flags, cmd_off_host, out, true);
+}
+
+int ochre_b200_build_atlas(ochre_b200_ctx* ctx, const uint8_t* colors, uint32_t flags, OchreAtlas* out) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    if (!out || (flags & ~OCHRE_OUT_DEVICE)) {
+        ctx->err = "null result pointer or unknown flag bits";
+        return OCHRE_E_INVALID_ARG;
+    }
+    memset(out, 0, sizeof *out);
+    if (!ctx->last_valid) {
+        ctx->err = "no rasterised result on this ctx: call ochre_b200_rasterize first";
+        return OCHRE_E_INVALID_ARG;
+    }
+    const uint32_t n_paths = ctx->last_n_paths, nt = ctx->last_n_tiles, ns = ctx->last_n_spans;
+    if (n_paths && !colors) {
+        ctx->err = "null colors";
+        return OCHRE_E_INVALID_ARG;
+    }
+    if ((uint64_t)nt + ns >= (1ull << 30)) {
+        ctx->err = "more than 2^30 quads";
+        return OCHRE_E_TOO_LARGE;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const uint32_t nq = nt + ns;
+    const uint32_t n_pages = nt ? (nt + AT_SLOTS - 1) / AT_SLOTS : 1;
+    CK(ctx->a_vtx.ensure((size_t)nq * 48 + 48));
+    CK(ctx->a_idx.ensure((size_t)nq * 24 + 24));
+    CK(ctx->a_atlas.ensure((size_t)n_pages * AT_PAGE_BYTES));
+    CK(ctx->a_span_tile.ensure((size_t)ns * 4 + 4));
+    CK(ctx->a_flag.ensure((size_t)nt + 4));
+    CK(ctx->a_sb.ensure((size_t)nt * 4 + 4));
+    CK(ctx->a_colors.ensure((size_t)n_paths * 4 + 4));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(nt) * 4));
+    CK(ctx->ha_page.ensure(((size_t)n_pages + 1) * 4));
+    uint64_t launches = 0;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (n_paths) CK(cudaMemcpyAsync(ctx->a_colors.p, colors, (size_t)n_paths * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->a_flag.p, 0, (size_t)nt + 4, st));
+    // the last page is the only one with unused slots (the reference's atlas starts zeroed, svg.rs:32)
+    CK(cudaMemsetAsync(ctx->a_atlas.as<uint8_t>() + (size_t)(n_pages - 1) * AT_PAGE_BYTES, 0, AT_PAGE_BYTES, st));
+    k_atlas_init<<<nblk((uint64_t)n_pages * 8, 256), 256, 0, st>>>(ctx->a_atlas.as<uint8_t>(), n_pages, nt);
+    launches += 1;
+    if (ns) {
+        k_atlas_span_tiles<<<nblk(ns, 256), 256, 0, st>>>(ctx->o_spans.as<OchreSpan>(), ns, ctx->o_span_off.as<uint32_t>(),
+                                                         ctx->o_tile_off.as<uint32_t>(), n_paths, ctx->o_tile_xy.as<uint32_t>(),
+                                                         ctx->a_span_tile.as<uint32_t>(), ctx->a_flag.as<uint8_t>());
+        launches += 1;
+    }
+    {
+        const uint8_t* flag = ctx->a_flag.as<uint8_t>();
+        uint32_t* sb = ctx->a_sb.as<uint32_t>();
+        launches += device_scan(
+            st, nt, [flag] __device__(uint32_t i) { return (uint32_t)flag[i]; },
+            [sb] __device__(uint32_t i, uint32_t excl, uint32_t) { sb[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(), nullptr);
+    }
+    if (nt) {
+        k_atlas_tiles<<<nblk(nt, 256), 256, 0, st>>>(ctx->o_alpha.as<uint4>(), ctx->o_tile_xy.as<uint32_t>(), nt, ctx->o_tile_off.as<uint32_t>(),
+                                                    n_paths, ctx->a_sb.as<uint32_t>(), ctx->a_colors.as<uint32_t>(), ctx->a_atlas.as<uint8_t>(),
+                                                    ctx->a_vtx.as<uint4>(), ctx->a_idx.as<uint2>());
+        launches += 1;
+    }
+    if (ns) {
+        k_atlas_spans<<<nblk(ns, 256), 256, 0, st>>>(ctx->o_spans.as<OchreSpan>(), ns, ctx->o_span_off.as<uint32_t>(), n_paths,
+                                                    ctx->a_span_tile.as<uint32_t>(), ctx->a_colors.as<uint32_t>(), ctx->a_vtx.as<uint4>(),
+                                                    ctx->a_idx.as<uint2>());
+        launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // page k's first quad = quad of its first tile
+    uint32_t* hp = ctx->ha_page.as<uint32_t>();
+    for (uint32_t k = 0; k < n_pages; ++k) {
+        const uint32_t t0 = k * AT_SLOTS;
+        hp[k] = 0;
+        if (t0 < nt && t0) CK(cudaMemcpyAsync(hp + k, ctx->a_sb.as<uint32_t>() + t0, 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (uint32_t k = 1; k < n_pages; ++k) hp[k] += k * AT_SLOTS;  // spans before the tile + the tile index
+    hp[0] = 0;
+    hp[n_pages] = nq;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    out->n_quads = nq;
+    out->n_pages = n_pages;
+    out->page_quad_off = hp;
+    out->device_ms = ms;
+    out->kernel_launches = launches;
+    if (flags & OCHRE_OUT_DEVICE) {
+        out->vertices = ctx->a_vtx.as<OchreVertex>();
+        out->indices = ctx->a_idx.as<uint32_t>();
+        out->atlas = ctx->a_atlas.as<uint8_t>();
+    } else {
+        CK(ctx->ha_vtx.ensure((size_t)nq * 48 + 48));
+        CK(ctx->ha_idx.ensure((size_t)nq * 24 + 24));
+        CK(ctx->ha_atlas.ensure((size_t)n_pages * AT_PAGE_BYTES));
+        if (nq) {
+            CK(cudaMemcpyAsync(ctx->ha_vtx.p, ctx->a_vtx.p, (size_t)nq * 48, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->ha_idx.p, ctx->a_idx.p, (size_t)nq * 24, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(ctx->ha_atlas.p, ctx->a_atlas.p, (size_t)n_pages * AT_PAGE_BYTES, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        out->vertices = ctx->ha_vtx.as<OchreVertex>();
+        out->indices = ctx->ha_idx.as<uint32_t>();
+        out->atlas = ctx->ha_atlas.as<uint8_t>();
+    }
+    return 0;
 }
 
 int ochre_b200_debug_lines(ochre_b200_ctx* ctx, float* outp, uint64_t cap, uint64_t* n) {
