@@ -300,6 +300,43 @@ __device__ __forceinline__ int pk_info_lo(uint32_t f) { return (int)(f & 0x1fffu
 __device__ __forceinline__ int pk_info_hi(uint32_t f) { return (int)((f >> 13) & 0x1fffu) - 4096; }
 __device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return (f >> 26) & 7u; }
 
+// Conic commands (path.rs:75-104) are rare: their subdivision runs in the command's own thread, out of line
+// so that its stack of pending intervals does not weigh on the common path.
+struct PkConicCount {
+    uint32_t n;
+    __device__ void operator()(V2) { ++n; }
+};
+__device__ __noinline__ uint32_t pk_conic_count(V2 last, V2 control, V2 point, float weight) {
+    PkConicCount cnt = {0u};
+    conic_for_each_point(last, control, point, weight, OC_CONIC_TOL, cnt);
+    return cnt.n;
+}
+struct PkConicEmit {
+    const PkScratch* G;
+    uint32_t* ccnt;
+    PkBBox* bb;
+    uint32_t at;
+    uint64_t pol;
+    V2 prev;
+    __device__ void operator()(V2 p) {
+        uint32_t info = PK_INFO_NONE;
+        if (!same(prev, p)) {
+            info = pk_line_info(prev, p, *bb);
+            atomicAdd(&ccnt[pk_info_cls(info)], 1u);
+        }
+        pk_st(&G->rec[at], make_uint2(0u, PK_OWNER_NONE), pol);
+        pk_st(&G->lines[at], make_float4(prev.x, prev.y, p.x, p.y), pol);
+        pk_st(&G->info[at], info, pol);
+        ++at;
+        prev = p;
+    }
+};
+__device__ __noinline__ void pk_conic_emit(const PkScratch& G, uint32_t* ccnt, PkBBox& bb, uint32_t first, uint64_t pol, V2 last,
+                                           V2 control, V2 point, float weight) {
+    PkConicEmit em = {&G, ccnt, &bb, first, pol, last};
+    conic_for_each_point(last, control, point, weight, OC_CONIC_TOL, em);
+}
+
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
 __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
@@ -535,11 +572,11 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 // validation: tag, and every transformed coordinate the command reads (its own points
                 // and `last`): finite, |v| < 32760
                 const uint32_t tag = (j < nc) ? pc[j].tag : (uint32_t)TAG_FINISH;
-                if (tag == TAG_CONIC) bad = 3;
-                else if (j < nc && tag > TAG_LINE_ABS) bad = 2;
+                if (j < nc && tag > TAG_LINE_ABS) bad = 2;
                 else {
                     c = decode_vcmd(pc, nc, j, m);
                     if (!(coord_ok(c.last) && coord_ok(c.a) && coord_ok(c.b) && coord_ok(c.c))) bad = 1;
+                    if (tag == TAG_CONIC && !(fabsf(pc[j].v[4]) < 3.0e38f)) bad = 1;  // the weight must be finite
                 }
                 if (!bad) {
                     my_tag = c.tag;
@@ -547,6 +584,11 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
                         case TAG_QUAD: my_dt = quad_dt(c.last, c.a, c.b); my_n = curve_count(my_dt); break;
                         case TAG_CUBIC: my_dt = cubic_dt(c.last, c.a, c.b, c.c); my_n = curve_count(my_dt); break;
+                        case TAG_CONIC: {  // path.rs:75-104: the command's thread runs the subdivision (twice: count, emit)
+                            my_dt = pc[j].v[4];  // weight
+                            my_n = pk_conic_count(c.last, c.a, c.b, my_dt);
+                            break;
+                        }
                         default: break;  // Close: rasterizer.rs:154
                     }
                 } else {
@@ -569,6 +611,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         t = fminf(t + my_dt, 1.0f);
                         pk_st(&G.rec[first + k], make_uint2(__float_as_uint(t), tid), pk_pol);
                     }
+                } else if (my_tag == TAG_CONIC) {
+                    pk_conic_emit(G, S.bcur, bb, first, pk_pol, c.last, c.a, c.b, my_dt);
                 } else {
                     uint32_t info = PK_INFO_NONE;  // degenerate lines are skipped by line_to, rasterizer.rs:73
                     if (!same(c.last, c.a)) {

@@ -152,6 +152,57 @@ OC_HD V2 cubic_eval(float t, V2 last, V2 c1, V2 c2, V2 p) {
     V2 p123 = lerp(t, p12, p23);
     return lerp(t, p012, p123);
 }
+// ---------------------------------------------------------------------------
+// Conic flattening, path.rs:75-104: recursive midpoint subdivision of a rational quadratic until the
+// midpoint is within `tol` of the chord's midpoint; every leaf emits two lines (midpoint, p1), left
+// subtree first.  Iterative form with an explicit stack of pending right halves; f(point) receives the
+// Line points in the reference's order.  The depth is capped at OC_CONIC_DEPTH (the reference recurses
+// without bound; its intervals collapse long before that for finite input).
+// ---------------------------------------------------------------------------
+#define OC_CONIC_TOL 0.1f /* TOLERANCE, rasterizer.rs:6 */
+#define OC_CONIC_DEPTH 40
+template <class F>
+OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, float tol, F& f) {
+    float st0[OC_CONIC_DEPTH], st1[OC_CONIC_DEPTH];
+    V2 sp0[OC_CONIC_DEPTH], sp1[OC_CONIC_DEPTH];
+    int depth[OC_CONIC_DEPTH];
+    int n = 0;
+    float t0 = 0.0f, t1 = 1.0f;
+    V2 p0 = last, p1 = point;
+    int d = 0;
+    const V2 wc = scale(weight, control);
+    for (;;) {
+        const float t = 0.5f * (t0 + t1);
+        const V2 p01 = lerp(t, last, wc);
+        const V2 p12 = lerp(t, wc, point);
+        const float denom = (1.0f - t) * (1.0f - t) + 2.0f * t * (1.0f - t) * weight + t * t;
+        const V2 mid = scale(1.0f / denom, lerp(t, p01, p12));
+        const float err = length(sub(mid, scale(0.5f, add(p0, p1))));
+        if (err > tol && d + 1 < OC_CONIC_DEPTH && n < OC_CONIC_DEPTH) {
+            // right half waits; descend into the left half
+            st0[n] = t;
+            st1[n] = t1;
+            sp0[n] = mid;
+            sp1[n] = p1;
+            depth[n] = d + 1;
+            ++n;
+            t1 = t;
+            p1 = mid;
+            ++d;
+            continue;
+        }
+        f(mid);
+        f(p1);
+        if (n == 0) break;
+        --n;
+        t0 = st0[n];
+        t1 = st1[n];
+        p0 = sp0[n];
+        p1 = sp1[n];
+        d = depth[n];
+    }
+}
+
 // Number of lines the t loop emits (>= 1 for finite input; dt is never 0 for
 // coordinates inside the accepted range, so the loop terminates).
 OC_HD uint32_t curve_count(float dt) {

@@ -229,7 +229,9 @@ def test_chunking_and_rerun_do_not_change_a_byte(ctx):
         assert a.spans.tobytes() == r.spans.tobytes()
 
 
-def test_conics_are_flattened_on_the_host(ctx):
+def test_conics(ctx):
+    """Conic commands (path.rs:75-104): flattened by the fused kernel on the device; the general pipeline
+    (mode general, or a handed-over path) has the host flatten them before upload."""
     rng = np.random.default_rng(11)
     paths = [_random_path(rng, int(rng.integers(2, 8)), 80.0, conic=True) for _ in range(60)]
     assert any((p["tag"] == CONIC).any() for p in paths)
@@ -237,6 +239,25 @@ def test_conics_are_flattened_on_the_host(ctx):
     cmds, off, xf = pack(paths, xfs)
     g = ctx.rasterize(cmds, off, xf)
     assert_batch_parity(g, oracle_batch(cmds, off, xf), what="conics")
+    assert g.used == (1 if ctx.mode_name == "auto" else 2)  # auto: no host pre-pass, no hand-over
+    # device-resident inputs: only the fused kernel can take conics (the general pipeline needs the host pre-pass)
+    import torch
+
+    d_cmds = torch.from_numpy(cmds.view(np.uint8).reshape(-1).copy()).cuda()
+    d_off = torch.from_numpy(off.view(np.int32).copy()).cuda()
+    d_xf = torch.from_numpy(np.ascontiguousarray(xf, np.float32).reshape(-1).copy()).cuda()
+    if ctx.mode_name == "auto":
+        r = ctx.rasterize_ptrs(d_cmds.data_ptr(), d_off.data_ptr(), d_xf.data_ptr(), len(off) - 1, off, in_device=True, out_device=False, copy=True)
+        assert np.array_equal(r.tile_off, g.tile_off) and np.array_equal(r.alpha, g.alpha)
+    # many wide conics (weights from near-degenerate to heavy), still bit-exact tiles and spans
+    big = []
+    for k in range(200):
+        w = float(rng.choice([0.05, 0.5, 0.70710678, 1.0, 3.0, 25.0]))
+        p0, c1, p1 = rng.uniform(-300, 900, 2), rng.uniform(-300, 900, 2), rng.uniform(-300, 900, 2)
+        big.append(make_cmds([(MOVE, *p0), (CONIC, c1[0], c1[1], p1[0], p1[1], w), (LINE, *rng.uniform(0, 600, 2)), (CLOSE,)]))
+    cmds, off, xf = pack(big)
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, oracle_batch(cmds, off, xf), what="wide conics")
 
 
 def test_strokes_match_reference_stroke(ctx):
