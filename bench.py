@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--ordered", action="store_true", help="copy the results into path order (k_gather_paths) instead of leaving them in the fused kernel's arena")
     ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: sub-batches per step whose tiles travel to GPU 0 behind the kernels")
     args = ap.parse_args()
 
@@ -250,9 +251,11 @@ def main():
             ctxs.append(c2)
     NC = len(ctxs)
 
+    UNORD = not args.ordered
+
     def raster_sub(c, a, b):
         return c.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr() + 4 * a, d_xf_t.data_ptr() + 24 * a, b - a, h_off[a:b + 1],
-                                in_device=True, out_device=True)
+                                in_device=True, out_device=True, unordered=UNORD)
 
     def step_pipelined():
         from ochre_b200 import sharding
@@ -297,7 +300,7 @@ def main():
         if gather:
             return step_pipelined()
         return ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,
-                                  out_device=True)
+                                  out_device=True, unordered=UNORD)
 
     if gather:
         # size every arena before anything is in flight: both contexts see every sub-batch once, and GPU 0's
@@ -317,7 +320,7 @@ def main():
 
     def step_e2e():
         return ctx.rasterize_ptrs(h_cmds_t.data_ptr(), h_off_t.data_ptr(), h_xf_t.data_ptr(), P, h_off, in_device=False,
-                                  out_device=False, copy=False)
+                                  out_device=False, copy=False, unordered=UNORD)
 
     # ---- value: device-resident ---------------------------------------------------------
     for _ in range(args.warmup):
@@ -352,11 +355,11 @@ def main():
     # ungathered figure for N > 1 (what a renderer that draws per GPU would see)
     ungathered = None
     if gather:
-        ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True)  # sizes the arenas
+        ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True, unordered=UNORD)  # sizes the arenas
         barrier()
         e0.record()
         for _ in range(args.steps):
-            ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True)
+            ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True, unordered=UNORD)
         e1.record()
         barrier()
         ug_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -377,7 +380,7 @@ def main():
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
         h2d = n_cmds * 28 + (P + 1) * 4 + P * 24
-        d2h = r2.n_tiles * 68 + r2.n_spans * 8 + 2 * (P + 1) * 4
+        d2h = r2.n_tiles * 68 + r2.n_spans * 8 + (16 * P if UNORD else 2 * (P + 1) * 4 + 16 * P)
         e2e = {"value": paths_total / (e2e_ms * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": n_e2e,
                "copy_ms_per_step": float(r2.stage_ms[7])}
@@ -404,9 +407,19 @@ def main():
         dom_name = STAGES[dom]
         stage_report = {STAGES[i]: float(stage_ms[i]) for i in range(8)}
     achieved = sb[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this command
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "kpath_traffic.json")) as f:
+            tj = json.load(f)
+        if dom_name == tj.get("stage"):
+            traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
+                       "paths_per_launch": tj["paths_per_launch"], "source": tj["source"]}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": kern[dom_name], "stage": dom_name, "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "stage_ms": stage_report,
         "stage_alg_GB": {k: v / 1e9 for k, v in sb.items()},
         "pipeline_b_alg_GB": b_alg / 1e9,
@@ -440,6 +453,8 @@ def main():
                 "lines_per_gpu": int(res.n_lines), "bin_records_per_gpu": int(res.n_records), "tiles_total": int(tiles_total),
                 "spans_total": int(spans_total), "tiles_per_s": tps, "alpha_MB_per_s": tps * 64e-6, "chunks": int(res.n_chunks),
                 "parallelism": f"path-batch x{world}" + (f", tiles gathered to GPU 0 (NCCL send/recv, pipelined in {K} sub-batches)" if gather else ""),
+                "layout": ("path-ordered lists (k_gather_paths)" if args.ordered else
+                           "per-path lists in completion order + per-path (start, count) ranges (OCHRE_OUT_UNORDERED)"),
                 "l2": "inputs (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (n_cmds * 28 / 1e9),
                 "timing": "CUDA events bracketing the K steps, max over ranks; library-reported device ms/step = %.3f, wall = %.3f"
                           % (dev_ms / args.steps, wall_ms / args.steps),

@@ -70,17 +70,26 @@ typedef struct OchreSpan {
 #define OCHRE_IN_DEVICE 0x1u   /* cmds / cmd_off / xf are device pointers (cmd_off is also read on the host: pass a host copy in cmd_off_host) */
 #define OCHRE_OUT_DEVICE 0x2u  /* leave results on the device: OchreResult pointers are device pointers */
 #define OCHRE_KEEP_STAGES 0x4u /* keep intermediate buffers of the LAST chunk readable through ochre_b200_debug_* */
+#define OCHRE_OUT_UNORDERED 0x8u /* skip the copy into path order: tiles / spans stay in the order the paths finished on the
+                                  * GPU; every path's lists are still contiguous and sorted, OchreResult.ranges locates them,
+                                  * tile_off / span_off are NULL.  Ignored (the result is ordered) in OCHRE_MODE_GENERAL and with
+                                  * a row band. */
 
 /* Result of one call.  Tiles and spans of path p are tile_off[p]..tile_off[p+1]
  * and span_off[p]..span_off[p+1]; inside a path tiles ascend by (tile_y, tile_x)
  * -- the order of the reference's TileBuilder::tile calls -- and a span belongs
  * right after the tile whose right edge it touches (span.x == tile.x + 8, same y).
  * Buffers are owned by the ctx and stay valid until the next call on it. */
+/* Where one path's tiles and spans are: tiles [tile_start, tile_start + n_tiles), spans likewise. */
+typedef struct OchrePathRange {
+    uint32_t tile_start, n_tiles, span_start, n_spans;
+} OchrePathRange;
+
 typedef struct OchreResult {
     uint32_t n_paths;
     uint32_t n_tiles;
     uint32_t n_spans;
-    uint32_t reserved;         /* bit 0: fused per-path kernel ran, bit 1: general pipeline ran */
+    uint32_t reserved;         /* bit 0: fused per-path kernel ran, bit 1: general pipeline ran, bit 2: unordered layout */
     const uint32_t* tile_off;  /* n_paths + 1 */
     const int16_t* tile_xy;    /* 2 * n_tiles: pixel x, y of each tile origin (multiples of 8) */
     const uint8_t* alpha;      /* 64 * n_tiles: row-major 8x8 coverage, TileBuilder::tile's `data` */
@@ -91,6 +100,7 @@ typedef struct OchreResult {
     uint64_t kernel_launches;  /* CUDA kernels this call launched */
     float device_ms;           /* device time of the kernels (first launch to last, CUDA events) */
     float stage_ms[8];         /* flatten, bin, sort, tile-heads, backdrop/winding scans, coverage, emit, copies */
+    const OchrePathRange* ranges; /* n_paths: always set; with tile_off == NULL (OCHRE_OUT_UNORDERED) the only index */
 } OchreResult;
 
 typedef struct ochre_b200_ctx ochre_b200_ctx;

@@ -10,6 +10,7 @@ SO = os.environ.get("OCHRE_B200_LIB") or os.path.join(PKG, "libochre_b200.so")  
 OCHRE_IN_DEVICE = 0x1
 OCHRE_OUT_DEVICE = 0x2
 OCHRE_KEEP_STAGES = 0x4
+OCHRE_OUT_UNORDERED = 0x8
 MODE_AUTO, MODE_GENERAL, MODE_FUSED = 0, 1, 2
 
 ERRORS = {
@@ -33,6 +34,7 @@ class OchreResult(C.Structure):
         ("spans", C.c_void_p),
         ("n_cmds", C.c_uint64), ("n_lines", C.c_uint64), ("n_records", C.c_uint64), ("n_chunks", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_ms", C.c_float), ("stage_ms", C.c_float * 8),
+        ("ranges", C.c_void_p),
     ]
 
 

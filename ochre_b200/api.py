@@ -35,8 +35,8 @@ class TileBuilder:
 
 @dataclass
 class BatchResult:
-    tile_off: np.ndarray  # (n_paths+1,) uint32
-    span_off: np.ndarray  # (n_paths+1,) uint32
+    tile_off: Optional[np.ndarray]  # (n_paths+1,) uint32; None for an unordered result
+    span_off: Optional[np.ndarray]  # (n_paths+1,) uint32
     tile_xy: Optional[np.ndarray]  # (n_tiles, 2) int16   (None when left on the device)
     alpha: Optional[np.ndarray]  # (n_tiles, 64) uint8
     spans: Optional[np.ndarray]  # (n_spans,) SPAN_DTYPE
@@ -50,12 +50,31 @@ class BatchResult:
     device_ms: float
     stage_ms: tuple
     device_ptrs: Optional[dict] = None  # OCHRE_OUT_DEVICE: raw device addresses
-    used: int = 0  # bit 0: fused per-path kernel ran, bit 1: general pipeline ran
+    used: int = 0  # bit 0: fused per-path kernel ran, bit 1: general pipeline ran, bit 2: unordered layout
+    ranges: Optional[np.ndarray] = None  # (n_paths, 4) uint32: tile_start, n_tiles, span_start, n_spans
+
+    def ordered(self) -> "BatchResult":
+        """Path-ordered copy of an unordered result (host arrays): what `ochre_b200_rasterize` returns without
+        OCHRE_OUT_UNORDERED, rebuilt from the per-path ranges."""
+        if self.tile_off is not None:
+            return self
+        r = self.ranges.astype(np.int64)
+        n = len(r)
+        tile_off = np.zeros(n + 1, np.uint32)
+        span_off = np.zeros(n + 1, np.uint32)
+        tile_off[1:] = np.cumsum(r[:, 1])
+        span_off[1:] = np.cumsum(r[:, 3])
+        ti = np.repeat(r[:, 0] - tile_off[:-1].astype(np.int64), r[:, 1]) + np.arange(int(tile_off[-1]))
+        si = np.repeat(r[:, 2] - span_off[:-1].astype(np.int64), r[:, 3]) + np.arange(int(span_off[-1]))
+        import dataclasses
+
+        return dataclasses.replace(self, tile_off=tile_off, span_off=span_off, tile_xy=self.tile_xy[ti], alpha=self.alpha[ti],
+                                   spans=self.spans[si])
 
     def replay(self, path: int, builder: TileBuilder) -> None:
         """TileBuilder calls of one path, in the reference's order (rasterizer.rs:241, :261-264)."""
-        t0, t1 = int(self.tile_off[path]), int(self.tile_off[path + 1])
-        s0, s1 = int(self.span_off[path]), int(self.span_off[path + 1])
+        t0, nt, s0, ns = (int(v) for v in self.ranges[path])
+        t1, s1 = t0 + nt, s0 + ns
         s = s0
         for t in range(t0, t1):
             x, y = int(self.tile_xy[t, 0]), int(self.tile_xy[t, 1])
@@ -148,7 +167,7 @@ class Context:
         return AtlasResult(view(res.vertices, nq * 48, VERTEX_DTYPE, (nq * 4,)), view(res.indices, nq * 24, np.uint32, (nq * 6,)),
                            view(res.atlas, npg * 4096 * 4096, np.uint8, (npg, 4096, 4096)), **common)
 
-    def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True) -> BatchResult:
+    def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True, unordered: bool = False) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.
 
         cmds: CMD_DTYPE array; cmd_off: uint32 offsets (n_paths+1); xf: (n_paths, 6) float32 rows
@@ -161,18 +180,19 @@ class Context:
         n_paths = len(cmd_off) - 1
         xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n_paths, 6) if n_paths else np.zeros((0, 6), np.float32)
         res = _lib.OchreResult()
-        flags = _lib.OCHRE_OUT_DEVICE if out_device else 0
+        flags = (_lib.OCHRE_OUT_DEVICE if out_device else 0) | (_lib.OCHRE_OUT_UNORDERED if unordered else 0)
         rc = L.ochre_b200_rasterize(self._h, cmds.ctypes.data, cmd_off.ctypes.data, xf.ctypes.data, n_paths, flags, None,
                                     C.byref(res))
         _check(self._h, rc)
         return self._wrap(res, n_paths, out_device, copy)
 
     def rasterize_ptrs(self, cmds_ptr: int, cmd_off_ptr: int, xf_ptr: int, n_paths: int, cmd_off_host: np.ndarray,
-                       in_device: bool, out_device: bool, copy: bool = False) -> BatchResult:
+                       in_device: bool, out_device: bool, copy: bool = False, unordered: bool = False) -> BatchResult:
         """Raw-pointer form (pinned host buffers or device buffers), used by bench.py."""
         L = _lib.load()
         res = _lib.OchreResult()
-        flags = (_lib.OCHRE_IN_DEVICE if in_device else 0) | (_lib.OCHRE_OUT_DEVICE if out_device else 0)
+        flags = ((_lib.OCHRE_IN_DEVICE if in_device else 0) | (_lib.OCHRE_OUT_DEVICE if out_device else 0)
+                 | (_lib.OCHRE_OUT_UNORDERED if unordered else 0))
         cmd_off_host = np.ascontiguousarray(cmd_off_host, dtype=np.uint32)
         rc = L.ochre_b200_rasterize(self._h, cmds_ptr, cmd_off_ptr, xf_ptr, n_paths, flags, cmd_off_host.ctypes.data,
                                     C.byref(res))
@@ -185,7 +205,8 @@ class Context:
                       n_records=int(res.n_records), n_chunks=int(res.n_chunks), kernel_launches=int(res.kernel_launches),
                       device_ms=float(res.device_ms), stage_ms=tuple(float(x) for x in res.stage_ms), used=int(res.reserved))
         if out_device:
-            ptrs = dict(tile_off=res.tile_off, span_off=res.span_off, tile_xy=res.tile_xy, alpha=res.alpha, spans=res.spans)
+            ptrs = dict(tile_off=res.tile_off, span_off=res.span_off, tile_xy=res.tile_xy, alpha=res.alpha, spans=res.spans,
+                        ranges=res.ranges)
             return BatchResult(None, None, None, None, None, device_ptrs=ptrs, **common)
 
         def view(ptr, nbytes, dtype, shape):
@@ -195,12 +216,14 @@ class Context:
             a = np.frombuffer(buf, dtype=dtype).reshape(shape)
             return a.copy() if copy else a
 
-        tile_off = view(res.tile_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
-        span_off = view(res.span_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
+        unordered = not res.tile_off
+        tile_off = None if unordered else view(res.tile_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
+        span_off = None if unordered else view(res.span_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
+        ranges = view(res.ranges, n_paths * 16, np.uint32, (n_paths, 4))
         tile_xy = view(res.tile_xy, nt * 4, np.int16, (nt, 2))
         alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64))
         spans = view(res.spans, ns * 8, SPAN_DTYPE, (ns,))
-        return BatchResult(tile_off, span_off, tile_xy, alpha, spans, **common)
+        return BatchResult(tile_off, span_off, tile_xy, alpha, spans, ranges=ranges, **common)
 
     def debug_lines(self) -> np.ndarray:
         L = _lib.load()

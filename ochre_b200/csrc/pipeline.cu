@@ -253,6 +253,14 @@ k_fill_offsets(uint32_t n_paths, uint32_t tile_base, uint32_t span_base, uint32_
     span_off[p] = span_base;
 }
 
+__global__ void __launch_bounds__(TPB)
+k_ranges_from_offsets(uint32_t n_paths, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ span_off,
+                      uint4* __restrict__ ranges) {
+    uint32_t p = blockIdx.x * TPB + threadIdx.x;
+    if (p >= n_paths) return;
+    ranges[p] = make_uint4(tile_off[p], tile_off[p + 1] - tile_off[p], span_off[p], span_off[p + 1] - span_off[p]);
+}
+
 // path_first[p] = first tile group of path p.  With a row band set a path may own no group at all:
 // its entry keeps the sentinel and it takes the offsets of the next path that has one.
 #define OC_NO_GROUP 0xffffffffu
@@ -583,7 +591,8 @@ struct ochre_b200_ctx {
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
     // atlas / quad builder (csrc/atlas.cuh)
     DevBuf a_vtx, a_idx, a_atlas, a_span_tile, a_flag, a_sb, a_colors;
-    HostBuf ha_vtx, ha_idx, ha_atlas, ha_page;
+    HostBuf ha_vtx, ha_idx, ha_atlas, ha_page, h_ranges;
+    bool last_unordered = false;
     uint32_t last_n_paths = 0, last_n_tiles = 0, last_n_spans = 0;
     bool last_valid = false;
     long l2_setaside_mb = -1;
@@ -839,9 +848,13 @@ enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_WORDS = 8 };
 
 int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
                     const uint32_t* h_off, uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base,
-                    uint32_t span_base, ChunkOut* co) {
+                    uint32_t span_base, ChunkOut* co, bool unordered, uint32_t n_paths_total) {
     cudaStream_t st = ctx->st;
     const uint32_t n_paths = p1 - p0;
+    // unordered: the arena the kernel fills IS the result (paths in completion order, one (start, count)
+    // record each), so it accumulates over the chunks of a call; ordered: the arena is a per-chunk staging
+    // area that k_gather_paths copies into path order.
+    const uint32_t base_t = unordered ? tile_base : 0u, base_s = unordered ? span_base : 0u;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM);
     {
@@ -860,23 +873,28 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         }
     }
     CK(ctx->d_pk_fb.ensure((size_t)n_paths * 4 + 4));
-    CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4)));
+    CK(ctx->d_pk_rec.ensure((size_t)(unordered ? n_paths_total : n_paths) * sizeof(uint4), unordered && p0 > 0, st));
     CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
     uint32_t* ctl = ctx->d_pk_ctl.as<uint32_t>();
     uint32_t* h_ctl = ctx->h_pk_ctl.as<uint32_t>();
-    uint4* rec = ctx->d_pk_rec.as<uint4>();
+    uint4* rec = ctx->d_pk_rec.as<uint4>() + (unordered ? p0 : 0u);
     for (int attempt = 0; attempt < 6; ++attempt) {
         // staging arena: estimate from the running tiles-per-command ratio, grow and retry on overflow
-        uint64_t want_t = (uint64_t)((double)(n_cmds + n_paths) * ctx->tiles_per_cmd * 1.15) + 1024;
-        uint64_t want_s = (uint64_t)((double)(n_cmds + n_paths) * ctx->spans_per_cmd * 1.15) + 1024;
+        uint64_t want_t = (uint64_t)((double)(n_cmds + n_paths) * ctx->tiles_per_cmd * 1.15) + 1024 + base_t;
+        uint64_t want_s = (uint64_t)((double)(n_cmds + n_paths) * ctx->spans_per_cmd * 1.15) + 1024 + base_s;
         if (want_t > 0xfffffff0ull) want_t = 0xfffffff0ull;
         if (want_s > 0xfffffff0ull) want_s = 0xfffffff0ull;
-        CK(ctx->s_tile_xy.ensure(want_t * 4));
-        CK(ctx->s_alpha.ensure(want_t * 64));
-        CK(ctx->s_spans.ensure(want_s * sizeof(OchreSpan)));
+        CK(ctx->s_tile_xy.ensure(want_t * 4, base_t > 0, st));
+        CK(ctx->s_alpha.ensure(want_t * 64, base_t > 0, st));
+        CK(ctx->s_spans.ensure(want_s * sizeof(OchreSpan), base_s > 0, st));
         const uint32_t cap_t = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::min<uint64_t>(ctx->s_alpha.cap / 64, ctx->s_tile_xy.cap / 4));
         const uint32_t cap_s = (uint32_t)std::min<uint64_t>(0xfffffff0ull, ctx->s_spans.cap / sizeof(OchreSpan));
         CK(cudaMemsetAsync(ctl, 0, PKC_WORDS * 4, st));
+        if (base_t | base_s) {  // the cursors continue where the previous chunk stopped
+            h_ctl[8] = base_t;
+            h_ctl[9] = base_s;
+            CK(cudaMemcpyAsync(ctl + PKC_CURSOR, h_ctl + 8, 8, cudaMemcpyHostToDevice, st));
+        }
         PathKernelArgs A;
         A.cmds = d_cmds_all + cmd_lo;
         A.cmd_off = d_cmd_off_all + p0;
@@ -912,17 +930,17 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
                 default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
             }
         }
-        uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];
+        uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];  // arena cursors (absolute)
         const uint32_t n_fb = (uint32_t)stt[1];
         if (n_fb && ctx->mode == OCHRE_MODE_FUSED) return RC_NEED_GENERAL;
-        if ((uint64_t)tile_base + nt >= 0xffffffffull || (uint64_t)span_base + ns >= 0xffffffffull) {
+        if ((uint64_t)tile_base + (nt - base_t) >= 0xffffffffull || (uint64_t)span_base + (ns - base_s) >= 0xffffffffull) {
             ctx->err = "more than 2^32 tiles or spans in one call";
             return OCHRE_E_TOO_LARGE;
         }
         // refine the growth estimates (the totals are exact even when the run overflowed)
         double denom = (double)(n_cmds + n_paths);
-        ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)nt / denom);
-        ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)ns / denom);
+        ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)(nt - base_t) / denom);
+        ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)(ns - base_s) / denom);
         if (stt[2]) continue;  // staging arena too small: grown at the top of the loop, run again
         if (n_fb) {
             // ---- hand-over: the general pipeline rasterises the paths that exceed the on-chip budgets ----
@@ -954,7 +972,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             OutTarget ot{&ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, ctx->f_tile_off.as<uint32_t>(), ctx->f_span_off.as<uint32_t>()};
             int rc = run_chunk(ctx, ctx->f_cmds.as<Cmd>(), ctx->f_off.as<uint32_t>(), ctx->f_xf.as<float>(), 0, n_fb, 0, n_sub, 0, 0, &co2, ot);
             if (rc != 0) return rc;
-            if ((uint64_t)tile_base + nt + co2.n_tiles >= 0xffffffffull || (uint64_t)span_base + ns + co2.n_spans >= 0xffffffffull) {
+            if ((uint64_t)tile_base + (nt - base_t) + co2.n_tiles >= 0xffffffffull ||
+                (uint64_t)span_base + (ns - base_s) + co2.n_spans >= 0xffffffffull) {
                 ctx->err = "more than 2^32 tiles or spans in one call";
                 return OCHRE_E_TOO_LARGE;
             }
@@ -979,6 +998,12 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             ns += co2.n_spans;
             ctx->used_paths |= 2u;
             ctx->fb_paths += n_fb;
+        }
+        if (unordered) {  // the arena is the result; the records are the per-path index
+            co->n_tiles = nt - base_t;
+            co->n_spans = ns - base_s;
+            ctx->dbg_valid = false;
+            return 0;
         }
         // path order: offsets by exclusive scan of the per-path counts, then the gather copy
         CK(ctx->o_tile_xy.ensure(((size_t)tile_base + nt + 1) * 4, true, st));
@@ -1036,6 +1061,7 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[1]);
     if (e != cudaSuccess) { delete ctx; return (int)e; }
     ctx->o_tile_xy.guard = ctx->o_alpha.guard = ctx->o_spans.guard = ctx->o_tile_off.guard = ctx->o_span_off.guard = ctx->st_out;
+    ctx->s_tile_xy.guard = ctx->s_alpha.guard = ctx->s_spans.guard = ctx->d_pk_rec.guard = ctx->st_out;
     for (int i = 0; i <= N_STAGE; ++i) {
         e = cudaEventCreate(&ctx->ev[i]);
         if (e != cudaSuccess) { delete ctx; return (int)e; }
@@ -1070,7 +1096,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
                     &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
+    HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1138,6 +1164,12 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     out->n_cmds = n_cmds;
 
     const bool out_dev = (flags & OCHRE_OUT_DEVICE) != 0;
+    const bool banded_call = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;
+    // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
+    const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && ctx->mode != OCHRE_MODE_GENERAL && !banded_call;
+    DevBuf& r_tile_xy = unordered ? ctx->s_tile_xy : ctx->o_tile_xy;
+    DevBuf& r_alpha = unordered ? ctx->s_alpha : ctx->o_alpha;
+    DevBuf& r_spans = unordered ? ctx->s_spans : ctx->o_spans;
     float copy_ms = 0;
     // ---- chunk plan -------------------------------------------------------------
     std::vector<uint32_t> cuts;  // chunk i = paths [cuts[i], cuts[i + 1])
@@ -1198,9 +1230,9 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(ctx->h_tile_xy.ensure_keep(est_t * 4, 0, ctx->st_out));
         CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
         CK(ctx->h_spans.ensure_keep(est_s * sizeof(OchreSpan), 0, ctx->st_out));
-        CK(ctx->o_tile_xy.ensure(est_t * 4));
-        CK(ctx->o_alpha.ensure(est_t * 64));
-        CK(ctx->o_spans.ensure(est_s * sizeof(OchreSpan)));
+        CK(r_tile_xy.ensure(est_t * 4));
+        CK(r_alpha.ensure(est_t * 64));
+        CK(r_spans.ensure(est_s * sizeof(OchreSpan)));
         CK(cudaEventRecord(ctx->ev_out[0], ctx->st_out));
     }
 
@@ -1214,7 +1246,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         int rc = RC_NEED_GENERAL;
         const bool banded = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;  // the row filter lives in the general pipeline
         if (ctx->mode != OCHRE_MODE_GENERAL && !banded) {
-            rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co);
+            rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, unordered,
+                                 n_paths);
             if (rc == 0) ctx->used_paths |= 1u;
             if (rc == RC_NEED_GENERAL && ctx->mode == OCHRE_MODE_FUSED) {
                 ctx->err = "a path exceeds the fused kernel's on-chip budgets (mode = fused only)";
@@ -1256,13 +1289,15 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             CK(ctx->h_alpha.ensure_keep((t0 + nt) * 64 + 64, t0 * 64, ctx->st_out));
             CK(ctx->h_spans.ensure_keep((s0 + ns) * sizeof(OchreSpan) + 8, s0 * sizeof(OchreSpan), ctx->st_out));
             if (nt) {
-                CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + t0 * 4, ctx->o_tile_xy.as<uint8_t>() + t0 * 4, nt * 4, cudaMemcpyDeviceToHost, ctx->st_out));
-                CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + t0 * 64, ctx->o_alpha.as<uint8_t>() + t0 * 64, nt * 64, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + t0 * 4, r_tile_xy.as<uint8_t>() + t0 * 4, nt * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + t0 * 64, r_alpha.as<uint8_t>() + t0 * 64, nt * 64, cudaMemcpyDeviceToHost, ctx->st_out));
             }
             if (ns)
-                CK(cudaMemcpyAsync(ctx->h_spans.as<OchreSpan>() + s0, ctx->o_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToHost, ctx->st_out));
-            CK(cudaMemcpyAsync(ctx->h_tile_off.as<uint32_t>() + p0, ctx->o_tile_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
-            CK(cudaMemcpyAsync(ctx->h_span_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_spans.as<OchreSpan>() + s0, r_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToHost, ctx->st_out));
+            if (!unordered) {
+                CK(cudaMemcpyAsync(ctx->h_tile_off.as<uint32_t>() + p0, ctx->o_tile_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_span_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+            }
         }
         tile_base += co.n_tiles;
         span_base += co.n_spans;
@@ -1299,30 +1334,47 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)span_base / ((double)n_cmds + n_paths));
     }
 
+    // ---- per-path ranges (both layouts) ---------------------------------------------
+    if (!unordered) {
+        CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4) + 16));
+        if (n_paths) {
+            k_ranges_from_offsets<<<nblk(n_paths, TPB), TPB, 0, st>>>(n_paths, ctx->o_tile_off.as<uint32_t>(), ctx->o_span_off.as<uint32_t>(),
+                                                                      ctx->d_pk_rec.as<uint4>());
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+        }
+    }
+
     // ---- outputs ---------------------------------------------------------------
     if (out_dev) {
-        out->tile_off = ctx->o_tile_off.as<uint32_t>();
-        out->span_off = ctx->o_span_off.as<uint32_t>();
-        out->tile_xy = ctx->o_tile_xy.as<int16_t>();
-        out->alpha = ctx->o_alpha.as<uint8_t>();
-        out->spans = ctx->o_spans.as<OchreSpan>();
+        out->tile_off = unordered ? nullptr : ctx->o_tile_off.as<uint32_t>();
+        out->span_off = unordered ? nullptr : ctx->o_span_off.as<uint32_t>();
+        out->tile_xy = r_tile_xy.as<int16_t>();
+        out->alpha = r_alpha.as<uint8_t>();
+        out->spans = r_spans.as<OchreSpan>();
+        out->ranges = ctx->d_pk_rec.as<OchrePathRange>();
     } else {
+        CK(ctx->h_ranges.ensure((size_t)n_paths * sizeof(uint4) + 16));
+        if (n_paths) CK(cudaMemcpyAsync(ctx->h_ranges.p, ctx->d_pk_rec.p, (size_t)n_paths * sizeof(uint4), cudaMemcpyDeviceToHost, ctx->st_out));
         ctx->h_tile_off.as<uint32_t>()[n_paths] = tile_base;  // (ordered after the downloads by the synchronize below)
         ctx->h_span_off.as<uint32_t>()[n_paths] = span_base;
         CK(cudaEventRecord(ctx->ev_out[1], ctx->st_out));
         CK(cudaStreamSynchronize(ctx->st_out));
         CK(cudaEventElapsedTime(&copy_ms, ctx->ev_out[0], ctx->ev_out[1]));
-        out->tile_off = ctx->h_tile_off.as<uint32_t>();
-        out->span_off = ctx->h_span_off.as<uint32_t>();
+        out->tile_off = unordered ? nullptr : ctx->h_tile_off.as<uint32_t>();
+        out->span_off = unordered ? nullptr : ctx->h_span_off.as<uint32_t>();
         out->tile_xy = ctx->h_tile_xy.as<int16_t>();
         out->alpha = ctx->h_alpha.as<uint8_t>();
         out->spans = ctx->h_spans.as<OchreSpan>();
+        out->ranges = ctx->h_ranges.as<OchrePathRange>();
     }
+    out->reserved = ctx->used_paths | (unordered ? 4u : 0u);
     out->stage_ms[7] = copy_ms;
     ctx->last_n_paths = n_paths;
     ctx->last_n_tiles = tile_base;
     ctx->last_n_spans = span_base;
     ctx->last_valid = true;
+    ctx->last_unordered = unordered;
     return 0;
 }
 
@@ -1333,7 +1385,7 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
         ctx->err = "null result pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES)) {
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED)) {
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }
@@ -1348,8 +1400,8 @@ int ochre_b200_build_atlas(ochre_b200_ctx* ctx, const uint8_t* colors, uint32_t 
         return OCHRE_E_INVALID_ARG;
     }
     memset(out, 0, sizeof *out);
-    if (!ctx->last_valid) {
-        ctx->err = "no rasterised result on this ctx: call ochre_b200_rasterize first";
+    if (!ctx->last_valid || ctx->last_unordered) {
+        ctx->err = "no path-ordered result on this ctx: call ochre_b200_rasterize (without OCHRE_OUT_UNORDERED) first";
         return OCHRE_E_INVALID_ARG;
     }
     const uint32_t n_paths = ctx->last_n_paths, nt = ctx->last_n_tiles, ns = ctx->last_n_spans;

@@ -56,10 +56,14 @@ struct OchreTransform { m: [f32; 4], ox: f32, oy: f32 }
 #[derive(Copy, Clone)]
 struct OchreSpan { x: i16, y: i16, w: u16, pad: u16 }
 #[repr(C)]
+#[derive(Copy, Clone)]
+struct OchrePathRange { tile_start: u32, n_tiles: u32, span_start: u32, n_spans: u32 }
+#[repr(C)]
 struct OchreResult {
     n_paths: u32, n_tiles: u32, n_spans: u32, reserved: u32,
     tile_off: *const u32, tile_xy: *const i16, alpha: *const u8, span_off: *const u32, spans: *const OchreSpan,
     n_cmds: u64, n_lines: u64, n_records: u64, n_chunks: u64, kernel_launches: u64, device_ms: f32, stage_ms: [f32; 8],
+    ranges: *const OchrePathRange,
 }
 #[repr(C)]
 struct Ctx { _p: [u8; 0] }

@@ -30,6 +30,7 @@ def test_struct_layout_matches_header():
     assert api.CMD_DTYPE.itemsize == 28 and api.SPAN_DTYPE.itemsize == 8
     assert C.sizeof(_lib.OchreResult) % 8 == 0
     assert _lib.OchreResult.tile_off.offset == 16 and _lib.OchreResult.n_cmds.offset == 56
+    assert _lib.OchreResult.ranges.offset == 136 and C.sizeof(_lib.OchreResult) == 144
 
 
 def test_no_cpu_fallback_without_device():

@@ -212,6 +212,54 @@ def test_row_bands_on_the_gpu_concatenate_to_the_whole_path(gctx):
         c.close()
 
 
+def test_unordered_result_is_the_ordered_result_in_completion_order():
+    """OCHRE_OUT_UNORDERED skips the copy into path order: the same per-path lists, located by `ranges`."""
+    b_cmds, b_off, b_xf = W.blobs(3000, first=31)
+    wide = make_cmds([(MOVE, 10, 10), (LINE, 30000, 14), (LINE, 30000, 40), (LINE, 10, 30), (CLOSE,)])  # handed over
+    cmds = np.concatenate([b_cmds[:b_off[1500]], wide, b_cmds[b_off[1500]:]])
+    off = np.concatenate([b_off[:1501], b_off[1500:] + len(wide)]).astype(np.uint32)
+    xf = np.concatenate([b_xf[:1500], ID[None], b_xf[1500:]])
+    c = ob.Context(0)
+    try:
+        a = c.rasterize(cmds, off, xf)
+        assert a.used == 3 and a.ranges is not None
+        assert np.array_equal(a.ranges[:, 0], a.tile_off[:-1]) and np.array_equal(a.ranges[:, 1], np.diff(a.tile_off))
+        for chunk in (0, 8192):
+            c.set_chunk(chunk)
+            u = c.rasterize(cmds, off, xf, unordered=True)
+            assert u.tile_off is None and u.used == 7 and u.n_tiles == a.n_tiles and u.n_spans == a.n_spans
+            assert (u.n_chunks > 4) == (chunk != 0)
+            # every path owns a disjoint slice of the arena
+            order = np.argsort(u.ranges[:, 0], kind="stable")
+            r = u.ranges[order].astype(np.int64)
+            assert np.all(r[1:, 0] >= r[:-1, 0] + r[:-1, 1]) and r[-1, 0] + r[-1, 1] <= u.n_tiles
+            o = u.ordered()
+            assert np.array_equal(o.tile_off, a.tile_off) and np.array_equal(o.span_off, a.span_off)
+            assert np.array_equal(o.tile_xy, a.tile_xy) and np.array_equal(o.alpha, a.alpha) and o.spans.tobytes() == a.spans.tobytes()
+
+            class Rec(ob.TileBuilder):
+                def __init__(self):
+                    self.calls = []
+
+                def tile(self, x, y, data):
+                    self.calls.append(("t", x, y, data))
+
+                def span(self, x, y, w):
+                    self.calls.append(("s", x, y, w))
+
+            for p in (0, 1500, 3000):
+                ra, ru = Rec(), Rec()
+                a.replay(p, ra)
+                u.replay(p, ru)
+                assert ra.calls == ru.calls and len(ra.calls) > 0
+        c.set_chunk(0)
+        c.set_mode("general")  # the general pipeline always orders: the flag is ignored
+        g = c.rasterize(cmds, off, xf, unordered=True)
+        assert g.tile_off is not None and g.used == 2
+    finally:
+        c.close()
+
+
 def test_chunking_and_rerun_do_not_change_a_byte(ctx):
     cmds, off, xf = W.blobs(1500, first=4242)
     a = ctx.rasterize(cmds, off, xf)
