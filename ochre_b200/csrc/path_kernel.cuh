@@ -54,8 +54,9 @@ constexpr int PK_THREADS = OC_PK_THREADS;
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
 constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the path's bounding grid (tiles)
 constexpr int PK_CTAS_PER_SM = OC_PK_CTAS;
-constexpr int PK_MAXLINES = 4095;   // line slots per path: keeps a cell's 16-bit increment count exact (<= 16 per line)
-constexpr int PK_LINECAP = 4096;    // scratch stride
+constexpr int PK_MAXLINES = 4095;   // lines marked together (a path, or one stripe of it): keeps a cell's 16-bit increment count exact (<= 16 per line)
+constexpr int PK_LINECAP = 16384;   // line slots per path (scratch stride)
+constexpr int PK_MAXSTRIPES = 8;    // stripes of tile rows for paths whose bounding grid or line count exceeds one pass
 constexpr int PK_SLINECAP = 2 * PK_LINECAP;  // bucketed copies (one per slot band a line touches)
 constexpr int PK_MAXCNT = 511;      // increments per tile: keeps the fixed-point sums inside int32
 constexpr int PK_ACCW = 72;         // accumulator words per tile: 8 pixel rows x (8 columns + 1 carry-out column)
@@ -89,7 +90,8 @@ struct PathKernelArgs {
     OchreSpan* spans;
     unsigned char* scratch;     // gridDim.x * PK_SCR_BYTES
     int* status;                // [0] input error (ST_*), [1] #paths left to the general pipeline, [2] arena overflow
-    uint32_t* fb_list;          // paths left to the general pipeline (chunk-local ids), status[1] entries
+    uint32_t* fb_list;          // paths left to the next stage (chunk-local ids), status[1] entries
+    const uint32_t* path_list;  // null: paths 0 .. n_paths-1; else the n_paths chunk-local ids to rasterise
 };
 
 struct PkCurves {  // decoded curve commands of the current command chunk (slot = thread id)
@@ -112,10 +114,11 @@ struct PkShared {
     uint16_t wbase[PK_WORDS + 2];
     uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
     uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
-    uint16_t brow[PK_MAXB + 2];             // first grid row of every slot band
+    uint16_t brow[PK_MAXB + 2];             // first row of every slot band (relative to the stripe)
+    uint16_t srow[PK_MAXSTRIPES + 2];       // first grid row of every stripe
     uint32_t ws[72];
     int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
-    uint32_t path, next_path, nbands, base_tiles, base_spans, flag;
+    uint32_t path, next_path, nbands, nstripes, base_tiles, base_spans, flag;
 };
 
 // touched cells before cell c (c may be one past the last cell)
@@ -340,7 +343,7 @@ __device__ __noinline__ void pk_conic_emit(const PkScratch& G, uint32_t* ccnt, P
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
 __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
-                                            uint64_t pk_pol) {
+                                            bool striped, uint64_t pk_pol) {
     uint32_t err = 0;
     uint32_t pos = threadIdx.x;
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -356,14 +359,21 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
         int prev_ty = w.y >> 3;
         for (;;) {
             const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0;
-            if ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
+            if ((unsigned)cy < (unsigned)H) {
+                if ((unsigned)cx < (unsigned)W) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
+            } else if (!striped) {
+                err = 1;  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
+            }
             float t1;
             const bool done = w.advance(t1);
             const int ty = w.y >> 3;
             if (ty != prev_ty) {  // rasterizer.rs:123-131
                 const int tiy = min(ty, prev_ty) - gy0, tix = (w.x >> 3) - gx0;
-                if ((unsigned)tix < (unsigned)W && (unsigned)tiy < (unsigned)H) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16);
-                else err = 1;
+                if ((unsigned)tiy < (unsigned)H) {
+                    if ((unsigned)tix < (unsigned)W) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16); else err = 1;
+                } else if (!striped) {
+                    err = 1;
+                }
                 prev_ty = ty;
             }
             if (done) break;
@@ -422,8 +432,8 @@ struct PkScan {
 
 // Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells),
 // S.u.cell = CF_* flags of every cell.
-__device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, PkScan& sc, uint32_t& n_touched,
-                                             uint32_t& n_spans, uint32_t& bad) {
+__device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, int wcarry, PkScan& sc, uint32_t& n_touched,
+                                             uint32_t& n_spans, int& wtotal, uint32_t& bad) {
     const uint32_t ncells = (uint32_t)(W * H);
     uint32_t* cell = S.u.cell;
     // every thread owns a contiguous run of cells -- whole 32-cell words, or a power-of-two fraction of
@@ -444,7 +454,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
     block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
     {
         uint32_t r = ex_t, word = 0;
-        int wp = (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
+        int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
         for (uint32_t c = sc.c0; c < sc.c1; ++c) {
             if ((c & 31u) == 0) S.wbase[c >> 5] = (uint16_t)r;
             const uint32_t w = cell[c];
@@ -464,6 +474,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         }
     }
     n_touched = tot_t;
+    wtotal = wcarry + (int)tot_w;
     if (threadIdx.x == 0 && (ncells & 31u) == 0) S.wbase[ncells >> 5] = (uint16_t)tot_t;  // rank(ncells) reads one word past the last cell
     __syncthreads();
     // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
@@ -527,6 +538,10 @@ __device__ __forceinline__ int pk_band_of(const PkShared& S, int nb, int r) {
     return lo;
 }
 
+// STRIPED = false: the lean instantiation every path goes through first; a path whose bounding grid or line count
+// exceeds one pass is left on the hand-over list.  STRIPED = true: the same kernel with the stripe machinery, run
+// over that list (A.path_list); what it cannot take either goes to the general pipeline.
+template <bool STRIPED>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelArgs A) {
     extern __shared__ __align__(16) unsigned char pk_smem_raw[];
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
@@ -547,8 +562,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         }
         if (tid < PK_NCLS) S.bcur[tid] = 0;  // lines per step-count class
         __syncthreads();
-        const uint32_t p = S.path;
-        if (p >= A.n_paths) return;
+        if (S.path >= A.n_paths) return;
+        const uint32_t p = A.path_list ? A.path_list[S.path] : S.path;
 
         const uint32_t c0 = A.cmd_off[p] - A.cmd_base, c1 = A.cmd_off[p + 1] - A.cmd_base;
         const uint32_t nc = c1 - c0, nv = nc + 1;  // + the virtual FINISH command (finish()'s auto-close)
@@ -597,7 +612,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             }
             uint32_t total;
             const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);
-            if (n_lines + total > PK_MAXLINES) fallback = true;
+            if (n_lines + total > PK_LINECAP - 1) fallback = true;
             if (my_n && !fallback) {
                 if (my_tag == TAG_QUAD || my_tag == TAG_CUBIC) {
                     S.u.v.last[tid] = c.last;
@@ -676,16 +691,79 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         }
         __syncthreads();
 
-        // ---- 2. the bounding grid; lines bucketed by step-count class --------------------------------
+        // ---- 2. the bounding grid and its stripes ---------------------------------------------------------
         const bool empty = !fallback && (S.bbox[0] > S.bbox[2]);  // no line with two distinct end points
         // one tile of margin: the DDA may overshoot its end pixel by one before the end snap
         const int gx0 = S.bbox[0] - 1, gy0 = S.bbox[1] - 1;
         const int W = empty ? 1 : S.bbox[2] - S.bbox[0] + 3, H = empty ? 1 : S.bbox[3] - S.bbox[1] + 3;
-        if (!fallback && !empty && (long long)W * H > PK_CELLS) fallback = true;
         const bool walk = !fallback && !empty;
-        uint32_t n_sorted = 0;
+        uint32_t nstripes = 1;
         if (walk) {
-            uint32_t cbase[PK_NCLS];
+            uint32_t n_nd = 0;  // lines with two distinct end points (counted per class while flattening)
+#pragma unroll
+            for (int k = 0; k < PK_NCLS; ++k) n_nd += S.bcur[k];
+            if (!STRIPED && ((long long)W * H > PK_CELLS || n_nd > PK_MAXLINES)) {
+                fallback = true;
+            } else if ((long long)W * H > PK_CELLS || n_nd > PK_MAXLINES) {
+                // The grid or the line count exceeds one pass: cut the grid into stripes of whole tile rows, each
+                // with at most PK_CELLS cells and PK_MAXLINES lines (a line counts in every row it may touch).
+                if (W > PK_CELLS || H > PK_CELLS) {
+                    fallback = true;
+                } else {
+                    __syncthreads();
+                    for (uint32_t i = tid; i < (uint32_t)H; i += PK_THREADS) S.u.cell[i] = 0;
+                    __syncthreads();
+                    for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                        const uint32_t info = pk_ld(&G.info[i], pk_pol);
+                        if (info == PK_INFO_NONE) continue;
+                        const int lo = max(pk_info_lo(info) - gy0, 0), hi = min(pk_info_hi(info) - gy0, H - 1);
+                        for (int r = lo; r <= hi; ++r) atomicAdd(&S.u.cell[r], 1u);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        uint32_t ns = 0, f = 0;
+                        int r = 0;
+                        while (r < H) {
+                            if (ns == PK_MAXSTRIPES) { f = 1; break; }
+                            S.srow[ns++] = (uint16_t)r;
+                            uint32_t lines = 0;
+                            int rows = 0;
+                            while (r < H && (rows + 1) * W <= PK_CELLS && lines + S.u.cell[r] <= PK_MAXLINES) {
+                                lines += S.u.cell[r];
+                                ++rows;
+                                ++r;
+                            }
+                            if (rows == 0) { f = 1; break; }  // one tile row alone is over the budgets
+                        }
+                        S.srow[ns] = (uint16_t)H;
+                        S.nstripes = ns;
+                        S.flag = f;
+                    }
+                    __syncthreads();
+                    nstripes = S.nstripes;
+                    if (S.flag) fallback = true;
+                    __syncthreads();
+                }
+            }
+        }
+
+        // ---- 3. one stripe: bucket its lines by step count, mark, scan, plan the slot bands --------------
+        // Rows [R0, R1) of the grid.  Returns false (uniformly) when a budget is exceeded.
+        auto stripe_setup = [&](int R0, int R1, bool whole, int wcarry, PkScan& sc, uint32_t& nt, uint32_t& ns, int& wtot,
+                                uint32_t& nbands) -> bool {
+            const int Hs = R1 - R0, y0s = gy0 + R0;  // the stripe's rows as absolute tile rows [y0s, y0s + Hs)
+            if (!whole) {  // (for the whole grid the class counts come from the flattening pass)
+                __syncthreads();
+                if (tid < PK_NCLS) S.bcur[tid] = 0;
+                __syncthreads();
+                for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                    const uint32_t info = pk_ld(&G.info[i], pk_pol);
+                    if (info == PK_INFO_NONE || pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs) continue;
+                    atomicAdd(&S.bcur[pk_info_cls(info)], 1u);
+                }
+                __syncthreads();
+            }
+            uint32_t cbase[PK_NCLS], n_sorted = 0;
 #pragma unroll
             for (int k = 0; k < PK_NCLS; ++k) {
                 cbase[k] = n_sorted;
@@ -697,14 +775,16 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 for (uint32_t k = 0; k < tid; ++k) o += S.bcur[k];
                 S.boff[tid] = o;
             }
-            for (uint32_t i = tid; i < (uint32_t)(W * H); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
-            for (uint32_t i = tid; i <= (uint32_t)(W * H) >> 5; i += PK_THREADS) S.bits[i] = 0;
+            for (uint32_t i = tid; i < (uint32_t)(W * Hs); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
+            for (uint32_t i = tid; i <= (uint32_t)(W * Hs) >> 5; i += PK_THREADS) S.bits[i] = 0;
             __syncthreads();
             if (tid < PK_NCLS) S.bcur[tid] = 0;
             __syncthreads();
+            if (n_sorted > PK_MAXLINES) return false;
             for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
                 const uint32_t info = pk_ld(&G.info[i], pk_pol);
                 if (info == PK_INFO_NONE) continue;
+                if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
                 const uint32_t k = pk_info_cls(info);
                 uint32_t base = 0;
 #pragma unroll
@@ -713,48 +793,41 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 pk_st(&G.slines[pos], pk_ld(&G.lines[i], pk_pol), pk_pol);
             }
             __syncthreads();
-        }
-
-        // ---- 3. mark + scan: tiles and spans of the path; slot bands -----------------------------------
-        uint32_t tot_tiles = 0, tot_spans = 0;
-        PkScan sc;
-        sc.c0 = sc.c1 = sc.span_excl = 0;
-        uint32_t nbands = 1;
-        if (walk) {
-            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, gy0, W, H, pk_pol);
+            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
             __syncthreads();
             uint32_t bad;
-            pk_grid_scan(S, W, H, err, sc, tot_tiles, tot_spans, bad);
+            pk_grid_scan(S, W, Hs, err, wcarry, sc, nt, ns, wtot, bad);
             // slot bands: as many whole tile rows as fit PK_SLOTS resident tiles
             if (tid == 0) {
                 uint32_t nb = 0, f = 0;
                 int r = 0;
-                while (r < H) {
+                while (r < Hs) {
                     if (nb == PK_MAXB) { f = 1; break; }
                     S.brow[nb++] = (uint16_t)r;
                     const uint32_t rk0 = pk_rank(S, (uint32_t)(r * W));
                     if (pk_rank(S, (uint32_t)((r + 1) * W)) - rk0 > PK_SLOTS) { f = 1; break; }  // a tile row must fit
                     ++r;
-                    while (r < H && pk_rank(S, (uint32_t)((r + 1) * W)) - rk0 <= PK_SLOTS) ++r;
+                    while (r < Hs && pk_rank(S, (uint32_t)((r + 1) * W)) - rk0 <= PK_SLOTS) ++r;
                 }
-                S.brow[nb] = (uint16_t)H;
+                S.brow[nb] = (uint16_t)Hs;
                 S.nbands = nb;
                 S.flag = f;
             }
             __syncthreads();
             nbands = S.nbands;
-            if (bad || S.flag) fallback = true;
+            if (bad || S.flag) return false;
             // more than one band: bucket the lines again, by (band, class), one copy per band a line touches
-            if (!fallback && nbands > 1) {
+            if (nbands > 1) {
                 const uint32_t nkeys = nbands * PK_NCLS;
                 for (uint32_t k = tid; k < nkeys; k += PK_THREADS) S.bcur[k] = 0;
                 __syncthreads();
                 for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
                     const uint32_t info = pk_ld(&G.info[i], pk_pol);
                     if (info == PK_INFO_NONE) continue;
-                    const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - gy0, 0));
+                    if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
+                    const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - y0s, 0));
                     int b1 = b0;  // lines are short: the last band is the first one or a neighbour
-                    const int rhi = min(pk_info_hi(info) - gy0, H - 1);
+                    const int rhi = min(pk_info_hi(info) - y0s, Hs - 1);
                     while (b1 + 1 < (int)nbands && (int)S.brow[b1 + 1] <= rhi) ++b1;
                     pk_st(&G.rec[i], make_uint2((uint32_t)b0 | ((uint32_t)b1 << 8), 0u), pk_pol);  // (rec is dead after flattening)
                     for (int b = b0; b <= b1; ++b) atomicAdd(&S.bcur[b * PK_NCLS + pk_info_cls(info)], 1u);
@@ -774,109 +847,151 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 }
                 if (tid == 0) S.boff[nkeys] = total;
                 __syncthreads();
-                if (total > PK_SLINECAP) {
-                    fallback = true;
-                } else {
-                    for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                        const uint32_t info = pk_ld(&G.info[i], pk_pol);
-                        if (info == PK_INFO_NONE) continue;
-                        const uint32_t bb01 = pk_ld(&G.rec[i], pk_pol).x;
-                        const int b0 = (int)(bb01 & 0xffu), b1 = (int)(bb01 >> 8);
-                        const float4 L = pk_ld(&G.lines[i], pk_pol);
-                        for (int b = b0; b <= b1; ++b) {
-                            const uint32_t k = b * PK_NCLS + pk_info_cls(info);
-                            pk_st(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L, pk_pol);
-                        }
+                if (total > PK_SLINECAP) return false;
+                for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
+                    const uint32_t info = pk_ld(&G.info[i], pk_pol);
+                    if (info == PK_INFO_NONE) continue;
+                    if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
+                    const uint32_t bb01 = pk_ld(&G.rec[i], pk_pol).x;
+                    const int b0 = (int)(bb01 & 0xffu), b1 = (int)(bb01 >> 8);
+                    const float4 L = pk_ld(&G.lines[i], pk_pol);
+                    for (int b = b0; b <= b1; ++b) {
+                        const uint32_t k = b * PK_NCLS + pk_info_cls(info);
+                        pk_st(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L, pk_pol);
                     }
                 }
                 // (the barrier before the first band's accumulate pass orders these stores)
             }
+            return true;
+        };
+
+        // ---- 5. one stripe: origins + spans, then per slot band: accumulate, carry, quantise, emit -------
+        auto stripe_emit = [&](int R0, const PkScan& sc, uint32_t nbands, uint32_t tile_at, uint32_t span_at) {
+            const int y0s = gy0 + R0;
+            pk_emit_index(S, A, sc, gx0, y0s, W, tile_at, span_at);
+            for (uint32_t b = 0; b < nbands; ++b) {
+                __syncthreads();  // also: the cell flags are dead from here on (the accumulators reuse them)
+                const int r0 = S.brow[b], r1 = S.brow[b + 1];
+                const uint32_t rank0 = pk_rank(S, (uint32_t)(r0 * W));
+                const uint32_t nslots = pk_rank(S, (uint32_t)(r1 * W)) - rank0;
+                if (!nslots) continue;
+                {
+                    uint4* z = reinterpret_cast<uint4*>(S.u.acc);
+                    for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncthreads();
+                pk_accumulate(S.u.acc, S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, y0s, W, y0s + r0, y0s + r1,
+                              rank0, pk_pol);
+                __syncthreads();
+                // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
+                for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
+                    int* d = &S.u.acc[(it >> 3) * PK_ACCW + (it & 7) * 9];
+                    int rs = 0;
+#pragma unroll
+                    for (int x = 0; x < 9; ++x) rs += d[x];
+                    d[8] = rs;
+                }
+                __syncthreads();
+                // row carry: one thread per (tile row, pixel row), left to right over the row's tiles, as an exact
+                // integer sum; the carry into a tile (x256, as f32) replaces its row sum
+                for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
+                    const int r = r0 + (it >> 3), y = it & 7;
+                    const uint32_t s0 = pk_rank(S, (uint32_t)(r * W)) - rank0, s1 = pk_rank(S, (uint32_t)((r + 1) * W)) - rank0;
+                    long long c = 0;
+                    for (uint32_t s = s0; s < s1; ++s) {
+                        int* d = &S.u.acc[s * PK_ACCW + y * 9 + 8];
+                        const int rs = *d;
+                        *d = __float_as_int((float)c * OC_FX_TO_256);
+                        c += rs;
+                    }
+                }
+                __syncthreads();
+                // quantise + emit: one thread per (tile, pixel row) -> one 8-byte store
+                for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
+                    const uint32_t s = it >> 3, y = it & 7;
+                    const int* d = &S.u.acc[s * PK_ACCW + y * 9];
+                    const float c = __int_as_float(d[8]);
+                    int run = 0;
+                    uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        run += d[x];
+                        // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
+                        const uint32_t q = (uint32_t)(int)fminf(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c)), 255.0f);  // (exact product: == mul, add)
+                        if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
+                    }
+                    const uint32_t ti = tile_at + rank0 + s;
+                    __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
+                }
+            }
+        };
+
+        // ---- 4. count, reserve, emit -------------------------------------------------------------------
+        // One stripe: set up once, reserve, emit.  Several: a counting sweep over the stripes, the reservation,
+        // then a second sweep that sets every stripe up again (its grid state was overwritten by the next one)
+        // and emits it.  (One loop nest, so that the set-up and emission code exists once.)
+        uint32_t tot_tiles = 0, tot_spans = 0;
+        uint32_t tile_at = 0, span_at = 0;
+        bool reserved = false, fits = true;
+        auto reserve = [&]() {
+            if (tid == 0) {
+                const uint32_t ts = atomicAdd(A.cursor, tot_tiles);
+                const uint32_t ss = atomicAdd(A.cursor + 1, tot_spans);
+                S.base_tiles = ts;
+                S.base_spans = ss;
+                A.rec[p] = make_uint4(ts, tot_tiles, ss, tot_spans);
+                if (fallback) A.fb_list[atomicAdd(A.status + 1, 1)] = p;
+            }
+            __syncthreads();
+            tile_at = S.base_tiles;  // arena index of this path's first tile
+            span_at = S.base_spans;
+            fits = (uint64_t)tile_at + tot_tiles <= A.cap_tiles && (uint64_t)span_at + tot_spans <= A.cap_spans;
+            if (!fits && !fallback && tid == 0) atomicMax(A.status + 2, 1);
+            reserved = true;
+        };
+        if (walk && !fallback) {
+            const uint32_t sweeps = (!STRIPED || nstripes == 1) ? 1u : 2u;
+            for (uint32_t sweep = 0; sweep < sweeps && !fallback && fits; ++sweep) {
+                const bool emitting = sweep + 1 == sweeps;
+                int wcarry = 0;
+                uint32_t t_at = tile_at, s_at = span_at;
+#pragma unroll 1
+                for (uint32_t st = 0; st < (STRIPED ? nstripes : 1u); ++st) {
+                    const int R0 = (!STRIPED || nstripes == 1) ? 0 : (int)S.srow[st], R1 = (!STRIPED || nstripes == 1) ? H : (int)S.srow[st + 1];
+                    uint32_t nt = 0, ns = 0, nbands = 1;
+                    int wtot = 0;
+                    PkScan sc;
+                    if (!stripe_setup(R0, R1, !STRIPED || nstripes == 1, wcarry, sc, nt, ns, wtot, nbands)) {
+                        fallback = true;  // (only ever in the first sweep)
+                        break;
+                    }
+                    if (sweep == 0) {
+                        tot_tiles += nt;
+                        tot_spans += ns;
+                    }
+                    if (emitting) {
+                        if (!reserved) {  // single stripe: the totals are this stripe's
+                            reserve();
+                            t_at = tile_at;
+                            s_at = span_at;
+                            if (!fits) break;
+                        }
+                        stripe_emit(R0, sc, nbands, t_at, s_at);
+                        t_at += nt;
+                        s_at += ns;
+                    }
+                    wcarry = wtot;
+                }
+                if (!emitting && !fallback) reserve();
+            }
         }
-        if (empty) tot_tiles = 1;  // the empty path's all-zero tile at (0,0), rasterizer.rs:194, :208
-        if (fallback) {
-            tot_tiles = 0;
+        if (!reserved) {  // an empty path, or one left to the general pipeline
+            tot_tiles = (empty && !fallback) ? 1u : 0u;  // the empty path's all-zero tile at (0,0), rasterizer.rs:194, :208
             tot_spans = 0;
-        }
-
-        // ---- 4. reserve the output range ---------------------------------------------------------------
-        if (tid == 0) {
-            const uint32_t ts = atomicAdd(A.cursor, tot_tiles);
-            const uint32_t ss = atomicAdd(A.cursor + 1, tot_spans);
-            S.base_tiles = ts;
-            S.base_spans = ss;
-            A.rec[p] = make_uint4(ts, tot_tiles, ss, tot_spans);
-            if (fallback) A.fb_list[atomicAdd(A.status + 1, 1)] = p;
-        }
-        __syncthreads();
-        if (fallback) continue;
-        const uint32_t tile_at = S.base_tiles;  // arena index of this path's first tile
-        const uint32_t span_at = S.base_spans;
-        const bool fits = (uint64_t)tile_at + tot_tiles <= A.cap_tiles && (uint64_t)span_at + tot_spans <= A.cap_spans;
-        if (!fits) {
-            if (tid == 0) atomicMax(A.status + 2, 1);
-            continue;
-        }
-        if (empty) {
-            if (tid < 16) reinterpret_cast<uint32_t*>(A.alpha + (size_t)tile_at * 64)[tid] = 0u;
-            if (tid == 0) reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at] = 0u;
-            continue;
-        }
-
-        // ---- 5. origins + spans, then per slot band: accumulate, carry, quantise, emit ---------------
-        pk_emit_index(S, A, sc, gx0, gy0, W, tile_at, span_at);
-        for (uint32_t b = 0; b < nbands; ++b) {
-            __syncthreads();  // also: the flags / tcell are dead from here on (the accumulators reuse them)
-            const int r0 = S.brow[b], r1 = S.brow[b + 1];
-            const uint32_t rank0 = pk_rank(S, (uint32_t)(r0 * W));
-            const uint32_t nslots = pk_rank(S, (uint32_t)(r1 * W)) - rank0;
-            if (!nslots) continue;
-            {
-                uint4* z = reinterpret_cast<uint4*>(S.u.acc);
-                for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-            }
-            __syncthreads();
-            pk_accumulate(S.u.acc, S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, gy0, W, gy0 + r0, gy0 + r1,
-                          rank0, pk_pol);
-            __syncthreads();
-            // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
-            for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
-                int* d = &S.u.acc[(it >> 3) * PK_ACCW + (it & 7) * 9];
-                int rs = 0;
-#pragma unroll
-                for (int x = 0; x < 9; ++x) rs += d[x];
-                d[8] = rs;
-            }
-            __syncthreads();
-            // row carry: one thread per (tile row, pixel row), left to right over the row's tiles, as an exact
-            // integer sum; the carry into a tile (x256, as f32) replaces its row sum
-            for (int it = tid; it < (r1 - r0) * 8; it += PK_THREADS) {
-                const int r = r0 + (it >> 3), y = it & 7;
-                const uint32_t s0 = pk_rank(S, (uint32_t)(r * W)) - rank0, s1 = pk_rank(S, (uint32_t)((r + 1) * W)) - rank0;
-                long long c = 0;
-                for (uint32_t s = s0; s < s1; ++s) {
-                    int* d = &S.u.acc[s * PK_ACCW + y * 9 + 8];
-                    const int rs = *d;
-                    *d = __float_as_int((float)c * OC_FX_TO_256);
-                    c += rs;
-                }
-            }
-            __syncthreads();
-            // quantise + emit: one thread per (tile, pixel row) -> one 8-byte store
-            for (uint32_t it = tid; it < nslots * 8; it += PK_THREADS) {
-                const uint32_t s = it >> 3, y = it & 7;
-                const int* d = &S.u.acc[s * PK_ACCW + y * 9];
-                const float c = __int_as_float(d[8]);
-                int run = 0;
-                uint32_t lo32 = 0, hi32 = 0;
-#pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    run += d[x];
-                    // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
-                    const uint32_t q = (uint32_t)(int)fminf(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c)), 255.0f);  // (exact product: == mul, add)
-                    if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
-                }
-                const uint32_t ti = tile_at + rank0 + s;
-                __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
+            reserve();
+            if (empty && !fallback && fits) {
+                if (tid < 16) reinterpret_cast<uint32_t*>(A.alpha + (size_t)tile_at * 64)[tid] = 0u;
+                if (tid == 0) reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at] = 0u;
             }
         }
     }

@@ -587,7 +587,7 @@ struct ochre_b200_ctx {
     int mode = OCHRE_MODE_AUTO;
     int band_lo = OC_BAND_MIN, band_hi = OC_BAND_MAX;  // tile rows rasterised (row-band sharding)
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb;
+    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2;
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
     // atlas / quad builder (csrc/atlas.cuh)
     DevBuf a_vtx, a_idx, a_atlas, a_span_tile, a_flag, a_sb, a_colors;
@@ -911,9 +911,10 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.spans = ctx->s_spans.as<OchreSpan>();
         A.scratch = ctx->d_pk_scratch.as<unsigned char>();
         A.fb_list = ctx->d_pk_fb.as<uint32_t>();
+        A.path_list = nullptr;
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
         CK(cudaEventRecord(ctx->ev[0], st));
-        k_path<<<grid, PK_THREADS, PK_SMEM, st>>>(A);
+        k_path<false><<<grid, PK_THREADS, PK_SMEM, st>>>(A);
         CK(cudaEventRecord(ctx->ev[1], st));
         CK(cudaMemcpyAsync(h_ctl, ctl, PKC_WORDS * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -930,6 +931,29 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
                 default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
             }
         }
+        // second stage: the paths the lean instantiation left over (bounding grid or line count beyond one pass)
+        // go through the striped instantiation; what that cannot take either goes to the general pipeline
+        const uint32_t* d_fb_final = ctx->d_pk_fb.as<uint32_t>();
+        if (stt[1] > 0 && !stt[2]) {
+            const uint32_t n1 = (uint32_t)stt[1];
+            CK(ctx->d_pk_fb2.ensure((size_t)n1 * 4 + 4));
+            CK(cudaMemsetAsync(ctl + PKC_TICKET, 0, 4, st));
+            CK(cudaMemsetAsync(ctl + PKC_STATUS + 1, 0, 4, st));
+            PathKernelArgs B = A;
+            B.n_paths = n1;
+            B.path_list = ctx->d_pk_fb.as<uint32_t>();
+            B.fb_list = ctx->d_pk_fb2.as<uint32_t>();
+            CK(cudaEventRecord(ctx->ev[0], st));
+            k_path<true><<<(uint32_t)std::min<uint64_t>(n1, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM), PK_THREADS, PK_SMEM, st>>>(B);
+            CK(cudaEventRecord(ctx->ev[1], st));
+            CK(cudaMemcpyAsync(h_ctl, ctl, PKC_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+            co->ms[0] += ms;
+            co->launches += 1;
+            d_fb_final = ctx->d_pk_fb2.as<uint32_t>();
+        }
         uint32_t nt = h_ctl[PKC_CURSOR], ns = h_ctl[PKC_CURSOR + 1];  // arena cursors (absolute)
         const uint32_t n_fb = (uint32_t)stt[1];
         if (n_fb && ctx->mode == OCHRE_MODE_FUSED) return RC_NEED_GENERAL;
@@ -945,7 +969,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         if (n_fb) {
             // ---- hand-over: the general pipeline rasterises the paths that exceed the on-chip budgets ----
             std::vector<uint32_t> fb(n_fb), sub_off((size_t)n_fb + 1);
-            CK(cudaMemcpyAsync(fb.data(), ctx->d_pk_fb.p, (size_t)n_fb * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(fb.data(), d_fb_final, (size_t)n_fb * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             std::sort(fb.begin(), fb.end());
             uint64_t acc = 0;
@@ -1068,7 +1092,8 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     }
     e = cudaFuncSetAttribute(k_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = ctx->d_pk_ctl.ensure(64);
     if (e == cudaSuccess) e = ctx->h_pk_ctl.ensure(64);
@@ -1094,7 +1119,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();
