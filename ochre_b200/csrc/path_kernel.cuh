@@ -301,7 +301,8 @@ __device__ __forceinline__ uint32_t pk_line_info(V2 a, V2 b, PkBBox& bb) {
 }
 __device__ __forceinline__ int pk_info_lo(uint32_t f) { return (int)(f & 0x1fffu) - 4096; }
 __device__ __forceinline__ int pk_info_hi(uint32_t f) { return (int)((f >> 13) & 0x1fffu) - 4096; }
-__device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return (f >> 26) & 7u; }
+// bucket of a line: its step-count class, longest first (the short lines fill the tail of a pass)
+__device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return 7u - ((f >> 26) & 7u); }
 
 // Conic commands (path.rs:75-104) are rare: their subdivision runs in the command's own thread, out of line
 // so that its stack of pending intervals does not weigh on the common path.
