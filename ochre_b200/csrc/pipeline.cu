@@ -429,20 +429,42 @@ k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals,
 // Fused path, stage 5b: copy each path's tiles / spans from the staging arena (completion order)
 // into the result arena in path order.  One warp per path, 16-byte words.
 // ---------------------------------------------------------------------------
+constexpr uint32_t GATHER_BIG = 4096;  // tiles (or spans) beyond which a path is copied by the whole grid
+
 __global__ void __launch_bounds__(TPB)
 k_gather_paths(const uint4* __restrict__ rec, uint32_t n_paths, const uint32_t* __restrict__ tile_off,
                const uint32_t* __restrict__ span_off, const uint4* __restrict__ st_alpha, const uint32_t* __restrict__ st_xy,
                const uint2* __restrict__ st_spans, uint4* __restrict__ alpha, uint32_t* __restrict__ xy,
-               uint2* __restrict__ spans) {
+               uint2* __restrict__ spans, uint32_t* __restrict__ big /* [0] count, [1..] paths */) {
     const uint32_t p = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (p >= n_paths) return;
     const uint4 r = rec[p];
+    if (r.y > GATHER_BIG || r.w > GATHER_BIG) {  // a giant path: left to k_gather_big
+        if (lane == 0) big[1 + atomicAdd(big, 1u)] = p;
+        return;
+    }
     const size_t src_t = r.x, dst_t = tile_off[p], src_s = r.z, dst_s = span_off[p];
     for (uint32_t i = lane; i < r.y * 4; i += 32) alpha[dst_t * 4 + i] = st_alpha[src_t * 4 + i];
     for (uint32_t i = lane; i < r.y; i += 32) xy[dst_t + i] = st_xy[src_t + i];
     for (uint32_t i = lane; i < r.w; i += 32) spans[dst_s + i] = st_spans[src_s + i];
 }
 
+// the giant paths: every one is copied by the whole grid
+__global__ void __launch_bounds__(TPB)
+k_gather_big(const uint4* __restrict__ rec, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ span_off,
+             const uint4* __restrict__ st_alpha, const uint32_t* __restrict__ st_xy, const uint2* __restrict__ st_spans,
+             uint4* __restrict__ alpha, uint32_t* __restrict__ xy, uint2* __restrict__ spans, const uint32_t* __restrict__ big) {
+    const uint32_t n_big = big[0];
+    const size_t tid = (size_t)blockIdx.x * TPB + threadIdx.x, nth = (size_t)gridDim.x * TPB;
+    for (uint32_t b = 0; b < n_big; ++b) {
+        const uint32_t p = big[1 + b];
+        const uint4 r = rec[p];
+        const size_t src_t = r.x, dst_t = tile_off[p], src_s = r.z, dst_s = span_off[p];
+        for (size_t i = tid; i < (size_t)r.y * 4; i += nth) alpha[dst_t * 4 + i] = st_alpha[src_t * 4 + i];
+        for (size_t i = tid; i < r.y; i += nth) xy[dst_t + i] = st_xy[src_t + i];
+        for (size_t i = tid; i < r.w; i += nth) spans[dst_s + i] = st_spans[src_s + i];
+    }
+}
 
 // ---------------------------------------------------------------------------
 // Fused path, hand-over: the paths the fused kernel left to the general pipeline are compacted
@@ -564,6 +586,7 @@ struct ochre_b200_ctx {
     cudaStream_t st_out = nullptr;   // device -> host result download, chunk by chunk behind the kernels
     std::vector<cudaEvent_t> ev_in;
     cudaEvent_t ev_out[2] = {};
+    cudaEvent_t ev_g[2] = {};  // gather stage of the fused path
     std::string err;
     uint32_t chunk_vcmds = DEFAULT_CHUNK_VCMDS;
     // inputs
@@ -587,7 +610,7 @@ struct ochre_b200_ctx {
     int mode = OCHRE_MODE_AUTO;
     int band_lo = OC_BAND_MIN, band_hi = OC_BAND_MAX;  // tile rows rasterised (row-band sharding)
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2;
+    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2, d_big;
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
     // atlas / quad builder (csrc/atlas.cuh)
     DevBuf a_vtx, a_idx, a_atlas, a_span_tile, a_flag, a_sb, a_colors;
@@ -1030,6 +1053,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             return 0;
         }
         // path order: offsets by exclusive scan of the per-path counts, then the gather copy
+        CK(cudaEventRecord(ctx->ev_g[0], st));
         CK(ctx->o_tile_xy.ensure(((size_t)tile_base + nt + 1) * 4, true, st));
         CK(ctx->o_alpha.ensure(((size_t)tile_base + nt + 1) * 64, true, st));
         CK(ctx->o_spans.ensure(((size_t)span_base + ns + 1) * sizeof(OchreSpan), true, st));
@@ -1043,14 +1067,19 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             st, n_paths, [rec] __device__(uint32_t i) { return rec[i].w; },
             [soff, span_base] __device__(uint32_t i, uint32_t excl, uint32_t) { soff[i] = span_base + excl; },
             ctx->d_scan_ws.as<uint32_t>(), nullptr);
+        CK(ctx->d_big.ensure(((size_t)n_paths + 1) * 4));
+        CK(cudaMemsetAsync(ctx->d_big.p, 0, 4, st));
         k_gather_paths<<<nblk((uint64_t)n_paths * 32, TPB), TPB, 0, st>>>(
             rec, n_paths, toff, soff, ctx->s_alpha.as<uint4>(), ctx->s_tile_xy.as<uint32_t>(), ctx->s_spans.as<uint2>(),
-            ctx->o_alpha.as<uint4>(), ctx->o_tile_xy.as<uint32_t>(), ctx->o_spans.as<uint2>());
-        co->launches += 1;
-        CK(cudaEventRecord(ctx->ev[2], st));
+            ctx->o_alpha.as<uint4>(), ctx->o_tile_xy.as<uint32_t>(), ctx->o_spans.as<uint2>(), ctx->d_big.as<uint32_t>());
+        k_gather_big<<<ctx->sm_count * 4, TPB, 0, st>>>(rec, toff, soff, ctx->s_alpha.as<uint4>(), ctx->s_tile_xy.as<uint32_t>(),
+                                                       ctx->s_spans.as<uint2>(), ctx->o_alpha.as<uint4>(), ctx->o_tile_xy.as<uint32_t>(),
+                                                       ctx->o_spans.as<uint2>(), ctx->d_big.as<uint32_t>());
+        co->launches += 2;
+        CK(cudaEventRecord(ctx->ev_g[1], st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
-        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev_g[0], ctx->ev_g[1]));
         co->ms[6] += ms;
         co->n_tiles = nt;
         co->n_spans = ns;
@@ -1083,6 +1112,8 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[1]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_g[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_g[1]);
     if (e != cudaSuccess) { delete ctx; return (int)e; }
     ctx->o_tile_xy.guard = ctx->o_alpha.guard = ctx->o_spans.guard = ctx->o_tile_off.guard = ctx->o_span_off.guard = ctx->st_out;
     ctx->s_tile_xy.guard = ctx->s_alpha.guard = ctx->s_spans.guard = ctx->d_pk_rec.guard = ctx->st_out;
@@ -1113,13 +1144,15 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_out)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_g)
+        if (e) cudaEventDestroy(e);
     if (ctx->st_in) cudaStreamDestroy(ctx->st_in);
     if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
     DevBuf* db[] = {&ctx->d_cmds, &ctx->d_cmd_off, &ctx->d_xf, &ctx->d_vpath, &ctx->d_line_off, &ctx->d_rec_off,
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
     for (DevBuf* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
     for (HostBuf* b : hb) b->release();

@@ -88,6 +88,32 @@ def test_config4_full_1m_blobs_properties():
         ctx.close()
 
 
+def test_config5a_full_single_16384_path_and_its_row_bands():
+    """BASELINE config 5a at full size: ONE path of 511 concentric rings (131k cubics, 17M pixel increments) on a
+    16384^2 canvas, tile by tile against the oracle; then cut into 8 row bands (what 8 GPUs would each rasterise)."""
+    from ochre_b200 import sharding as S
+
+    cmds, off, xf = W.rings(511, 16.0, 256)
+    ctx = ob.Context(0)
+    try:
+        g = ctx.rasterize(cmds, off, xf)
+        o = O.rasterize_batch(cmds, off.astype(np.uint64), xf, threads=0)
+        stats = assert_batch_parity(g, o, what="G5a full")
+        assert g.n_tiles > 2_000_000 and stats["alpha_mismatch_frac"] < 1e-5
+        rows = g.tile_xy[:, 1] // 8
+        lo, hi = int(rows.min()), int(rows.max()) + 1
+        parts = []
+        for b in S.plan_row_bands(lo, hi, 8, S.band_weights_from_bbox(cmds, xf, lo, hi)):
+            ctx.set_row_band(*b)
+            parts.append(S.Shard.of(ctx.rasterize(cmds, off, xf)))
+        m, w = S.concat_row_bands(parts), S.Shard.of(g)
+        assert max(p.n_tiles for p in parts) < 0.25 * w.n_tiles  # the plan balances by boundary length, not by rows
+        assert np.array_equal(m.tile_off, w.tile_off) and np.array_equal(m.tile_xy, w.tile_xy)
+        assert np.array_equal(m.alpha, w.alpha) and m.spans.tobytes() == w.spans.tobytes()
+    finally:
+        ctx.close()
+
+
 def test_batch_order_does_not_change_a_path():
     """Paths are independent (rasterizer.rs:40-46): reversing the batch reverses the result, nothing else."""
     n = 20_000
