@@ -30,6 +30,7 @@
 // scheduling; tests/emu reproduces the arithmetic byte for byte.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/ochre_b200.h"
@@ -341,12 +342,20 @@ __device__ __noinline__ void pk_conic_emit(const PkScratch& G, uint32_t* ccnt, P
     conic_for_each_point(last, control, point, weight, OC_CONIC_TOL, em);
 }
 
+// Shared-memory reductions on a 32-bit shared-window address (computed once per pass): the generic-pointer
+// form makes the compiler rebuild the window base (S2UR + ULEA) at every atomic of the DDA loops.
+__device__ __forceinline__ uint32_t pk_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pk_red_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
-__device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
+__device__ __forceinline__ uint32_t pk_mark(uint32_t cell_s /* shared-window address of the cells */, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
                                             bool striped, uint64_t pk_pol) {
     uint32_t err = 0;
     uint32_t pos = threadIdx.x;
+    asm volatile("" : "+r"(cell_s));  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     if (pos < n) Ln = pk_ld(&sl[pos], pk_pol);
     // (the trip count is warp-uniform: bounded by the warp's first lane)
@@ -361,7 +370,7 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
         for (;;) {
             const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0;
             if ((unsigned)cy < (unsigned)H) {
-                if ((unsigned)cx < (unsigned)W) atomicAdd(&cell[cy * W + cx], 1u); else err = 1;
+                if ((unsigned)cx < (unsigned)W) pk_red_add(cell_s + 4u * (uint32_t)(cy * W + cx), 1u); else err = 1;
             } else if (!striped) {
                 err = 1;  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
             }
@@ -371,7 +380,7 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
             if (ty != prev_ty) {  // rasterizer.rs:123-131
                 const int tiy = min(ty, prev_ty) - gy0, tix = (w.x >> 3) - gx0;
                 if ((unsigned)tiy < (unsigned)H) {
-                    if ((unsigned)tix < (unsigned)W) atomicAdd(&cell[tiy * W + tix], (uint32_t)(ty - prev_ty) << 16); else err = 1;
+                    if ((unsigned)tix < (unsigned)W) pk_red_add(cell_s + 4u * (uint32_t)(tiy * W + tix), (uint32_t)(ty - prev_ty) << 16); else err = 1;
                 } else if (!striped) {
                     err = 1;
                 }
@@ -385,9 +394,10 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t* cell, const float4* __rest
 
 // Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
 // tile rows; slot = rank - rank0.
-__device__ __forceinline__ void pk_accumulate(int* acc, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
+__device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window address of the accumulators */, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
                                               int gx0, int gy0, int W, int R0, int R1, uint32_t rank0, uint64_t pk_pol) {
     uint32_t pos = p0 + threadIdx.x;
+    asm volatile("" : "+r"(acc_s));
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     if (pos < p1) Ln = pk_ld(&sl[pos], pk_pol);
     for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
@@ -411,10 +421,10 @@ __device__ __forceinline__ void pk_accumulate(int* acc, const PkShared& S, const
             const int ry = y0 >> 3;
             if (ry >= R0 && ry < R1) {
                 const uint32_t slot = pk_rank(S, (uint32_t)((ry - gy0) * W + ((x0 >> 3) - gx0))) - rank0;
-                int* d = &acc[slot * PK_ACCW + (y0 & 7) * 9 + (x0 & 7)];
+                const uint32_t d = acc_s + 4u * (slot * PK_ACCW + (uint32_t)((y0 & 7) * 9 + (x0 & 7)));
                 const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
-                atomicAdd(d, qa);
-                atomicAdd(d + 1, qh - qa);
+                pk_red_add(d, (uint32_t)qa);
+                pk_red_add(d + 4u, (uint32_t)(qh - qa));
             } else if ((w.y_dir > 0) ? (ry >= R1) : (ry < R0)) {
                 break;  // the walk is monotone in y: it has left the band for good
             }
@@ -546,6 +556,7 @@ template <bool STRIPED>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelArgs A) {
     extern __shared__ __align__(16) unsigned char pk_smem_raw[];
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
+    const uint32_t smem_s = pk_saddr(pk_smem_raw);  // shared-window address of S (for the DDA loops' reductions)
     const uint32_t tid = threadIdx.x;
     const PkScratch G(A.scratch + (size_t)blockIdx.x * PK_SCR_BYTES);
     PK_POLICY_DECL
@@ -794,7 +805,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 pk_st(&G.slines[pos], pk_ld(&G.lines[i], pk_pol), pk_pol);
             }
             __syncthreads();
-            const uint32_t err = pk_mark(S.u.cell, G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
+            const uint32_t err = pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
             __syncthreads();
             uint32_t bad;
             pk_grid_scan(S, W, Hs, err, wcarry, sc, nt, ns, wtot, bad);
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 __syncthreads();
-                pk_accumulate(S.u.acc, S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, y0s, W, y0s + r0, y0s + r1,
+                pk_accumulate(smem_s + (uint32_t)offsetof(PkShared, u), S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, y0s, W, y0s + r0, y0s + r1,
                               rank0, pk_pol);
                 __syncthreads();
                 // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
