@@ -397,7 +397,9 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t cell_s /* shared-window add
 __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window address of the accumulators */, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
                                               int gx0, int gy0, int W, int R0, int R1, uint32_t rank0, uint64_t pk_pol) {
     uint32_t pos = p0 + threadIdx.x;
-    asm volatile("" : "+r"(acc_s));
+    uint32_t bits_s = acc_s + (uint32_t)(offsetof(PkShared, bits) - offsetof(PkShared, u));
+    uint32_t wbase_s = acc_s + (uint32_t)(offsetof(PkShared, wbase) - offsetof(PkShared, u));
+    asm volatile("" : "+r"(acc_s), "+r"(bits_s), "+r"(wbase_s));
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     if (pos < p1) Ln = pk_ld(&sl[pos], pk_pol);
     for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
@@ -420,7 +422,12 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
             const float area = 0.5f * height * ((right - p0x) + (right - p1x));
             const int ry = y0 >> 3;
             if (ry >= R0 && ry < R1) {
-                const uint32_t slot = pk_rank(S, (uint32_t)((ry - gy0) * W + ((x0 >> 3) - gx0))) - rank0;
+                // slot = rank(cell) - rank0, the rank structure read through its shared-window address
+                const uint32_t cidx = (uint32_t)((ry - gy0) * W + ((x0 >> 3) - gx0));
+                uint32_t wbits, wb;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wbits) : "r"(bits_s + 4u * (cidx >> 5)));
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(wb) : "r"(wbase_s + 2u * (cidx >> 5)));
+                const uint32_t slot = wb + (uint32_t)__popc(wbits & ((1u << (cidx & 31u)) - 1u)) - rank0;
                 const uint32_t d = acc_s + 4u * (slot * PK_ACCW + (uint32_t)((y0 & 7) * 9 + (x0 & 7)));
                 const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
                 pk_red_add(d, (uint32_t)qa);
