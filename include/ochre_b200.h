@@ -115,6 +115,15 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx);
 int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
                          uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out);
 
+/* Rasterizer::fill / Rasterizer::stroke + finish for n_paths paints (src/rasterizer.rs:161-165, :169-171).
+ * stroke_width[p] > 0: paint p is `stroke(path, stroke_width[p], xf[p])` -- flatten(path, 0.1) in untransformed
+ * space (src/path.rs:114-144), stroke(polygon, width) (src/path.rs:152-274), then fill -- all on the device;
+ * otherwise paint p is `fill(path, xf[p])`.  stroke_width == NULL: every paint is a fill.  With OCHRE_IN_DEVICE
+ * stroke_width is a device pointer too.  Result as ochre_b200_rasterize; n_cmds counts the commands handed to fill. */
+int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
+                                const float* stroke_width, uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host,
+                                OchreResult* out);
+
 /* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default. */
 int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
 
@@ -183,6 +192,10 @@ void ochre_b200_free(void* p);
  * records: sorted (key, val) pairs of stage 2 (layout documented in csrc/raster_core.cuh). */
 int ochre_b200_debug_lines(ochre_b200_ctx* ctx, float* out, uint64_t cap, uint64_t* n);
 int ochre_b200_debug_records(ochre_b200_ctx* ctx, uint64_t* keys, uint64_t* vals, uint64_t cap, uint64_t* n);
+
+/* The batch the device stroker handed to the rasteriser in the last ochre_b200_rasterize_paints call that had a
+ * stroke_width array: *n commands (copied to cmds up to cap; cmds may be NULL to query *n), cmd_off[n_paths + 1]. */
+int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, uint64_t* n, uint32_t* cmd_off);
 
 /* Version string of the library ("ochre_b200 <semver> sm_100a"). */
 const char* ochre_b200_version(void);

@@ -20,10 +20,10 @@ ERRORS = {
 
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
-    "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_set_chunk", "ochre_b200_set_mode",
+    "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_rasterize_paints", "ochre_b200_set_chunk", "ochre_b200_set_mode",
     "ochre_b200_set_row_band", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
-    "ochre_b200_debug_records", "ochre_b200_version",
+    "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_version",
 ]
 
 
@@ -69,6 +69,7 @@ def load():
     L.ochre_b200_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.ochre_b200_destroy.argtypes = [vp]
     L.ochre_b200_rasterize.argtypes = [vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
+    L.ochre_b200_rasterize_paints.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
     L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
     L.ochre_b200_set_row_band.argtypes = [vp, C.c_int32, C.c_int32]
@@ -81,6 +82,7 @@ def load():
     L.ochre_b200_free.restype = None
     L.ochre_b200_debug_lines.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.ochre_b200_debug_records.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.ochre_b200_debug_stroked.argtypes = [vp, vp, u64, C.POINTER(u64), vp]
     L.ochre_b200_version.restype = C.c_char_p
     for f in SYMBOLS:
         getattr(L, f)  # AttributeError here = the library does not export what the header declares

@@ -186,6 +186,25 @@ class Context:
         _check(self._h, rc)
         return self._wrap(res, n_paths, out_device, copy)
 
+    def rasterize_paints(self, cmds, cmd_off, xf, stroke_width, out_device: bool = False, copy: bool = True,
+                         unordered: bool = False) -> BatchResult:
+        """fill / stroke + finish of a batch of paints (rasterizer.rs:161-171): stroke_width[p] > 0 makes paint p
+        `Rasterizer::stroke(path, stroke_width[p], xf[p])`, flattened and offset on the device; others are fills."""
+        L = _lib.load()
+        cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
+        cmd_off = np.ascontiguousarray(cmd_off, dtype=np.uint32)
+        n_paths = len(cmd_off) - 1
+        xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n_paths, 6) if n_paths else np.zeros((0, 6), np.float32)
+        sw = np.ascontiguousarray(stroke_width, dtype=np.float32)
+        if sw.shape != (n_paths,):
+            raise ValueError("stroke_width needs one entry per path")
+        res = _lib.OchreResult()
+        flags = (_lib.OCHRE_OUT_DEVICE if out_device else 0) | (_lib.OCHRE_OUT_UNORDERED if unordered else 0)
+        rc = L.ochre_b200_rasterize_paints(self._h, cmds.ctypes.data, cmd_off.ctypes.data, xf.ctypes.data, sw.ctypes.data, n_paths,
+                                           flags, None, C.byref(res))
+        _check(self._h, rc)
+        return self._wrap(res, n_paths, out_device, copy)
+
     def rasterize_ptrs(self, cmds_ptr: int, cmd_off_ptr: int, xf_ptr: int, n_paths: int, cmd_off_host: np.ndarray,
                        in_device: bool, out_device: bool, copy: bool = False, unordered: bool = False) -> BatchResult:
         """Raw-pointer form (pinned host buffers or device buffers), used by bench.py."""
@@ -224,6 +243,16 @@ class Context:
         alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64))
         spans = view(res.spans, ns * 8, SPAN_DTYPE, (ns,))
         return BatchResult(tile_off, span_off, tile_xy, alpha, spans, ranges=ranges, **common)
+
+    def debug_stroked(self, n_paths: int):
+        """(cmds, cmd_off) of the batch the device stroker produced in the last `rasterize_paints` call."""
+        L = _lib.load()
+        n = C.c_uint64()
+        off = np.zeros(n_paths + 1, np.uint32)
+        _check(self._h, L.ochre_b200_debug_stroked(self._h, None, 0, C.byref(n), off.ctypes.data))
+        cmds = np.zeros(int(n.value), CMD_DTYPE)
+        _check(self._h, L.ochre_b200_debug_stroked(self._h, cmds.ctypes.data, len(cmds), C.byref(n), None))
+        return cmds, off
 
     def debug_lines(self) -> np.ndarray:
         L = _lib.load()

@@ -30,19 +30,15 @@
 #include "radix_sort.cuh"
 #include "raster_core.cuh"
 #include "scan.cuh"
+#include "stroke_kernels.cuh"
 
 using namespace oc;
-
-// host-side path utilities (host_path.cpp)
-int oc_host_has_conic(const OchreCmd* cmds, uint64_t n);
-int oc_host_preflatten_conics(const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf, uint32_t n_paths,
-                              std::vector<OchreCmd>& out_cmds, std::vector<uint32_t>& out_off);
 
 namespace {
 
 constexpr int TPB = 256;  // threads per block of the per-command kernels
 
-enum { ST_OK = 0, ST_BAD_COORD = 1, ST_BAD_TAG = 2, ST_CONIC = 3 };
+enum { ST_OK = 0, ST_BAD_COORD = 1, ST_BAD_TAG = 2 };
 
 // ---------------------------------------------------------------------------
 // Stage 1a: lines per virtual command
@@ -71,16 +67,12 @@ k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_o
     vpath[v] = p;
     if (j < c1 - c0) {
         uint32_t tag = pc[j].tag;
-        if (tag == TAG_CONIC) {
-            atomicMax(status, (int)ST_CONIC);
-        } else if (tag > TAG_LINE_ABS) {
-            atomicMax(status, (int)ST_BAD_TAG);
-        }
+        if (tag > TAG_LINE_ABS) atomicMax(status, (int)ST_BAD_TAG);
         int np = cmd_npts(tag);
         bool ok = true;
         for (int i = 0; i < np; ++i) ok = ok && coord_ok(cmd_point(pc[j], i, m));
         if (!ok) atomicMax(status, (int)ST_BAD_COORD);
-        if (!ok || tag == TAG_CONIC || tag > TAG_LINE_ABS) {
+        if (!ok || tag > TAG_LINE_ABS) {
             nlines[v] = 0;
             return;
         }
@@ -622,6 +614,10 @@ struct ochre_b200_ctx {
     uint64_t fb_paths = 0;  // paths the fused kernel left to the general pipeline in the last call  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
     HostBuf h_pk_ctl;
+    // device stroker (csrc/stroke_kernels.cuh): inputs, widths, flattened polygons, the batch handed to the rasteriser
+    DevBuf k_cmds, k_off, k_xf, k_width, k_nflat, k_flat_off, k_flat, k_nout, k_out_off, k_out;
+    HostBuf hk_off;
+    uint32_t k_last_paths = 0;  // paints of the last ochre_b200_rasterize_paints call (0: none)
     uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
     double tiles_per_cmd = 4.0, spans_per_cmd = 0.75;  // arena growth estimates, refined every call
 };
@@ -721,7 +717,6 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     if (h_sc[SC_STATUS] != ST_OK) {
         switch (h_sc[SC_STATUS]) {
             case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
-            case ST_CONIC: ctx->err = "conic"; return 1000;  // RC_CONIC: handled by the caller (host pre-flatten)
             default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
         }
     }
@@ -866,7 +861,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
 // RC_NEED_GENERAL when some path does not fit the kernel's on-chip budgets (the caller then
 // runs the general pipeline for this chunk).
 // ---------------------------------------------------------------------------
-enum { RC_CONIC = 1000, RC_NEED_GENERAL = 1001 };
+enum { RC_NEED_GENERAL = 1001 };
 enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_WORDS = 8 };
 
 int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
@@ -950,7 +945,6 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         if (stt[0] != ST_OK) {
             switch (stt[0]) {
                 case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
-                case ST_CONIC: ctx->err = "conic"; return RC_CONIC;
                 default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
             }
         }
@@ -1152,9 +1146,11 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans};
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
+                    &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_nflat, &ctx->k_flat_off, &ctx->k_flat, &ctx->k_nout,
+                    &ctx->k_out_off, &ctx->k_out};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl};
+    HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1190,7 +1186,7 @@ int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t ti
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 
 static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
-                          uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out, bool allow_conic_retry) {
+                          uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out) {
     ctx->err.clear();
     ctx->dbg_valid = false;
     ctx->used_paths = 0;
@@ -1317,23 +1313,6 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, ot);
             if (rc == 0) ctx->used_paths |= 2u;
         }
-        if (rc == RC_CONIC) {
-            // A Conic reached the device.  Flatten conics on the host (reference path.rs:75-104,
-            // recursive; device recursion is a later row of SURVEY.md section 8f) and run again.
-            CK(cudaStreamSynchronize(ctx->st_in));
-            CK(cudaStreamSynchronize(ctx->st_out));
-            if (!allow_conic_retry || in_dev) {
-                ctx->err = "Conic commands need host-resident inputs (they are flattened on the host)";
-                return OCHRE_E_BAD_TAG;
-            }
-            std::vector<OchreCmd> ncmds;
-            std::vector<uint32_t> noff;
-            if (oc_host_preflatten_conics(cmds, h_off, xf, n_paths, ncmds, noff) != 0) {
-                ctx->err = "conic pre-flatten failed (path too large)";
-                return OCHRE_E_TOO_LARGE;
-            }
-            return rasterize_impl(ctx, ncmds.data(), noff.data(), xf, n_paths, flags, nullptr, out, false);
-        }
         if (rc != 0) {
             cudaStreamSynchronize(ctx->st_in);
             cudaStreamSynchronize(ctx->st_out);
@@ -1447,7 +1426,137 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }
-    return rasterize_impl(ctx, cmds, cmd_off, xf, n_paths, flags, cmd_off_host, out, true);
+    return rasterize_impl(ctx, cmds, cmd_off, xf, n_paths, flags, cmd_off_host, out);
+}
+
+// Rasterizer::fill / Rasterizer::stroke + finish for a batch of paints (src/rasterizer.rs:161-171).  Stroke paints are
+// flattened in untransformed space and offset into fill polygons on the device (csrc/stroke_kernels.cuh), fill paints
+// are copied; the resulting batch goes through rasterize_impl as device-resident input.
+int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
+                                const float* stroke_width, uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host,
+                                OchreResult* out) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    if (!out) {
+        ctx->err = "null result pointer";
+        return OCHRE_E_INVALID_ARG;
+    }
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED)) {
+        ctx->err = "unknown flag bits";
+        return OCHRE_E_INVALID_ARG;
+    }
+    ctx->k_last_paths = 0;
+    if (!stroke_width || n_paths == 0) return rasterize_impl(ctx, cmds, cmd_off, xf, n_paths, flags, cmd_off_host, out);
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->st;
+    const bool in_dev = (flags & OCHRE_IN_DEVICE) != 0;
+    const uint32_t* h_off = in_dev ? cmd_off_host : cmd_off;
+    if (!cmd_off || !xf || !h_off) {
+        ctx->err = "null input pointer";
+        return OCHRE_E_INVALID_ARG;
+    }
+    for (uint32_t p = 0; p < n_paths; ++p) {
+        if (h_off[p + 1] < h_off[p]) {
+            ctx->err = "cmd_off is not monotone";
+            return OCHRE_E_INVALID_ARG;
+        }
+    }
+    const uint32_t base = h_off[0], n_cmds = h_off[n_paths] - base;
+    if (n_cmds && !cmds) {
+        ctx->err = "null cmds";
+        return OCHRE_E_INVALID_ARG;
+    }
+    const Cmd* d_cmds;
+    const uint32_t* d_off;
+    const float* d_width;
+    const OchreTransform* d_xf;
+    if (in_dev) {
+        d_cmds = reinterpret_cast<const Cmd*>(cmds) + base;  // kernels index with (cmd_off - base)
+        d_off = cmd_off;
+        d_width = stroke_width;
+        d_xf = xf;
+    } else {
+        CK(ctx->k_cmds.ensure((size_t)n_cmds * sizeof(OchreCmd) + 16));
+        CK(ctx->k_off.ensure(((size_t)n_paths + 1) * 4));
+        CK(ctx->k_xf.ensure((size_t)n_paths * sizeof(OchreTransform)));
+        CK(ctx->k_width.ensure((size_t)n_paths * 4));
+        if (n_cmds) CK(cudaMemcpyAsync(ctx->k_cmds.p, cmds + base, (size_t)n_cmds * sizeof(OchreCmd), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->k_off.p, h_off, ((size_t)n_paths + 1) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->k_xf.p, xf, (size_t)n_paths * sizeof(OchreTransform), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->k_width.p, stroke_width, (size_t)n_paths * 4, cudaMemcpyHostToDevice, st));
+        d_cmds = ctx->k_cmds.as<Cmd>();
+        d_off = ctx->k_off.as<uint32_t>();
+        d_width = ctx->k_width.as<float>();
+        d_xf = ctx->k_xf.as<OchreTransform>();
+    }
+    CK(ctx->k_nflat.ensure((size_t)n_paths * 4));
+    CK(ctx->k_nout.ensure((size_t)n_paths * 4));
+    CK(ctx->k_flat_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->k_out_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
+    CK(ctx->hk_off.ensure(((size_t)n_paths + 1) * 4));
+    uint32_t* hs = ctx->h_scalars.as<uint32_t>();
+    uint32_t* d_sc = ctx->d_scalars.as<uint32_t>();
+    const uint32_t nb = nblk(n_paths, SK_TPB);
+    CK(cudaMemsetAsync(d_sc, 0, SC_COUNT * sizeof(uint32_t), st));
+    // flatten(path, TOLERANCE) of the stroke paints: count -> offsets -> polygons
+    uint32_t* nflat = ctx->k_nflat.as<uint32_t>();
+    uint32_t* flat_off = ctx->k_flat_off.as<uint32_t>();
+    k_stroke_flat_count<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, nflat, d_sc + SC_STATUS);
+    device_scan(st, n_paths, [nflat] __device__(uint32_t i) { return nflat[i]; },
+                [flat_off] __device__(uint32_t i, uint32_t excl, uint32_t) { flat_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                flat_off + n_paths);
+    CK(cudaMemcpyAsync(hs, d_sc, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hs + 1, flat_off + n_paths, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hs[0] != 0) {
+        ctx->err = "unknown command tag in a stroke paint";
+        return OCHRE_E_BAD_TAG;
+    }
+    const uint32_t n_flat = hs[1];
+    CK(ctx->k_flat.ensure((size_t)n_flat * sizeof(OchreCmd) + 16));
+    k_stroke_flat_emit<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>());
+    // stroke(polygon, width) per stroke paint, the path itself per fill paint: count -> offsets -> commands
+    uint32_t* nout = ctx->k_nout.as<uint32_t>();
+    uint32_t* out_off = ctx->k_out_off.as<uint32_t>();
+    k_stroke_count<<<nb, SK_TPB, 0, st>>>(d_off, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>(), nout);
+    device_scan(st, n_paths, [nout] __device__(uint32_t i) { return nout[i]; },
+                [out_off] __device__(uint32_t i, uint32_t excl, uint32_t) { out_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                out_off + n_paths);
+    CK(cudaMemcpyAsync(ctx->hk_off.p, out_off, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const uint32_t n_out = ctx->hk_off.as<uint32_t>()[n_paths];
+    CK(ctx->k_out.ensure((size_t)n_out * sizeof(OchreCmd) + 16));
+    k_stroke_emit<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>(), out_off,
+                                         ctx->k_out.as<Cmd>());
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    const int rc = rasterize_impl(ctx, ctx->k_out.as<OchreCmd>(), out_off, d_xf, n_paths, flags | OCHRE_IN_DEVICE,
+                                  ctx->hk_off.as<uint32_t>(), out);
+    if (rc == 0) {
+        out->kernel_launches += 10;  // 4 stroker kernels + 2 scans of 3 launches
+        ctx->k_last_paths = n_paths;
+    }
+    return rc;
+}
+
+int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, uint64_t* n, uint32_t* cmd_off) {
+    if (!ctx || !n) return OCHRE_E_INVALID_ARG;
+    if (!ctx->k_last_paths) {
+        ctx->err = "no ochre_b200_rasterize_paints call with strokes on this ctx yet";
+        return OCHRE_E_INVALID_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t* h = ctx->hk_off.as<uint32_t>();
+    *n = h[ctx->k_last_paths];
+    if (cmd_off) memcpy(cmd_off, h, ((size_t)ctx->k_last_paths + 1) * 4);
+    if (cmds) {
+        const uint64_t m = std::min<uint64_t>(cap, *n);
+        if (m) CK(cudaMemcpy(cmds, ctx->k_out.p, m * sizeof(OchreCmd), cudaMemcpyDeviceToHost));
+    }
+    return 0;
 }
 
 int ochre_b200_build_atlas(ochre_b200_ctx* ctx, const uint8_t* colors, uint32_t flags, OchreAtlas* out) {

@@ -493,6 +493,22 @@ struct VCmd {
     uint32_t tag;
     V2 last;   // `self.last` when the command starts
     V2 a, b, c;  // device-space points of the command; for MOVE/FINISH: a = `self.first` (close target)
+    float w;     // Conic weight
+};
+
+struct ConicCountF {
+    uint32_t n;
+    OC_HD void operator()(V2) { ++n; }
+};
+template <class F>
+struct ConicLineF {  // conic_for_each_point -> f(k, prev, next)
+    F* f;
+    V2 prev;
+    uint32_t k;
+    OC_HD void operator()(V2 p) {
+        (*f)(k++, prev, p);
+        prev = p;
+    }
 };
 
 // Decode virtual command j of a path (pc = its commands, nc = their count).
@@ -501,6 +517,7 @@ OC_HD VCmd decode_vcmd(const Cmd* pc, uint32_t nc, uint32_t j, const float* xf) 
     r.tag = (j == nc) ? (uint32_t)TAG_FINISH : pc[j].tag;
     r.last = mk(0.0f, 0.0f);
     r.a = r.b = r.c = mk(0.0f, 0.0f);
+    r.w = (r.tag == TAG_CONIC) ? pc[j].v[4] : 0.0f;
     for (uint32_t i = j; i > 0; --i) {
         if (pc[i - 1].tag != TAG_CLOSE) {  // Close leaves `last` alone, rasterizer.rs:154
             r.last = cmd_endpoint(pc[i - 1], xf);
@@ -532,7 +549,12 @@ OC_HD uint32_t vcmd_line_count(const VCmd& c) {
         case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: return 1;
         case TAG_QUAD: return curve_count(quad_dt(c.last, c.a, c.b));
         case TAG_CUBIC: return curve_count(cubic_dt(c.last, c.a, c.b, c.c));
-        default: return 0;  // Close (and Conic, which the host layer never lets through)
+        case TAG_CONIC: {  // path.rs:75-104, two lines per leaf of the subdivision
+            ConicCountF cnt = {0u};
+            conic_for_each_point(c.last, c.a, c.b, c.w, OC_CONIC_TOL, cnt);
+            return cnt.n;
+        }
+        default: return 0;  // Close
     }
 }
 
@@ -567,6 +589,11 @@ OC_HD void vcmd_for_each_line(const VCmd& c, F& f) {
                 f(k++, prev, p);
                 prev = p;
             }
+            break;
+        }
+        case TAG_CONIC: {
+            ConicLineF<F> cl = {&f, c.last, 0u};
+            conic_for_each_point(c.last, c.a, c.b, c.w, OC_CONIC_TOL, cl);
             break;
         }
         default: break;

@@ -94,6 +94,22 @@ def svg_paints(name: str):
     return cmds, d["cmd_off"].astype(np.uint32), d["xf"].astype(np.float32), d["kind"], d["width"]
 
 
+def svg_paint_batch(name: str, scale: float = 1.0):
+    """Config 2 as a batch for `Context.rasterize_paints`: the source paths of every paint, untouched, plus
+    the per-paint stroke width (0 for fills) and `t.then(Transform::scale(scale))`."""
+    from .geom import Mat2x2, Transform, Vec2
+
+    cmds, off, xf, kind, width = svg_paints(name)
+    xfs = []
+    for i in range(len(off) - 1):
+        t = Transform(Mat2x2.new(*xf[i, :4]), Vec2.new(xf[i, 4], xf[i, 5]))
+        if scale != 1.0:
+            t = t.then(Transform.scale(scale))
+        xfs.append(t.as_row())
+    sw = np.where(kind == 1, width, 0.0).astype(np.float32)
+    return cmds, off, np.asarray(xfs, np.float32).reshape(-1, 6), sw
+
+
 def svg(name: str, scale: float = 1.0, stroker=None):
     """Config 2 as a batch for `Context.rasterize`: one path per paint; stroke paints are expanded on the
     host by `stroker(cmds, width)` (default: the library's `Rasterizer::stroke` pre-pass,

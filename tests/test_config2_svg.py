@@ -67,3 +67,27 @@ def test_gpu_matches_oracle(key, mode):
         assert stats["alpha_mismatch_frac"] < 1e-3
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [("tiger", 1.0), ("tiger", 4.0), ("calabi_yau", 1.0)])
+def test_device_stroker_on_svg_paints(key):
+    """Rasterizer::stroke's pre-pass on the device (rasterize_paints): the batch it hands to the rasteriser is
+    byte-identical to the oracle's flatten + stroke of every stroke paint, and the result meets the parity bar."""
+    import ochre_b200 as ob
+
+    name, scale = key
+    cmds, off, xf, sw = W.svg_paint_batch(name, scale)
+    want_cmds, want_off, want_xf = W.svg(name, scale, stroker=oracle_stroker)
+    assert np.array_equal(xf, want_xf)
+    ctx = ob.Context(0)
+    try:
+        g = ctx.rasterize_paints(cmds, off, xf, sw)
+        got_cmds, got_off = ctx.debug_stroked(len(off) - 1)
+        assert np.array_equal(got_off, want_off)
+        assert got_cmds.tobytes() == want_cmds.tobytes()
+        o = O.rasterize_batch(cmds, off.astype(np.uint64), xf, stroke_width=sw, threads=0)
+        stats = assert_batch_parity(g, o, what=f"{name} {scale}x (device stroker)")
+        assert stats["tiles"] == KNOWN[key][4] and stats["spans"] == KNOWN[key][5]
+    finally:
+        ctx.close()

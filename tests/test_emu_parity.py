@@ -71,6 +71,18 @@ def test_random_paths(seed):
     assert_batch_parity(e, o, what=f"seed {seed}")
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_paths_with_conics(seed):
+    """Conic commands (path.rs:75-104) through the general pipeline's per-command flatten."""
+    rng = np.random.default_rng(7000 + seed)
+    paths = [_random_path(rng, int(rng.integers(1, 10)), float(rng.choice([6.0, 30.0, 120.0, 700.0])), conic=True) for _ in range(20)]
+    e, o = run_both(paths)
+    assert_batch_parity(e, o, what=f"conic seed {seed}")
+    for path in paths[:5]:
+        e1, _ = run_both([path])
+        lines_match(e1.lines, O.rasterize_path(path).lines)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_integer_grid_polygons(seed):
     """Integer and half-integer vertices: every DDA tie rule and end snap fires."""

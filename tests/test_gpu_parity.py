@@ -321,6 +321,45 @@ def test_strokes_match_reference_stroke(ctx):
     assert_batch_parity(g, o, what="strokes")
 
 
+def test_device_stroker_matches_reference_stroke(ctx):
+    """rasterize_paints: strokes (lines, curves, conics, open and closed contours, repeated points, several
+    contours after a Close -- the never-reset `closed` flag of path.rs:221-263) mixed with fills."""
+    rng = np.random.default_rng(77)
+    src, widths = [], []
+    for k in range(120):
+        p = _random_path(rng, int(rng.integers(1, 7)), 80.0)
+        if k % 5 == 0:  # an open contour after a closed one, with a repeated point
+            q = make_cmds([(MOVE, 5, 5), (LINE, 40, 9), (LINE, 40, 9), (LINE, 22, 50), (CLOSE,), (MOVE, 60, 60), (LINE, 90, 64),
+                           (QUADRATIC, 100, 80, 70, 95), (MOVE, 3, 70), (LINE, 30, 90)])
+            p = np.concatenate([p, q])
+        if k % 7 == 0:
+            p = np.concatenate([p, make_cmds([(MOVE, 10, 100), (CONIC, 60, 130, 110, 100, 0.5 + 0.25 * (k % 4)), (LINE, 10, 100)])])
+        src.append(p)
+        widths.append(0.0 if k % 3 == 0 else float(rng.uniform(0.3, 6.0)))
+    src.append(make_cmds([(MOVE, 1, 1)]))           # stroke of a lone Move
+    widths.append(2.0)
+    src.append(np.zeros(0, O.CMD_DTYPE))            # stroke of nothing
+    widths.append(1.0)
+    widths = np.asarray(widths, np.float32)
+    xf = np.tile(np.array([0.9, 0.1, -0.1, 0.9, 12.0, 7.0], np.float32), (len(src), 1))
+    cmds, off, _ = pack(src)
+    g = ctx.rasterize_paints(cmds, off, xf, widths)
+    got_cmds, got_off = ctx.debug_stroked(len(src))
+    want = [O.path_stroke(O.path_flatten(p, 0.1), float(w)) if w > 0 else p for p, w in zip(src, widths)]
+    wc, wo, _ = pack(want)
+    assert np.array_equal(got_off, wo)
+    assert got_cmds.tobytes() == wc.tobytes()
+    o = O.rasterize_batch(cmds, off.astype(np.uint64), xf, stroke_width=widths)
+    assert_batch_parity(g, o, what="device stroker")
+    # an unknown tag inside a stroke paint is refused
+    bad = cmds.copy()
+    k = int(np.flatnonzero(widths > 0)[0])
+    bad["tag"][off[k]] = 9
+    with pytest.raises(ob._lib.OchreError) as e:
+        ctx.rasterize_paints(bad, off, xf, widths)
+    assert e.value.code == -3
+
+
 def test_rasterizer_facade_replays_in_reference_order(ctx):
     class Rec(ob.TileBuilder):
         def __init__(self):
