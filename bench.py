@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--ref-paths", type=int, default=40_000, help="paths per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=0, help="paths in the cpu_baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-gather", action="store_true", help="N>1: leave each rank's tiles on its own GPU")
+    ap.add_argument("--gather", default="arena", choices=["arena", "nccl"],
+                    help="N>1: arena = the fused kernel stores its alpha tiles straight into GPU 0's memory over NVLink (CUDA IPC peer "
+                         "mapping; origins / spans / ranges follow by peer copy); nccl = send/recv of finished sub-batches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--chunk", type=int, default=0)
@@ -232,7 +235,10 @@ def main():
         return float(t.item())
 
     gather = world > 1 and not args.no_gather
+    use_arena = gather and args.gather == "arena"
     gbuf = {}
+    arena = None
+    arena_info = {}
 
     # N > 1: the gather is pipelined behind the kernels.  The rank's batch is cut into sub-batches that alternate
     # between two contexts (each owns its result arenas); while sub-batch j + 1 is rasterised, sub-batch j's tiles
@@ -241,7 +247,7 @@ def main():
     subs = [(P * j // K, P * (j + 1) // K) for j in range(K)]
     ctxs = [ctx]
     gather_blocks = []
-    if gather:
+    if gather and not use_arena:
         # GPU 0 keeps its own sub-batches where they were produced (one context per sub-batch, no copy);
         # the other ranks alternate between two contexts while the previous sub-batch is on the wire
         for _ in range((K if rank == 0 else 2) - 1):
@@ -297,12 +303,39 @@ def main():
         return x
 
     def step_device():
-        if gather:
+        if gather and not use_arena:
             return step_pipelined()
         return ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,
                                   out_device=True, unordered=UNORD)
 
-    if gather:
+    if use_arena:
+        # One local run sizes the slices; GPU 0 allocates the arena and hands its IPC handle round; from then on every
+        # rank's fused kernel stores its alpha tiles into its slice of GPU 0's memory while it rasterises.
+        r = ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True,
+                               unordered=True)
+        local_sum = int(torch.as_tensor(CudaArray(r.device_ptrs["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64]
+                        .sum(dtype=torch.int64).item())
+        mine = torch.tensor([r.n_tiles, r.n_spans, P, local_sum], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        allc = torch.stack(allc).cpu().numpy()
+        t_cap = [int(v) + 4096 for v in allc[:, 0]]
+        s_cap = [int(v) + 4096 for v in allc[:, 1]]
+        t_start = np.concatenate([[0], np.cumsum(t_cap)]).astype(np.int64)
+        s_start = np.concatenate([[0], np.cumsum(s_cap)]).astype(np.int64)
+        p_start = np.concatenate([[0], np.cumsum(allc[:, 2])]).astype(np.int64)
+        caps = (int(t_start[-1]), int(s_start[-1]), int(p_start[-1]))
+        box = [None]
+        if rank == 0:
+            arena = ctx.arena_create(*caps)
+            box[0] = arena.handle
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            arena = ctx.arena_open(box[0], *caps)
+        ctx.set_output_arena(arena, int(t_start[rank]), t_cap[rank], int(s_start[rank]), s_cap[rank], int(p_start[rank]), P)
+        arena_info = {"allc": allc, "t_start": t_start, "s_start": s_start, "p_start": p_start, "bytes": int(arena.c.bytes)}
+        UNORD = True
+    elif gather:
         # size every arena before anything is in flight: both contexts see every sub-batch once, and GPU 0's
         # gather buffers are sized from the all-rank totals
         nt = ns = 0
@@ -351,6 +384,24 @@ def main():
     tiles_total = sum_over_ranks(float(res.n_tiles))
     spans_total = sum_over_ranks(float(res.n_spans))
     stage_ms /= args.steps
+
+    # the arena on GPU 0 must hold every rank's result: per-slice tile counts (from the ranges) and alpha byte sums
+    gather_check = None
+    if use_arena:
+        barrier()
+        if rank == 0:
+            ok = True
+            for q in range(world):
+                rg = ctx.to_host(arena.ptrs["ranges"] + 16 * int(arena_info["p_start"][q]), 16 * P, np.uint32).reshape(P, 4)
+                nt_q = int(rg[:, 1].astype(np.int64).sum())
+                a = torch.as_tensor(CudaArray(arena.ptrs["alpha"] + 64 * int(arena_info["t_start"][q]), max(nt_q * 64, 1)), device="cuda")
+                sum_q = int(a[: nt_q * 64].sum(dtype=torch.int64).item())
+                ok = ok and nt_q == int(arena_info["allc"][q, 0]) and sum_q == int(arena_info["allc"][q, 3])
+            gather_check = {"slices": world, "tile_counts_and_alpha_sums_match_local_runs": bool(ok), "arena_GB": arena_info["bytes"] / 1e9}
+            if not ok:
+                raise SystemExit("bench.py: the arena on GPU 0 does not hold every rank's result")
+        barrier()
+        ctx.set_output_arena(None)
 
     # ungathered figure for N > 1 (what a renderer that draws per GPU would see)
     ungathered = None
@@ -452,7 +503,9 @@ def main():
                 "workload": WORKLOAD, "paths_per_gpu": P, "paths_total": paths_total, "cmds_per_gpu": int(res.n_cmds),
                 "lines_per_gpu": int(res.n_lines), "bin_records_per_gpu": int(res.n_records), "tiles_total": int(tiles_total),
                 "spans_total": int(spans_total), "tiles_per_s": tps, "alpha_MB_per_s": tps * 64e-6, "chunks": int(res.n_chunks),
-                "parallelism": f"path-batch x{world}" + (f", tiles gathered to GPU 0 (NCCL send/recv, pipelined in {K} sub-batches)" if gather else ""),
+                "parallelism": f"path-batch x{world}" + ((", tiles gathered to GPU 0 inside the kernel: alpha stores go to an arena in GPU 0's memory over NVLink (CUDA IPC peer "
+                                                              "mapping), origins / spans / ranges follow by peer copy behind the kernels") if use_arena else
+                                                             f", tiles gathered to GPU 0 (NCCL send/recv, pipelined in {K} sub-batches)" if gather else ""),
                 "layout": ("path-ordered lists (k_gather_paths)" if args.ordered else
                            "per-path lists in completion order + per-path (start, count) ranges (OCHRE_OUT_UNORDERED)"),
                 "l2": "inputs (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (n_cmds * 28 / 1e9),
@@ -463,6 +516,8 @@ def main():
         }
         if ungathered:
             line["ungathered"] = ungathered
+        if gather_check:
+            line["gather_check"] = gather_check
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -146,6 +146,40 @@ int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode);
  * fused per-path kernel is not used. */
 int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t tile_row_hi);
 
+/* ---- output arenas: the gather of SURVEY.md section 8e fused into the rasteriser's stores -----------
+ * BASELINE north_star: "the compacted tile lists are gathered to GPU 0 over NVLink ... and that gather is
+ * timed as part of the run".  One process per GPU: the process of GPU 0 creates an arena and passes its
+ * 64-byte handle to the others (any channel); they open it (CUDA IPC, peer access over NVLink / NVSwitch)
+ * and each rank points its ctx at its own slice.  From then on the fused per-path kernel stores every
+ * finished alpha tile directly into GPU 0's memory while it rasterises; tile origins, spans and per-path
+ * ranges (slice-relative indices) follow by peer copy behind the kernels.  When every rank's call has
+ * returned (plus a barrier), GPU 0 holds the whole result: slice r = rank r's paths. */
+typedef struct OchreArena {
+    void* base;            /* one device allocation (or its mapping in an opening process) */
+    uint64_t bytes;
+    uint64_t cap_tiles, cap_spans, cap_paths;
+    uint8_t* alpha;        /* 64 * cap_tiles */
+    int16_t* tile_xy;      /* 2 * cap_tiles */
+    OchreSpan* spans;      /* cap_spans */
+    OchrePathRange* ranges; /* cap_paths */
+    unsigned char ipc[64]; /* cudaIpcMemHandle_t of `base` */
+    int32_t owner;         /* 1: created by this process, 0: opened from a handle */
+    int32_t pad;
+} OchreArena;
+int ochre_b200_arena_create(ochre_b200_ctx* ctx, uint64_t cap_tiles, uint64_t cap_spans, uint64_t cap_paths, OchreArena* out);
+int ochre_b200_arena_open(ochre_b200_ctx* ctx, const unsigned char* ipc_handle /* 64 bytes */, uint64_t cap_tiles,
+                          uint64_t cap_spans, uint64_t cap_paths, OchreArena* out);
+int ochre_b200_arena_close(ochre_b200_ctx* ctx, OchreArena* arena);
+/* Results of the following ochre_b200_rasterize calls on ctx (flags must hold OCHRE_OUT_DEVICE | OCHRE_OUT_UNORDERED)
+ * land in the slice tiles [tile_start, +tile_cap), spans [span_start, +span_cap), ranges [path_start, +path_cap) of
+ * the arena; OchreResult points into the slice.  A call that needs more fails with OCHRE_E_TOO_LARGE.
+ * arena == NULL: back to the ctx's own buffers. */
+int ochre_b200_set_output_arena(ochre_b200_ctx* ctx, const OchreArena* arena, uint64_t tile_start, uint64_t tile_cap,
+                                uint64_t span_start, uint64_t span_cap, uint64_t path_start, uint64_t path_cap);
+
+/* Synchronous device -> host copy of `bytes` bytes on the ctx's device (reading back an arena or an OCHRE_OUT_DEVICE result). */
+int ochre_b200_copy_to_host(ochre_b200_ctx* ctx, void* dst, const void* src_device, uint64_t bytes);
+
 /* ---- device-side consumer of the tile list: atlas packer + quad builder ----------------------
  * What the reference's examples/svg.rs does on the CPU inside its TileBuilder (svg.rs:22-88):
  * every tile's 64 alpha bytes go to the next 8x8 slot of a 4096x4096 R8 atlas (slot 0 = an

@@ -21,7 +21,8 @@ ERRORS = {
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
     "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_rasterize_paints", "ochre_b200_set_chunk", "ochre_b200_set_mode",
-    "ochre_b200_set_row_band", "ochre_b200_build_atlas", "ochre_b200_last_error",
+    "ochre_b200_set_row_band", "ochre_b200_arena_create", "ochre_b200_arena_open", "ochre_b200_arena_close",
+    "ochre_b200_set_output_arena", "ochre_b200_copy_to_host", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_version",
 ]
@@ -42,6 +43,14 @@ class OchreAtlas(C.Structure):
     _fields_ = [
         ("n_quads", C.c_uint32), ("n_pages", C.c_uint32), ("vertices", C.c_void_p), ("indices", C.c_void_p),
         ("atlas", C.c_void_p), ("page_quad_off", C.c_void_p), ("device_ms", C.c_float), ("kernel_launches", C.c_uint64),
+    ]
+
+
+class OchreArena(C.Structure):
+    _fields_ = [
+        ("base", C.c_void_p), ("bytes", C.c_uint64), ("cap_tiles", C.c_uint64), ("cap_spans", C.c_uint64),
+        ("cap_paths", C.c_uint64), ("alpha", C.c_void_p), ("tile_xy", C.c_void_p), ("spans", C.c_void_p),
+        ("ranges", C.c_void_p), ("ipc", C.c_ubyte * 64), ("owner", C.c_int32), ("pad", C.c_int32),
     ]
 
 
@@ -73,6 +82,11 @@ def load():
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
     L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
     L.ochre_b200_set_row_band.argtypes = [vp, C.c_int32, C.c_int32]
+    L.ochre_b200_arena_create.argtypes = [vp, u64, u64, u64, C.POINTER(OchreArena)]
+    L.ochre_b200_arena_open.argtypes = [vp, vp, u64, u64, u64, C.POINTER(OchreArena)]
+    L.ochre_b200_arena_close.argtypes = [vp, C.POINTER(OchreArena)]
+    L.ochre_b200_set_output_arena.argtypes = [vp, C.POINTER(OchreArena), u64, u64, u64, u64, u64, u64]
+    L.ochre_b200_copy_to_host.argtypes = [vp, vp, vp, u64]
     L.ochre_b200_build_atlas.argtypes = [vp, vp, u32, C.POINTER(OchreAtlas)]
     L.ochre_b200_last_error.argtypes = [vp]
     L.ochre_b200_last_error.restype = C.c_char_p

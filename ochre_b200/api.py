@@ -109,6 +109,30 @@ def _check(ctx_handle, rc: int):
         raise _lib.OchreError(rc, msg)
 
 
+class Arena:
+    """`OchreArena`: result buffers of several ranks' calls on one GPU (slice per rank)."""
+
+    def __init__(self, ctx: "Context", c):
+        self.ctx, self.c = ctx, c
+
+    @property
+    def handle(self) -> bytes:
+        return bytes(self.c.ipc)
+
+    @property
+    def caps(self):
+        return int(self.c.cap_tiles), int(self.c.cap_spans), int(self.c.cap_paths)
+
+    @property
+    def ptrs(self) -> dict:
+        return dict(alpha=self.c.alpha, tile_xy=self.c.tile_xy, spans=self.c.spans, ranges=self.c.ranges)
+
+    def close(self):
+        if self.c is not None and self.ctx._h:
+            _check(self.ctx._h, _lib.load().ochre_b200_arena_close(self.ctx._h, C.byref(self.c)))
+        self.c = None
+
+
 class Context:
     """One device + its stream and workspaces (`ochre_b200_ctx`).  Not thread-safe."""
 
@@ -243,6 +267,46 @@ class Context:
         alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64))
         spans = view(res.spans, ns * 8, SPAN_DTYPE, (ns,))
         return BatchResult(tile_off, span_off, tile_xy, alpha, spans, ranges=ranges, **common)
+
+    # ---- output arenas (include/ochre_b200.h): the gather to one GPU fused into the kernel's stores ----
+    def arena_create(self, cap_tiles: int, cap_spans: int, cap_paths: int) -> "Arena":
+        a = _lib.OchreArena()
+        _check(self._h, _lib.load().ochre_b200_arena_create(self._h, cap_tiles, cap_spans, cap_paths, C.byref(a)))
+        return Arena(self, a)
+
+    def arena_open(self, handle: bytes, cap_tiles: int, cap_spans: int, cap_paths: int) -> "Arena":
+        """Maps another process's arena (its 64-byte `Arena.handle`) into this ctx's device (CUDA IPC, peer access)."""
+        a = _lib.OchreArena()
+        buf = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        _check(self._h, _lib.load().ochre_b200_arena_open(self._h, C.addressof(buf), cap_tiles, cap_spans, cap_paths, C.byref(a)))
+        return Arena(self, a)
+
+    def set_output_arena(self, arena: "Optional[Arena]", tile_start=0, tile_cap=0, span_start=0, span_cap=0, path_start=0, path_cap=0):
+        """Following `rasterize*` calls (out_device=True, unordered=True) write into this slice of the arena."""
+        L = _lib.load()
+        if arena is None:
+            _check(self._h, L.ochre_b200_set_output_arena(self._h, None, 0, 0, 0, 0, 0, 0))
+        else:
+            _check(self._h, L.ochre_b200_set_output_arena(self._h, C.byref(arena.c), tile_start, tile_cap, span_start, span_cap,
+                                                          path_start, path_cap))
+
+    def to_host(self, dev_ptr: int, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """Synchronous device -> host copy of raw device memory (arenas, out_device results)."""
+        out = np.empty(nbytes, np.uint8)
+        _check(self._h, _lib.load().ochre_b200_copy_to_host(self._h, out.ctypes.data, dev_ptr, nbytes))
+        return out.view(dtype)
+
+    def read_arena_slice(self, arena: "Arena", tile_start: int, span_start: int, path_start: int, n_paths: int) -> BatchResult:
+        """One rank's slice of an arena as a host BatchResult (unordered layout: `ranges` index the slice)."""
+        p = arena.ptrs
+        ranges = self.to_host(p["ranges"] + 16 * path_start, 16 * n_paths, np.uint32).reshape(n_paths, 4)
+        nt = int((ranges[:, 0].astype(np.int64) + ranges[:, 1]).max()) if n_paths else 0
+        ns = int((ranges[:, 2].astype(np.int64) + ranges[:, 3]).max()) if n_paths else 0
+        xy = self.to_host(p["tile_xy"] + 4 * tile_start, 4 * nt, np.int16).reshape(nt, 2)
+        alpha = self.to_host(p["alpha"] + 64 * tile_start, 64 * nt).reshape(nt, 64)
+        spans = self.to_host(p["spans"] + 8 * span_start, 8 * ns, SPAN_DTYPE)
+        return BatchResult(None, None, xy, alpha, spans, ranges=ranges, n_tiles=nt, n_spans=ns, n_cmds=0, n_lines=0, n_records=0,
+                           n_chunks=0, kernel_launches=0, device_ms=0.0, stage_ms=(0.0,) * 8, used=5)
 
     def debug_stroked(self, n_paths: int):
         """(cmds, cmd_off) of the batch the device stroker produced in the last `rasterize_paints` call."""

@@ -618,6 +618,14 @@ struct ochre_b200_ctx {
     DevBuf k_cmds, k_off, k_xf, k_width, k_nflat, k_flat_off, k_flat, k_nout, k_out_off, k_out;
     HostBuf hk_off;
     uint32_t k_last_paths = 0;  // paints of the last ochre_b200_rasterize_paints call (0: none)
+    // output arena (ochre_b200_set_output_arena): the fused kernel stores alpha tiles straight into it -- for a peer-mapped
+    // arena that is the gather to GPU 0, tile by tile over NVLink; tile origins, spans and ranges follow by copy
+    bool x_on = false;
+    uint8_t* x_alpha = nullptr;
+    int16_t* x_tile_xy = nullptr;
+    OchreSpan* x_spans = nullptr;
+    OchrePathRange* x_ranges = nullptr;
+    uint64_t x_tile_cap = 0, x_span_cap = 0, x_path_cap = 0;
     uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
     double tiles_per_cmd = 4.0, spans_per_cmd = 0.75;  // arena growth estimates, refined every call
 };
@@ -902,11 +910,13 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         uint64_t want_s = (uint64_t)((double)(n_cmds + n_paths) * ctx->spans_per_cmd * 1.15) + 1024 + base_s;
         if (want_t > 0xfffffff0ull) want_t = 0xfffffff0ull;
         if (want_s > 0xfffffff0ull) want_s = 0xfffffff0ull;
+        const bool ext = ctx->x_on;  // alpha tiles go straight into the output arena (its capacity is fixed)
         CK(ctx->s_tile_xy.ensure(want_t * 4, base_t > 0, st));
-        CK(ctx->s_alpha.ensure(want_t * 64, base_t > 0, st));
+        if (!ext) CK(ctx->s_alpha.ensure(want_t * 64, base_t > 0, st));
         CK(ctx->s_spans.ensure(want_s * sizeof(OchreSpan), base_s > 0, st));
-        const uint32_t cap_t = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::min<uint64_t>(ctx->s_alpha.cap / 64, ctx->s_tile_xy.cap / 4));
-        const uint32_t cap_s = (uint32_t)std::min<uint64_t>(0xfffffff0ull, ctx->s_spans.cap / sizeof(OchreSpan));
+        uint8_t* const alpha_base = ext ? ctx->x_alpha : ctx->s_alpha.as<uint8_t>();
+        const uint32_t cap_t = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::min<uint64_t>(ext ? ctx->x_tile_cap : ctx->s_alpha.cap / 64, ctx->s_tile_xy.cap / 4));
+        const uint32_t cap_s = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(0xfffffff0ull, ext ? ctx->x_span_cap : ~0ull), ctx->s_spans.cap / sizeof(OchreSpan));
         CK(cudaMemsetAsync(ctl, 0, PKC_WORDS * 4, st));
         if (base_t | base_s) {  // the cursors continue where the previous chunk stopped
             h_ctl[8] = base_t;
@@ -925,7 +935,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.cap_tiles = cap_t;
         A.cap_spans = cap_s;
         A.tile_xy = ctx->s_tile_xy.as<int16_t>();
-        A.alpha = ctx->s_alpha.as<uint8_t>();
+        A.alpha = alpha_base;
         A.spans = ctx->s_spans.as<OchreSpan>();
         A.scratch = ctx->d_pk_scratch.as<unsigned char>();
         A.fb_list = ctx->d_pk_fb.as<uint32_t>();
@@ -982,6 +992,10 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         double denom = (double)(n_cmds + n_paths);
         ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)(nt - base_t) / denom);
         ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)(ns - base_s) / denom);
+        if (stt[2] && ext && (nt > ctx->x_tile_cap || ns > ctx->x_span_cap)) {
+            ctx->err = "the output arena slice is too small for this call's tiles or spans";
+            return OCHRE_E_TOO_LARGE;
+        }
         if (stt[2]) continue;  // staging arena too small: grown at the top of the loop, run again
         if (n_fb) {
             // ---- hand-over: the general pipeline rasterises the paths that exceed the on-chip budgets ----
@@ -1019,17 +1033,22 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
                 return OCHRE_E_TOO_LARGE;
             }
             // append to the staging arena and point the paths' records at it
+            if (ext && ((uint64_t)nt + co2.n_tiles > ctx->x_tile_cap || (uint64_t)ns + co2.n_spans > ctx->x_span_cap)) {
+                ctx->err = "the output arena slice is too small for this call's tiles or spans";
+                return OCHRE_E_TOO_LARGE;
+            }
             CK(ctx->s_tile_xy.ensure(((size_t)nt + co2.n_tiles + 1) * 4, true, st));
-            CK(ctx->s_alpha.ensure(((size_t)nt + co2.n_tiles + 1) * 64, true, st));
+            if (!ext) CK(ctx->s_alpha.ensure(((size_t)nt + co2.n_tiles + 1) * 64, true, st));
             CK(ctx->s_spans.ensure(((size_t)ns + co2.n_spans + 1) * sizeof(OchreSpan), true, st));
             if (co2.n_tiles) {
                 CK(cudaMemcpyAsync(ctx->s_tile_xy.as<uint32_t>() + nt, ctx->f_tile_xy.p, (size_t)co2.n_tiles * 4, cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(ctx->s_alpha.as<uint8_t>() + (size_t)nt * 64, ctx->f_alpha.p, (size_t)co2.n_tiles * 64, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync((ext ? ctx->x_alpha : ctx->s_alpha.as<uint8_t>()) + (size_t)nt * 64, ctx->f_alpha.p, (size_t)co2.n_tiles * 64, cudaMemcpyDeviceToDevice, st));
             }
             if (co2.n_spans)
                 CK(cudaMemcpyAsync(ctx->s_spans.as<OchreSpan>() + ns, ctx->f_spans.p, (size_t)co2.n_spans * sizeof(OchreSpan), cudaMemcpyDeviceToDevice, st));
             k_fb_records<<<nblk(n_fb, TPB), TPB, 0, st>>>(ctx->f_fb.as<uint32_t>(), n_fb, ctx->f_tile_off.as<uint32_t>(),
                                                          ctx->f_span_off.as<uint32_t>(), co2.n_tiles, co2.n_spans, nt, ns, rec);
+            CK(cudaStreamSynchronize(st));  // callers copy the chunk's results on another stream
             co->launches += co2.launches + 1;
             for (int k = 1; k < 7; ++k) co->ms[k] += co2.ms[k];  // (stage 0 keeps the fused kernel's own time)
             co->ms[1] += co2.ms[0];
@@ -1221,6 +1240,15 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     const bool banded_call = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;
     // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
     const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && ctx->mode != OCHRE_MODE_GENERAL && !banded_call;
+    const bool ext = ctx->x_on;
+    if (ext && !(out_dev && unordered)) {
+        ctx->err = "an output arena needs OCHRE_OUT_DEVICE | OCHRE_OUT_UNORDERED, mode auto or fused, and no row band";
+        return OCHRE_E_INVALID_ARG;
+    }
+    if (ext && n_paths > ctx->x_path_cap) {
+        ctx->err = "the output arena slice holds fewer path ranges than this call has paths";
+        return OCHRE_E_TOO_LARGE;
+    }
     DevBuf& r_tile_xy = unordered ? ctx->s_tile_xy : ctx->o_tile_xy;
     DevBuf& r_alpha = unordered ? ctx->s_alpha : ctx->o_alpha;
     DevBuf& r_spans = unordered ? ctx->s_spans : ctx->o_spans;
@@ -1336,6 +1364,15 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 CK(cudaMemcpyAsync(ctx->h_span_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
             }
         }
+        if (ext) {
+            // the chunk's alpha tiles are in the arena already (stored there by the kernel); its tile origins, spans and
+            // path ranges follow on the download stream while the next chunk is rasterised
+            const size_t t0 = tile_base, nt = co.n_tiles, s0 = span_base, ns = co.n_spans;
+            if (nt) CK(cudaMemcpyAsync(ctx->x_tile_xy + 2 * t0, ctx->s_tile_xy.as<int16_t>() + 2 * t0, nt * 4, cudaMemcpyDeviceToDevice, ctx->st_out));
+            if (ns) CK(cudaMemcpyAsync(ctx->x_spans + s0, ctx->s_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToDevice, ctx->st_out));
+            CK(cudaMemcpyAsync(ctx->x_ranges + p0, ctx->d_pk_rec.as<OchrePathRange>() + p0, (size_t)(p1 - p0) * sizeof(OchrePathRange),
+                               cudaMemcpyDeviceToDevice, ctx->st_out));
+        }
         tile_base += co.n_tiles;
         span_base += co.n_spans;
         total.n_lines += co.n_lines;
@@ -1383,7 +1420,13 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
 
     // ---- outputs ---------------------------------------------------------------
-    if (out_dev) {
+    if (ext) {
+        CK(cudaStreamSynchronize(ctx->st_out));  // the arena holds the whole result
+        out->tile_xy = ctx->x_tile_xy;
+        out->alpha = ctx->x_alpha;
+        out->spans = ctx->x_spans;
+        out->ranges = ctx->x_ranges;
+    } else if (out_dev) {
         out->tile_off = unordered ? nullptr : ctx->o_tile_off.as<uint32_t>();
         out->span_off = unordered ? nullptr : ctx->o_span_off.as<uint32_t>();
         out->tile_xy = r_tile_xy.as<int16_t>();
@@ -1410,7 +1453,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     ctx->last_n_paths = n_paths;
     ctx->last_n_tiles = tile_base;
     ctx->last_n_spans = span_base;
-    ctx->last_valid = true;
+    ctx->last_valid = !ext;  // (the atlas builder reads the ctx's own result buffers)
     ctx->last_unordered = unordered;
     return 0;
 }
@@ -1556,6 +1599,116 @@ int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, 
         const uint64_t m = std::min<uint64_t>(cap, *n);
         if (m) CK(cudaMemcpy(cmds, ctx->k_out.p, m * sizeof(OchreCmd), cudaMemcpyDeviceToHost));
     }
+    return 0;
+}
+
+// ---- output arenas: the gather to one GPU, fused into the kernel's stores ---------------------------
+static void arena_layout(OchreArena* a) {
+    unsigned char* b = static_cast<unsigned char*>(a->base);
+    auto up = [](uint64_t v) { return (v + 255u) & ~(uint64_t)255u; };
+    uint64_t o = 0;
+    a->alpha = b + o;
+    o = up(o + 64 * a->cap_tiles);
+    a->tile_xy = reinterpret_cast<int16_t*>(b + o);
+    o = up(o + 4 * a->cap_tiles);
+    a->spans = reinterpret_cast<OchreSpan*>(b + o);
+    o = up(o + sizeof(OchreSpan) * a->cap_spans);
+    a->ranges = reinterpret_cast<OchrePathRange*>(b + o);
+    o = up(o + sizeof(OchrePathRange) * a->cap_paths);
+    a->bytes = o + 256;
+}
+
+int ochre_b200_arena_create(ochre_b200_ctx* ctx, uint64_t cap_tiles, uint64_t cap_spans, uint64_t cap_paths, OchreArena* out) {
+    if (!ctx || !out) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof *out);
+    out->cap_tiles = cap_tiles;
+    out->cap_spans = cap_spans;
+    out->cap_paths = cap_paths;
+    arena_layout(out);  // (base == NULL: computes the size)
+    void* base = nullptr;
+    CK(cudaMalloc(&base, out->bytes));
+    out->base = base;
+    arena_layout(out);
+    out->owner = 1;
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, base);
+    if (e != cudaSuccess) {
+        cudaFree(base);
+        memset(out, 0, sizeof *out);
+        ctx->err = std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == sizeof out->ipc, "handle size");
+    memcpy(out->ipc, &h, sizeof h);
+    return 0;
+}
+
+int ochre_b200_arena_open(ochre_b200_ctx* ctx, const unsigned char* ipc_handle, uint64_t cap_tiles, uint64_t cap_spans,
+                          uint64_t cap_paths, OchreArena* out) {
+    if (!ctx || !out || !ipc_handle) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    out->base = base;
+    out->cap_tiles = cap_tiles;
+    out->cap_spans = cap_spans;
+    out->cap_paths = cap_paths;
+    arena_layout(out);
+    memcpy(out->ipc, ipc_handle, sizeof out->ipc);
+    out->owner = 0;
+    return 0;
+}
+
+int ochre_b200_arena_close(ochre_b200_ctx* ctx, OchreArena* arena) {
+    if (!ctx || !arena) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->x_on && arena->base && ctx->x_alpha >= arena->alpha && ctx->x_alpha < static_cast<uint8_t*>(arena->base) + arena->bytes)
+        ctx->x_on = false;
+    if (arena->base) {
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaStreamSynchronize(ctx->st_out));
+        if (arena->owner) CK(cudaFree(arena->base)); else CK(cudaIpcCloseMemHandle(arena->base));
+    }
+    memset(arena, 0, sizeof *arena);
+    return 0;
+}
+
+int ochre_b200_copy_to_host(ochre_b200_ctx* ctx, void* dst, const void* src_device, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst || !src_device))) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    CK(cudaSetDevice(ctx->device));
+    if (bytes) CK(cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ochre_b200_set_output_arena(ochre_b200_ctx* ctx, const OchreArena* arena, uint64_t tile_start, uint64_t tile_cap,
+                                uint64_t span_start, uint64_t span_cap, uint64_t path_start, uint64_t path_cap) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    if (!arena) {
+        ctx->x_on = false;
+        return 0;
+    }
+    if (!arena->base || tile_start + tile_cap > arena->cap_tiles || span_start + span_cap > arena->cap_spans ||
+        path_start + path_cap > arena->cap_paths) {
+        ctx->err = "output arena slice outside the arena";
+        return OCHRE_E_INVALID_ARG;
+    }
+    ctx->x_on = true;
+    ctx->x_alpha = arena->alpha + 64 * tile_start;
+    ctx->x_tile_xy = arena->tile_xy + 2 * tile_start;
+    ctx->x_spans = arena->spans + span_start;
+    ctx->x_ranges = arena->ranges + path_start;
+    ctx->x_tile_cap = tile_cap;
+    ctx->x_span_cap = span_cap;
+    ctx->x_path_cap = path_cap;
     return 0;
 }
 
