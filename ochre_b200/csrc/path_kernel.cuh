@@ -120,6 +120,7 @@ struct PkShared {
     uint32_t ws[72];
     int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
     uint32_t path, next_path, nbands, nstripes, base_tiles, base_spans, flag;
+    uint32_t merr;  // set by the mark pass when a walk leaves the grid (never, by construction: the path is handed over)
 };
 
 // touched cells before cell c (c may be one past the last cell)
@@ -190,8 +191,8 @@ __device__ __forceinline__ void block_excl_scan_pair(uint32_t a, uint32_t b, uin
 struct LineWalk {
     float lx, ly, px, py;
     float row_t1, col_t1, x_step, y_step;
-    int x, y, x_dir, y_dir, end_x, end_y;
-    __device__ __forceinline__ void init(const float4 L) {
+    int x, y, x_dir, y_dir, end_x, end_y;  // pixel coordinates relative to (ox, oy), multiples of 8: tile and sub-tile bits are unchanged
+    __device__ __forceinline__ void init(const float4 L, int ox, int oy) {
         lx = L.x;
         ly = L.y;
         px = L.z;
@@ -200,33 +201,34 @@ struct LineWalk {
         x_dir = sign_dir(dx);
         y_dir = sign_dir(dy);
         const float dtdx = 1.0f / dx, dtdy = 1.0f / dy;
-        x = floor_px(lx);
-        y = floor_px(ly);
+        const int ax = floor_px(lx), ay = floor_px(ly);
         row_t1 = INFINITY;
         col_t1 = INFINITY;
-        if (ly != py) row_t1 = fminf(dtdy * (((py > ly) ? (float)(y + 1) : (float)y) - ly), 1.0f);
-        if (lx != px) col_t1 = fminf(dtdx * (((px > lx) ? (float)(x + 1) : (float)x) - lx), 1.0f);
+        if (ly != py) row_t1 = fminf(dtdy * (((py > ly) ? (float)(ay + 1) : (float)ay) - ly), 1.0f);
+        if (lx != px) col_t1 = fminf(dtdx * (((px > lx) ? (float)(ax + 1) : (float)ax) - lx), 1.0f);
         x_step = fabsf(dtdx);
         y_step = fabsf(dtdy);
-        end_x = floor_px(px);
-        end_y = floor_px(py);
+        x = ax - ox;
+        y = ay - oy;
+        end_x = floor_px(px) - ox;
+        end_y = floor_px(py) - oy;
     }
-    // one loop trip's control flow: returns the trip's t1, moves to the next pixel (or the end snap)
-    __device__ __forceinline__ bool advance(float& t1) {
-        t1 = fminf(row_t1, col_t1);
-        if (row_t1 < col_t1) {
-            row_t1 = fminf(row_t1 + y_step, 1.0f);
-            y += y_dir;
-        } else {
-            col_t1 = fminf(col_t1 + x_step, 1.0f);
-            x += x_dir;
-        }
-        const bool done = (t1 == 1.0f);
-        if (done) {
-            x = end_x;
-            y = end_y;
-        }
-        return done;
+    // One loop trip's control flow, branch-free: returns the trip's t1 and whether it was a row step; moves to the next
+    // pixel.  (The stepped bound is t1 itself: min(row_t1, col_t1) is row_t1 on a row step, col_t1 otherwise -- ties
+    // go to columns, rasterizer.rs:118-122.)  The end snap (rasterizer.rs:119-121) is the caller's: `if (done) snap()`.
+    __device__ __forceinline__ float advance(bool& row) {
+        row = row_t1 < col_t1;
+        const float t1 = fminf(row_t1, col_t1);
+        const float nt = fminf(t1 + (row ? y_step : x_step), 1.0f);
+        row_t1 = row ? nt : row_t1;
+        col_t1 = row ? col_t1 : nt;
+        y += row ? y_dir : 0;
+        x += row ? 0 : x_dir;
+        return t1;
+    }
+    __device__ __forceinline__ void snap() {
+        x = end_x;
+        y = end_y;
     }
 };
 
@@ -349,11 +351,17 @@ __device__ __forceinline__ void pk_red_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
+// (1 << n) - 1 for n in [0, 32)
+__device__ __forceinline__ uint32_t pk_below(uint32_t n) {
+    uint32_t m;
+    asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(n));
+    return m;
+}
+
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
-__device__ __forceinline__ uint32_t pk_mark(uint32_t cell_s /* shared-window address of the cells */, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
-                                            bool striped, uint64_t pk_pol) {
-    uint32_t err = 0;
+__device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address of the cells */, uint32_t merr_s /* ... of PkShared::merr */, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
+                                        bool striped, uint64_t pk_pol) {
     uint32_t pos = threadIdx.x;
     asm volatile("" : "+r"(cell_s));  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -365,31 +373,27 @@ __device__ __forceinline__ uint32_t pk_mark(uint32_t cell_s /* shared-window add
         const float4 L = Ln;
         if (pos + PK_THREADS < n) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
         LineWalk w;
-        w.init(L);
+        w.init(L, gx0 * 8, gy0 * 8);
         int prev_ty = w.y >> 3;
-        for (;;) {
-            const int cx = (w.x >> 3) - gx0, cy = (w.y >> 3) - gy0;
-            if ((unsigned)cy < (unsigned)H) {
-                if ((unsigned)cx < (unsigned)W) pk_red_add(cell_s + 4u * (uint32_t)(cy * W + cx), 1u); else err = 1;
-            } else if (!striped) {
-                err = 1;  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
-            }
-            float t1;
-            const bool done = w.advance(t1);
+        bool done;
+        do {
+            const int cx = w.x >> 3, cy = w.y >> 3;
+            const bool inx = (unsigned)cx < (unsigned)W, iny = (unsigned)cy < (unsigned)H;
+            if (inx && iny) pk_red_add(cell_s + 4u * (uint32_t)(cy * W + cx), 1u);
+            else if (!inx || !striped) asm volatile("st.shared.u32 [%0], %1;" ::"r"(merr_s), "r"(1u) : "memory");  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
+            bool row;
+            done = w.advance(row) == 1.0f;
+            if (done) w.snap();
             const int ty = w.y >> 3;
             if (ty != prev_ty) {  // rasterizer.rs:123-131
-                const int tiy = min(ty, prev_ty) - gy0, tix = (w.x >> 3) - gx0;
-                if ((unsigned)tiy < (unsigned)H) {
-                    if ((unsigned)tix < (unsigned)W) pk_red_add(cell_s + 4u * (uint32_t)(tiy * W + tix), (uint32_t)(ty - prev_ty) << 16); else err = 1;
-                } else if (!striped) {
-                    err = 1;
-                }
+                const int tiy = min(ty, prev_ty), tix = w.x >> 3;
+                const bool jnx = (unsigned)tix < (unsigned)W, jny = (unsigned)tiy < (unsigned)H;
+                if (jnx && jny) pk_red_add(cell_s + 4u * (uint32_t)(tiy * W + tix), (uint32_t)(ty - prev_ty) << 16);
+                else if (!jnx || !striped) asm volatile("st.shared.u32 [%0], %1;" ::"r"(merr_s), "r"(1u) : "memory");
                 prev_ty = ty;
             }
-            if (done) break;
-        }
+        } while (!done);
     }
-    return err;
 }
 
 // Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
@@ -399,7 +403,10 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
     uint32_t pos = p0 + threadIdx.x;
     uint32_t bits_s = acc_s + (uint32_t)(offsetof(PkShared, bits) - offsetof(PkShared, u));
     uint32_t wbase_s = acc_s + (uint32_t)(offsetof(PkShared, wbase) - offsetof(PkShared, u));
-    asm volatile("" : "+r"(acc_s), "+r"(bits_s), "+r"(wbase_s));
+    uint32_t slot0_s = acc_s - rank0 * (uint32_t)(4 * PK_ACCW);  // accumulator block of rank 0 (slot = rank - rank0)
+    const int r0 = R0 - gy0;                       // the band's rows relative to the grid
+    const uint32_t nrows = (uint32_t)(R1 - R0);
+    asm volatile("" : "+r"(slot0_s), "+r"(bits_s), "+r"(wbase_s));
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     if (pos < p1) Ln = pk_ld(&sl[pos], pk_pol);
     for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
@@ -408,37 +415,43 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
         const float4 L = Ln;
         if (pos + PK_THREADS < p1) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
         LineWalk w;
-        w.init(L);
+        w.init(L, gx0 * 8, gy0 * 8);
         // p0 of the first increment: t0 = max(0, 0) = 0 (rasterizer.rs:99-101)
         float p0x = (1.0f - 0.0f) * w.lx + 0.0f * w.px, p0y = (1.0f - 0.0f) * w.ly + 0.0f * w.py;
-        for (;;) {
+        // `right` = (x + 1) as f32 (rasterizer.rs:107) follows the column steps in f32 (small integers: exact)
+        float right = (float)(w.x + gx0 * 8 + 1);
+        const float right_step = (float)w.x_dir;
+        // the walk is monotone in y: it has left the band for good once ry passes `lim` in its direction
+        const int lim = (w.y_dir > 0) ? r0 + (int)nrows : r0 - 1;
+        bool more;
+        do {
             const int x0 = w.x, y0 = w.y;
-            float t1;
-            const bool done = w.advance(t1);
+            const float rt = right;
+            bool row;
+            const float t1 = w.advance(row);
+            right += row ? 0.0f : right_step;
             const float omt = 1.0f - t1;
             const float p1x = omt * w.lx + t1 * w.px, p1y = omt * w.ly + t1 * w.py;
             const float height = p1y - p0y;
-            const float right = (float)(x0 + 1);
-            const float area = 0.5f * height * ((right - p0x) + (right - p1x));
+            const float area = 0.5f * height * ((rt - p0x) + (rt - p1x));
             const int ry = y0 >> 3;
-            if (ry >= R0 && ry < R1) {
+            if ((uint32_t)(ry - r0) < nrows) {
                 // slot = rank(cell) - rank0, the rank structure read through its shared-window address
-                const uint32_t cidx = (uint32_t)((ry - gy0) * W + ((x0 >> 3) - gx0));
+                const uint32_t cidx = (uint32_t)(ry * W + (x0 >> 3));
                 uint32_t wbits, wb;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wbits) : "r"(bits_s + 4u * (cidx >> 5)));
                 asm volatile("ld.shared.u16 %0, [%1];" : "=r"(wb) : "r"(wbase_s + 2u * (cidx >> 5)));
-                const uint32_t slot = wb + (uint32_t)__popc(wbits & ((1u << (cidx & 31u)) - 1u)) - rank0;
-                const uint32_t d = acc_s + 4u * (slot * PK_ACCW + (uint32_t)((y0 & 7) * 9 + (x0 & 7)));
+                const uint32_t rank = wb + (uint32_t)__popc(wbits & pk_below(cidx));
+                const uint32_t d = slot0_s + rank * (uint32_t)(4 * PK_ACCW) + 4u * (uint32_t)((y0 & 7) * 9 + (x0 & 7));
+                // (|height| exceeds 1 by a few ulps of the lerp: no mantissa trick for the rounding, F2I it is)
                 const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
                 pk_red_add(d, (uint32_t)qa);
                 pk_red_add(d + 4u, (uint32_t)(qh - qa));
-            } else if ((w.y_dir > 0) ? (ry >= R1) : (ry < R0)) {
-                break;  // the walk is monotone in y: it has left the band for good
             }
             p0x = p1x;
             p0y = p1y;
-            if (done) break;
-        }
+            more = (t1 != 1.0f) && ((ry - lim) * w.y_dir < 0);
+        } while (more);
     }
 }
 
@@ -796,6 +809,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             }
             for (uint32_t i = tid; i < (uint32_t)(W * Hs); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
             for (uint32_t i = tid; i <= (uint32_t)(W * Hs) >> 5; i += PK_THREADS) S.bits[i] = 0;
+            if (tid == 0) S.merr = 0;
             __syncthreads();
             if (tid < PK_NCLS) S.bcur[tid] = 0;
             __syncthreads();
@@ -812,8 +826,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 pk_st(&G.slines[pos], pk_ld(&G.lines[i], pk_pol), pk_pol);
             }
             __syncthreads();
-            const uint32_t err = pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
+            pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), smem_s + (uint32_t)offsetof(PkShared, merr), G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
             __syncthreads();
+            const uint32_t err = S.merr;
             uint32_t bad;
             pk_grid_scan(S, W, Hs, err, wcarry, sc, nt, ns, wtot, bad);
             // slot bands: as many whole tile rows as fit PK_SLOTS resident tiles
