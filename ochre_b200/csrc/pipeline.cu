@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -488,6 +489,21 @@ k_fb_records(const uint32_t* __restrict__ fb, uint32_t n_fb, const uint32_t* __r
     rec[fb[q]] = make_uint4(tile_at + t0, t1 - t0, span_at + s0, s1 - s0);
 }
 
+// Control words travel between host and device in kernels, never through a copy engine: a few bytes queued on a
+// copy engine wait behind whatever bulk transfer another stream has put there (the result download, the input
+// upload) and would serialise the chunks of a call with those transfers.
+__global__ void k_words_to_host(const uint32_t* __restrict__ src, volatile uint32_t* __restrict__ host, uint32_t n) {
+    if (threadIdx.x < n) host[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+__global__ void k_ctl_reset(uint32_t* __restrict__ ctl, uint32_t n, uint32_t cursor_at, uint32_t cur_t, uint32_t cur_s) {
+    if (threadIdx.x < n) ctl[threadIdx.x] = threadIdx.x == cursor_at ? cur_t : threadIdx.x == cursor_at + 1 ? cur_s : 0u;
+}
+__global__ void k_set_words2(uint32_t* __restrict__ a, uint32_t va, uint32_t* __restrict__ b, uint32_t vb) {
+    *a = va;
+    *b = vb;
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -555,6 +571,16 @@ struct HostBuf {  // pinned
         cap = ncap;
         return cudaSuccess;
     }
+    // small block that kernels write directly (k_words_to_host): mapped into the device address space
+    void* dev = nullptr;
+    cudaError_t ensure_mapped(size_t bytes) {
+        if (p) return cudaSuccess;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocMapped);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = bytes;
+        e = cudaHostGetDevicePointer(&dev, p, 0);
+        return e;
+    }
     void release() {
         if (p) cudaFreeHost(p);
         p = nullptr;
@@ -567,6 +593,7 @@ struct HostBuf {  // pinned
 #define OC_L2_SETASIDE_MB 0
 #endif
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
+constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 20;
 constexpr int N_STAGE = 8;
 
 }  // namespace
@@ -660,7 +687,7 @@ struct ChunkOut {
 };
 
 int read_scalars(ochre_b200_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->h_scalars.p, ctx->d_scalars.p, SC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->st));
+    k_words_to_host<<<1, 32, 0, ctx->st>>>(ctx->d_scalars.as<uint32_t>(), static_cast<uint32_t*>(ctx->h_scalars.dev), SC_COUNT);
     CK(cudaStreamSynchronize(ctx->st));
     return 0;
 }
@@ -917,12 +944,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         uint8_t* const alpha_base = ext ? ctx->x_alpha : ctx->s_alpha.as<uint8_t>();
         const uint32_t cap_t = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::min<uint64_t>(ext ? ctx->x_tile_cap : ctx->s_alpha.cap / 64, ctx->s_tile_xy.cap / 4));
         const uint32_t cap_s = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(0xfffffff0ull, ext ? ctx->x_span_cap : ~0ull), ctx->s_spans.cap / sizeof(OchreSpan));
-        CK(cudaMemsetAsync(ctl, 0, PKC_WORDS * 4, st));
-        if (base_t | base_s) {  // the cursors continue where the previous chunk stopped
-            h_ctl[8] = base_t;
-            h_ctl[9] = base_s;
-            CK(cudaMemcpyAsync(ctl + PKC_CURSOR, h_ctl + 8, 8, cudaMemcpyHostToDevice, st));
-        }
+        // zeroed; the cursors continue where the previous chunk stopped
+        k_ctl_reset<<<1, 32, 0, st>>>(ctl, PKC_WORDS, PKC_CURSOR, base_t, base_s);
         PathKernelArgs A;
         A.cmds = d_cmds_all + cmd_lo;
         A.cmd_off = d_cmd_off_all + p0;
@@ -944,7 +967,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         CK(cudaEventRecord(ctx->ev[0], st));
         k_path<false><<<grid, PK_THREADS, PK_SMEM, st>>>(A);
         CK(cudaEventRecord(ctx->ev[1], st));
-        CK(cudaMemcpyAsync(h_ctl, ctl, PKC_WORDS * 4, cudaMemcpyDeviceToHost, st));
+        k_words_to_host<<<1, 32, 0, st>>>(ctl, static_cast<uint32_t*>(ctx->h_pk_ctl.dev), PKC_WORDS);
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         float ms = 0;
@@ -973,7 +996,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             CK(cudaEventRecord(ctx->ev[0], st));
             k_path<true><<<(uint32_t)std::min<uint64_t>(n1, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM), PK_THREADS, PK_SMEM, st>>>(B);
             CK(cudaEventRecord(ctx->ev[1], st));
-            CK(cudaMemcpyAsync(h_ctl, ctl, PKC_WORDS * 4, cudaMemcpyDeviceToHost, st));
+            k_words_to_host<<<1, 32, 0, st>>>(ctl, static_cast<uint32_t*>(ctx->h_pk_ctl.dev), PKC_WORDS);
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
             CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
@@ -1140,9 +1163,9 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = ctx->d_pk_ctl.ensure(64);
-    if (e == cudaSuccess) e = ctx->h_pk_ctl.ensure(64);
+    if (e == cudaSuccess) e = ctx->h_pk_ctl.ensure_mapped(256);
     if (e == cudaSuccess) e = ctx->d_scalars.ensure(SC_COUNT * sizeof(uint32_t));
-    if (e == cudaSuccess) e = ctx->h_scalars.ensure(SC_COUNT * sizeof(uint32_t));
+    if (e == cudaSuccess) e = ctx->h_scalars.ensure_mapped(256);
     if (e != cudaSuccess) { ochre_b200_destroy(ctx); return (int)e; }
     *out = ctx;
     return 0;
@@ -1256,12 +1279,16 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     // ---- chunk plan -------------------------------------------------------------
     std::vector<uint32_t> cuts;  // chunk i = paths [cuts[i], cuts[i + 1])
     cuts.push_back(0);
+    // Host-resident results: the download of a chunk starts when its kernels are done, so the first chunks are small
+    // (1 Mi virtual commands, doubling) -- the PCIe link is busy almost from the start of the call.
+    const bool ramp = !out_dev && ctx->chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
         uint32_t p1 = p0;
         uint64_t nv = 0;
+        const uint64_t limit = ramp ? std::min<uint64_t>(ctx->chunk_vcmds, (uint64_t)RAMP_FIRST_VCMDS << std::min<size_t>(cuts.size() - 1, 16)) : ctx->chunk_vcmds;
         while (p1 < n_paths) {
             uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
-            if (p1 > p0 && nv + add > ctx->chunk_vcmds) break;
+            if (p1 > p0 && nv + add > limit) break;
             nv += add;
             ++p1;
         }
@@ -1319,6 +1346,9 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
 
     // ---- chunks ---------------------------------------------------------------
+    const bool trace = getenv("OCHRE_B200_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
     uint32_t tile_base = 0, span_base = 0;
     ChunkOut total;
     for (size_t c = 0; c < n_chunks; ++c) {
@@ -1346,6 +1376,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             cudaStreamSynchronize(ctx->st_out);
             return rc;
         }
+        if (trace) fprintf(stderr, "[ochre_b200] chunk %zu: paths [%u, %u) tiles %u done at %.3f ms\n", c, p0, p1, co.n_tiles, now_ms());
         if (!out_dev) {
             // the chunk is complete on the device (run_chunk* drained the kernel stream): its slice of the
             // result goes to the host while the next chunk is being rasterised
@@ -1384,11 +1415,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     if (!in_dev) CK(cudaStreamSynchronize(ctx->st_in));
     // closing entries of the offset arrays
     {
-        uint32_t* hs = ctx->h_scalars.as<uint32_t>();
-        hs[0] = tile_base;
-        hs[1] = span_base;
-        CK(cudaMemcpyAsync(ctx->o_tile_off.as<uint32_t>() + n_paths, hs, 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->o_span_off.as<uint32_t>() + n_paths, hs + 1, 4, cudaMemcpyHostToDevice, st));
+        k_set_words2<<<1, 1, 0, st>>>(ctx->o_tile_off.as<uint32_t>() + n_paths, tile_base, ctx->o_span_off.as<uint32_t>() + n_paths, span_base);
         CK(cudaStreamSynchronize(st));
     }
     out->n_tiles = tile_base;
@@ -1439,7 +1466,9 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         ctx->h_tile_off.as<uint32_t>()[n_paths] = tile_base;  // (ordered after the downloads by the synchronize below)
         ctx->h_span_off.as<uint32_t>()[n_paths] = span_base;
         CK(cudaEventRecord(ctx->ev_out[1], ctx->st_out));
+        if (trace) fprintf(stderr, "[ochre_b200] kernels done at %.3f ms\n", now_ms());
         CK(cudaStreamSynchronize(ctx->st_out));
+        if (trace) fprintf(stderr, "[ochre_b200] download done at %.3f ms\n", now_ms());
         CK(cudaEventElapsedTime(&copy_ms, ctx->ev_out[0], ctx->ev_out[1]));
         out->tile_off = unordered ? nullptr : ctx->h_tile_off.as<uint32_t>();
         out->span_off = unordered ? nullptr : ctx->h_span_off.as<uint32_t>();
@@ -1549,8 +1578,8 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
     device_scan(st, n_paths, [nflat] __device__(uint32_t i) { return nflat[i]; },
                 [flat_off] __device__(uint32_t i, uint32_t excl, uint32_t) { flat_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
                 flat_off + n_paths);
-    CK(cudaMemcpyAsync(hs, d_sc, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hs + 1, flat_off + n_paths, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(d_sc + 1, flat_off + n_paths, 4, cudaMemcpyDeviceToDevice, st));
+    k_words_to_host<<<1, 32, 0, st>>>(d_sc, static_cast<uint32_t*>(ctx->h_scalars.dev), 2);
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (hs[0] != 0) {
