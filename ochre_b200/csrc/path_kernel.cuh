@@ -69,10 +69,11 @@ constexpr int PK_MAXB = 32;         // slot bands per path
 #define PK_INFO_NONE 0xffffffffu
 #define PK_OWNER_NONE 0xffffffffu
 
-// Per-CTA scratch in global memory (stays in L2).
+// Per-CTA scratch in global memory (stays in L2).  Lines are written once, in path order; the bucketed orders
+// the DDA passes walk them in are lists of 16-bit line indices.
 constexpr size_t PK_SCR_LINES = 0;                                             // float4[LINECAP]   lines in path order
-constexpr size_t PK_SCR_SLINES = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;   // float4[SLINECAP]  lines in bucket order
-constexpr size_t PK_SCR_REC = PK_SCR_SLINES + sizeof(float4) * PK_SLINECAP;    // uint2[LINECAP]    (t, owner) of every line
+constexpr size_t PK_SCR_SIDX = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;     // uint16[SLINECAP]  line indices in bucket order
+constexpr size_t PK_SCR_REC = PK_SCR_SIDX + sizeof(uint16_t) * PK_SLINECAP;    // uint2[LINECAP]    (t, owner) of every line
 constexpr size_t PK_SCR_INFO = PK_SCR_REC + sizeof(uint2) * PK_LINECAP;        // uint32[LINECAP]   tile rows + class
 constexpr size_t PK_SCR_BYTES = PK_SCR_INFO + 4 * (size_t)PK_LINECAP;
 
@@ -253,6 +254,14 @@ __device__ __forceinline__ void pk_st(uint2* p, uint2 v, uint64_t pol) {
 __device__ __forceinline__ void pk_st(uint32_t* p, uint32_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void pk_st(uint16_t* p, uint16_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint16_t pk_ld(const uint16_t* p, uint64_t pol) {
+    uint16_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ float4 pk_ld(const float4* p, uint64_t pol) {
     float4 v;
     asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
@@ -276,11 +285,11 @@ template <class T> __device__ __forceinline__ T pk_ld(const T* p, uint64_t) { re
 
 struct PkScratch {
     float4* lines;
-    float4* slines;
+    uint16_t* sidx;
     uint2* rec;
     uint32_t* info;
     __device__ __forceinline__ explicit PkScratch(unsigned char* b)
-        : lines(reinterpret_cast<float4*>(b + PK_SCR_LINES)), slines(reinterpret_cast<float4*>(b + PK_SCR_SLINES)),
+        : lines(reinterpret_cast<float4*>(b + PK_SCR_LINES)), sidx(reinterpret_cast<uint16_t*>(b + PK_SCR_SIDX)),
           rec(reinterpret_cast<uint2*>(b + PK_SCR_REC)), info(reinterpret_cast<uint32_t*>(b + PK_SCR_INFO)) {}
 };
 
@@ -360,18 +369,22 @@ __device__ __forceinline__ uint32_t pk_below(uint32_t n) {
 
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
-__device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address of the cells */, uint32_t merr_s /* ... of PkShared::merr */, const float4* __restrict__ sl, uint32_t n, int gx0, int gy0, int W, int H,
-                                        bool striped, uint64_t pk_pol) {
+__device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address of the cells */, uint32_t merr_s /* ... of PkShared::merr */, const float4* __restrict__ lines,
+                                        const uint16_t* __restrict__ sidx, uint32_t n, int gx0, int gy0, int W, int H, bool striped, uint64_t pk_pol) {
     uint32_t pos = threadIdx.x;
     asm volatile("" : "+r"(cell_s));  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
+    // two-deep prefetch: the index of the line after next, the end points of the next line
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pos < n) Ln = pk_ld(&sl[pos], pk_pol);
+    uint32_t inn = 0;
+    if (pos < n) Ln = pk_ld(&lines[pk_ld(&sidx[pos], pk_pol)], pk_pol);
+    if (pos + PK_THREADS < n) inn = pk_ld(&sidx[pos + PK_THREADS], pk_pol);
     // (the trip count is warp-uniform: bounded by the warp's first lane)
     for (uint32_t wpos = threadIdx.x & ~31u; wpos < n; wpos += PK_THREADS, pos += PK_THREADS) {
         __syncwarp();  // lanes of a warp hold lines of (nearly) equal step count: keep them in lockstep
         if (pos >= n) continue;
         const float4 L = Ln;
-        if (pos + PK_THREADS < n) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
+        if (pos + PK_THREADS < n) Ln = pk_ld(&lines[inn], pk_pol);
+        if (pos + 2 * PK_THREADS < n) inn = pk_ld(&sidx[pos + 2 * PK_THREADS], pk_pol);
         LineWalk w;
         w.init(L, gx0 * 8, gy0 * 8);
         int prev_ty = w.y >> 3;
@@ -398,8 +411,9 @@ __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address
 
 // Accumulate pass over the bucketed lines [p0, p1) of one slot band: grid rows [R0, R1) as absolute
 // tile rows; slot = rank - rank0.
-__device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window address of the accumulators */, const PkShared& S, const float4* __restrict__ sl, uint32_t p0, uint32_t p1,
-                                              int gx0, int gy0, int W, int R0, int R1, uint32_t rank0, uint64_t pk_pol) {
+__device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window address of the accumulators */, const PkShared& S, const float4* __restrict__ lines,
+                                              const uint16_t* __restrict__ sidx, uint32_t p0, uint32_t p1, int gx0, int gy0, int W, int R0, int R1, uint32_t rank0,
+                                              uint64_t pk_pol) {
     uint32_t pos = p0 + threadIdx.x;
     uint32_t bits_s = acc_s + (uint32_t)(offsetof(PkShared, bits) - offsetof(PkShared, u));
     uint32_t wbase_s = acc_s + (uint32_t)(offsetof(PkShared, wbase) - offsetof(PkShared, u));
@@ -408,12 +422,15 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
     const uint32_t nrows = (uint32_t)(R1 - R0);
     asm volatile("" : "+r"(slot0_s), "+r"(bits_s), "+r"(wbase_s));
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (pos < p1) Ln = pk_ld(&sl[pos], pk_pol);
+    uint32_t inn = 0;
+    if (pos < p1) Ln = pk_ld(&lines[pk_ld(&sidx[pos], pk_pol)], pk_pol);
+    if (pos + PK_THREADS < p1) inn = pk_ld(&sidx[pos + PK_THREADS], pk_pol);
     for (uint32_t wpos = p0 + (threadIdx.x & ~31u); wpos < p1; wpos += PK_THREADS, pos += PK_THREADS) {
         __syncwarp();
         if (pos >= p1) continue;
         const float4 L = Ln;
-        if (pos + PK_THREADS < p1) Ln = pk_ld(&sl[pos + PK_THREADS], pk_pol);
+        if (pos + PK_THREADS < p1) Ln = pk_ld(&lines[inn], pk_pol);
+        if (pos + 2 * PK_THREADS < p1) inn = pk_ld(&sidx[pos + 2 * PK_THREADS], pk_pol);
         LineWalk w;
         w.init(L, gx0 * 8, gy0 * 8);
         // p0 of the first increment: t0 = max(0, 0) = 0 (rasterizer.rs:99-101)
@@ -823,10 +840,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
 #pragma unroll
                 for (int q = 0; q < PK_NCLS; ++q) base = (k == (uint32_t)q) ? cbase[q] : base;
                 const uint32_t pos = base + atomicAdd(&S.bcur[k], 1u);
-                pk_st(&G.slines[pos], pk_ld(&G.lines[i], pk_pol), pk_pol);
+                pk_st(&G.sidx[pos], (uint16_t)i, pk_pol);
             }
             __syncthreads();
-            pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), smem_s + (uint32_t)offsetof(PkShared, merr), G.slines, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
+            pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), smem_s + (uint32_t)offsetof(PkShared, merr), G.lines, G.sidx, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
             __syncthreads();
             const uint32_t err = S.merr;
             uint32_t bad;
@@ -888,10 +905,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
                     const uint32_t bb01 = pk_ld(&G.rec[i], pk_pol).x;
                     const int b0 = (int)(bb01 & 0xffu), b1 = (int)(bb01 >> 8);
-                    const float4 L = pk_ld(&G.lines[i], pk_pol);
                     for (int b = b0; b <= b1; ++b) {
                         const uint32_t k = b * PK_NCLS + pk_info_cls(info);
-                        pk_st(&G.slines[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], L, pk_pol);
+                        pk_st(&G.sidx[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], (uint16_t)i, pk_pol);
                     }
                 }
                 // (the barrier before the first band's accumulate pass orders these stores)
@@ -914,7 +930,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += PK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 __syncthreads();
-                pk_accumulate(smem_s + (uint32_t)offsetof(PkShared, u), S, G.slines, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, y0s, W, y0s + r0, y0s + r1,
+                pk_accumulate(smem_s + (uint32_t)offsetof(PkShared, u), S, G.lines, G.sidx, S.boff[b * PK_NCLS], S.boff[(b + 1) * PK_NCLS], gx0, y0s, W, y0s + r0, y0s + r1,
                               rank0, pk_pol);
                 __syncthreads();
                 // row sums: one thread per (tile, pixel row); the sum of the 9 columns is the row's total height
