@@ -137,6 +137,13 @@ int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
 #define OCHRE_MODE_FUSED 2
 int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode);
 
+/* The fused per-path kernel exists in two CTA shapes: 128 threads per path (ordinary and large paths) and a warp per
+ * path (small paths such as glyphs: four times as many paths in flight per SM).  In calls with at least `min_paths`
+ * paths, every path whose transformed control points span a bounding grid of at most `small_max_cells` tiles (one
+ * tile of margin on each side included) takes the small shape.  Defaults: 64 cells, 8192 paths; small_max_cells = 0
+ * switches the small shape off.  Results do not depend on the routing (integer accumulation). */
+int ochre_b200_set_routing(ochre_b200_ctx* ctx, int32_t small_max_cells, uint32_t min_paths);
+
 /* Row-band sharding of one huge path across GPUs (BASELINE config 5): only
  * tiles and spans whose tile row ty = y / 8 lies in [tile_row_lo, tile_row_hi) are produced.  Every
  * tile row of the reference's output depends only on the increments of that row

@@ -21,7 +21,7 @@ ERRORS = {
 #: every symbol include/ochre_b200.h declares
 SYMBOLS = [
     "ochre_b200_create", "ochre_b200_destroy", "ochre_b200_rasterize", "ochre_b200_rasterize_paints", "ochre_b200_set_chunk", "ochre_b200_set_mode",
-    "ochre_b200_set_row_band", "ochre_b200_arena_create", "ochre_b200_arena_open", "ochre_b200_arena_close",
+    "ochre_b200_set_row_band", "ochre_b200_set_routing", "ochre_b200_arena_create", "ochre_b200_arena_open", "ochre_b200_arena_close",
     "ochre_b200_set_output_arena", "ochre_b200_copy_to_host", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_version",
@@ -81,6 +81,7 @@ def load():
     L.ochre_b200_rasterize_paints.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, C.POINTER(OchreResult)]
     L.ochre_b200_set_chunk.argtypes = [vp, u32]
     L.ochre_b200_set_mode.argtypes = [vp, C.c_int]
+    L.ochre_b200_set_routing.argtypes = [vp, C.c_int32, u32]
     L.ochre_b200_set_row_band.argtypes = [vp, C.c_int32, C.c_int32]
     L.ochre_b200_arena_create.argtypes = [vp, u64, u64, u64, C.POINTER(OchreArena)]
     L.ochre_b200_arena_open.argtypes = [vp, vp, u64, u64, u64, C.POINTER(OchreArena)]

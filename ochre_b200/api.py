@@ -164,6 +164,10 @@ class Context:
         m = {"auto": 0, "general": 1, "fused": 2}.get(mode, mode)
         _check(self._h, _lib.load().ochre_b200_set_mode(self._h, int(m)))
 
+    def set_routing(self, small_max_cells: int = 64, min_paths: int = 8192):
+        """Which paths take the warp-per-path shape of the fused kernel (`ochre_b200_set_routing`)."""
+        _check(self._h, _lib.load().ochre_b200_set_routing(self._h, small_max_cells, min_paths))
+
     def set_row_band(self, tile_row_lo: int = 0, tile_row_hi: int = 0):
         """Rasterise only tile rows [lo, hi) (row-band sharding of one huge path); lo >= hi resets."""
         _check(self._h, _lib.load().ochre_b200_set_row_band(self._h, int(tile_row_lo), int(tile_row_hi)))

@@ -28,46 +28,29 @@
 // HBM traffic is the compulsory B_alg (commands in, tiles/spans out) plus an L2-resident per-CTA
 // line scratch.  Accumulation is order-independent (integer adds), so results do not depend on
 // scheduling; tests/emu reproduces the arithmetic byte for byte.
-#pragma once
-#include <cuda_runtime.h>
-#include <stddef.h>
-#include <stdint.h>
+//
+// This file is a template in the preprocessor sense: pipeline.cu includes it once per CTA configuration, with
+// OC_PK_NS (namespace of the instantiation), OC_PK_THREADS, OC_PK_SLOTS, OC_PK_CELLS and OC_PK_CTAS defined:
+//   oc::pkl  128 threads, 80 accumulator slots, 5888-cell grids, 8 CTAs per SM   ordinary and large paths
+//   oc::pks   32 threads, 20 accumulator slots, 1024-cell grids, 32 CTAs per SM  small paths (glyphs): a warp per path,
+//             CTA barriers cost next to nothing and four times as many paths are in flight per SM
+#include "path_kernel_common.cuh"
 
-#include "../../include/ochre_b200.h"
-#include "raster_core.cuh"
-#include "scan.cuh"
+#if !defined(OC_PK_NS) || !defined(OC_PK_THREADS) || !defined(OC_PK_SLOTS) || !defined(OC_PK_CELLS) || !defined(OC_PK_CTAS) || !defined(OC_PK_LINECAP) || !defined(OC_PK_MAXB)
+#error "define OC_PK_NS, OC_PK_THREADS, OC_PK_SLOTS, OC_PK_CELLS, OC_PK_CTAS, OC_PK_LINECAP before including path_kernel.cuh"
+#endif
 
 namespace oc {
+namespace OC_PK_NS {
 
-#ifndef OC_PK_THREADS
-#define OC_PK_THREADS 128
-#endif
-#ifndef OC_PK_SLOTS
-#define OC_PK_SLOTS 80
-#endif
-#ifndef OC_PK_CELLS
-#define OC_PK_CELLS 5888
-#endif
-#ifndef OC_PK_CTAS
-#define OC_PK_CTAS 8
-#endif
 constexpr int PK_THREADS = OC_PK_THREADS;
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
 constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the path's bounding grid (tiles)
 constexpr int PK_CTAS_PER_SM = OC_PK_CTAS;
-constexpr int PK_MAXLINES = 4095;   // lines marked together (a path, or one stripe of it): keeps a cell's 16-bit increment count exact (<= 16 per line)
-constexpr int PK_LINECAP = 16384;   // line slots per path (scratch stride)
-constexpr int PK_MAXSTRIPES = 8;    // stripes of tile rows for paths whose bounding grid or line count exceeds one pass
-constexpr int PK_SLINECAP = 2 * PK_LINECAP;  // bucketed copies (one per slot band a line touches)
-constexpr int PK_MAXCNT = 511;      // increments per tile: keeps the fixed-point sums inside int32
-constexpr int PK_ACCW = 72;         // accumulator words per tile: 8 pixel rows x (8 columns + 1 carry-out column)
-constexpr int PK_NCLS = 8;          // step-count classes: 1, 2, 3, 4, 5-6, 7-9, 10-15, 16+
-constexpr int PK_MAXB = 32;         // slot bands per path
-#define OC_FX_SCALE 4194304.0f      /* 2^22 */
-#define OC_FX_TO_256 (1.0f / 16384.0f) /* 2^-22 * 256 */
-#define PK_CELL_INIT 0x80000000u    /* increments 0, winding delta 0 (biased by 0x8000) */
-#define PK_INFO_NONE 0xffffffffu
-#define PK_OWNER_NONE 0xffffffffu
+constexpr int PK_MAXB = OC_PK_MAXB;         // slot bands per path
+constexpr int PK_LINECAP = OC_PK_LINECAP;   // line slots per path (scratch stride)
+constexpr int PK_SLINECAP = 2 * PK_LINECAP;  // bucketed index lists (one entry per slot band a line touches)
+constexpr int PK_MAXLINES = PK_LINECAP > 4096 ? 4095 : PK_LINECAP - 1;   // lines marked together (a path, or one stripe of it): keeps a cell's 16-bit increment count exact (<= 16 per line)
 
 // Per-CTA scratch in global memory (stays in L2).  Lines are written once, in path order; the bucketed orders
 // the DDA passes walk them in are lists of 16-bit line indices.
@@ -76,212 +59,6 @@ constexpr size_t PK_SCR_SIDX = PK_SCR_LINES + sizeof(float4) * PK_LINECAP;     /
 constexpr size_t PK_SCR_REC = PK_SCR_SIDX + sizeof(uint16_t) * PK_SLINECAP;    // uint2[LINECAP]    (t, owner) of every line
 constexpr size_t PK_SCR_INFO = PK_SCR_REC + sizeof(uint2) * PK_LINECAP;        // uint32[LINECAP]   tile rows + class
 constexpr size_t PK_SCR_BYTES = PK_SCR_INFO + 4 * (size_t)PK_LINECAP;
-
-struct PathKernelArgs {
-    const Cmd* cmds;            // chunk base (index with cmd_off[p] - cmd_base)
-    const uint32_t* cmd_off;    // cmd_off[0 .. n_paths] of this chunk
-    uint32_t cmd_base;
-    const float* xf;            // 6 floats per path
-    uint32_t n_paths;
-    uint32_t* ticket;           // work counter (dynamic path assignment)
-    uint32_t* cursor;           // [0] tiles, [1] spans handed out so far in the arena
-    uint4* rec;                 // per path: (tile start, n_tiles, span start, n_spans) in the arena
-    uint32_t cap_tiles, cap_spans;
-    int16_t* tile_xy;
-    uint8_t* alpha;
-    OchreSpan* spans;
-    unsigned char* scratch;     // gridDim.x * PK_SCR_BYTES
-    int* status;                // [0] input error (ST_*), [1] #paths left to the general pipeline, [2] arena overflow
-    uint32_t* fb_list;          // paths left to the next stage (chunk-local ids), status[1] entries
-    const uint32_t* path_list;  // null: paths 0 .. n_paths-1; else the n_paths chunk-local ids to rasterise
-};
-
-struct PkCurves {  // decoded curve commands of the current command chunk (slot = thread id)
-    V2 last[PK_THREADS], a[PK_THREADS], b[PK_THREADS], c[PK_THREADS];
-    uint32_t loff[PK_THREADS];  // first line of the command
-    uint32_t tag[PK_THREADS];
-};
-enum : uint32_t { CF_TOUCHED = 1, CF_WIND = 2, CF_SPAN = 4 };
-constexpr int PK_WORDS = (PK_CELLS + 31) / 32;
-
-struct PkShared {
-    union {  // phase-aliased: flatten | mark + scan + span/origin emission | accumulate + quantise
-        int acc[PK_SLOTS * PK_ACCW];
-        uint32_t cell[PK_CELLS];  // mark pass: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: CF_* flags
-        PkCurves v;
-    } u;
-    // touched cells of the grid in (tile_y, tile_x) order, kept across the slot bands:
-    // rank(c) = wbase[c >> 5] + popc(bits[c >> 5] & below(c & 31))
-    uint32_t bits[PK_WORDS + 1];
-    uint16_t wbase[PK_WORDS + 2];
-    uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
-    uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
-    uint16_t brow[PK_MAXB + 2];             // first row of every slot band (relative to the stripe)
-    uint16_t srow[PK_MAXSTRIPES + 2];       // first grid row of every stripe
-    uint32_t ws[72];
-    int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
-    uint32_t path, next_path, nbands, nstripes, base_tiles, base_spans, flag;
-    uint32_t merr;  // set by the mark pass when a walk leaves the grid (never, by construction: the path is handed over)
-};
-
-// touched cells before cell c (c may be one past the last cell)
-__device__ __forceinline__ uint32_t pk_rank(const PkShared& S, uint32_t c) {
-    return (uint32_t)S.wbase[c >> 5] + (uint32_t)__popc(S.bits[c >> 5] & ((1u << (c & 31u)) - 1u));
-}
-// first touched cell in [c, end), or `end`
-__device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t c, uint32_t end) {
-    while (c < end) {
-        const uint32_t w = S.bits[c >> 5] >> (c & 31u);
-        if (w) return min(end, c + (uint32_t)__ffs((int)w) - 1u);
-        c = (c | 31u) + 1u;
-    }
-    return end;
-}
-
-// Exclusive scan of two values per thread across the CTA in one pass.  `ws` must hold 72 words.
-__device__ __forceinline__ void block_excl_scan_pair(uint32_t a, uint32_t b, uint32_t* ws, uint32_t& ex_a, uint32_t& ex_b,
-                                                     uint32_t& tot_a, uint32_t& tot_b) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t ia = a, ib = b;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t na = __shfl_up_sync(0xffffffffu, ia, d);
-        uint32_t nb = __shfl_up_sync(0xffffffffu, ib, d);
-        if (lane >= (unsigned)d) {
-            ia += na;
-            ib += nb;
-        }
-    }
-    if (lane == 31) {
-        ws[warp] = ia;
-        ws[36 + warp] = ib;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const unsigned nw = blockDim.x >> 5;
-        uint32_t wa = (lane < nw) ? ws[lane] : 0u, wb = (lane < nw) ? ws[36 + lane] : 0u;
-        uint32_t sa = wa, sb = wb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t na = __shfl_up_sync(0xffffffffu, sa, d);
-            uint32_t nb = __shfl_up_sync(0xffffffffu, sb, d);
-            if (lane >= (unsigned)d) {
-                sa += na;
-                sb += nb;
-            }
-        }
-        ws[lane] = sa - wa;
-        ws[36 + lane] = sb - wb;
-        if (lane == 31) {
-            ws[32] = sa;
-            ws[68] = sb;
-        }
-    }
-    __syncthreads();
-    ex_a = ia - a + ws[warp];
-    ex_b = ib - b + ws[36 + warp];
-    tot_a = ws[32];
-    tot_b = ws[68];
-    __syncthreads();
-}
-
-// The DDA of Rasterizer::line_to (rasterizer.rs:74-136), device form.  Same operations in the
-// same order as raster_core.cuh's Walker; the loop exit `row_t0 == 1 || col_t0 == 1` is tested
-// as `t1 == 1`: the t0 a trip stores is the t1 it consumed, and an earlier one would have ended
-// the loop already.
-struct LineWalk {
-    float lx, ly, px, py;
-    float row_t1, col_t1, x_step, y_step;
-    int x, y, x_dir, y_dir, end_x, end_y;  // pixel coordinates relative to (ox, oy), multiples of 8: tile and sub-tile bits are unchanged
-    __device__ __forceinline__ void init(const float4 L, int ox, int oy) {
-        lx = L.x;
-        ly = L.y;
-        px = L.z;
-        py = L.w;
-        const float dx = px - lx, dy = py - ly;
-        x_dir = sign_dir(dx);
-        y_dir = sign_dir(dy);
-        const float dtdx = 1.0f / dx, dtdy = 1.0f / dy;
-        const int ax = floor_px(lx), ay = floor_px(ly);
-        row_t1 = INFINITY;
-        col_t1 = INFINITY;
-        if (ly != py) row_t1 = fminf(dtdy * (((py > ly) ? (float)(ay + 1) : (float)ay) - ly), 1.0f);
-        if (lx != px) col_t1 = fminf(dtdx * (((px > lx) ? (float)(ax + 1) : (float)ax) - lx), 1.0f);
-        x_step = fabsf(dtdx);
-        y_step = fabsf(dtdy);
-        x = ax - ox;
-        y = ay - oy;
-        end_x = floor_px(px) - ox;
-        end_y = floor_px(py) - oy;
-    }
-    // One loop trip's control flow, branch-free: returns the trip's t1 and whether it was a row step; moves to the next
-    // pixel.  (The stepped bound is t1 itself: min(row_t1, col_t1) is row_t1 on a row step, col_t1 otherwise -- ties
-    // go to columns, rasterizer.rs:118-122.)  The end snap (rasterizer.rs:119-121) is the caller's: `if (done) snap()`.
-    __device__ __forceinline__ float advance(bool& row) {
-        row = row_t1 < col_t1;
-        const float t1 = fminf(row_t1, col_t1);
-        const float nt = fminf(t1 + (row ? y_step : x_step), 1.0f);
-        row_t1 = row ? nt : row_t1;
-        col_t1 = row ? col_t1 : nt;
-        y += row ? y_dir : 0;
-        x += row ? 0 : x_dir;
-        return t1;
-    }
-    __device__ __forceinline__ void snap() {
-        x = end_x;
-        y = end_y;
-    }
-};
-
-// Scratch accesses carry an L2 evict_last policy (OC_PK_EVICT_LAST=1): the per-CTA line scratch is
-// rewritten for every path and should not be flushed to HBM by the streaming results.
-#ifndef OC_PK_EVICT_LAST
-#define OC_PK_EVICT_LAST 0
-#endif
-#if OC_PK_EVICT_LAST
-__device__ __forceinline__ uint64_t pk_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-#define PK_POLICY_DECL const uint64_t pk_pol = pk_policy();
-__device__ __forceinline__ void pk_st(float4* p, float4 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void pk_st(uint2* p, uint2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void pk_st(uint32_t* p, uint32_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void pk_st(uint16_t* p, uint16_t v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"(v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint16_t pk_ld(const uint16_t* p, uint64_t pol) {
-    uint16_t v;
-    asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float4 pk_ld(const float4* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ uint2 pk_ld(const uint2* p, uint64_t pol) {
-    uint2 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ uint32_t pk_ld(const uint32_t* p, uint64_t pol) {
-    uint32_t v;
-    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-#else
-#define PK_POLICY_DECL const uint64_t pk_pol = 0;
-template <class T> __device__ __forceinline__ void pk_st(T* p, T v, uint64_t) { __stcg(p, v); }
-template <class T> __device__ __forceinline__ T pk_ld(const T* p, uint64_t) { return __ldcg(p); }
-#endif
 
 struct PkScratch {
     float4* lines;
@@ -293,28 +70,6 @@ struct PkScratch {
           rec(reinterpret_cast<uint2*>(b + PK_SCR_REC)), info(reinterpret_cast<uint32_t*>(b + PK_SCR_INFO)) {}
 };
 
-struct PkBBox {
-    int x0, y0, x1, y1;
-};
-
-// Per-line record for bucketing: [12:0] first tile row + 4096, [25:13] last tile row + 4096 (both
-// padded by one pixel for the DDA's overshoot before the end snap), [28:26] step-count class.
-// Also grows the bounding box (tile units).  Only called for lines with two distinct end points.
-__device__ __forceinline__ uint32_t pk_line_info(V2 a, V2 b, PkBBox& bb) {
-    const int ax = floor_px(a.x), ay = floor_px(a.y), ex = floor_px(b.x), ey = floor_px(b.y);
-    bb.x0 = min(bb.x0, min(ax, ex) >> 3);
-    bb.x1 = max(bb.x1, max(ax, ex) >> 3);
-    bb.y0 = min(bb.y0, min(ay, ey) >> 3);
-    bb.y1 = max(bb.y1, max(ay, ey) >> 3);
-    const int lo = ((min(ay, ey) - 1) >> 3) + 4096, hi = ((max(ay, ey) + 1) >> 3) + 4096;
-    const int n = abs(ex - ax) + abs(ey - ay) + 1;  // DDA trips of the line, up to rounding overshoot
-    const int cls = n <= 4 ? n - 1 : 4 + (n > 6) + (n > 9) + (n > 15);
-    return (uint32_t)lo | ((uint32_t)hi << 13) | ((uint32_t)cls << 26);
-}
-__device__ __forceinline__ int pk_info_lo(uint32_t f) { return (int)(f & 0x1fffu) - 4096; }
-__device__ __forceinline__ int pk_info_hi(uint32_t f) { return (int)((f >> 13) & 0x1fffu) - 4096; }
-// bucket of a line: its step-count class, longest first (the short lines fill the tail of a pass)
-__device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return 7u - ((f >> 26) & 7u); }
 
 // Conic commands (path.rs:75-104) are rare: their subdivision runs in the command's own thread, out of line
 // so that its stack of pending intervals does not weigh on the common path.
@@ -353,18 +108,46 @@ __device__ __noinline__ void pk_conic_emit(const PkScratch& G, uint32_t* ccnt, P
     conic_for_each_point(last, control, point, weight, OC_CONIC_TOL, em);
 }
 
-// Shared-memory reductions on a 32-bit shared-window address (computed once per pass): the generic-pointer
-// form makes the compiler rebuild the window base (S2UR + ULEA) at every atomic of the DDA loops.
-__device__ __forceinline__ uint32_t pk_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pk_red_add(uint32_t saddr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
 
-// (1 << n) - 1 for n in [0, 32)
-__device__ __forceinline__ uint32_t pk_below(uint32_t n) {
-    uint32_t m;
-    asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(n));
-    return m;
+struct PkCurves {  // decoded curve commands of the current command chunk (slot = thread id)
+    V2 last[PK_THREADS], a[PK_THREADS], b[PK_THREADS], c[PK_THREADS];
+    uint32_t loff[PK_THREADS];  // first line of the command
+    uint32_t tag[PK_THREADS];
+};
+constexpr int PK_WORDS = (PK_CELLS + 31) / 32;
+
+struct PkShared {
+    union {  // phase-aliased: flatten | mark + scan + span/origin emission | accumulate + quantise
+        int acc[PK_SLOTS * PK_ACCW];
+        uint32_t cell[PK_CELLS];  // mark pass: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: CF_* flags
+        PkCurves v;
+    } u;
+    // touched cells of the grid in (tile_y, tile_x) order, kept across the slot bands:
+    // rank(c) = wbase[c >> 5] + popc(bits[c >> 5] & below(c & 31))
+    uint32_t bits[PK_WORDS + 1];
+    uint16_t wbase[PK_WORDS + 2];
+    uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
+    uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
+    uint16_t brow[PK_MAXB + 2];             // first row of every slot band (relative to the stripe)
+    uint16_t srow[PK_MAXSTRIPES + 2];       // first grid row of every stripe
+    uint32_t ws[72];
+    int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
+    uint32_t path, next_path, nbands, nstripes, base_tiles, base_spans, flag;
+    uint32_t merr;  // set by the mark pass when a walk leaves the grid (never, by construction: the path is handed over)
+};
+
+// touched cells before cell c (c may be one past the last cell)
+__device__ __forceinline__ uint32_t pk_rank(const PkShared& S, uint32_t c) {
+    return (uint32_t)S.wbase[c >> 5] + (uint32_t)__popc(S.bits[c >> 5] & ((1u << (c & 31u)) - 1u));
+}
+// first touched cell in [c, end), or `end`
+__device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t c, uint32_t end) {
+    while (c < end) {
+        const uint32_t w = S.bits[c >> 5] >> (c & 31u);
+        if (w) return min(end, c + (uint32_t)__ffs((int)w) - 1u);
+        c = (c | 31u) + 1u;
+    }
+    return end;
 }
 
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
@@ -598,6 +381,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
     const PkScratch G(A.scratch + (size_t)blockIdx.x * PK_SCR_BYTES);
     PK_POLICY_DECL
 
+    const uint32_t n_take = A.n_paths_dev ? *A.n_paths_dev : A.n_paths;  // paths (or list entries) this launch works through
     if (tid == 0) S.next_path = atomicAdd(A.ticket, 1u);
     for (;;) {
         __syncthreads();
@@ -605,14 +389,14 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             const uint32_t np = S.next_path;
             S.path = np;
             // the next ticket is fetched while this path is processed (hides the L2 round trip)
-            if (np < A.n_paths) S.next_path = atomicAdd(A.ticket, 1u);
+            if (np < n_take) S.next_path = atomicAdd(A.ticket, 1u);
             S.bbox[0] = S.bbox[1] = 0x7fffffff;
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
         }
         if (tid < PK_NCLS) S.bcur[tid] = 0;  // lines per step-count class
         __syncthreads();
-        if (S.path >= A.n_paths) return;
-        const uint32_t p = A.path_list ? A.path_list[S.path] : S.path;
+        if (S.path >= n_take) return;
+        const uint32_t p = A.path_list ? A.path_list[A.list_rev ? A.n_paths - 1u - S.path : S.path] : S.path;
 
         const uint32_t c0 = A.cmd_off[p] - A.cmd_base, c1 = A.cmd_off[p + 1] - A.cmd_base;
         const uint32_t nc = c1 - c0, nv = nc + 1;  // + the virtual FINISH command (finish()'s auto-close)
@@ -1049,4 +833,13 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
 
 constexpr size_t PK_SMEM = sizeof(PkShared);
 
+}  // namespace OC_PK_NS
 }  // namespace oc
+
+#undef OC_PK_NS
+#undef OC_PK_THREADS
+#undef OC_PK_SLOTS
+#undef OC_PK_CELLS
+#undef OC_PK_CTAS
+#undef OC_PK_LINECAP
+#undef OC_PK_MAXB

@@ -27,6 +27,45 @@
 
 #include "../../include/ochre_b200.h"
 #include "atlas.cuh"
+// the fused per-path kernel, twice: ordinary / large paths, and small paths (a warp per path)
+#ifndef OC_PK_THREADS
+#define OC_PK_THREADS 128
+#endif
+#ifndef OC_PK_SLOTS
+#define OC_PK_SLOTS 80
+#endif
+#ifndef OC_PK_CELLS
+#define OC_PK_CELLS 5888
+#endif
+#ifndef OC_PK_CTAS
+#define OC_PK_CTAS 8
+#endif
+#define OC_PK_LINECAP 16384
+#define OC_PK_MAXB 32
+#define OC_PK_NS pkl
+#include "path_kernel.cuh"
+#ifndef OC_PKS_THREADS
+#define OC_PKS_THREADS 32
+#endif
+#ifndef OC_PKS_SLOTS
+#define OC_PKS_SLOTS 20
+#endif
+#ifndef OC_PKS_CELLS
+#define OC_PKS_CELLS 1024
+#endif
+#ifndef OC_PKS_CTAS
+#define OC_PKS_CTAS 32
+#endif
+#define OC_PK_THREADS OC_PKS_THREADS
+#define OC_PK_SLOTS OC_PKS_SLOTS
+#define OC_PK_CELLS OC_PKS_CELLS
+#define OC_PK_CTAS OC_PKS_CTAS
+#define OC_PK_LINECAP 2048
+#ifndef OC_PKS_MAXB
+#define OC_PKS_MAXB 8
+#endif
+#define OC_PK_MAXB OC_PKS_MAXB
+#define OC_PK_NS pks
 #include "path_kernel.cuh"
 #include "radix_sort.cuh"
 #include "raster_core.cuh"
@@ -489,6 +528,53 @@ k_fb_records(const uint32_t* __restrict__ fb, uint32_t n_fb, const uint32_t* __r
     rec[fb[q]] = make_uint4(tile_at + t0, t1 - t0, span_at + s0, s1 - s0);
 }
 
+// ---------------------------------------------------------------------------
+// Routing of a chunk's paths to the two instantiations of the fused kernel: a warp per path takes the bounding box
+// of the transformed control points (curves stay inside the hull of their control points; Conics with a negative
+// weight do not, they count as large).  Small paths fill `list` from the front, the others from the back.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB)
+k_classify(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, const float* __restrict__ xf,
+           uint32_t n_paths, int max_cells, uint32_t max_cmds, uint32_t* __restrict__ counts /* [0] small, [1] large */,
+           uint32_t* __restrict__ list) {
+    const uint32_t p = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (p >= n_paths) return;
+    const uint32_t c0 = cmd_off[p] - cmd_base, nc = cmd_off[p + 1] - cmd_off[p];
+    const float* m = xf + 6 * (size_t)p;
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff, odd = 0;
+    if (nc <= max_cmds) {
+        for (uint32_t j = lane; j < nc; j += 32) {
+            const Cmd& c = cmds[c0 + j];
+            const int np = cmd_npts(c.tag);
+            if (c.tag > TAG_CLOSE || (c.tag == TAG_CONIC && !(c.v[4] >= 0.0f))) odd = 1;
+            for (int i = 0; i < np; ++i) {
+                const V2 q = cmd_point(c, i, m);
+                if (!coord_ok(q)) odd = 1;
+                else {
+                    const int tx = floor_px(q.x) >> 3, ty = floor_px(q.y) >> 3;
+                    x0 = min(x0, tx); x1 = max(x1, tx);
+                    y0 = min(y0, ty); y1 = max(y1, ty);
+                }
+            }
+        }
+    } else {
+        odd = 1;
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
+    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
+    odd = __reduce_or_sync(0xffffffffu, (unsigned)odd);
+    if (lane == 0) {
+        // the path starts at (0, 0) unless it opens with a Move (rasterizer.rs:54-55): a first line from the origin counts
+        bool small = !odd;
+        if (small && x0 <= x1) {
+            if (nc && cmds[c0].tag != TAG_MOVE) { x0 = min(x0, 0); y0 = min(y0, 0); x1 = max(x1, 0); y1 = max(y1, 0); }
+            small = (long long)(x1 - x0 + 3) * (y1 - y0 + 3) <= max_cells;
+        }
+        if (small) list[atomicAdd(&counts[0], 1u)] = p;
+        else list[n_paths - 1u - atomicAdd(&counts[1], 1u)] = p;
+    }
+}
+
 // Control words travel between host and device in kernels, never through a copy engine: a few bytes queued on a
 // copy engine wait behind whatever bulk transfer another stream has put there (the result download, the input
 // upload) and would serialise the chunks of a call with those transfers.
@@ -592,6 +678,9 @@ struct HostBuf {  // pinned
 #ifndef OC_L2_SETASIDE_MB
 #define OC_L2_SETASIDE_MB 0
 #endif
+#ifndef OC_ROUTE_CELLS
+#define OC_ROUTE_CELLS 64
+#endif
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
 constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 20;
 constexpr int N_STAGE = 8;
@@ -629,7 +718,9 @@ struct ochre_b200_ctx {
     int mode = OCHRE_MODE_AUTO;
     int band_lo = OC_BAND_MIN, band_hi = OC_BAND_MAX;  // tile rows rasterised (row-band sharding)
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2, d_big;
+    DevBuf d_pk_scratch, d_pk_scratch_s, d_pk_list, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2, d_big;
+    uint32_t route_min_paths = 8192;
+    int route_cells = OC_ROUTE_CELLS;  // paths whose control points span at most this many tiles (bounding grid incl. margins) take the small-path kernel
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
     // atlas / quad builder (csrc/atlas.cuh)
     DevBuf a_vtx, a_idx, a_atlas, a_span_tile, a_flag, a_sb, a_colors;
@@ -897,7 +988,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
 // runs the general pipeline for this chunk).
 // ---------------------------------------------------------------------------
 enum { RC_NEED_GENERAL = 1001 };
-enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_WORDS = 8 };
+enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_NSMALL = 8, PKC_NLARGE = 9, PKC_TICKET2 = 10, PKC_WORDS = 12 };
 
 int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
                     const uint32_t* h_off, uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base,
@@ -909,10 +1000,19 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
     // area that k_gather_paths copies into path order.
     const uint32_t base_t = unordered ? tile_base : 0u, base_s = unordered ? span_base : 0u;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM);
+    // Small paths (bounding grid of the control points <= route_cells tiles) go to the warp-per-path instantiation
+    // (pks), the rest to the 128-thread one (pkl); route_cells == 0: everything goes to pkl.
+    const int route_cells = ctx->route_cells;
+    // (a batch with fewer paths than a few waves of CTAs is latency bound: one launch, every path on its own CTA)
+    const bool route = route_cells > 0 && n_paths >= ctx->route_min_paths;
+    const uint32_t grid_l = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * pkl::PK_CTAS_PER_SM);
+    const uint32_t grid_s = (uint32_t)std::min<uint64_t>(n_paths, (uint64_t)ctx->sm_count * pks::PK_CTAS_PER_SM);
     {
-        const size_t scr_bytes = (size_t)ctx->sm_count * PK_CTAS_PER_SM * PK_SCR_BYTES;
-        CK(ctx->d_pk_scratch.ensure(scr_bytes));
+        CK(ctx->d_pk_scratch.ensure((size_t)ctx->sm_count * pkl::PK_CTAS_PER_SM * pkl::PK_SCR_BYTES));
+        if (route) {
+            CK(ctx->d_pk_scratch_s.ensure((size_t)ctx->sm_count * pks::PK_CTAS_PER_SM * pks::PK_SCR_BYTES));
+            CK(ctx->d_pk_list.ensure((size_t)n_paths * 4 + 4));
+        }
         // L2 set-aside for the kernel's evict_last accesses to its line scratch (path_kernel.cuh)
         const char* env = getenv("OCHRE_B200_L2_PERSIST_MB");
         const long mb = env ? atol(env) : OC_L2_SETASIDE_MB;
@@ -963,9 +1063,29 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.scratch = ctx->d_pk_scratch.as<unsigned char>();
         A.fb_list = ctx->d_pk_fb.as<uint32_t>();
         A.path_list = nullptr;
+        A.n_paths_dev = nullptr;
+        A.list_rev = 0;
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
         CK(cudaEventRecord(ctx->ev[0], st));
-        k_path<false><<<grid, PK_THREADS, PK_SMEM, st>>>(A);
+        if (route) {
+            uint32_t* list = ctx->d_pk_list.as<uint32_t>();
+            k_classify<<<nblk((uint64_t)n_paths * 32, TPB), TPB, 0, st>>>(A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, route_cells, 256u,
+                                                                         ctl + PKC_NSMALL, list);
+            PathKernelArgs S = A;  // small paths: list[0 .. n_small)
+            S.path_list = list;
+            S.n_paths_dev = ctl + PKC_NSMALL;
+            S.scratch = ctx->d_pk_scratch_s.as<unsigned char>();
+            pks::k_path<false><<<grid_s, pks::PK_THREADS, pks::PK_SMEM, st>>>(S);
+            PathKernelArgs Lg = A;  // the others: list[n_paths - 1], list[n_paths - 2], ...
+            Lg.path_list = list;
+            Lg.n_paths_dev = ctl + PKC_NLARGE;
+            Lg.list_rev = 1;
+            Lg.ticket = ctl + PKC_TICKET2;
+            pkl::k_path<false><<<grid_l, pkl::PK_THREADS, pkl::PK_SMEM, st>>>(Lg);
+            co->launches += 2;
+        } else {
+            pkl::k_path<false><<<grid_l, pkl::PK_THREADS, pkl::PK_SMEM, st>>>(A);
+        }
         CK(cudaEventRecord(ctx->ev[1], st));
         k_words_to_host<<<1, 32, 0, st>>>(ctl, static_cast<uint32_t*>(ctx->h_pk_ctl.dev), PKC_WORDS);
         CK(cudaStreamSynchronize(st));
@@ -994,7 +1114,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             B.path_list = ctx->d_pk_fb.as<uint32_t>();
             B.fb_list = ctx->d_pk_fb2.as<uint32_t>();
             CK(cudaEventRecord(ctx->ev[0], st));
-            k_path<true><<<(uint32_t)std::min<uint64_t>(n1, (uint64_t)ctx->sm_count * PK_CTAS_PER_SM), PK_THREADS, PK_SMEM, st>>>(B);
+            pkl::k_path<true><<<(uint32_t)std::min<uint64_t>(n1, (uint64_t)ctx->sm_count * pkl::PK_CTAS_PER_SM), pkl::PK_THREADS, pkl::PK_SMEM, st>>>(B);
             CK(cudaEventRecord(ctx->ev[1], st));
             k_words_to_host<<<1, 32, 0, st>>>(ctl, static_cast<uint32_t*>(ctx->h_pk_ctl.dev), PKC_WORDS);
             CK(cudaStreamSynchronize(st));
@@ -1159,8 +1279,15 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     }
     e = cudaFuncSetAttribute(k_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pks::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pks::PK_SMEM);
+    {
+        const char* env = getenv("OCHRE_B200_ROUTE_CELLS");  // tuning / tests: 0 switches the small-path instantiation off
+        if (env) ctx->route_cells = atoi(env);
+        env = getenv("OCHRE_B200_ROUTE_MIN_PATHS");
+        if (env) ctx->route_min_paths = (uint32_t)atol(env);
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = ctx->d_pk_ctl.ensure(64);
     if (e == cudaSuccess) e = ctx->h_pk_ctl.ensure_mapped(256);
@@ -1188,7 +1315,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_nflat, &ctx->k_flat_off, &ctx->k_flat, &ctx->k_nout,
                     &ctx->k_out_off, &ctx->k_out};
     for (DevBuf* b : db) b->release();
@@ -1210,6 +1337,13 @@ int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds) {
 int ochre_b200_set_mode(ochre_b200_ctx* ctx, int mode) {
     if (!ctx || mode < OCHRE_MODE_AUTO || mode > OCHRE_MODE_FUSED) return OCHRE_E_INVALID_ARG;
     ctx->mode = mode;
+    return 0;
+}
+
+int ochre_b200_set_routing(ochre_b200_ctx* ctx, int32_t small_max_cells, uint32_t min_paths) {
+    if (!ctx || small_max_cells < 0) return OCHRE_E_INVALID_ARG;
+    ctx->route_cells = small_max_cells > (int32_t)pks::PK_CELLS ? (int32_t)pks::PK_CELLS : small_max_cells;
+    ctx->route_min_paths = min_paths;
     return 0;
 }
 

@@ -23,13 +23,17 @@ pytestmark = pytest.mark.gpu
 ID = O.IDENTITY
 
 
-@pytest.fixture(scope="module", params=["general", "auto"])
+@pytest.fixture(scope="module", params=["general", "auto", "routed"])
 def ctx(request):
-    """Both implementations behind ochre_b200_rasterize: the general global-memory pipeline and
-    (mode auto) the fused per-path kernel with the general pipeline as its fallback."""
+    """The implementations behind ochre_b200_rasterize: the general global-memory pipeline; (mode auto) the fused
+    per-path kernel with the general pipeline as its fallback; and the same with small paths routed to the
+    warp-per-path shape of the fused kernel even in these small batches (by default only batches of >= 8192 paths
+    are routed)."""
     c = ob.Context(0)  # raises loudly without a device / without the built extension
-    c.set_mode(request.param)
-    c.mode_name = request.param
+    c.set_mode("auto" if request.param == "routed" else request.param)
+    if request.param == "routed":
+        c.set_routing(1024, 0)   # everything whose control points fit the small shape's grid
+    c.mode_name = "auto" if request.param == "routed" else request.param
     yield c
     c.close()
 
