@@ -443,7 +443,7 @@ def main():
         # fused per-path kernel: commands in, tiles/spans out -- its algorithmic bytes ARE B_alg
         sb = {"k_path": b_alg, "gather": 2 * (68 * res.n_tiles + 8 * res.n_spans) + 24 * P}
         names = {0: "k_path", 6: "gather"}
-        kern = {"k_path": "k_path (flatten + bin + coverage + backdrop + emission per path)",
+        kern = {"k_path": "k_path (flatten + bin + coverage + backdrop + emission per path; two CTA shapes, pkl 91 % / pks 7.5 % of the step, + k_classify)",
                 "gather": "device_scan x2 + k_gather_paths (staging arena -> path order)"}
         dom = max(names, key=lambda i: stage_ms[i])
         dom_name = names[dom]
@@ -460,22 +460,24 @@ def main():
     achieved = sb[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
     # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of this command
     traffic = None
+    traffic_detail = None
     try:
         with open(os.path.join(ROOT, "profiles", "kpath_traffic.json")) as f:
             tj = json.load(f)
         if dom_name == tj.get("stage"):
-            traffic = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
-                       "paths_per_launch": tj["paths_per_launch"], "source": tj["source"]}
+            traffic = tj["dram_bytes_per_launch"]
+            traffic_detail = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
+                              "paths_per_launch": tj["paths_per_launch"], "kernel": tj.get("kernel"), "source": tj["source"]}
     except Exception:
         pass
     roofline = {
         "bound": "hbm", "kernel": kern[dom_name], "stage": dom_name, "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
         "stage_ms": stage_report,
         "stage_alg_GB": {k: v / 1e9 for k, v in sb.items()},
         "pipeline_b_alg_GB": b_alg / 1e9,
         "pipeline_frac": b_alg / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-        "note": "the kernel is instruction-issue bound (per-pixel f32 DDA), not HBM bound: see DESIGN.md section 4",
+        "note": "the kernel is instruction-issue and barrier bound (per-pixel f32 DDA, many short phases per path), not HBM bound: 62 % of the issue slots busy in ncu; see DESIGN.md section 6",
     }
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------

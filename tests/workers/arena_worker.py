@@ -24,6 +24,7 @@ def main():
     ctx = ob.Context(dev)
     if chunk:
         ctx.set_chunk(chunk)
+        ctx.set_routing(1024, 0)  # the chunked variant also sends small paths through the warp-per-path shape
     cmds, off, xf = W.blobs(n_per * world)
     # a wide path per rank: handed over to the general pipeline inside the same call
     lo, hi = rank * n_per, (rank + 1) * n_per
