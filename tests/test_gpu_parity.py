@@ -156,6 +156,66 @@ def test_integer_grid_polygons(ctx, seed):
     assert_batch_parity(g, oracle_batch(cmds, off, xf), what=f"seed {seed}")
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_extreme_geometry(ctx, seed):
+    """Shapes at the edges of every budget: far from the origin (|coord| up to 32 000 px, negative), thousands of pixels
+    long and one pixel wide (stripes / hand-over to the general pipeline), curves whose control points coincide
+    (dt = inf or NaN: one line), sub-pixel specks on tile corners, hundreds of sub-paths in one path, Conics."""
+    rng = np.random.default_rng(31000 + seed)
+    paths = []
+    for k in range(240):
+        kind = k % 8
+        if kind == 0:    # far away, moderate size
+            c = rng.uniform(-31000, 31000, 2)
+            pts = c + rng.uniform(-300, 300, (5, 2))
+            pts = np.clip(pts, -32700, 32700)
+            rows = [(MOVE, *pts[0]), (CUBIC, *pts[1], *pts[2], *pts[3]), (LINE, *pts[4]), (CLOSE,)]
+        elif kind == 1:  # long and thin, any direction
+            a = rng.uniform(-2000, 2000, 2)
+            d = rng.uniform(-1, 1, 2)
+            d = d / np.linalg.norm(d) * rng.uniform(500, 9000)
+            n = np.array([-d[1], d[0]]) / np.linalg.norm(d) * rng.uniform(0.3, 3.0)
+            rows = [(MOVE, *a), (LINE, *(a + d)), (LINE, *(a + d + n)), (LINE, *(a + n)), (CLOSE,)]
+        elif kind == 2:  # degenerate curves
+            q = rng.uniform(0, 200, 2)
+            r_ = rng.uniform(0, 200, 2)
+            rows = [(MOVE, *q), (QUADRATIC, *q, *q), (CUBIC, *q, *q, *q), (QUADRATIC, *((q + r_) / 2), *r_), (CUBIC, *r_, *r_, *q), (CLOSE,)]
+        elif kind == 3:  # specks on tile corners and pixel centres
+            c = np.round(rng.uniform(-50, 300, 2) / 8) * 8 + rng.choice([0.0, 0.5, -1e-3, 1e-3])
+            e = float(rng.choice([1e-4, 0.25, 0.5, 1.0]))
+            rows = [(MOVE, c[0] - e, c[1] - e), (LINE, c[0] + e, c[1] - e), (LINE, c[0] + e, c[1] + e), (LINE, c[0] - e, c[1] + e), (CLOSE,)]
+        elif kind == 4:  # many sub-paths
+            rows = []
+            for _ in range(int(rng.integers(50, 300))):
+                c = rng.uniform(0, 400, 2)
+                rows += [(MOVE, *c), (LINE, *(c + rng.uniform(-9, 9, 2))), (QUADRATIC, *(c + rng.uniform(-9, 9, 2)), *(c + rng.uniform(-9, 9, 2)))]
+                if rng.random() < 0.5:
+                    rows.append((CLOSE,))
+        elif kind == 5:  # conics
+            p0, c1, p1 = rng.uniform(-100, 500, 2), rng.uniform(-100, 500, 2), rng.uniform(-100, 500, 2)
+            rows = [(MOVE, *p0), (CONIC, *c1, *p1, float(rng.choice([0.0, 0.1, 0.7071, 1.0, 4.0, 50.0]))), (CLOSE,)]
+        elif kind == 6:  # tall and thin: hundreds of tile rows, a few tiles each
+            x = rng.uniform(-500, 500)
+            y0_, h = rng.uniform(-3000, 0), rng.uniform(1000, 6000)
+            rows = [(MOVE, x, y0_), (CUBIC, x + 30, y0_ + h / 3, x - 30, y0_ + 2 * h / 3, x + 2, y0_ + h), (LINE, x - 2, y0_ + h), (CLOSE,)]
+        else:            # big blob: thousands of lines, thousands of tiles
+            c = rng.uniform(0, 3000, 2)
+            R = rng.uniform(300, 1500)
+            m = int(rng.integers(3, 12))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, m))
+            v = c + R * np.stack([np.cos(ang), np.sin(ang)], 1)
+            rows = [(MOVE, *v[0])]
+            for i in range(1, m + 1):
+                w = v[i % m]
+                rows.append((CUBIC, *(v[i - 1] + rng.uniform(-R, R, 2) * 0.4), *(w + rng.uniform(-R, R, 2) * 0.4), *w))
+            rows.append((CLOSE,))
+        paths.append(make_cmds(rows))
+    cmds, off, xf = pack(paths)
+    g = ctx.rasterize(cmds, off, xf)
+    stats = assert_batch_parity(g, oracle_batch(cmds, off, xf), what=f"extreme geometry, seed {seed}")
+    assert stats["tiles"] > 50_000
+
+
 def test_config3_glyph_sample(ctx):
     cmds, off, xf = W.glyphs(20000)
     g = ctx.rasterize(cmds, off, xf)
