@@ -382,14 +382,17 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
     PK_POLICY_DECL
 
     const uint32_t n_take = A.n_paths_dev ? *A.n_paths_dev : A.n_paths;  // paths (or list entries) this launch works through
-    if (tid == 0) S.next_path = atomicAdd(A.ticket, 1u);
+    // The next ticket is fetched while this path is processed: thread 0 keeps it in a register, so the atomic's L2
+    // round trip is only waited for where the value is consumed, one path later (a store of it to shared memory
+    // right here would stall thread 0 in front of the barrier below for the whole round trip).
+    uint32_t next_ticket = 0;
+    if (tid == 0) next_ticket = atomicAdd(A.ticket, 1u);
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            const uint32_t np = S.next_path;
+            const uint32_t np = next_ticket;
             S.path = np;
-            // the next ticket is fetched while this path is processed (hides the L2 round trip)
-            if (np < n_take) S.next_path = atomicAdd(A.ticket, 1u);
+            if (np < n_take) next_ticket = atomicAdd(A.ticket, 1u);
             S.bbox[0] = S.bbox[1] = 0x7fffffff;
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
         }
