@@ -238,6 +238,10 @@ int ochre_b200_debug_records(ochre_b200_ctx* ctx, uint64_t* keys, uint64_t* vals
  * stroke_width array: *n commands (copied to cmds up to cap; cmds may be NULL to query *n), cmd_off[n_paths + 1]. */
 int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, uint64_t* n, uint32_t* cmd_off);
 
+/* Device time (ms, CUDA events; host synchronisations between its passes included) of the stroker pre-pass of the last
+ * ochre_b200_rasterize_paints call on this ctx. */
+float ochre_b200_debug_stroker_ms(const ochre_b200_ctx* ctx);
+
 /* Version string of the library ("ochre_b200 <semver> sm_100a"). */
 const char* ochre_b200_version(void);
 

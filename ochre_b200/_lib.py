@@ -24,7 +24,7 @@ SYMBOLS = [
     "ochre_b200_set_row_band", "ochre_b200_set_routing", "ochre_b200_arena_create", "ochre_b200_arena_open", "ochre_b200_arena_close",
     "ochre_b200_set_output_arena", "ochre_b200_copy_to_host", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
-    "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_version",
+    "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_debug_stroker_ms", "ochre_b200_version",
 ]
 
 
@@ -98,6 +98,8 @@ def load():
     L.ochre_b200_debug_lines.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.ochre_b200_debug_records.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
     L.ochre_b200_debug_stroked.argtypes = [vp, vp, u64, C.POINTER(u64), vp]
+    L.ochre_b200_debug_stroker_ms.argtypes = [vp]
+    L.ochre_b200_debug_stroker_ms.restype = C.c_float
     L.ochre_b200_version.restype = C.c_char_p
     for f in SYMBOLS:
         getattr(L, f)  # AttributeError here = the library does not export what the header declares

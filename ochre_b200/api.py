@@ -312,6 +312,10 @@ class Context:
         return BatchResult(None, None, xy, alpha, spans, ranges=ranges, n_tiles=nt, n_spans=ns, n_cmds=0, n_lines=0, n_records=0,
                            n_chunks=0, kernel_launches=0, device_ms=0.0, stage_ms=(0.0,) * 8, used=5)
 
+    def stroker_ms(self) -> float:
+        """Device time of the stroker pre-pass of the last `rasterize_paints` call."""
+        return float(_lib.load().ochre_b200_debug_stroker_ms(self._h))
+
     def debug_stroked(self, n_paths: int):
         """(cmds, cmd_off) of the batch the device stroker produced in the last `rasterize_paints` call."""
         L = _lib.load()

@@ -733,9 +733,11 @@ struct ochre_b200_ctx {
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
     HostBuf h_pk_ctl;
     // device stroker (csrc/stroke_kernels.cuh): inputs, widths, flattened polygons, the batch handed to the rasteriser
-    DevBuf k_cmds, k_off, k_xf, k_width, k_nflat, k_flat_off, k_flat, k_nout, k_out_off, k_out;
+    DevBuf k_cmds, k_off, k_xf, k_width, k_foff, k_flat_off, k_fpt, k_ftag, k_flags, k_closes, k_con_start, k_con_len, k_con_pc, k_item_off,
+        k_item_out, k_item0, k_nout, k_out_off, k_out;
     HostBuf hk_off;
     uint32_t k_last_paths = 0;  // paints of the last ochre_b200_rasterize_paints call (0: none)
+    float k_last_ms = 0.0f;     // device time of its stroker pre-pass
     // output arena (ochre_b200_set_output_arena): the fused kernel stores alpha tiles straight into it -- for a peer-mapped
     // arena that is the gather to GPU 0, tile by tile over NVLink; tile origins, spans and ranges follow by copy
     bool x_on = false;
@@ -1316,8 +1318,9 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
                     &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
-                    &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_nflat, &ctx->k_flat_off, &ctx->k_flat, &ctx->k_nout,
-                    &ctx->k_out_off, &ctx->k_out};
+                    &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
+                    &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
+                    &ctx->k_nout, &ctx->k_out_off, &ctx->k_out};
     for (DevBuf* b : db) b->release();
     HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
     for (HostBuf* b : hb) b->release();
@@ -1695,58 +1698,142 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
         d_width = ctx->k_width.as<float>();
         d_xf = ctx->k_xf.as<OchreTransform>();
     }
-    CK(ctx->k_nflat.ensure((size_t)n_paths * 4));
-    CK(ctx->k_nout.ensure((size_t)n_paths * 4));
-    CK(ctx->k_flat_off.ensure(((size_t)n_paths + 1) * 4));
-    CK(ctx->k_out_off.ensure(((size_t)n_paths + 1) * 4));
-    CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
-    CK(ctx->hk_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(cudaEventRecord(ctx->ev_g[0], st));
+    // ---- flatten(path, TOLERANCE) of the stroke paints: entries per source command -> offsets -> entries -------------
     uint32_t* hs = ctx->h_scalars.as<uint32_t>();
     uint32_t* d_sc = ctx->d_scalars.as<uint32_t>();
-    const uint32_t nb = nblk(n_paths, SK_TPB);
+    uint32_t* h_dev = static_cast<uint32_t*>(ctx->h_scalars.dev);
+    uint32_t launches = 0;
+    CK(ctx->k_foff.ensure(((size_t)n_cmds + 1) * 4));
+    CK(ctx->k_flat_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->k_nout.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->k_item0.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->k_out_off.ensure(((size_t)n_paths + 1) * 4));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(std::max<uint64_t>(n_cmds, n_paths)) * 4));
+    CK(ctx->hk_off.ensure(((size_t)n_paths + 1) * 4));
     CK(cudaMemsetAsync(d_sc, 0, SC_COUNT * sizeof(uint32_t), st));
-    // flatten(path, TOLERANCE) of the stroke paints: count -> offsets -> polygons
-    uint32_t* nflat = ctx->k_nflat.as<uint32_t>();
+    uint32_t* foff = ctx->k_foff.as<uint32_t>();
     uint32_t* flat_off = ctx->k_flat_off.as<uint32_t>();
-    k_stroke_flat_count<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, nflat, d_sc + SC_STATUS);
-    device_scan(st, n_paths, [nflat] __device__(uint32_t i) { return nflat[i]; },
-                [flat_off] __device__(uint32_t i, uint32_t excl, uint32_t) { flat_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
-                flat_off + n_paths);
-    CK(cudaMemcpyAsync(d_sc + 1, flat_off + n_paths, 4, cudaMemcpyDeviceToDevice, st));
-    k_words_to_host<<<1, 32, 0, st>>>(d_sc, static_cast<uint32_t*>(ctx->h_scalars.dev), 2);
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if (hs[0] != 0) {
-        ctx->err = "unknown command tag in a stroke paint";
-        return OCHRE_E_BAD_TAG;
+    uint32_t n_flat = 0;
+    if (n_cmds) {
+        k_sf_count<<<nblk(n_cmds, SK_TPB), SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, n_cmds, foff, d_sc + SC_STATUS);
+        launches += 1 + device_scan(st, n_cmds, [foff] __device__(uint32_t i) { return foff[i]; },
+                                    [foff] __device__(uint32_t i, uint32_t excl, uint32_t) { foff[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(), d_sc + 1);
+        k_words_to_host<<<1, 32, 0, st>>>(d_sc, h_dev, 2);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (hs[0] != 0) {
+            ctx->err = "unknown command tag in a stroke paint";
+            return OCHRE_E_BAD_TAG;
+        }
+        n_flat = hs[1];
     }
-    const uint32_t n_flat = hs[1];
-    CK(ctx->k_flat.ensure((size_t)n_flat * sizeof(OchreCmd) + 16));
-    k_stroke_flat_emit<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>());
-    // stroke(polygon, width) per stroke paint, the path itself per fill paint: count -> offsets -> commands
+    CK(ctx->k_fpt.ensure((size_t)n_flat * 8 + 16));
+    CK(ctx->k_ftag.ensure((size_t)n_flat + 16));
+    CK(ctx->k_flags.ensure((size_t)n_flat + 16));
+    CK(ctx->k_closes.ensure(((size_t)n_flat + 1) * 4));
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(std::max<uint64_t>(n_flat, 1)) * 4));
+    float2* fpt = ctx->k_fpt.as<float2>();
+    uint8_t* ftag = ctx->k_ftag.as<uint8_t>();
+    uint8_t* fflags = ctx->k_flags.as<uint8_t>();
+    uint32_t* closes = ctx->k_closes.as<uint32_t>();
+    if (n_cmds) {
+        k_sf_emit<<<nblk(n_cmds, SK_TPB), SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, n_cmds, foff, fpt, ftag);
+        launches += 1;
+    }
+    k_sf_path_off<<<nblk((uint64_t)n_paths + 1, SK_TPB), SK_TPB, 0, st>>>(d_off, base, n_paths, n_cmds, foff, n_flat, flat_off);
+    launches += 1;
+    // ---- contours: starts, `closed` flags, lengths; one work item per trip of offset()'s loop -------------------------
+    uint32_t n_con = 0, n_items = 0;
+    if (n_flat) {
+        k_ss_flags<<<nblk(n_flat, SK_TPB), SK_TPB, 0, st>>>(ftag, n_flat, flat_off, n_paths, fflags);
+        launches += 1 + device_scan(st, n_flat, [fflags] __device__(uint32_t i) { return (uint32_t)(fflags[i] >> 1) & 1u; },
+                                    [closes] __device__(uint32_t i, uint32_t excl, uint32_t) { closes[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                                    closes + n_flat);
+        CK(ctx->k_con_start.ensure((size_t)n_flat * 4 + 16));  // (at most one contour per entry; trimmed below)
+        uint32_t* con_start = ctx->k_con_start.as<uint32_t>();
+        launches += device_scan(st, n_flat, [fflags] __device__(uint32_t i) { return (uint32_t)fflags[i] & 1u; },
+                                [con_start] __device__(uint32_t i, uint32_t excl, uint32_t v) { if (v) con_start[excl] = i; },
+                                ctx->d_scan_ws.as<uint32_t>(), d_sc + 2);
+        k_words_to_host<<<1, 32, 0, st>>>(d_sc, h_dev, 3);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        n_con = hs[2];
+    }
+    CK(ctx->k_con_len.ensure((size_t)n_con * 4 + 16));
+    CK(ctx->k_con_pc.ensure((size_t)n_con * 4 + 16));
+    CK(ctx->k_item_off.ensure(((size_t)n_con + 1) * 4));
+    CK(ctx->k_con_start.ensure(16));
+    uint32_t* con_start = ctx->k_con_start.as<uint32_t>();
+    uint32_t* con_len = ctx->k_con_len.as<uint32_t>();
+    uint32_t* con_pc = ctx->k_con_pc.as<uint32_t>();
+    uint32_t* item_off = ctx->k_item_off.as<uint32_t>();
+    if (n_con) {
+        CK(ctx->d_scan_ws.ensure(scan_ws_words(n_con) * 4));
+        k_ss_contours<<<nblk(n_con, SK_TPB), SK_TPB, 0, st>>>(ftag, n_flat, flat_off, n_paths, closes, con_start, n_con, con_len, con_pc, item_off);
+        launches += 1 + device_scan(st, n_con, [item_off] __device__(uint32_t i) { return item_off[i]; },
+                                    [item_off] __device__(uint32_t i, uint32_t excl, uint32_t) { item_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                                    item_off + n_con);
+        k_words_to_host<<<1, 32, 0, st>>>(item_off + n_con, h_dev + 3, 1);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        n_items = hs[3];
+        if ((uint64_t)n_items >= 0xfffffff0ull) {
+            ctx->err = "stroke paints too large for one call";
+            return OCHRE_E_TOO_LARGE;
+        }
+    } else {
+        CK(cudaMemsetAsync(item_off, 0, 4, st));
+    }
+    // ---- offset(): commands per item -> offsets; commands per paint -> the batch's cmd_off ---------------------------
+    CK(ctx->k_item_out.ensure(((size_t)n_items + 1) * 4));
+    uint32_t* item_out = ctx->k_item_out.as<uint32_t>();
+    if (n_items) {
+        CK(ctx->d_scan_ws.ensure(scan_ws_words(n_items) * 4));
+        k_ss_count<<<nblk(n_items, SK_TPB), SK_TPB, 0, st>>>(fpt, d_width, item_off, n_items, n_con, con_start, con_len, con_pc, item_out);
+        launches += 1 + device_scan(st, n_items, [item_out] __device__(uint32_t i) { return item_out[i]; },
+                                    [item_out] __device__(uint32_t i, uint32_t excl, uint32_t) { item_out[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                                    item_out + n_items);
+    } else {
+        CK(cudaMemsetAsync(item_out, 0, 4, st));
+    }
     uint32_t* nout = ctx->k_nout.as<uint32_t>();
+    uint32_t* item0 = ctx->k_item0.as<uint32_t>();
     uint32_t* out_off = ctx->k_out_off.as<uint32_t>();
-    k_stroke_count<<<nb, SK_TPB, 0, st>>>(d_off, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>(), nout);
-    device_scan(st, n_paths, [nout] __device__(uint32_t i) { return nout[i]; },
-                [out_off] __device__(uint32_t i, uint32_t excl, uint32_t) { out_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
-                out_off + n_paths);
+    k_ss_path_count<<<nblk((uint64_t)n_paths + 1, SK_TPB), SK_TPB, 0, st>>>(d_off, d_width, n_paths, flat_off, con_start, n_con, item_off, item_out, item0, nout);
+    k_ss_path_count2<<<nblk(n_paths, SK_TPB), SK_TPB, 0, st>>>(d_width, n_paths, item0, nout);
+    CK(ctx->d_scan_ws.ensure(scan_ws_words(n_paths) * 4));
+    launches += 2 + device_scan(st, n_paths, [nout] __device__(uint32_t i) { return nout[i]; },
+                                [out_off] __device__(uint32_t i, uint32_t excl, uint32_t) { out_off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(),
+                                out_off + n_paths);
     CK(cudaMemcpyAsync(ctx->hk_off.p, out_off, ((size_t)n_paths + 1) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     const uint32_t n_out = ctx->hk_off.as<uint32_t>()[n_paths];
     CK(ctx->k_out.ensure((size_t)n_out * sizeof(OchreCmd) + 16));
-    k_stroke_emit<<<nb, SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, flat_off, ctx->k_flat.as<Cmd>(), out_off,
-                                         ctx->k_out.as<Cmd>());
+    if (n_items) {
+        k_ss_emit<<<nblk(n_items, SK_TPB), SK_TPB, 0, st>>>(fpt, d_width, item_off, n_items, n_con, con_start, con_len, con_pc, item_out, item0, out_off,
+                                                          ctx->k_out.as<Cmd>());
+        launches += 1;
+    }
+    if (n_cmds) {
+        k_ss_copy_fills<<<nblk((uint64_t)n_cmds * 7, SK_TPB), SK_TPB, 0, st>>>(d_cmds, d_off, base, d_width, n_paths, n_cmds, out_off, ctx->k_out.as<Cmd>());
+        launches += 1;
+    }
+    CK(cudaEventRecord(ctx->ev_g[1], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    CK(cudaEventElapsedTime(&ctx->k_last_ms, ctx->ev_g[0], ctx->ev_g[1]));
     const int rc = rasterize_impl(ctx, ctx->k_out.as<OchreCmd>(), out_off, d_xf, n_paths, flags | OCHRE_IN_DEVICE,
                                   ctx->hk_off.as<uint32_t>(), out);
     if (rc == 0) {
-        out->kernel_launches += 10;  // 4 stroker kernels + 2 scans of 3 launches
+        out->kernel_launches += launches;
         ctx->k_last_paths = n_paths;
     }
     return rc;
 }
+
+float ochre_b200_debug_stroker_ms(const ochre_b200_ctx* ctx) { return ctx ? ctx->k_last_ms : 0.0f; }
 
 int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, uint64_t* n, uint32_t* cmd_off) {
     if (!ctx || !n) return OCHRE_E_INVALID_ARG;

@@ -10,10 +10,12 @@ ctx = ob.Context(0)
 cmds, off, xf = W.blobs(n)
 sw = np.full(n, 1.5, np.float32)
 best = 1e9
+pre = 1e9
 for i in range(4):
     t0 = time.perf_counter()
     r = ctx.rasterize_paints(cmds, off, xf, sw, out_device=True)
     best = min(best, time.perf_counter() - t0)
+    pre = min(pre, ctx.stroker_ms())
 sc, so = ctx.debug_stroked(n)
 t0 = time.perf_counter()
 m = min(n, 2000)
@@ -26,5 +28,9 @@ for i in range(3):
     b2 = min(b2, time.perf_counter() - t0)
 print(f"stroke paints: {n} paths, {len(cmds)} source cmds -> {len(sc)} stroked cmds, {r.n_tiles} tiles")
 print(f"  rasterize_paints (host cmds in, device stroker + rasteriser, results on device): {best*1e3:.2f} ms wall = {n/best/1e6:.2f} M paints/s")
-print(f"  rasterize of the pre-stroked batch alone: {b2*1e3:.2f} ms wall (k_path {r2.stage_ms[0]:.2f} ms) -> device stroker pre-pass ~ {(best-b2)*1e3:.2f} ms")
+nflat = (len(sc) - 2 * n) // 2
+alg = len(cmds) * 28 + len(sc) * 28
+print(f"  device stroker pre-pass alone: {pre:.2f} ms (CUDA events) = {alg / pre / 1e6:.0f} GB/s of commands in + stroked commands out "
+      f"({alg / pre / 1e6 / 6527.8 * 100:.0f} % of the measured HBM peak); k_path on the stroked batch {r.stage_ms[0]:.2f} ms")
+print(f"  rasterize of the pre-stroked batch from host memory: {b2*1e3:.2f} ms wall")
 print(f"  host stroker (ochre_b200_stroke_path, one thread, extrapolated from {m} paths): {host_s*1e3:.0f} ms")
