@@ -133,6 +133,8 @@ struct PkShared {
     uint32_t ws[72];
     int bbox[4];                            // min tx, min ty, max tx, max ty over every non-degenerate line
     uint32_t path, next_path, nbands, nstripes, base_tiles, base_spans, flag;
+    uint32_t cw[2 * ((PK_THREADS + 31) / 32)];  // flatten: per-warp ballots of the command chunk (Move commands | commands that move `last`)
+    float carry[4];                             // flatten: `last` and `first` as the previous command chunks left them
     uint32_t merr;  // set by the mark pass when a walk leaves the grid (never, by construction: the path is handed over)
 };
 
@@ -395,6 +397,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             if (np < n_take) next_ticket = atomicAdd(A.ticket, 1u);
             S.bbox[0] = S.bbox[1] = 0x7fffffff;
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
+            S.carry[0] = S.carry[1] = S.carry[2] = S.carry[3] = 0.0f;  // last = first = (0, 0), rasterizer.rs:54-55
         }
         if (tid < PK_NCLS) S.bcur[tid] = 0;  // lines per step-count class
         __syncthreads();
@@ -419,13 +422,45 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             int bad = 0;
             VCmd c;
             c.last = c.a = c.b = c.c = mk(0.0f, 0.0f);
+            c.w = 0.0f;
+            // `self.last` and `self.first` when command j starts (rasterizer.rs:61-69, :145-157): the end point of the nearest
+            // earlier command that is not a Close, the point of the nearest earlier Move.  Inside the chunk they come from
+            // two ballots (no backward walk over the commands: a polyline has thousands between two Moves), before it from
+            // the carry the previous chunks left.
+            const uint32_t lane = tid & 31u, warp = tid >> 5;
+            constexpr uint32_t NW = (PK_THREADS + 31) / 32;
+            const uint32_t tag = (j < nc) ? pc[j].tag : (j == nc ? (uint32_t)TAG_FINISH : (uint32_t)TAG_CLOSE);
+            const uint32_t bm = __ballot_sync(0xffffffffu, j < nc && tag == TAG_MOVE);
+            const uint32_t bp = __ballot_sync(0xffffffffu, j < nc && tag != TAG_CLOSE);
+            if (lane == 0) {
+                S.cw[warp] = bm;
+                S.cw[NW + warp] = bp;
+            }
+            __syncthreads();
+            auto nearest_before = [&](const uint32_t* words, uint32_t own) -> int {  // chunk-local index, or -1
+                const uint32_t below = own & ((1u << lane) - 1u);
+                if (below) return (int)(warp * 32u + 31u) - __clz((int)below);
+                for (int w = (int)warp - 1; w >= 0; --w)
+                    if (words[w]) return w * 32 + 31 - __clz((int)words[w]);
+                return -1;
+            };
             if (j < nv) {
                 // validation: tag, and every transformed coordinate the command reads (its own points
                 // and `last`): finite, |v| < 32760
-                const uint32_t tag = (j < nc) ? pc[j].tag : (uint32_t)TAG_FINISH;
-                if (j < nc && tag > TAG_LINE_ABS) bad = 2;
+                if (j < nc && tag > TAG_CLOSE) bad = 2;
                 else {
-                    c = decode_vcmd(pc, nc, j, m);
+                    c.tag = tag;
+                    const int ip = nearest_before(S.cw + NW, bp);
+                    c.last = ip >= 0 ? cmd_endpoint(pc[jb + (uint32_t)ip], m) : mk(S.carry[0], S.carry[1]);
+                    if (tag == TAG_MOVE || tag == TAG_FINISH) {
+                        const int im = nearest_before(S.cw, bm);
+                        c.a = im >= 0 ? cmd_point(pc[jb + (uint32_t)im], 0, m) : mk(S.carry[2], S.carry[3]);
+                    } else {
+                        const int np = cmd_npts(tag);
+                        if (np > 0) c.a = cmd_point(pc[j], 0, m);
+                        if (np > 1) c.b = cmd_point(pc[j], 1, m);
+                        if (np > 2) c.c = cmd_point(pc[j], 2, m);
+                    }
                     if (!(coord_ok(c.last) && coord_ok(c.a) && coord_ok(c.b) && coord_ok(c.c))) bad = 1;
                     if (tag == TAG_CONIC && !(fabsf(pc[j].v[4]) < 3.0e38f)) bad = 1;  // the weight must be finite
                 }
@@ -448,6 +483,22 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             }
             uint32_t total;
             const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);
+            if (tid == 0) {  // the carry for the next chunk (everybody has read this chunk's: the scan has barriers)
+                for (int w = (int)NW - 1; w >= 0; --w)
+                    if (S.cw[NW + w]) {
+                        const V2 q = cmd_endpoint(pc[jb + (uint32_t)(w * 32 + 31 - __clz((int)S.cw[NW + w]))], m);
+                        S.carry[0] = q.x;
+                        S.carry[1] = q.y;
+                        break;
+                    }
+                for (int w = (int)NW - 1; w >= 0; --w)
+                    if (S.cw[w]) {
+                        const V2 q = cmd_point(pc[jb + (uint32_t)(w * 32 + 31 - __clz((int)S.cw[w]))], 0, m);
+                        S.carry[2] = q.x;
+                        S.carry[3] = q.y;
+                        break;
+                    }
+            }
             if (n_lines + total > PK_LINECAP - 1) fallback = true;
             if (my_n && !fallback) {
                 if (my_tag == TAG_QUAD || my_tag == TAG_CUBIC) {

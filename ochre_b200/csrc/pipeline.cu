@@ -107,12 +107,12 @@ k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_o
     vpath[v] = p;
     if (j < c1 - c0) {
         uint32_t tag = pc[j].tag;
-        if (tag > TAG_LINE_ABS) atomicMax(status, (int)ST_BAD_TAG);
+        if (tag > TAG_CLOSE) atomicMax(status, (int)ST_BAD_TAG);
         int np = cmd_npts(tag);
         bool ok = true;
         for (int i = 0; i < np; ++i) ok = ok && coord_ok(cmd_point(pc[j], i, m));
         if (!ok) atomicMax(status, (int)ST_BAD_COORD);
-        if (!ok || tag > TAG_LINE_ABS) {
+        if (!ok || tag > TAG_CLOSE) {
             nlines[v] = 0;
             return;
         }

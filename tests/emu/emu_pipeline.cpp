@@ -89,7 +89,7 @@ EmuResult* emu_rasterize_band(const OchreCmd* cmds_, const uint32_t* cmd_off, co
         bool has_inc = false;
         for (uint32_t j = 0; j <= nc; ++j) {
             if (j < nc) {
-                if (pc[j].tag > TAG_LINE_ABS) { R->status = OCHRE_E_BAD_TAG; return R; }
+                if (pc[j].tag > TAG_CLOSE) { R->status = OCHRE_E_BAD_TAG; return R; }
                 for (int i = 0; i < cmd_npts(pc[j].tag); ++i)
                     if (!coord_ok(cmd_point(pc[j], i, m))) { R->status = OCHRE_E_BAD_COORD; return R; }
             }
