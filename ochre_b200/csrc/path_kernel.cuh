@@ -536,11 +536,17 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             {
                 const uint32_t lane = tid & 31u, warp = tid >> 5;
                 const uint32_t end = n_lines + total;
-                for (uint32_t base = n_lines + warp * 31u; base < end; base += (PK_THREADS / 32) * 31u) {
+                constexpr uint32_t STRIDE = (PK_THREADS / 32) * 31u;
+                uint2 r_n = make_uint2(0u, PK_OWNER_NONE);  // (one trip ahead)
+                {
+                    const uint32_t b0 = n_lines + warp * 31u, i0 = b0 + lane - 1u;
+                    if (b0 < end && (lane != 0 || b0 > n_lines) && i0 < end) r_n = pk_ld(&G.rec[i0], pk_pol);
+                }
+                for (uint32_t base = n_lines + warp * 31u; base < end; base += STRIDE) {
                     const uint32_t i = base + lane - 1u;  // (lane 0 of the very first pass: n_lines - 1, out of range)
-                    const bool inr = (lane != 0 || base > n_lines) && i < end;
-                    uint2 r = make_uint2(0u, PK_OWNER_NONE);
-                    if (inr) r = pk_ld(&G.rec[i], pk_pol);
+                    const uint2 r = r_n;
+                    r_n = make_uint2(0u, PK_OWNER_NONE);
+                    if (base + STRIDE < end && i + STRIDE < end) r_n = pk_ld(&G.rec[i + STRIDE], pk_pol);
                     const bool curve = r.y != PK_OWNER_NONE;
                     const uint32_t o = curve ? r.y : 0u;
                     V2 b = mk(0.0f, 0.0f);
@@ -669,8 +675,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             if (tid < PK_NCLS) S.bcur[tid] = 0;
             __syncthreads();
             if (n_sorted > PK_MAXLINES) return false;
+            uint32_t info_n = tid < n_lines ? pk_ld(&G.info[tid], pk_pol) : PK_INFO_NONE;  // (one trip ahead: the L2 round trip overlaps the trip's work)
             for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                const uint32_t info = pk_ld(&G.info[i], pk_pol);
+                const uint32_t info = info_n;
+                if (i + PK_THREADS < n_lines) info_n = pk_ld(&G.info[i + PK_THREADS], pk_pol);
                 if (info == PK_INFO_NONE) continue;
                 if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
                 const uint32_t k = pk_info_cls(info);
@@ -710,15 +718,20 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 const uint32_t nkeys = nbands * PK_NCLS;
                 for (uint32_t k = tid; k < nkeys; k += PK_THREADS) S.bcur[k] = 0;
                 __syncthreads();
+                uint32_t* const plan = reinterpret_cast<uint32_t*>(G.rec);  // (rec is dead after flattening) per line: first band | last band << 8 | class << 16
+                info_n = tid < n_lines ? pk_ld(&G.info[tid], pk_pol) : PK_INFO_NONE;
                 for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                    const uint32_t info = pk_ld(&G.info[i], pk_pol);
-                    if (info == PK_INFO_NONE) continue;
-                    if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
+                    const uint32_t info = info_n;
+                    if (i + PK_THREADS < n_lines) info_n = pk_ld(&G.info[i + PK_THREADS], pk_pol);
+                    if (info == PK_INFO_NONE || (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs))) {
+                        pk_st(&plan[i], PK_INFO_NONE, pk_pol);
+                        continue;
+                    }
                     const int b0 = pk_band_of(S, (int)nbands, max(pk_info_lo(info) - y0s, 0));
                     int b1 = b0;  // lines are short: the last band is the first one or a neighbour
                     const int rhi = min(pk_info_hi(info) - y0s, Hs - 1);
                     while (b1 + 1 < (int)nbands && (int)S.brow[b1 + 1] <= rhi) ++b1;
-                    pk_st(&G.rec[i], make_uint2((uint32_t)b0 | ((uint32_t)b1 << 8), 0u), pk_pol);  // (rec is dead after flattening)
+                    pk_st(&plan[i], (uint32_t)b0 | ((uint32_t)b1 << 8) | (pk_info_cls(info) << 16), pk_pol);
                     for (int b = b0; b <= b1; ++b) atomicAdd(&S.bcur[b * PK_NCLS + pk_info_cls(info)], 1u);
                 }
                 __syncthreads();
@@ -737,14 +750,15 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 if (tid == 0) S.boff[nkeys] = total;
                 __syncthreads();
                 if (total > PK_SLINECAP) return false;
+                uint32_t plan_n = tid < n_lines ? pk_ld(&plan[tid], pk_pol) : PK_INFO_NONE;
                 for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
-                    const uint32_t info = pk_ld(&G.info[i], pk_pol);
-                    if (info == PK_INFO_NONE) continue;
-                    if (!whole && (pk_info_hi(info) < y0s || pk_info_lo(info) >= y0s + Hs)) continue;
-                    const uint32_t bb01 = pk_ld(&G.rec[i], pk_pol).x;
-                    const int b0 = (int)(bb01 & 0xffu), b1 = (int)(bb01 >> 8);
+                    const uint32_t pl = plan_n;
+                    if (i + PK_THREADS < n_lines) plan_n = pk_ld(&plan[i + PK_THREADS], pk_pol);
+                    if (pl == PK_INFO_NONE) continue;
+                    const int b0 = (int)(pl & 0xffu), b1 = (int)((pl >> 8) & 0xffu);
+                    const uint32_t cls = pl >> 16;
                     for (int b = b0; b <= b1; ++b) {
-                        const uint32_t k = b * PK_NCLS + pk_info_cls(info);
+                        const uint32_t k = b * PK_NCLS + cls;
                         pk_st(&G.sidx[S.boff[k] + atomicAdd(&S.bcur[k], 1u)], (uint16_t)i, pk_pol);
                     }
                 }
