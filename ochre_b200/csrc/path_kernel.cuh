@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 if (!bad) {
                     my_tag = c.tag;
                     switch (c.tag) {
-                        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: my_n = 1; break;
+                        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: my_n = 1; break;
                         case TAG_QUAD: my_dt = quad_dt(c.last, c.a, c.b); my_n = curve_count(my_dt); break;
                         case TAG_CUBIC: my_dt = cubic_dt(c.last, c.a, c.b, c.c); my_n = curve_count(my_dt); break;
                         case TAG_CONIC: {  // path.rs:75-104: the command's thread runs the subdivision (twice: count, emit)

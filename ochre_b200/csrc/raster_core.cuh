@@ -35,7 +35,6 @@ enum : uint32_t {
     TAG_CUBIC = 3,
     TAG_CONIC = 4,
     TAG_CLOSE = 5,
-    TAG_LINE_ABS = 6,  // internal: a Line whose point is already in device space (host-flattened conics)
     TAG_FINISH = 7     // internal: the virtual command appended to every path (finish()'s auto-close)
 };
 
@@ -103,7 +102,7 @@ OC_HD int sign_dir(float d) {  // signum(d) as i16 for non-NaN d: -1 for negativ
 // Number of points a command carries / index of its end point.
 OC_HD int cmd_npts(uint32_t tag) {
     switch (tag) {
-        case TAG_MOVE: case TAG_LINE: case TAG_LINE_ABS: return 1;
+        case TAG_MOVE: case TAG_LINE: return 1;
         case TAG_QUAD: case TAG_CONIC: return 2;
         case TAG_CUBIC: return 3;
         default: return 0;
@@ -113,7 +112,7 @@ OC_HD int cmd_npts(uint32_t tag) {
 // Point i of a command in device space (PathCmd::transform, path.rs:16-37).
 OC_HD V2 cmd_point(const Cmd& c, int i, const float* xf) {
     V2 p = mk(c.v[2 * i], c.v[2 * i + 1]);
-    return (c.tag == TAG_LINE_ABS) ? p : xf_apply(xf, p);
+    return xf_apply(xf, p);
 }
 // End point of a command = what `self.last` equals after Rasterizer::command ran it.
 // (A flattened curve's final lerp at t == 1.0 returns `point` itself.)
@@ -546,7 +545,7 @@ OC_HD VCmd decode_vcmd(const Cmd* pc, uint32_t nc, uint32_t j, const float* xf) 
 // (and skipped) when last == first.
 OC_HD uint32_t vcmd_line_count(const VCmd& c) {
     switch (c.tag) {
-        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS: return 1;
+        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: return 1;
         case TAG_QUAD: return curve_count(quad_dt(c.last, c.a, c.b));
         case TAG_CUBIC: return curve_count(cubic_dt(c.last, c.a, c.b, c.c));
         case TAG_CONIC: {  // path.rs:75-104, two lines per leaf of the subdivision
@@ -562,7 +561,7 @@ OC_HD uint32_t vcmd_line_count(const VCmd& c) {
 template <class F>
 OC_HD void vcmd_for_each_line(const VCmd& c, F& f) {
     switch (c.tag) {
-        case TAG_MOVE: case TAG_FINISH: case TAG_LINE: case TAG_LINE_ABS:
+        case TAG_MOVE: case TAG_FINISH: case TAG_LINE:
             f(0u, c.last, c.a);
             break;
         case TAG_QUAD: {
