@@ -414,8 +414,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         bb.x0 = bb.y0 = 0x7fffffff;
         bb.x1 = bb.y1 = -0x7fffffff;
         uint32_t n_lines = 0;
-        bool fallback = false, bad_path = false;
-        for (uint32_t jb = 0; jb < nv; jb += PK_THREADS) {
+        // (a path with more commands than line slots is handed over at once, without flattening its first 16 k lines:
+        // the next stage validates it)
+        bool fallback = nv > (uint32_t)PK_LINECAP, bad_path = false;
+        for (uint32_t jb = 0; jb < nv && !fallback; jb += PK_THREADS) {
             const uint32_t j = jb + tid;
             uint32_t my_n = 0, my_tag = TAG_CLOSE;
             float my_dt = 0.0f;
