@@ -412,23 +412,43 @@ class Rasterizer:
     def __init__(self, ctx: Optional[Context] = None):
         self._ctx = ctx
         self._chunks = []
+        self._paint = None  # a lone `stroke` call, kept as (path, width, transform row): stroked on the device in finish
+
+    def _materialize(self):
+        """A second call follows a lone stroke: expand it on the host after all (rasterizer.rs:169-171)."""
+        if self._paint is not None:
+            path, width, row = self._paint
+            self._paint = None
+            self._chunks.append(_apply_rows(stroke_to_fill(path, width), Transform.from_row(row)))
 
     def move_to(self, point: Vec2):
+        self._materialize()
         self._chunks.append(cmds_to_array([PathCmd.Move(point)]))
 
     def line_to(self, point: Vec2):
+        self._materialize()
         self._chunks.append(cmds_to_array([PathCmd.Line(point)]))
 
     def command(self, command: PathCmd):
+        self._materialize()
         self._chunks.append(cmds_to_array([command]))
 
     def fill(self, path, transform: Transform):
+        self._materialize()
         self._chunks.append(_apply_rows(cmds_to_array(path), transform))
 
     def stroke(self, path, width: float, transform: Transform):
-        self.fill(stroke_to_fill(path, width), transform)
+        """`Rasterizer::stroke` (rasterizer.rs:169-171).  The usual case -- one rasteriser per stroke paint, as in the
+        reference's examples/svg.rs:152-154 -- is flattened and offset on the device inside `finish`; a stroke mixed
+        with other calls into the same rasteriser is expanded on the host."""
+        if not self._chunks and self._paint is None and width > 0:
+            self._paint = (cmds_to_array(path), float(width), np.asarray(transform.as_row(), np.float32))
+        else:
+            self._materialize()
+            self.fill(stroke_to_fill(path, width), transform)
 
     def _cmds(self) -> np.ndarray:
+        self._materialize()
         return np.concatenate(self._chunks) if self._chunks else np.zeros(0, CMD_DTYPE)
 
     def finish(self, builder: TileBuilder):
@@ -438,14 +458,28 @@ class Rasterizer:
 def finish_batch(rasterizers: Sequence[Rasterizer], builders: Sequence[TileBuilder], ctx: Optional[Context] = None) -> BatchResult:
     """`finish` for many rasterisers in one GPU submission; builder i receives path i's calls."""
     ctx = ctx or default_context()
-    paths = [r._cmds() for r in rasterizers]
+    paths, xfs, widths = [], [], []
+    for r in rasterizers:
+        if r._paint is not None:  # a lone stroke: source path, its transform, its width -> the device stroker
+            path, width, row = r._paint
+            paths.append(path)
+            xfs.append(row)
+            widths.append(width)
+        else:
+            paths.append(r._cmds())
+            xfs.append(IDENTITY_ROW)
+            widths.append(0.0)
     cmds = np.concatenate(paths) if paths else np.zeros(0, CMD_DTYPE)
     off = np.zeros(len(paths) + 1, np.uint32)
     off[1:] = np.cumsum([len(p) for p in paths])
-    xf = np.tile(IDENTITY_ROW, (len(paths), 1))
-    res = ctx.rasterize(cmds, off, xf)
+    xf = np.asarray(xfs, np.float32).reshape(len(paths), 6)
+    if any(w > 0 for w in widths):
+        res = ctx.rasterize_paints(cmds, off, xf, np.asarray(widths, np.float32))
+    else:
+        res = ctx.rasterize(cmds, off, xf)
     for i, b in enumerate(builders):
         res.replay(i, b)
     for r in rasterizers:
         r._chunks = []
+        r._paint = None
     return res

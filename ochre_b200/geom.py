@@ -121,6 +121,11 @@ class Transform:
         """`OchreTransform` layout: m[4], ox, oy."""
         return np.array([*self.matrix.m, self.offset.x, self.offset.y], dtype=np.float32)
 
+    @staticmethod
+    def from_row(row) -> "Transform":
+        r = [float(v) for v in row]
+        return Transform(Mat2x2.new(r[0], r[1], r[2], r[3]), Vec2.new(r[4], r[5]))
+
 
 class PathCmd:
     """Constructors named as the reference's enum variants (path.rs:5-12).

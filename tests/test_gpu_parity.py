@@ -454,6 +454,45 @@ def test_rasterizer_facade_replays_in_reference_order(ctx):
     assert b.calls == want
 
 
+def test_facade_strokes_go_through_the_device_stroker(ctx):
+    """`Rasterizer.stroke` + `finish_batch`: a rasteriser holding one stroke (examples/svg.rs:152-154) is stroked on the
+    device, one that mixes a stroke with other calls on the host; both equal the reference's stroke."""
+    class Rec(ob.TileBuilder):
+        def __init__(self):
+            self.tiles, self.spans = [], []
+
+        def tile(self, x, y, data):
+            self.tiles.append((x, y, bytes(data)))
+
+        def span(self, x, y, w):
+            self.spans.append((x, y, w))
+
+    rng = np.random.default_rng(5)
+    t = ob.Transform.translate(3.5, 1.25).then(ob.Transform.scale(1.5))
+    row = t.as_row()
+    p1 = _random_path(rng, 6, 70.0)
+    p2 = _random_path(rng, 5, 50.0)
+    lone, mixed = ob.Rasterizer(ctx), ob.Rasterizer(ctx)
+    lone.stroke(p1, 2.5, t)
+    mixed.stroke(p1, 2.5, t)
+    mixed.fill(p2, t)
+    assert lone._paint is not None and mixed._paint is None
+    b1, b2 = Rec(), Rec()
+    ob.finish_batch([lone, mixed], [b1, b2], ctx)
+    o1 = O.Rasterizer()
+    o1.stroke(p1, 2.5, row)
+    r1 = o1.finish()
+    o2 = O.Rasterizer()
+    o2.stroke(p1, 2.5, row)
+    o2.fill(p2, row)
+    r2 = o2.finish()
+    for b, r in ((b1, r1), (b2, r2)):
+        assert [(x, y) for x, y, _ in b.tiles] == [tuple(int(v) for v in xy) for xy in r.tile_xy]
+        assert b.spans == [(int(s["x"]), int(s["y"]), int(s["w"])) for s in r.spans]
+        got = np.frombuffer(b"".join(d for _, _, d in b.tiles), np.uint8).astype(int)
+        assert np.abs(got - r.alpha.reshape(-1).astype(int)).max() <= 1
+
+
 def test_fill_twice_then_finish_is_the_union(ctx):
     sq = [ob.PathCmd.Move(ob.Vec2(2, 2)), ob.PathCmd.Line(ob.Vec2(6, 2)), ob.PathCmd.Line(ob.Vec2(6, 6)),
           ob.PathCmd.Line(ob.Vec2(2, 6)), ob.PathCmd.Close]
