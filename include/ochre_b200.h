@@ -124,7 +124,9 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
                                 const float* stroke_width, uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host,
                                 OchreResult* out);
 
-/* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default. */
+/* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default: 16 Mi, ramping up
+ * from 1 Mi when the results go to host memory (the download starts early); 64 Mi for device-resident results of the fused
+ * kernel (nothing is pipelined behind the chunks). */
 int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
 
 /* Which implementation ochre_b200_rasterize uses.  AUTO (default): the fused per-path kernel

@@ -683,6 +683,7 @@ struct HostBuf {  // pinned
 #endif
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
 constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 20;
+constexpr uint32_t DEVICE_CHUNK_VCMDS = 64u << 20;
 constexpr int N_STAGE = 8;
 
 }  // namespace
@@ -696,7 +697,7 @@ struct ochre_b200_ctx {
     cudaEvent_t ev_out[2] = {};
     cudaEvent_t ev_g[2] = {};  // gather stage of the fused path
     std::string err;
-    uint32_t chunk_vcmds = DEFAULT_CHUNK_VCMDS;
+    uint32_t chunk_vcmds = 0;  // 0: default (DEFAULT_CHUNK_VCMDS; DEVICE_CHUNK_VCMDS for device-resident results of the fused kernel)
     // inputs
     DevBuf d_cmds, d_cmd_off, d_xf;
     // per virtual command
@@ -1333,7 +1334,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
 
 int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds) {
     if (!ctx) return OCHRE_E_INVALID_ARG;
-    ctx->chunk_vcmds = max_vcmds ? max_vcmds : DEFAULT_CHUNK_VCMDS;
+    ctx->chunk_vcmds = max_vcmds;
     return 0;
 }
 
@@ -1418,11 +1419,15 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     cuts.push_back(0);
     // Host-resident results: the download of a chunk starts when its kernels are done, so the first chunks are small
     // (1 Mi virtual commands, doubling) -- the PCIe link is busy almost from the start of the call.
-    const bool ramp = !out_dev && ctx->chunk_vcmds > RAMP_FIRST_VCMDS;
+    // Device-resident results of the fused kernel: nothing is pipelined behind the chunks, fewer and larger launches win
+    // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk.
+    const uint32_t chunk_vcmds = ctx->chunk_vcmds ? ctx->chunk_vcmds
+                                 : (out_dev && ctx->mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
+    const bool ramp = !out_dev && chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
         uint32_t p1 = p0;
         uint64_t nv = 0;
-        const uint64_t limit = ramp ? std::min<uint64_t>(ctx->chunk_vcmds, (uint64_t)RAMP_FIRST_VCMDS << std::min<size_t>(cuts.size() - 1, 16)) : ctx->chunk_vcmds;
+        const uint64_t limit = ramp ? std::min<uint64_t>(chunk_vcmds, (uint64_t)RAMP_FIRST_VCMDS << std::min<size_t>(cuts.size() - 1, 16)) : chunk_vcmds;
         while (p1 < n_paths) {
             uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
             if (p1 > p0 && nv + add > limit) break;
