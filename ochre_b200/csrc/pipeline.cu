@@ -1420,9 +1420,10 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     // Host-resident results: the download of a chunk starts when its kernels are done, so the first chunks are small
     // (1 Mi virtual commands, doubling) -- the PCIe link is busy almost from the start of the call.
     // Device-resident results of the fused kernel: nothing is pipelined behind the chunks, fewer and larger launches win
-    // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk.
+    // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk, and
+    // with an output arena the origins / spans / ranges of a chunk travel behind the next chunk's kernels.
     const uint32_t chunk_vcmds = ctx->chunk_vcmds ? ctx->chunk_vcmds
-                                 : (out_dev && ctx->mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
+                                 : (out_dev && !ctx->x_on && ctx->mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
     const bool ramp = !out_dev && chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
         uint32_t p1 = p0;
