@@ -1739,7 +1739,7 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
     CK(ctx->k_flags.ensure((size_t)n_flat + 16));
     CK(ctx->k_closes.ensure(((size_t)n_flat + 1) * 4));
     CK(ctx->d_scan_ws.ensure(scan_ws_words(std::max<uint64_t>(n_flat, 1)) * 4));
-    float2* fpt = ctx->k_fpt.as<float2>();
+    V2* fpt = ctx->k_fpt.as<V2>();
     uint8_t* ftag = ctx->k_ftag.as<uint8_t>();
     uint8_t* fflags = ctx->k_flags.as<uint8_t>();
     uint32_t* closes = ctx->k_closes.as<uint32_t>();

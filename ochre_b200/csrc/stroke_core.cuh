@@ -153,4 +153,102 @@ struct CmdStoreSink {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// The stroker as flat data-parallel passes (csrc/stroke_kernels.cuh runs them as kernels, tests/emu as loops): the
+// element-wise rules.  See stroke_kernels.cuh for the decomposition.
+// ---------------------------------------------------------------------------------------------------------------
+
+// last index p in [0, n) with off[p] - base <= v   (off[0] - base == 0 <= v; entries are non-decreasing, so among
+// equal entries -- empty ranges -- the last one is the range that holds v)
+OC_HD uint32_t sk_find(const uint32_t* off, uint32_t base, uint32_t n, uint32_t v) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (off[mid] - base <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// `last` of the free flatten when command c of the path starts: the end point of the nearest earlier command that
+// has points (Close leaves it alone), else (0, 0).  path.rs:115-143
+OC_HD V2 sk_last(const Cmd* path, uint32_t c) {
+    for (uint32_t i = c; i > 0; --i) {
+        const int np = cmd_npts(path[i - 1].tag);
+        if (np > 0) return cmd_pt(path[i - 1], np - 1);
+    }
+    return mk(0.0f, 0.0f);
+}
+
+// per flattened entry: bit 0 = a contour starts here, bit 1 = it is a Close  (path.rs:216-263: a contour starts at a
+// Move, after a Close, or with the path)
+enum : uint8_t { SKF_START = 1, SKF_CLOSE = 2 };
+OC_HD uint8_t sk_flags(uint32_t tag, bool first_in_path, uint32_t prev_tag) {
+    const bool close = tag == TAG_CLOSE;
+    const bool start = !close && (tag == TAG_MOVE || first_in_path || prev_tag == TAG_CLOSE);
+    return (uint8_t)((start ? SKF_START : 0) | (close ? SKF_CLOSE : 0));
+}
+
+// A contour from its start s: its point entries are contiguous up to `limit` (the next contour's start or the end of
+// the path); `closes` = exclusive prefix count of Close entries.  path.rs:221-263: `closed` is set by the first Close of
+// the path and never reset.
+OC_HD void sk_contour(const uint8_t* ftag, const uint32_t* closes, uint32_t s, uint32_t limit, uint32_t path_begin, uint32_t path_end,
+                      uint32_t& len, bool& closed) {
+    len = (limit - s) - (closes[limit] - closes[s]);
+    const uint32_t term = s + len;
+    closed = (closes[s] - closes[path_begin]) > 0u || (term < path_end && ftag[term] == TAG_CLOSE);
+}
+
+// One trip of offset()'s loop (path.rs:182-214) for walk `rev` of a contour: what it emits.
+struct SkTrip {
+    int n;            // commands emitted by the join: 0 (skipped trip), 1, 2 (bevel)
+    bool first;       // no earlier trip of this walk emitted anything: its first command opens the walk
+    V2 a, b;          // the join's points
+};
+OC_HD V2 sk_normal(V2 from, V2 to) {  // path.rs:196-199
+    const V2 tangent = sub(to, from);
+    V2 normal = mk(-tangent.y, tangent.x);
+    const float nl = length(normal);
+    return (nl == 0.0f) ? mk(0.0f, 0.0f) : scale_r(normal, 1.0f / nl);
+}
+OC_HD SkTrip sk_trip(const V2* P /* the contour's points */, uint32_t len, bool closed, bool rev, uint32_t i, float width) {
+    SkTrip r;
+    r.n = 0;
+    r.first = true;
+    r.a = r.b = mk(0.0f, 0.0f);
+    const V2 first_point = (closed == rev) ? P[0] : P[len - 1];                                 // path.rs:175-179
+    auto Q = [&](uint32_t k) { return k < len ? P[rev ? len - 1 - k : k] : first_point; };      // next_point of trip k
+    const V2 prev_point = i == 0 ? first_point : Q(i - 1);  // (a skipped trip's point equals prev_point)
+    const V2 next_point = Q(i);
+    if (same(next_point, prev_point) && i != len) return r;  // path.rs:191
+    const V2 normal = sk_normal(prev_point, next_point);
+    V2 prev_normal = mk(0.0f, 0.0f);
+    for (uint32_t k = i; k > 0; --k) {  // the nearest earlier trip k - 1 that was not skipped
+        const V2 a = (k - 1 == 0) ? first_point : Q(k - 2), b = Q(k - 1);
+        if (!same(b, a)) {
+            prev_normal = sk_normal(a, b);
+            r.first = false;
+            break;
+        }
+    }
+    // join(), path.rs:163-171
+    const float offset = 1.0f / (1.0f + dot2(prev_normal, normal));
+    if (fabsf(offset) > 2.0f) {
+        r.n = 2;
+        r.a = add(prev_point, scale(0.5f * width, prev_normal));
+        r.b = add(prev_point, scale(0.5f * width, normal));
+    } else {
+        r.n = 1;
+        r.a = add(prev_point, scale(0.5f * width * offset, add(prev_normal, normal)));
+    }
+    return r;
+}
+// commands a trip emits: the join's, + the Close that ends the walk (forward: only when closed; reversed: always)
+OC_HD uint32_t sk_trip_count(const SkTrip& t, uint32_t i, uint32_t len, bool closed, bool rev) {
+    return (uint32_t)t.n + ((i == len && (rev || closed)) ? 1u : 0u);
+}
+// tag of a trip's first command: the forward walk always opens with a Move, the reversed one only when closed (path.rs:236-249)
+OC_HD uint32_t sk_first_tag(const SkTrip& t, bool closed, bool rev) {
+    return (t.first && (!rev || closed)) ? (uint32_t)TAG_MOVE : (uint32_t)TAG_LINE;
+}
+
 }  // namespace oc

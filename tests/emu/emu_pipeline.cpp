@@ -16,6 +16,7 @@
 
 #include "../../include/ochre_b200.h"
 #include "../../ochre_b200/csrc/raster_core.cuh"
+#include "../../ochre_b200/csrc/stroke_core.cuh"
 
 using namespace oc;
 
@@ -251,4 +252,165 @@ void emu_get(const EmuResult* r, uint32_t* tile_off, uint32_t* span_off, int16_t
     if (vals) memcpy(vals, r->vals.data(), r->vals.size() * 8);
 }
 void emu_free(EmuResult* r) { delete r; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The device stroker (csrc/stroke_kernels.cuh) as loops: the same passes -- flatten per source command, contour flags,
+// Close prefix counts, one work item per trip of offset()'s loop, scans -- over the same element-wise rules
+// (csrc/stroke_core.cuh), run sequentially.  tests/test_emu_parity.py compares it with the oracle's flatten + stroke.
+// ---------------------------------------------------------------------------------------------------------------
+struct EmuStroke {
+    std::vector<Cmd> out;
+    std::vector<uint32_t> off;
+    int status = 0;
+};
+namespace {
+struct EsCount {
+    uint32_t n;
+    void push(uint32_t, V2) { ++n; }
+};
+struct EsFlat {
+    std::vector<V2>* pt;
+    std::vector<uint8_t>* tag;
+    uint32_t at;
+    void push(uint32_t t, V2 p) {
+        (*pt)[at] = p;
+        (*tag)[at] = (uint8_t)t;
+        ++at;
+    }
+};
+template <class T>
+uint32_t excl_scan(std::vector<T>& v) {  // in place; returns the total
+    uint32_t acc = 0;
+    for (auto& x : v) {
+        const uint32_t t = (uint32_t)x;
+        x = (T)acc;
+        acc += t;
+    }
+    return acc;
+}
+}  // namespace
+
+extern "C" {
+EmuStroke* emu_stroke_batch(const OchreCmd* cmds_, const uint32_t* cmd_off, const float* width, uint32_t n_paths) {
+    EmuStroke* R = new EmuStroke();
+    const Cmd* cmds = reinterpret_cast<const Cmd*>(cmds_);
+    const uint32_t base = cmd_off[0], n_cmds = cmd_off[n_paths] - base;
+    cmds += base;
+    // flatten: entries per source command -> offsets -> entries
+    std::vector<uint32_t> foff(n_cmds + 1, 0);
+    for (uint32_t c = 0; c < n_cmds; ++c) {
+        const uint32_t p = sk_find(cmd_off, base, n_paths, c);
+        if (!(width[p] > 0.0f)) continue;
+        const uint32_t c0 = cmd_off[p] - base;
+        if (cmds[c].tag > (uint32_t)TAG_CLOSE) R->status = OCHRE_E_BAD_TAG;
+        EsCount s = {0u};
+        flatten_cmd_sink(cmds[c], sk_last(cmds + c0, c - c0), OC_CONIC_TOL, s);
+        foff[c] = s.n;
+    }
+    if (R->status) return R;
+    const uint32_t n_flat = excl_scan(foff);
+    foff[n_cmds] = n_flat;
+    std::vector<V2> fpt(n_flat);
+    std::vector<uint8_t> ftag(n_flat), flags(n_flat);
+    for (uint32_t c = 0; c < n_cmds; ++c) {
+        const uint32_t p = sk_find(cmd_off, base, n_paths, c);
+        if (!(width[p] > 0.0f)) continue;
+        const uint32_t c0 = cmd_off[p] - base;
+        EsFlat s = {&fpt, &ftag, foff[c]};
+        flatten_cmd_sink(cmds[c], sk_last(cmds + c0, c - c0), OC_CONIC_TOL, s);
+    }
+    std::vector<uint32_t> flat_off(n_paths + 1);
+    for (uint32_t p = 0; p <= n_paths; ++p) {
+        const uint32_t c = cmd_off[p] - base;
+        flat_off[p] = c < n_cmds ? foff[c] : n_flat;
+    }
+    // contours
+    std::vector<uint32_t> closes(n_flat + 1, 0), con_start;
+    for (uint32_t j = 0; j < n_flat; ++j) {
+        const uint32_t p = sk_find(flat_off.data(), 0u, n_paths, j);
+        const bool first = j == flat_off[p];
+        flags[j] = sk_flags(ftag[j], first, first ? (uint32_t)TAG_CLOSE : (uint32_t)ftag[j - 1]);
+        closes[j] = (flags[j] >> 1) & 1u;
+        if (flags[j] & SKF_START) con_start.push_back(j);
+    }
+    excl_scan(closes);  // (closes[n_flat] was 0: it now holds the total)
+    const uint32_t n_con = (uint32_t)con_start.size();
+    std::vector<uint32_t> con_len(n_con), con_pc(n_con), item_off(n_con + 1, 0);
+    for (uint32_t c = 0; c < n_con; ++c) {
+        const uint32_t s = con_start[c];
+        const uint32_t p = sk_find(flat_off.data(), 0u, n_paths, s);
+        const uint32_t limit = std::min(c + 1 < n_con ? con_start[c + 1] : n_flat, flat_off[p + 1]);
+        uint32_t len;
+        bool closed;
+        sk_contour(ftag.data(), closes.data(), s, limit, flat_off[p], flat_off[p + 1], len, closed);
+        con_len[c] = len;
+        con_pc[c] = (p << 1) | (closed ? 1u : 0u);
+        item_off[c] = 2u * (len + 1u);
+    }
+    const uint32_t n_items = excl_scan(item_off);  // (item_off[n_con] was 0)
+    // offset(): commands per item -> offsets
+    std::vector<uint32_t> item_out(n_items + 1, 0);
+    auto item = [&](uint32_t g, uint32_t& c, uint32_t& i, bool& rev) {
+        c = sk_find(item_off.data(), 0u, n_con, g);
+        const uint32_t local = g - item_off[c];
+        rev = local > con_len[c];
+        i = rev ? local - (con_len[c] + 1u) : local;
+    };
+    for (uint32_t g = 0; g < n_items; ++g) {
+        uint32_t c, i;
+        bool rev;
+        item(g, c, i, rev);
+        const bool closed = (con_pc[c] & 1u) != 0;
+        const SkTrip t = sk_trip(fpt.data() + con_start[c], con_len[c], closed, rev, i, width[con_pc[c] >> 1]);
+        item_out[g] = sk_trip_count(t, i, con_len[c], closed, rev);
+    }
+    excl_scan(item_out);
+    // commands per paint -> the batch's cmd_off
+    std::vector<uint32_t> item0(n_paths + 1);
+    R->off.assign(n_paths + 1, 0);
+    for (uint32_t p = 0; p <= n_paths; ++p) {
+        const uint32_t lo = (uint32_t)(std::lower_bound(con_start.begin(), con_start.end(), flat_off[p]) - con_start.begin());
+        item0[p] = item_out[item_off[lo]];
+    }
+    for (uint32_t p = 0; p < n_paths; ++p) R->off[p] = width[p] > 0.0f ? item0[p + 1] - item0[p] : cmd_off[p + 1] - cmd_off[p];
+    const uint32_t n_out = excl_scan(R->off);
+    R->off[n_paths] = n_out;
+    R->out.assign(n_out, Cmd());
+    auto store = [&](uint32_t at, uint32_t tag, V2 q) {
+        Cmd c;
+        memset(&c, 0, sizeof c);
+        c.tag = tag;
+        c.v[0] = q.x;
+        c.v[1] = q.y;
+        R->out[at] = c;
+    };
+    for (uint32_t g = 0; g < n_items; ++g) {
+        uint32_t c, i;
+        bool rev;
+        item(g, c, i, rev);
+        const bool closed = (con_pc[c] & 1u) != 0;
+        const uint32_t p = con_pc[c] >> 1;
+        const SkTrip t = sk_trip(fpt.data() + con_start[c], con_len[c], closed, rev, i, width[p]);
+        uint32_t at = R->off[p] + (item_out[g] - item0[p]);
+        if (t.n > 0) {
+            store(at++, sk_first_tag(t, closed, rev), t.a);
+            if (t.n > 1) store(at++, TAG_LINE, t.b);
+        }
+        if (i == con_len[c] && (rev || closed)) store(at, TAG_CLOSE, mk(0.0f, 0.0f));
+    }
+    for (uint32_t c = 0; c < n_cmds; ++c) {
+        const uint32_t p = sk_find(cmd_off, base, n_paths, c);
+        if (width[p] > 0.0f) continue;
+        R->out[R->off[p] + (c - (cmd_off[p] - base))] = cmds[c];
+    }
+    return R;
+}
+int emu_stroke_status(const EmuStroke* r) { return r->status; }
+uint64_t emu_stroke_n(const EmuStroke* r) { return r->out.size(); }
+void emu_stroke_get(const EmuStroke* r, OchreCmd* cmds, uint32_t* off) {
+    if (cmds && !r->out.empty()) memcpy(cmds, r->out.data(), r->out.size() * sizeof(Cmd));
+    if (off) memcpy(off, r->off.data(), r->off.size() * 4);
+}
+void emu_stroke_free(EmuStroke* r) { delete r; }
 }

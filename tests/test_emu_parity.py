@@ -102,3 +102,38 @@ def test_out_of_range_coordinate_is_rejected():
         E.rasterize(make_cmds([(MOVE, 0, 0), (LINE, 40000.0, 3)]), np.array([0, 2], np.uint32), ID[None])
     with pytest.raises(ValueError):
         E.rasterize(make_cmds([(MOVE, 0, 0), (LINE, float("nan"), 3)]), np.array([0, 2], np.uint32), ID[None])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_device_stroker_passes_match_reference_stroke(seed):
+    """The data-parallel formulation of Rasterizer::stroke's pre-pass (csrc/stroke_kernels.cuh, run here as loops over the
+    same element-wise rules) against the oracle's sequential flatten + stroke: byte-identical command lists."""
+    rng = np.random.default_rng(8100 + seed)
+    src, widths = [], []
+    for k in range(60):
+        p = _random_path(rng, int(rng.integers(0, 8)), float(rng.choice([8.0, 60.0, 400.0])), conic=(k % 4 == 0))
+        if k % 5 == 0:  # closed contour, then open ones (the never-reset `closed` flag), repeated points, a trailing Move
+            q = make_cmds([(MOVE, 5, 5), (LINE, 40, 9), (LINE, 40, 9), (LINE, 40, 9), (LINE, 22, 50), (CLOSE,), (CLOSE,), (LINE, 60, 60),
+                           (LINE, 90, 64), (QUADRATIC, 100, 80, 70, 95), (MOVE, 3, 70), (LINE, 3, 70), (LINE, 30, 90), (MOVE, 1, 1)])
+            p = np.concatenate([p, q])
+        src.append(p)
+        widths.append(0.0 if k % 3 == 0 else float(rng.uniform(0.2, 9.0)))
+    src += [make_cmds([(MOVE, 1, 1)]), np.zeros(0, O.CMD_DTYPE), make_cmds([(CLOSE,), (CLOSE,)]), make_cmds([(LINE, 7, 7)])]
+    widths += [2.0, 1.0, 3.0, 1.5]
+    widths = np.asarray(widths, np.float32)
+    cmds = np.concatenate(src)
+    off = np.cumsum([0] + [len(p) for p in src]).astype(np.uint32)
+    got_cmds, got_off = E.stroke_batch(cmds, off, widths)
+    want = [O.path_stroke(O.path_flatten(p, 0.1), float(w)) if w > 0 else p for p, w in zip(src, widths)]
+    want_off = np.cumsum([0] + [len(p) for p in want]).astype(np.uint32)
+    assert np.array_equal(got_off, want_off)
+    assert got_cmds.tobytes() == np.concatenate(want).tobytes()
+
+
+def test_device_stroker_passes_on_tiger():
+    from ochre_b200 import workloads as W
+
+    cmds, off, xf, sw = W.svg_paint_batch("tiger", 1.0)
+    got_cmds, got_off = E.stroke_batch(cmds, off, sw)
+    want_cmds, want_off, _ = W.svg("tiger", 1.0, stroker=lambda c, w: O.path_stroke(O.path_flatten(c, 0.1), w))
+    assert np.array_equal(got_off, want_off) and got_cmds.tobytes() == want_cmds.tobytes()
