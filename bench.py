@@ -480,7 +480,8 @@ def main():
         if dom_name == tj.get("stage"):
             traffic = tj["dram_bytes_per_launch"]
             traffic_detail = {"dram_bytes_per_launch": tj["dram_bytes_per_launch"], "algorithmic_bytes_per_launch": tj["algorithmic_bytes_per_launch"],
-                              "paths_per_launch": tj["paths_per_launch"], "kernel": tj.get("kernel"), "source": tj["source"]}
+                              "paths_per_launch": tj["paths_per_launch"], "kernel": tj.get("kernel"), "source": tj["source"],
+                              "ncu": tj.get("ncu")}
     except Exception:
         pass
     roofline = {
