@@ -57,6 +57,7 @@ struct Transform {
         Vec2 r = matrix * v;
         return Vec2(r.x + offset.x, r.y + offset.y);
     }
+    OchreTransform to_c() const { return OchreTransform{{matrix.m[0], matrix.m[1], matrix.m[2], matrix.m[3]}, offset.x, offset.y}; }
 };
 
 struct PathCmd : OchreCmd {
@@ -144,6 +145,33 @@ class Rasterizer {
     std::vector<PathCmd> cmds_;
 };
 
+// One paint of a document, as examples/svg.rs:140-154 hands them to a fresh Rasterizer each: fill(path, transform) when
+// stroke_width <= 0, else stroke(path, stroke_width, transform).
+struct Paint {
+    std::vector<PathCmd> path;
+    Transform transform;
+    float stroke_width = 0.0f;
+};
+inline void replay(const OchreResult& res, size_t n_paths, std::vector<TileBuilder*>& builders);
+
+// All paints of a document in one GPU submission; strokes are flattened and offset on the device
+// (ochre_b200_rasterize_paints).  builders[i] receives paint i's calls in the reference's order.
+inline void finish_paints(Context& ctx, const std::vector<Paint>& paints, std::vector<TileBuilder*>& builders) {
+    std::vector<OchreCmd> cmds;
+    std::vector<uint32_t> off{0};
+    std::vector<OchreTransform> xf;
+    std::vector<float> width;
+    for (const Paint& p : paints) {
+        cmds.insert(cmds.end(), p.path.begin(), p.path.end());
+        off.push_back((uint32_t)cmds.size());
+        xf.push_back(p.transform.to_c());
+        width.push_back(p.stroke_width);
+    }
+    OchreResult res;
+    ctx.check(ochre_b200_rasterize_paints(ctx.raw(), cmds.data(), off.data(), xf.data(), width.data(), (uint32_t)paints.size(), 0, nullptr, &res));
+    replay(res, paints.size(), builders);
+}
+
 // finish() for many rasterisers in one GPU submission; builder i receives path i's calls in
 // the reference's order (tiles ascending (tile_y, tile_x); a span right after the tile on its left).
 inline void finish_batch(Context& ctx, std::vector<Rasterizer*>& rasterizers, std::vector<TileBuilder*>& builders) {
@@ -157,7 +185,13 @@ inline void finish_batch(Context& ctx, std::vector<Rasterizer*>& rasterizers, st
     }
     OchreResult res;
     ctx.check(ochre_b200_rasterize(ctx.raw(), cmds.data(), off.data(), xf.data(), (uint32_t)rasterizers.size(), 0, nullptr, &res));
-    for (size_t p = 0; p < builders.size() && p < rasterizers.size(); ++p) {
+    replay(res, rasterizers.size(), builders);
+    for (Rasterizer* r : rasterizers) r->clear();
+}
+
+// TileBuilder calls of every path of a result, in the reference's order (rasterizer.rs:241, :261-264)
+inline void replay(const OchreResult& res, size_t n_paths, std::vector<TileBuilder*>& builders) {
+    for (size_t p = 0; p < builders.size() && p < n_paths; ++p) {
         uint32_t s = res.span_off[p], s1 = res.span_off[p + 1];
         for (uint32_t t = res.tile_off[p]; t < res.tile_off[p + 1]; ++t) {
             int16_t x = res.tile_xy[2 * t], y = res.tile_xy[2 * t + 1];
@@ -170,7 +204,6 @@ inline void finish_batch(Context& ctx, std::vector<Rasterizer*>& rasterizers, st
             }
         }
     }
-    for (Rasterizer* r : rasterizers) r->clear();
 }
 
 }  // namespace ochre

@@ -41,6 +41,7 @@ impl Transform {
         Transform::new(t.matrix.mul(self.matrix), Vec2::new(mo.x + t.offset.x, mo.y + t.offset.y))
     }
     pub fn apply(self, v: Vec2) -> Vec2 { let r = self.matrix.apply(v); Vec2::new(r.x + self.offset.x, r.y + self.offset.y) }
+    fn to_c(&self) -> OchreTransform { OchreTransform { m: self.matrix.0, ox: self.offset.x, oy: self.offset.y } }
 }
 
 #[derive(Copy, Clone)]
@@ -73,6 +74,9 @@ extern "C" {
     fn ochre_b200_destroy(ctx: *mut Ctx) -> c_int;
     fn ochre_b200_rasterize(ctx: *mut Ctx, cmds: *const OchreCmd, cmd_off: *const u32, xf: *const OchreTransform,
                             n_paths: u32, flags: u32, cmd_off_host: *const u32, out: *mut OchreResult) -> c_int;
+    fn ochre_b200_rasterize_paints(ctx: *mut Ctx, cmds: *const OchreCmd, cmd_off: *const u32, xf: *const OchreTransform,
+                                   stroke_width: *const f32, n_paths: u32, flags: u32, cmd_off_host: *const u32,
+                                   out: *mut OchreResult) -> c_int;
     fn ochre_b200_last_error(ctx: *const Ctx) -> *const c_char;
     fn ochre_b200_stroke_path(path: *const OchreCmd, n: usize, width: f32, out: *mut *mut OchreCmd, n_out: *mut usize) -> c_int;
     fn ochre_b200_free(p: *mut std::ffi::c_void);
@@ -146,20 +150,48 @@ impl Rasterizer {
     }
 }
 
+/// One paint of a document, as `examples/svg.rs:140-154` hands them to a fresh `Rasterizer` each:
+/// `fill(path, transform)` when `stroke_width` is `None`, else `stroke(path, width, transform)`.
+pub struct Paint<'a> { pub path: &'a [PathCmd], pub transform: Transform, pub stroke_width: Option<f32> }
+
+/// All paints of a document in one GPU submission; strokes are flattened and offset on the device
+/// (`ochre_b200_rasterize_paints`).  `builders[i]` receives paint i's calls in the reference's order.
+pub fn finish_paints<B: TileBuilder>(paints: &[Paint], builders: &mut [B]) {
+    let mut cmds = Vec::new();
+    let mut off = vec![0u32];
+    let mut xf = Vec::with_capacity(paints.len());
+    let mut width = Vec::with_capacity(paints.len());
+    for p in paints {
+        cmds.extend(p.path.iter().map(|c| c.to_c()));
+        off.push(cmds.len() as u32);
+        xf.push(p.transform.to_c());
+        width.push(p.stroke_width.unwrap_or(0.0));
+    }
+    submit(&cmds, &off, &xf, Some(&width), builders);
+}
+
 /// `finish` for many rasterisers in one GPU submission (the throughput entry point).
 pub fn finish_batch<B: TileBuilder>(rasterizers: Vec<Rasterizer>, builders: &mut [B]) {
     let mut cmds = Vec::new();
     let mut off = vec![0u32];
     for r in &rasterizers { cmds.extend_from_slice(&r.cmds); off.push(cmds.len() as u32); }
     let xf = vec![OchreTransform { m: [1.0, 0.0, 0.0, 1.0], ox: 0.0, oy: 0.0 }; rasterizers.len()];
+    submit(&cmds, &off, &xf, None, builders);
+}
+
+fn submit<B: TileBuilder>(cmds: &[OchreCmd], off: &[u32], xf: &[OchreTransform], width: Option<&[f32]>, builders: &mut [B]) {
+    let n_paths = off.len() - 1;
     DEFAULT.with(|dev| unsafe {
         let mut res: OchreResult = std::mem::zeroed();
-        let rc = ochre_b200_rasterize(dev.ctx, cmds.as_ptr(), off.as_ptr(), xf.as_ptr(), rasterizers.len() as u32, 0, std::ptr::null(), &mut res);
+        let rc = match width {
+            Some(w) => ochre_b200_rasterize_paints(dev.ctx, cmds.as_ptr(), off.as_ptr(), xf.as_ptr(), w.as_ptr(), n_paths as u32, 0, std::ptr::null(), &mut res),
+            None => ochre_b200_rasterize(dev.ctx, cmds.as_ptr(), off.as_ptr(), xf.as_ptr(), n_paths as u32, 0, std::ptr::null(), &mut res),
+        };
         if rc != 0 {
             panic!("ochre_b200_rasterize: {} ({})", std::ffi::CStr::from_ptr(ochre_b200_last_error(dev.ctx)).to_string_lossy(), rc);
         }
-        let tile_off = std::slice::from_raw_parts(res.tile_off, rasterizers.len() + 1);
-        let span_off = std::slice::from_raw_parts(res.span_off, rasterizers.len() + 1);
+        let tile_off = std::slice::from_raw_parts(res.tile_off, n_paths + 1);
+        let span_off = std::slice::from_raw_parts(res.span_off, n_paths + 1);
         let xy = std::slice::from_raw_parts(res.tile_xy, 2 * res.n_tiles as usize);
         let alpha = std::slice::from_raw_parts(res.alpha, 64 * res.n_tiles as usize);
         let spans = std::slice::from_raw_parts(res.spans, res.n_spans as usize);
