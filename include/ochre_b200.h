@@ -125,7 +125,7 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
                                 OchreResult* out);
 
 /* Upper bound of virtual commands (commands + paths) processed per pipeline pass; 0 restores the default: 16 Mi, ramping up
- * from 1 Mi when the results go to host memory (the download starts early); 64 Mi for device-resident results of the fused
+ * from 256 Ki when the results go to host memory (the download starts early); 64 Mi for device-resident results of the fused
  * kernel (nothing is pipelined behind the chunks). */
 int ochre_b200_set_chunk(ochre_b200_ctx* ctx, uint32_t max_vcmds);
 

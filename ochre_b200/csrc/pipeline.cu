@@ -682,7 +682,7 @@ struct HostBuf {  // pinned
 #define OC_ROUTE_CELLS 64
 #endif
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
-constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 20;
+constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 18;
 constexpr uint32_t DEVICE_CHUNK_VCMDS = 64u << 20;
 constexpr int N_STAGE = 8;
 
@@ -1418,7 +1418,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     std::vector<uint32_t> cuts;  // chunk i = paths [cuts[i], cuts[i + 1])
     cuts.push_back(0);
     // Host-resident results: the download of a chunk starts when its kernels are done, so the first chunks are small
-    // (1 Mi virtual commands, doubling) -- the PCIe link is busy almost from the start of the call.
+    // (256 Ki virtual commands, doubling) -- the PCIe link is busy almost from the start of the call.
     // Device-resident results of the fused kernel: nothing is pipelined behind the chunks, fewer and larger launches win
     // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk, and
     // with an output arena the origins / spans / ranges of a chunk travel behind the next chunk's kernels.
