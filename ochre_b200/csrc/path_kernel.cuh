@@ -263,6 +263,142 @@ struct PkScan {
     uint32_t span_excl;   // spans of the path before this thread's run
 };
 
+// The grid scan and the emission of tile origins / spans exist in two forms: for the 128-thread shape (large grids, mostly
+// untouched cells) the loops skip untouched cells four at a time and walk touched cells through the bitmask; for the
+// warp-per-path shape (a cell or two per thread) the plain per-cell loops are cheaper (1 M glyphs: 8.2 vs 8.8 ms).
+#if OC_PK_THREADS >= 64
+// Calls f(c, word) for every cell of [c0, c1) whose mark word is not the untouched pattern, in order.  Most cells of a
+// path's bounding grid are untouched: four are read and dismissed at a time.
+template <class F>
+__device__ __forceinline__ void pk_for_marked(const uint32_t* cell, uint32_t c0, uint32_t c1, F&& f) {
+    uint32_t c = c0;
+    for (; c < c1 && (c & 3u); ++c) {
+        const uint32_t w = cell[c];
+        if (w != PK_CELL_INIT) f(c, w);
+    }
+    for (; c + 4u <= c1; c += 4u) {
+        const uint4 q = *reinterpret_cast<const uint4*>(&cell[c]);
+        if ((q.x & q.y & q.z & q.w) == PK_CELL_INIT && (q.x | q.y | q.z | q.w) == PK_CELL_INIT) continue;
+        if (q.x != PK_CELL_INIT) f(c, q.x);
+        if (q.y != PK_CELL_INIT) f(c + 1u, q.y);
+        if (q.z != PK_CELL_INIT) f(c + 2u, q.z);
+        if (q.w != PK_CELL_INIT) f(c + 3u, q.w);
+    }
+    for (; c < c1; ++c) {
+        const uint32_t w = cell[c];
+        if (w != PK_CELL_INIT) f(c, w);
+    }
+}
+// Calls f(c) for every touched cell of [c0, c1), in order (from the finished bitmask).
+template <class F>
+__device__ __forceinline__ void pk_for_touched(const PkShared& S, uint32_t c0, uint32_t c1, F&& f) {
+    for (uint32_t cw = c0; cw < c1; cw = (cw | 31u) + 1u) {
+        const uint32_t wend = min(c1, (cw | 31u) + 1u);
+        uint32_t m = S.bits[cw >> 5] & ~((1u << (cw & 31u)) - 1u);
+        if (wend & 31u) m &= (1u << (wend & 31u)) - 1u;  // (wend is inside this word)
+        while (m) {
+            const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            f((cw & ~31u) + bit);
+        }
+    }
+}
+
+// Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells); S.u.cell holds the
+// CF_* flags (low bits) of every marked cell, unmarked cells keep PK_CELL_INIT (its low bits are clear).
+__device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, int wcarry, PkScan& sc, uint32_t& n_touched,
+                                             uint32_t& n_spans, int& wtotal, uint32_t& bad) {
+    const uint32_t ncells = (uint32_t)(W * H);
+    uint32_t* cell = S.u.cell;
+    // every thread owns a contiguous run of cells -- whole 32-cell words, or a power-of-two fraction of
+    // one on small grids: local sums, one CTA scan, local prefix
+    uint32_t per = (ncells + PK_THREADS - 1) / PK_THREADS;
+    per = per >= 32u ? ((per + 31u) & ~31u) : (per <= 1u ? 1u : 1u << (32 - __clz((int)per - 1)));
+    sc.c0 = min(ncells, threadIdx.x * per);
+    sc.c1 = min(ncells, sc.c0 + per);
+    uint32_t lt = 0, lw = 0;
+    pk_for_marked(cell, sc.c0, sc.c1, [&](uint32_t, uint32_t w) {
+        const uint32_t cnt = w & 0xffffu;
+        if (cnt > PK_MAXCNT) err = 1;  // keeps the fixed-point sums inside int32
+        lt += cnt ? 1u : 0u;
+        lw += (w >> 16) - 0x8000u;
+    });
+    uint32_t ex_t, ex_w, tot_t, tot_w;
+    block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
+    {
+        uint32_t r = ex_t;
+        int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
+        for (uint32_t cw = sc.c0; cw < sc.c1; cw = (cw | 31u) + 1u) {  // word by word
+            if ((cw & 31u) == 0) S.wbase[cw >> 5] = (uint16_t)r;
+            uint32_t word = 0;
+            pk_for_marked(cell, cw, min(sc.c1, (cw | 31u) + 1u), [&](uint32_t c, uint32_t w) {
+                wp += (int)((w >> 16) - 0x8000u);
+                uint32_t f = 0;
+                if (w & 0xffffu) {
+                    word |= 1u << (c & 31u);
+                    ++r;
+                    f = CF_TOUCHED | (wp != 0 ? CF_WIND : 0u);
+                }
+                cell[c] = f;
+            });
+            if (word) atomicOr(&S.bits[cw >> 5], word);  // (runs shorter than a word share it)
+        }
+    }
+    n_touched = tot_t;
+    wtotal = wcarry + (int)tot_w;
+    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.wbase[ncells >> 5] = (uint16_t)tot_t;  // rank(ncells) reads one word past the last cell
+    __syncthreads();
+    // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
+    uint32_t ls = 0;
+    if (sc.c0 < sc.c1) {
+        uint32_t row_end = (sc.c0 / (uint32_t)W + 1u) * (uint32_t)W;
+        pk_for_touched(S, sc.c0, sc.c1, [&](uint32_t c) {
+            while (c >= row_end) row_end += (uint32_t)W;
+            const uint32_t f = cell[c];
+            if (f & CF_WIND) {
+                const uint32_t nx = pk_next_touched(S, c + 1, row_end);
+                if (nx > c + 1 && nx < row_end) {
+                    cell[c] = f | CF_SPAN;
+                    ++ls;
+                }
+            }
+        });
+    }
+    uint32_t tot_s;
+    sc.span_excl = block_excl_scan(ls, S.ws, tot_s);
+    n_spans = tot_s;
+    bad = __syncthreads_or((int)err);
+}
+
+// Tile origins and spans (needs the CF_* flags, i.e. runs before the accumulators reuse that
+// shared memory).
+__device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKernelArgs& A, const PkScan& sc, int gx0, int gy0,
+                                              int W, uint32_t tile_at, uint32_t span_at) {
+    if (sc.c0 >= sc.c1) return;
+    const uint32_t* cell = S.u.cell;
+    int cy = (int)(sc.c0 / (uint32_t)W);
+    uint32_t row_start = (uint32_t)cy * (uint32_t)W;
+    uint32_t sidx = span_at + sc.span_excl;
+    uint32_t r = pk_rank(S, sc.c0);
+    pk_for_touched(S, sc.c0, sc.c1, [&](uint32_t c) {
+        while (c >= row_start + (uint32_t)W) {
+            row_start += (uint32_t)W;
+            ++cy;
+        }
+        const int cx = (int)(c - row_start);
+        const int px = (gx0 + cx) * 8, py = (gy0 + cy) * 8;
+        __stcs(reinterpret_cast<uint32_t*>(A.tile_xy) + tile_at + r, (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16));
+        ++r;
+        if (cell[c] & CF_SPAN) {
+            const uint32_t nx = pk_next_touched(S, c + 1, row_start + (uint32_t)W);
+            // OchreSpan {x, y, w, pad}; streaming store: results must not push the line scratch out of L2
+            __stcs(reinterpret_cast<uint2*>(A.spans) + sidx++,
+                   make_uint2((uint32_t)(uint16_t)(int16_t)(px + 8) | ((uint32_t)(uint16_t)(int16_t)py << 16), (nx - c - 1) * 8u));
+        }
+    });
+}
+
+#else
 // Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells),
 // S.u.cell = CF_* flags of every cell.
 __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, int wcarry, PkScan& sc, uint32_t& n_touched,
@@ -360,6 +496,8 @@ __device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKerne
         }
     }
 }
+
+#endif
 
 // slot band of grid row r (S.brow[b] <= r < S.brow[b + 1])
 __device__ __forceinline__ int pk_band_of(const PkShared& S, int nb, int r) {
