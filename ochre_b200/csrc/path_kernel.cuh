@@ -959,7 +959,9 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     for (int x = 0; x < 8; ++x) {
                         run += d[x];
                         // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
-                        const uint32_t q = (uint32_t)(int)fminf(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c)), 255.0f);  // (exact product: == mul, add)
+                        // (exact product: the fma equals mul, add; the conversion truncates and saturates at 255: min(|v|, 255) as u8)
+                        uint32_t q;
+                        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c))));
                         if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                     }
                     const uint32_t ti = tile_at + rank0 + s;
