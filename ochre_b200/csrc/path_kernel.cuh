@@ -235,7 +235,10 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
             const float omt = 1.0f - t1;
             const float p1x = omt * w.lx + t1 * w.px, p1y = omt * w.ly + t1 * w.py;
             const float height = p1y - p0y;
-            const float area = 0.5f * height * ((rt - p0x) + (rt - p1x));
+            // area = 0.5 * height * ((right - p0.x) + (right - p1.x)), rasterizer.rs:108, in 2^-22 units: the scaling by a power
+            // of two commutes with the product's rounding, so (height * 2^22 * 0.5) * sum rounds to the same integer
+            const float hq = height * OC_FX_SCALE;
+            const float aq = (hq * 0.5f) * ((rt - p0x) + (rt - p1x));
             const int ry = y0 >> 3;
             if ((uint32_t)(ry - r0) < nrows) {
                 // slot = rank(cell) - rank0, the rank structure read through its shared-window address
@@ -246,7 +249,7 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
                 const uint32_t rank = wb + (uint32_t)__popc(wbits & pk_below(cidx));
                 const uint32_t d = slot0_s + rank * (uint32_t)(4 * PK_ACCW) + 4u * (uint32_t)((y0 & 7) * 9 + (x0 & 7));
                 // (|height| exceeds 1 by a few ulps of the lerp: no mantissa trick for the rounding, F2I it is)
-                const int qa = __float2int_rn(area * OC_FX_SCALE), qh = __float2int_rn(height * OC_FX_SCALE);
+                const int qa = __float2int_rn(aq), qh = __float2int_rn(hq);
                 pk_red_add(d, (uint32_t)qa);
                 pk_red_add(d + 4u, (uint32_t)(qh - qa));
             }
