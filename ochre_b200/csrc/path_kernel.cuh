@@ -123,9 +123,8 @@ struct PkShared {
         PkCurves v;
     } u;
     // touched cells of the grid in (tile_y, tile_x) order, kept across the slot bands:
-    // rank(c) = wbase[c >> 5] + popc(bits[c >> 5] & below(c & 31))
-    uint32_t bits[PK_WORDS + 1];
-    uint16_t wbase[PK_WORDS + 2];
+    // rank(c) = rk[c >> 5].y + popc(rk[c >> 5].x & below(c & 31))
+    uint2 rk[PK_WORDS + 2];  // per 32-cell word: x = bitmask of its touched cells, y = touched cells before the word (one 8-byte read)
     uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
     uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
     uint16_t brow[PK_MAXB + 2];             // first row of every slot band (relative to the stripe)
@@ -140,12 +139,13 @@ struct PkShared {
 
 // touched cells before cell c (c may be one past the last cell)
 __device__ __forceinline__ uint32_t pk_rank(const PkShared& S, uint32_t c) {
-    return (uint32_t)S.wbase[c >> 5] + (uint32_t)__popc(S.bits[c >> 5] & ((1u << (c & 31u)) - 1u));
+    const uint2 w = S.rk[c >> 5];
+    return w.y + (uint32_t)__popc(w.x & ((1u << (c & 31u)) - 1u));
 }
 // first touched cell in [c, end), or `end`
 __device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t c, uint32_t end) {
     while (c < end) {
-        const uint32_t w = S.bits[c >> 5] >> (c & 31u);
+        const uint32_t w = S.rk[c >> 5].x >> (c & 31u);
         if (w) return min(end, c + (uint32_t)__ffs((int)w) - 1u);
         c = (c | 31u) + 1u;
     }
@@ -200,12 +200,11 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
                                               const uint16_t* __restrict__ sidx, uint32_t p0, uint32_t p1, int gx0, int gy0, int W, int R0, int R1, uint32_t rank0,
                                               uint64_t pk_pol) {
     uint32_t pos = p0 + threadIdx.x;
-    uint32_t bits_s = acc_s + (uint32_t)(offsetof(PkShared, bits) - offsetof(PkShared, u));
-    uint32_t wbase_s = acc_s + (uint32_t)(offsetof(PkShared, wbase) - offsetof(PkShared, u));
+    uint32_t rk_s = acc_s + (uint32_t)(offsetof(PkShared, rk) - offsetof(PkShared, u));
     uint32_t slot0_s = acc_s - rank0 * (uint32_t)(4 * PK_ACCW);  // accumulator block of rank 0 (slot = rank - rank0)
     const int r0 = R0 - gy0;                       // the band's rows relative to the grid
     const uint32_t nrows = (uint32_t)(R1 - R0);
-    asm volatile("" : "+r"(slot0_s), "+r"(bits_s), "+r"(wbase_s));
+    asm volatile("" : "+r"(slot0_s), "+r"(rk_s));
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t inn = 0;
     if (pos < p1) Ln = pk_ld(&lines[pk_ld(&sidx[pos], pk_pol)], pk_pol);
@@ -244,8 +243,7 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
                 // slot = rank(cell) - rank0, the rank structure read through its shared-window address
                 const uint32_t cidx = (uint32_t)(ry * W + (x0 >> 3));
                 uint32_t wbits, wb;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wbits) : "r"(bits_s + 4u * (cidx >> 5)));
-                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(wb) : "r"(wbase_s + 2u * (cidx >> 5)));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wbits), "=r"(wb) : "r"(rk_s + 8u * (cidx >> 5)));
                 const uint32_t rank = wb + (uint32_t)__popc(wbits & pk_below(cidx));
                 const uint32_t d = slot0_s + rank * (uint32_t)(4 * PK_ACCW) + 4u * (uint32_t)((y0 & 7) * 9 + (x0 & 7));
                 // (|height| exceeds 1 by a few ulps of the lerp: no mantissa trick for the rounding, F2I it is)
@@ -297,7 +295,7 @@ template <class F>
 __device__ __forceinline__ void pk_for_touched(const PkShared& S, uint32_t c0, uint32_t c1, F&& f) {
     for (uint32_t cw = c0; cw < c1; cw = (cw | 31u) + 1u) {
         const uint32_t wend = min(c1, (cw | 31u) + 1u);
-        uint32_t m = S.bits[cw >> 5] & ~((1u << (cw & 31u)) - 1u);
+        uint32_t m = S.rk[cw >> 5].x & ~((1u << (cw & 31u)) - 1u);
         if (wend & 31u) m &= (1u << (wend & 31u)) - 1u;  // (wend is inside this word)
         while (m) {
             const uint32_t bit = (uint32_t)__ffs((int)m) - 1u;
@@ -307,7 +305,7 @@ __device__ __forceinline__ void pk_for_touched(const PkShared& S, uint32_t c0, u
     }
 }
 
-// Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells); S.u.cell holds the
+// Ordered scan of the marked grid.  On return: S.rk (the ordered set of touched cells); S.u.cell holds the
 // CF_* flags (low bits) of every marked cell, unmarked cells keep PK_CELL_INIT (its low bits are clear).
 __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, int wcarry, PkScan& sc, uint32_t& n_touched,
                                              uint32_t& n_spans, int& wtotal, uint32_t& bad) {
@@ -332,7 +330,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         uint32_t r = ex_t;
         int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
         for (uint32_t cw = sc.c0; cw < sc.c1; cw = (cw | 31u) + 1u) {  // word by word
-            if ((cw & 31u) == 0) S.wbase[cw >> 5] = (uint16_t)r;
+            if ((cw & 31u) == 0) S.rk[cw >> 5].y = r;
             uint32_t word = 0;
             pk_for_marked(cell, cw, min(sc.c1, (cw | 31u) + 1u), [&](uint32_t c, uint32_t w) {
                 wp += (int)((w >> 16) - 0x8000u);
@@ -344,12 +342,12 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
                 }
                 cell[c] = f;
             });
-            if (word) atomicOr(&S.bits[cw >> 5], word);  // (runs shorter than a word share it)
+            if (word) atomicOr(&S.rk[cw >> 5].x, word);  // (runs shorter than a word share it)
         }
     }
     n_touched = tot_t;
     wtotal = wcarry + (int)tot_w;
-    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.wbase[ncells >> 5] = (uint16_t)tot_t;  // rank(ncells) reads one word past the last cell
+    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.rk[ncells >> 5].y = tot_t;  // rank(ncells) reads one word past the last cell
     __syncthreads();
     // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
     uint32_t ls = 0;
@@ -402,7 +400,7 @@ __device__ __forceinline__ void pk_emit_index(const PkShared& S, const PathKerne
 }
 
 #else
-// Ordered scan of the marked grid.  On return: S.bits / S.wbase (the ordered set of touched cells),
+// Ordered scan of the marked grid.  On return: S.rk (the ordered set of touched cells),
 // S.u.cell = CF_* flags of every cell.
 __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t err, int wcarry, PkScan& sc, uint32_t& n_touched,
                                              uint32_t& n_spans, int& wtotal, uint32_t& bad) {
@@ -428,7 +426,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         uint32_t r = ex_t, word = 0;
         int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
         for (uint32_t c = sc.c0; c < sc.c1; ++c) {
-            if ((c & 31u) == 0) S.wbase[c >> 5] = (uint16_t)r;
+            if ((c & 31u) == 0) S.rk[c >> 5].y = r;
             const uint32_t w = cell[c];
             const uint32_t cnt = w & 0xffffu;
             wp += (int)((w >> 16) - 0x8000u);
@@ -440,14 +438,14 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
             }
             cell[c] = f;
             if ((c & 31u) == 31u || c + 1 == sc.c1) {
-                if (word) atomicOr(&S.bits[c >> 5], word);  // (runs shorter than a word share it)
+                if (word) atomicOr(&S.rk[c >> 5].x, word);  // (runs shorter than a word share it)
                 word = 0;
             }
         }
     }
     n_touched = tot_t;
     wtotal = wcarry + (int)tot_w;
-    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.wbase[ncells >> 5] = (uint16_t)tot_t;  // rank(ncells) reads one word past the last cell
+    if (threadIdx.x == 0 && (ncells & 31u) == 0) S.rk[ncells >> 5].y = tot_t;  // rank(ncells) reads one word past the last cell
     __syncthreads();
     // spans: touched cell with non-zero winding whose next touched cell is on the same row, further than one tile
     uint32_t ls = 0;
@@ -812,7 +810,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 S.boff[tid] = o;
             }
             for (uint32_t i = tid; i < (uint32_t)(W * Hs); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
-            for (uint32_t i = tid; i <= (uint32_t)(W * Hs) >> 5; i += PK_THREADS) S.bits[i] = 0;
+            for (uint32_t i = tid; i <= (uint32_t)(W * Hs) >> 5; i += PK_THREADS) S.rk[i].x = 0;
             if (tid == 0) S.merr = 0;
             __syncthreads();
             if (tid < PK_NCLS) S.bcur[tid] = 0;
@@ -1045,6 +1043,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
 }
 
 constexpr size_t PK_SMEM = sizeof(PkShared);
+// the 128-thread shape lives on 8 CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA
+static_assert(PK_THREADS != 128 || PK_CTAS_PER_SM != 8 || PK_SMEM <= (233472 - 8 * 1024) / 8, "PkShared no longer fits 8 CTAs per SM");
 
 }  // namespace OC_PK_NS
 }  // namespace oc
