@@ -37,6 +37,15 @@ METRIC = "paths/s (8x8 alpha tiles/s and alpha MB/s in config)"
 WORKLOAD = "config4: synthetic stress, random closed cubic paths (3-64 segments) on a 4096x4096 canvas, generator G4"
 
 
+def host_threads() -> int:
+    """Threads for the CPU arm: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not
+    what "all the host threads it can use" means; the oracle takes the count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -121,7 +130,7 @@ def run_reference(args, rank, world):
     import oracle as O
     from ochre_b200 import workloads as W
 
-    threads = O.max_threads()
+    threads = host_threads()
     sample = args.ref_paths
     cmds, off, xf = W.blobs(sample, 0)
     off64 = off.astype(np.uint64)
@@ -499,7 +508,7 @@ def main():
     if world == 1 and not args.no_cpu:
         import oracle as O
 
-        threads = O.max_threads()
+        threads = host_threads()
         probe = 2000
         r0 = O.rasterize_batch(h_cmds[: off[probe]], off[: probe + 1].astype(np.uint64), h_xf[:probe], threads=threads, count_only=True)
         rate = probe / max(r0.seconds, 1e-6)
