@@ -43,10 +43,32 @@ struct VecSink {
     void push(uint32_t tag, V2 p) { out->push_back(tag == oc::TAG_CLOSE ? cmd0(OCHRE_CLOSE) : cmd1(tag, p)); }
 };
 
-// free flatten(), path.rs:114-144 (untransformed space; Close does not move `last`)
-void flatten_path(const OchreCmd* path, size_t n, float tol, std::vector<OchreCmd>& out) {
+// Every coordinate finite, Conic weights finite and > -1: anything else makes the reference's flatten loop forever
+// (path.rs:50-53, :63-66, :84-88); here it is OCHRE_E_BAD_COORD, as on the device (stroke_kernels.cuh: k_sf_count).
+bool path_finite(const OchreCmd* path, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const oc::Cmd& c = reinterpret_cast<const oc::Cmd&>(path[i]);
+        for (int k = 0; k < 2 * oc::cmd_npts(c.tag); ++k)
+            if (!(fabsf(c.v[k]) < 3.0e38f)) return false;
+        if (c.tag == oc::TAG_CONIC && !oc::conic_weight_ok(c.v[4])) return false;
+    }
+    return true;
+}
+
+// free flatten(), path.rs:114-144 (untransformed space; Close does not move `last`).  Returns false when one command
+// flattens to OC_CURVE_CAP entries or more (a dt that cannot advance t: the capped loop gave up).
+bool flatten_path(const OchreCmd* path, size_t n, float tol, std::vector<OchreCmd>& out) {
     VecSink s{&out};
-    oc::flatten_path_sink(reinterpret_cast<const oc::Cmd*>(path), n, tol, s);
+    V2 last = oc::mk(0.0f, 0.0f);
+    const oc::Cmd* pc = reinterpret_cast<const oc::Cmd*>(path);
+    for (size_t i = 0; i < n; ++i) {  // == oc::flatten_path_sink, with the per-command entry count checked
+        const size_t before = out.size();
+        oc::flatten_cmd_sink(pc[i], last, tol, s);
+        if (out.size() - before >= OC_CURVE_CAP) return false;
+        const int np = oc::cmd_npts(pc[i].tag);
+        if (np > 0) last = oc::cmd_pt(pc[i], np - 1);
+    }
+    return true;
 }
 
 // stroke(), path.rs:152-274; returns false when the polygon holds a curve (the reference panics, path.rs:264-266)
@@ -70,14 +92,14 @@ extern "C" {
 int ochre_b200_flatten_path(const OchreCmd* path, size_t n, float tolerance, OchreCmd** out, size_t* n_out) {
     if ((!path && n) || !out || !n_out) return OCHRE_E_INVALID_ARG;
     std::vector<OchreCmd> flat;
-    flatten_path(path, n, tolerance, flat);
+    if (!path_finite(path, n) || !flatten_path(path, n, tolerance, flat)) return OCHRE_E_BAD_COORD;
     return to_c_array(flat, out, n_out);
 }
 
 int ochre_b200_stroke_path(const OchreCmd* path, size_t n, float width, OchreCmd** out, size_t* n_out) {
     if ((!path && n) || !out || !n_out) return OCHRE_E_INVALID_ARG;
     std::vector<OchreCmd> flat, poly;
-    flatten_path(path, n, 0.1f, flat);  // TOLERANCE, rasterizer.rs:6
+    if (!path_finite(path, n) || !flatten_path(path, n, 0.1f, flat)) return OCHRE_E_BAD_COORD;  // TOLERANCE, rasterizer.rs:6
     if (!stroke_polygon(flat, width, poly)) return OCHRE_E_NOT_POLYLINE;
     return to_c_array(poly, out, n_out);
 }

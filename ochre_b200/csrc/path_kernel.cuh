@@ -75,12 +75,17 @@ struct PkScratch {
 // so that its stack of pending intervals does not weigh on the common path.
 struct PkConicCount {
     uint32_t n;
-    __device__ void operator()(V2) { ++n; }
+    bool ok;
+    __device__ void operator()(V2 p) {
+        ++n;
+        ok = ok && coord_ok(p);
+    }
 };
+// number of lines, or OC_CURVE_CAP when a generated point leaves the accepted coordinate range
 __device__ __noinline__ uint32_t pk_conic_count(V2 last, V2 control, V2 point, float weight) {
-    PkConicCount cnt = {0u};
+    PkConicCount cnt = {0u, true};
     conic_for_each_point(last, control, point, weight, OC_CONIC_TOL, cnt);
-    return cnt.n;
+    return cnt.ok ? cnt.n : OC_CURVE_CAP;
 }
 struct PkConicEmit {
     const PkScratch* G;
@@ -603,7 +608,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         if (np > 2) c.c = cmd_point(pc[j], 2, m);
                     }
                     if (!(coord_ok(c.last) && coord_ok(c.a) && coord_ok(c.b) && coord_ok(c.c))) bad = 1;
-                    if (tag == TAG_CONIC && !(fabsf(pc[j].v[4]) < 3.0e38f)) bad = 1;  // the weight must be finite
+                    if (tag == TAG_CONIC && !conic_weight_ok(pc[j].v[4])) bad = 1;  // finite and > -1
                 }
                 if (!bad) {
                     my_tag = c.tag;
@@ -618,9 +623,13 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         }
                         default: break;  // Close: rasterizer.rs:154
                     }
-                } else {
-                    atomicMax(A.status, bad);
+                    if (my_n >= OC_CURVE_CAP) {  // a Conic point out of range (or a dt that cannot advance t: unreachable for validated points)
+                        bad = 1;
+                        my_n = 0;
+                        my_tag = TAG_CLOSE;
+                    }
                 }
+                if (bad) atomicMax(A.status, bad);
             }
             uint32_t total;
             const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);

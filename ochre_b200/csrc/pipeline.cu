@@ -118,7 +118,16 @@ k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_o
         }
     }
     VCmd c = decode_vcmd(pc, c1 - c0, j, m);
-    nlines[v] = vcmd_line_count(c);
+    // `last` (and `first`, for the closing lines) are inherited from earlier commands: a curve that starts at a rejected
+    // point gets a dt its t loop cannot advance with, so the command is dropped here, not only the one that owns the point
+    uint32_t n = 0;
+    if (coord_ok(c.last) && coord_ok(c.a) && (c.tag != TAG_CONIC || conic_weight_ok(c.w))) n = vcmd_line_count(c);
+    else atomicMax(status, (int)ST_BAD_COORD);
+    if (n >= OC_CURVE_CAP) {  // a Conic point out of range
+        atomicMax(status, (int)ST_BAD_COORD);
+        n = 0;
+    }
+    nlines[v] = n;
 }
 
 // ---------------------------------------------------------------------------
@@ -1728,6 +1737,10 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
         k_words_to_host<<<1, 32, 0, st>>>(d_sc, h_dev, 2);
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+        if (hs[0] == 1) {
+            ctx->err = "a stroke paint holds a non-finite coordinate, a Conic weight <= -1, or a curve too large to flatten";
+            return OCHRE_E_BAD_COORD;
+        }
         if (hs[0] != 0) {
             ctx->err = "unknown command tag in a stroke paint";
             return OCHRE_E_BAD_TAG;

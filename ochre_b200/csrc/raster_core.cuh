@@ -121,6 +121,16 @@ OC_HD V2 cmd_endpoint(const Cmd& c, const float* xf) {
     return np > 0 ? cmd_point(c, np - 1, xf) : mk(0.0f, 0.0f);  // np == 0: rejected tag, result unused
 }
 
+// Input validation: device-space coordinates must be finite and inside the
+// range where the reference's i16 pixel arithmetic cannot overflow.
+#define OC_COORD_LIMIT 32760.0f
+#define OC_CURVE_CAP (1u << 20) /* bound of every flattening loop; a command that reaches it is rejected */
+OC_HD bool coord_ok(V2 p) { return fabsf(p.x) < OC_COORD_LIMIT && fabsf(p.y) < OC_COORD_LIMIT; }  // false for NaN/inf
+// Conic weights: the rational quadratic's denominator (1-t)^2 + 2t(1-t)w + t^2 has its minimum (1+w)/2 at t = 1/2;
+// w <= -1 divides by zero at the first midpoint (path.rs:84-88 then recurses without end).  Rejected with the
+// non-finite ones; weights in (-1, 0) are accepted as long as every point they generate stays in range.
+OC_HD bool conic_weight_ok(float w) { return w > -1.0f && w < 3.0e38f; }
+
 // ---------------------------------------------------------------------------
 // Curve flattening, path.rs:49-74.  The parameter sequence is the *rounded*
 // recurrence t = min(t + dt, 1), so it is generated sequentially.
@@ -161,7 +171,7 @@ OC_HD V2 cubic_eval(float t, V2 last, V2 c1, V2 c2, V2 p) {
 #define OC_CONIC_TOL 0.1f /* TOLERANCE, rasterizer.rs:6 */
 #define OC_CONIC_DEPTH 40
 template <class F>
-OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, float tol, F& f) {
+OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, float tol, F& f, float limit = OC_COORD_LIMIT) {
     float st0[OC_CONIC_DEPTH], st1[OC_CONIC_DEPTH];
     V2 sp0[OC_CONIC_DEPTH], sp1[OC_CONIC_DEPTH];
     int depth[OC_CONIC_DEPTH];
@@ -169,6 +179,7 @@ OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, flo
     float t0 = 0.0f, t1 = 1.0f;
     V2 p0 = last, p1 = point;
     int d = 0;
+    uint32_t emitted = 0;
     const V2 wc = scale(weight, control);
     for (;;) {
         const float t = 0.5f * (t0 + t1);
@@ -177,7 +188,9 @@ OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, flo
         const float denom = (1.0f - t) * (1.0f - t) + 2.0f * t * (1.0f - t) * weight + t * t;
         const V2 mid = scale(1.0f / denom, lerp(t, p01, p12));
         const float err = length(sub(mid, scale(0.5f, add(p0, p1))));
-        if (err > tol && d + 1 < OC_CONIC_DEPTH && n < OC_CONIC_DEPTH) {
+        // (a midpoint beyond `limit` ends the subdivision -- the rasteriser's count pass sees the point and rejects the
+        // path -- and so do OC_CURVE_CAP emitted points: the work stays bounded whatever the weight)
+        if (err > tol && fabsf(mid.x) < limit && fabsf(mid.y) < limit && emitted < OC_CURVE_CAP && d + 1 < OC_CONIC_DEPTH && n < OC_CONIC_DEPTH) {
             // right half waits; descend into the left half
             st0[n] = t;
             st1[n] = t1;
@@ -192,6 +205,7 @@ OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, flo
         }
         f(mid);
         f(p1);
+        emitted += 2;
         if (n == 0) break;
         --n;
         t0 = st0[n];
@@ -202,12 +216,14 @@ OC_HD void conic_for_each_point(V2 last, V2 control, V2 point, float weight, flo
     }
 }
 
-// Number of lines the t loop emits (>= 1 for finite input; dt is never 0 for
-// coordinates inside the accepted range, so the loop terminates).
+// Number of lines the t loop emits (>= 1 for finite input).  For coordinates inside the accepted
+// range dt >= 5e-4 (|second difference| <= 4 * 32760 * sqrt 2), so the loop ends after < 2000 trips;
+// OC_CURVE_CAP bounds it for anything else (a dt of 0 or below one ulp of t never advances t: the
+// reference loops forever there, path.rs:50-53, :63-66).  A count of OC_CURVE_CAP means "rejected".
 OC_HD uint32_t curve_count(float dt) {
     uint32_t n = 0;
     float t = 0.0f;
-    while (t < 1.0f) {
+    while (t < 1.0f && n < OC_CURVE_CAP) {
         t = fminf(t + dt, 1.0f);
         n++;
     }
@@ -495,9 +511,13 @@ struct VCmd {
     float w;     // Conic weight
 };
 
-struct ConicCountF {
+struct ConicCountF {  // counts the points and checks every one of them (a weight near -1 sends midpoints far away)
     uint32_t n;
-    OC_HD void operator()(V2) { ++n; }
+    bool ok;
+    OC_HD void operator()(V2 p) {
+        ++n;
+        ok = ok && coord_ok(p);
+    }
 };
 template <class F>
 struct ConicLineF {  // conic_for_each_point -> f(k, prev, next)
@@ -549,9 +569,9 @@ OC_HD uint32_t vcmd_line_count(const VCmd& c) {
         case TAG_QUAD: return curve_count(quad_dt(c.last, c.a, c.b));
         case TAG_CUBIC: return curve_count(cubic_dt(c.last, c.a, c.b, c.c));
         case TAG_CONIC: {  // path.rs:75-104, two lines per leaf of the subdivision
-            ConicCountF cnt = {0u};
+            ConicCountF cnt = {0u, true};
             conic_for_each_point(c.last, c.a, c.b, c.w, OC_CONIC_TOL, cnt);
-            return cnt.n;
+            return cnt.ok ? cnt.n : OC_CURVE_CAP;
         }
         default: return 0;  // Close
     }
@@ -569,7 +589,7 @@ OC_HD void vcmd_for_each_line(const VCmd& c, F& f) {
             float t = 0.0f;
             V2 prev = c.last;
             uint32_t k = 0;
-            while (t < 1.0f) {
+            while (t < 1.0f && k < OC_CURVE_CAP) {
                 t = fminf(t + dt, 1.0f);
                 V2 p = quad_eval(t, c.last, c.a, c.b);
                 f(k++, prev, p);
@@ -582,7 +602,7 @@ OC_HD void vcmd_for_each_line(const VCmd& c, F& f) {
             float t = 0.0f;
             V2 prev = c.last;
             uint32_t k = 0;
-            while (t < 1.0f) {
+            while (t < 1.0f && k < OC_CURVE_CAP) {
                 t = fminf(t + dt, 1.0f);
                 V2 p = cubic_eval(t, c.last, c.a, c.b, c.c);
                 f(k++, prev, p);
@@ -599,10 +619,6 @@ OC_HD void vcmd_for_each_line(const VCmd& c, F& f) {
     }
 }
 
-// Input validation: device-space coordinates must be finite and inside the
-// range where the reference's i16 pixel arithmetic cannot overflow.
-#define OC_COORD_LIMIT 32760.0f
-OC_HD bool coord_ok(V2 p) { return fabsf(p.x) < OC_COORD_LIMIT && fabsf(p.y) < OC_COORD_LIMIT; }  // false for NaN/inf
 
 // ---------------------------------------------------------------------------
 // Coverage of one tile from one record: accumulate the increments of the

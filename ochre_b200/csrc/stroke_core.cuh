@@ -32,7 +32,9 @@ OC_HD void flatten_cmd_sink(const Cmd& c, V2 last, float tol, Sink& out) {
             const V2 d = add(sub(last, scale(2.0f, ctl)), p);
             const float dt = sqrtf((4.0f * tol) / length(d));
             float t = 0.0f;
-            while (t < 1.0f) {
+            // (capped like curve_count: a dt of 0 or below one ulp of t -- huge or non-finite control points --
+            // never advances t; callers reject a command that reaches OC_CURVE_CAP entries)
+            for (uint32_t k = 0; t < 1.0f && k < OC_CURVE_CAP; ++k) {
                 t = fminf(t + dt, 1.0f);
                 out.push(TAG_LINE, quad_eval(t, last, ctl, p));
             }
@@ -45,7 +47,7 @@ OC_HD void flatten_cmd_sink(const Cmd& c, V2 last, float tol, Sink& out) {
             const float conc = fmaxf(length(b), length(add(a, b)));
             const float dt = sqrtf((sqrtf(8.0f) * tol) / conc);
             float t = 0.0f;
-            while (t < 1.0f) {
+            for (uint32_t k = 0; t < 1.0f && k < OC_CURVE_CAP; ++k) {
                 t = fminf(t + dt, 1.0f);
                 out.push(TAG_LINE, cubic_eval(t, last, c1, c2, p));
             }
@@ -53,7 +55,7 @@ OC_HD void flatten_cmd_sink(const Cmd& c, V2 last, float tol, Sink& out) {
         }
         case TAG_CONIC: {
             LinePointSink<Sink> lp{&out};
-            conic_for_each_point(last, cmd_pt(c, 0), cmd_pt(c, 1), c.v[4], tol, lp);
+            conic_for_each_point(last, cmd_pt(c, 0), cmd_pt(c, 1), c.v[4], tol, lp, 3.0e38f);  // untransformed space: any finite point
             break;
         }
         default: out.push(TAG_CLOSE, mk(0.0f, 0.0f)); break;

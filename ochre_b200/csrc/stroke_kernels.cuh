@@ -51,10 +51,24 @@ k_sf_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, u
     uint32_t n = 0;
     if (width[p] > 0.0f) {
         const uint32_t c0 = cmd_off[p] - cmd_base;
-        if (cmds[c].tag > (uint32_t)TAG_CLOSE) *status = 1u;  // fill paints are validated by the rasteriser itself
-        SkCountSink s = {0u};
-        flatten_cmd_sink(cmds[c], sk_last(cmds + c0, c - c0), OC_CONIC_TOL, s);
-        n = s.n;
+        if (cmds[c].tag > (uint32_t)TAG_CLOSE) atomicMax(status, 2u);  // fill paints are validated by the rasteriser itself
+        // Stroke paints are flattened here, in untransformed space, before the rasteriser sees a coordinate: every source
+        // coordinate the command reads (its own points and `last`) must be finite, a Conic weight finite and > -1, and
+        // the flattening must end (a huge second difference gives a dt that cannot advance t) -- else OCHRE_E_BAD_COORD.
+        const V2 last = sk_last(cmds + c0, c - c0);
+        bool ok = fabsf(last.x) < 3.0e38f && fabsf(last.y) < 3.0e38f;
+        for (int i = 0; i < 2 * cmd_npts(cmds[c].tag); ++i) ok = ok && fabsf(cmds[c].v[i]) < 3.0e38f;
+        if (cmds[c].tag == TAG_CONIC) ok = ok && conic_weight_ok(cmds[c].v[4]);
+        if (ok) {
+            SkCountSink s = {0u};
+            flatten_cmd_sink(cmds[c], last, OC_CONIC_TOL, s);
+            n = s.n;
+            if (n >= OC_CURVE_CAP) ok = false;
+        }
+        if (!ok) {
+            atomicMax(status, 1u);
+            n = 0;
+        }
     }
     cnt[c] = n;
 }

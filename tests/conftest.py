@@ -1,3 +1,4 @@
+import ctypes
 import os
 import sys
 
@@ -13,7 +14,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _cuda_devices() -> int:
+    """Devices the CUDA runtime sees (0 on the CPU-only build container), without importing torch."""
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+        except OSError:
+            continue
+        n = ctypes.c_int(0)
+        return n.value if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 else 0
+    return 0
+
+
 def pytest_collection_modifyitems(config, items):
-    # A `-m gpu` run on a box without a GPU must fail loudly, never skip silently;
-    # on the CPU-only build container gpu tests are simply deselected by `-m "not gpu"`.
-    pass
+    """A plain `pytest tests` on a box without a GPU runs the CPU suite and reports every gpu-marked test as skipped
+    with one clear reason.  An explicit `-m gpu` run is never softened: without a device (or without the built
+    extension) those tests fail loudly when they create their Context -- a GPU tier that silently skipped would
+    look green."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    if _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box: gpu-marked parity tests run on the B200 box (pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

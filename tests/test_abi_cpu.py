@@ -63,3 +63,26 @@ def test_null_arguments_are_rejected():
     assert L.ochre_b200_rasterize(None, None, None, None, 0, 0, None, None) == -1
     n = C.c_size_t(0)
     assert L.ochre_b200_flatten_path(None, 3, 0.1, None, C.byref(n)) == -1
+
+
+def test_host_stroker_rejects_inputs_the_reference_never_finishes():
+    """path.rs:50-53 / :63-66 loop forever when dt cannot advance t (non-finite or huge control points), :84-88 when a
+    Conic's denominator vanishes; the host twins of the device stroker return OCHRE_E_BAD_COORD instead."""
+    import numpy as np
+    import pytest
+
+    import ochre_b200 as ob
+    from ochre_b200.geom import CONIC, CUBIC, LINE, MOVE, QUADRATIC, make_cmds
+
+    for cmds in ([(MOVE, 0, 0), (QUADRATIC, float("inf"), 10.0, 20.0, 0.0)],
+                 [(MOVE, 0, 0), (CUBIC, 1e30, 10.0, 20.0, 1e30, 30.0, 5.0)],
+                 [(MOVE, 0, 0), (LINE, float("nan"), 1.0)],
+                 [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -1.0)]):
+        with pytest.raises(ob._lib.OchreError) as e:
+            ob.stroke_to_fill(make_cmds(cmds), 2.0)
+        assert e.value.code == -2
+        with pytest.raises(ob._lib.OchreError):
+            ob.flatten(make_cmds(cmds), 0.1)
+    # ordinary input still goes through
+    out = ob.stroke_to_fill(make_cmds([(MOVE, 0, 0), (QUADRATIC, 5.0, 10.0, 20.0, 0.0)]), 2.0)
+    assert len(out) > 4

@@ -523,3 +523,47 @@ def test_errors(ctx):
     assert g.n_tiles == 0 and g.tile_off.tolist() == [0]
     g = ctx.rasterize(np.zeros(0, O.CMD_DTYPE), np.array([0, 0, 0], np.uint32), np.tile(ID, (2, 1)))
     assert g.n_tiles == 2 and g.tile_xy.tolist() == [[0, 0], [0, 0]] and not g.alpha.any()
+
+
+def _bad(ctx, cmds, code=-2, paints=None):
+    cmds = make_cmds(cmds)
+    off = np.array([0, len(cmds)], np.uint32)
+    with pytest.raises(ob._lib.OchreError) as e:
+        if paints is None:
+            ctx.rasterize(cmds, off, ID[None])
+        else:
+            ctx.rasterize_paints(cmds, off, ID[None], np.array([paints], np.float32))
+    assert e.value.code == code
+
+
+def test_inputs_that_would_never_end_are_rejected_not_walked(ctx):
+    """The reference loops forever on these (path.rs:50-53, :63-66, :84-88: a dt that cannot advance t, a Conic whose
+    denominator vanishes); here every one is OCHRE_E_BAD_COORD -- in every mode, with and without a row band, and for
+    stroke paints, which are flattened before the rasteriser validates a coordinate."""
+    for band in (None, (0, 4)):
+        if band:
+            ctx.set_row_band(*band)
+        try:
+            # a curve that inherits a rejected `last` from the command before it
+            _bad(ctx, [(MOVE, 0, 0), (LINE, 1e30, 0.0), (QUADRATIC, 10.0, 10.0, 20.0, 0.0)])
+            _bad(ctx, [(MOVE, 0, 0), (LINE, 1e15, 0.0), (CUBIC, 10.0, 10.0, 20.0, 0.0, 30.0, 5.0)])
+            _bad(ctx, [(MOVE, 1e15, 0), (QUADRATIC, 10.0, 10.0, 20.0, 0.0)])
+            # Conic weights <= -1: the denominator is 0 at t = 1/2; near -1: the midpoints leave the coordinate range
+            _bad(ctx, [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -1.0)])
+            _bad(ctx, [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -7.5)])
+            _bad(ctx, [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -0.9999999)])
+            _bad(ctx, [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, float("nan"))])
+        finally:
+            ctx.set_row_band(0, 0)
+    # stroke paints
+    _bad(ctx, [(MOVE, 0, 0), (QUADRATIC, float("inf"), 10.0, 20.0, 0.0)], paints=2.0)
+    _bad(ctx, [(MOVE, 0, 0), (CUBIC, 1e30, 10.0, 20.0, 1e30, 30.0, 5.0)], paints=2.0)
+    _bad(ctx, [(MOVE, 0, 0), (LINE, float("nan"), 1.0), (QUADRATIC, 5.0, 10.0, 20.0, 0.0)], paints=2.0)
+    _bad(ctx, [(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -1.0)], paints=2.0)
+    # a negative weight that stays in range is legal and matches the oracle
+    cmds = make_cmds([(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -0.25), (LINE, 10.0, -8.0)])
+    off = np.array([0, 3], np.uint32)
+    assert_batch_parity(ctx.rasterize(cmds, off, ID[None]), oracle_batch(cmds, off, ID[None]), what="conic w=-0.25")
+    # the host twins of the stroker reject the same inputs
+    with pytest.raises(Exception):
+        ob.stroke_to_fill(make_cmds([(MOVE, 0, 0), (QUADRATIC, float("inf"), 10.0, 20.0, 0.0)]), 2.0)
