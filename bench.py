@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the path rasteriser hot path (fill -> finish) on B200.
 
-One "step" = one pass of the whole pipeline over one batch of synthetic paths
-(BASELINE.json config 4: random closed cubic paths, 3-64 segments, 4096x4096 canvas,
-generator G4 of SURVEY.md section 8d; default 1,000,000 paths per GPU).
+One "step" = one pass of the whole pipeline over one batch of synthetic paths.  The headline is BASELINE.json
+config 4: random closed cubic paths, 3-64 segments, 4096x4096 canvas (generator G4 of SURVEY.md section 8d),
+1,000,000 paths per GPU.
 
-  value  : paths/s with inputs already resident in HBM and results left in HBM
-           (for N > 1: weak scaling, every rank rasterises its own path range and the
-           compacted tile/span lists are gathered to GPU 0 over NCCL inside the timed region)
-  e2e    : paths/s through the public host API (pinned host PathCmd arrays in, pinned host
-           tile/span arrays out; H2D and D2H inside the timed region)
+  value      paths/s with inputs already resident in HBM and results left in HBM, per-path lists in the order
+             the paths finished + per-path (start, count) ranges (OCHRE_OUT_UNORDERED; `config.ordered` holds the
+             same run with the lists copied into path order).  N > 1: weak scaling, every rank rasterises its own
+             path range and the compacted tile / span lists are gathered to GPU 0 inside the timed region (the
+             fused kernel stores its tiles straight into an arena in GPU 0's memory over NVLink).
+  e2e        paths/s through the public host API: pinned host PathCmd arrays in, pinned host tile / span arrays
+             out AND replayed into a counting TileBuilder by host threads (the reference's end point: the last
+             TileBuilder call returned); H2D, D2H and the replay inside the timed region.
+  config.workloads   the other BASELINE configs (1: examples/basic.rs x 1 M, 2: the bundled SVGs x 64 at 1x and
+             4x, 3: 100 k glyphs, 5a: one 16384^2 path sharded by canvas row bands, 5b: 10 M paths sharded by
+             path), each with paths/s, tiles/s, algorithmic bytes and their fraction of the HBM roofline.
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
-`--impl reference` times the reference algorithm's CPU implementation (the oracle port: the
-reference is Rust and cannot be built in this image) on the host cores, on a bounded sample
-of the same workload.
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port: the reference is Rust and
+cannot be built in this image) on the host cores, on the same batch when that fits the time budget.
 """
 from __future__ import annotations
 
@@ -35,6 +40,7 @@ import numpy as np
 
 METRIC = "paths/s (8x8 alpha tiles/s and alpha MB/s in config)"
 WORKLOAD = "config4: synthetic stress, random closed cubic paths (3-64 segments) on a 4096x4096 canvas, generator G4"
+REF_BUDGET_S = 240.0  # the reference arm sizes its per-step sample so that warm-up + steps stay inside this
 
 
 def host_threads() -> int:
@@ -52,6 +58,53 @@ def peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def bind_to_gpu_numa(local_rank: int, world: int) -> dict:
+    """Best effort: run this rank (and allocate its pinned host buffers) on the NUMA node its GPU hangs off, and give
+    every rank of a node its own share of the node's cores.  Eight ranks that pin 11 GB each from whatever node they
+    happened to start on push most of the result across the inter-socket link (the 89 GB/s aggregate of round 1)."""
+    info = {"node": None, "cpus": None}
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = []
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return info
+        # ranks whose GPUs share the node split its cores
+        peers = []
+        for r in range(world):
+            try:
+                b2 = subprocess.run(["nvidia-smi", f"--id={r}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                    capture_output=True, text=True, timeout=10).stdout.strip().lower()
+                if b2.startswith("00000000:"):
+                    b2 = b2[4:]
+                with open(f"/sys/bus/pci/devices/{b2}/numa_node") as f:
+                    if int(f.read().strip()) == node:
+                        peers.append(r)
+            except Exception:
+                pass
+        if local_rank in peers and len(peers) > 1 and len(allowed) >= len(peers):
+            k = peers.index(local_rank)
+            share = len(allowed) // len(peers)
+            allowed = allowed[k * share:(k + 1) * share]
+        os.sched_setaffinity(0, allowed)
+        info = {"node": node, "cpus": len(allowed)}
+    except Exception as exc:  # noqa: BLE001 -- reported in the JSON line
+        info["error"] = str(exc)[:120]
+    return info
 
 
 class ClockSampler:
@@ -103,7 +156,7 @@ class ClockSampler:
 
 
 def stage_bytes(n_cmds, n_paths, n_lines, n_rec, n_tiles, n_spans, sort_passes):
-    """Algorithmic (compulsory) HBM bytes per stage for one step -- DESIGN.md 'Kernels and rooflines'."""
+    """Algorithmic (compulsory) HBM bytes per stage of the general pipeline -- DESIGN.md 'Kernels and rooflines'."""
     return {
         "flatten": 28 * n_cmds + 24 * n_paths + 16 * n_lines,
         "bin": 16 * n_lines + 16 * n_rec,
@@ -123,35 +176,58 @@ STAGE_KERNELS = {
 }
 
 
+def b_alg(n_cmds, n_paths, n_tiles, n_spans):
+    """Algorithmic bytes of one pass: commands, transforms and offsets in; tiles (64 B alpha + 4 B origin) and spans out."""
+    return 28 * n_cmds + 24 * n_paths + 4 * (n_paths + 1) + 68 * n_tiles + 8 * n_spans
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference (one fresh rasteriser per path, OpenMP over paths)."""
+    """CPU arm: the oracle port of the reference (one fresh rasteriser per path, OpenMP over paths) on the headline batch."""
     if rank != 0:
         return
     import oracle as O
     from ochre_b200 import workloads as W
 
     threads = host_threads()
-    sample = args.ref_paths
-    cmds, off, xf = W.blobs(sample, 0)
+    P = args.paths
+    n_steps = args.warmup + args.steps
+    if args.ref_paths:
+        sample = min(P, args.ref_paths)
+    else:
+        # the whole batch if warm-up + steps of it fit the budget, else the longest prefix that does
+        probe = min(P, 4000)
+        c0, o0, x0 = W.blobs(probe, 0)
+        r0 = O.rasterize_batch(c0, o0.astype(np.uint64), x0, threads=threads, count_only=True)
+        rate = probe / max(r0.seconds, 1e-6)
+        sample = int(min(P, max(probe, rate * REF_BUDGET_S / max(1, n_steps))))
+    n_cmds = W.count_cmds(4, 0, sample)
+    cmds = np.zeros(n_cmds, O.CMD_DTYPE)
+    off = np.zeros(sample + 1, np.uint32)
+    xf = np.zeros((sample, 6), np.float32)
+    W.gen_into(4, 0, sample, cmds, off, xf)
     off64 = off.astype(np.uint64)
-    times, tiles = [], 0
-    for i in range(args.warmup + args.steps):
+    times, tiles, spans = [], 0, 0
+    for i in range(n_steps):
         r = O.rasterize_batch(cmds, off64, xf, threads=threads, count_only=True)
         if i >= args.warmup:
             times.append(r.seconds)
-        tiles = r.n_tiles
+        tiles, spans = r.n_tiles, r.n_spans
     sec = float(np.mean(times))
     v = sample / sec
+    whole = sample == P
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "paths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "paths_per_step": sample, "tiles_per_s": tiles / sec,
-                   "alpha_MB_per_s": 64e-6 * tiles / sec,
-                   "note": "CPU oracle port of the reference (Rust reference cannot be built here: no rustc/cargo); "
-                           "each step is a bounded sample (first paths of the same generator)"},
+        "config": {"workload": WORKLOAD, "paths_per_gpu": P, "paths_total": P, "paths_per_step": sample,
+                   "tiles_per_s": tiles / sec, "alpha_MB_per_s": 64e-6 * tiles / sec,
+                   "note": "CPU oracle port of the reference (Rust reference cannot be built here: no rustc/cargo), TileBuilder = "
+                           "count + checksum sink; " + ("every step is the whole batch of the GPU arm's rank 0" if whole else
+                           f"every step is a bounded sample (the first {sample} paths of the same batch: warm-up + steps of the whole batch "
+                           f"would exceed {REF_BUDGET_S:.0f} s on these {threads} threads)")},
         "cpu_baseline": {"value": v, "unit": "paths/s", "cores": threads, "kind": "port",
-                         "sample": f"first {sample} paths of G4, count+checksum sink, OpenMP dynamic over paths"},
+                         "sample": f"first {sample} of {P} paths of G4, count+checksum sink, OpenMP dynamic over paths",
+                         "tiles": int(tiles), "spans": int(spans), "checksum": {"geom_sum": int(r.geom_sum), "alpha_sum": int(r.alpha_sum)}},
         "e2e": {"value": v, "unit": "paths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -172,17 +248,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--paths", type=int, default=1_000_000, help="paths per GPU per step")
-    ap.add_argument("--ref-paths", type=int, default=40_000, help="paths per step of the CPU reference arm")
+    ap.add_argument("--ref-paths", type=int, default=0, help="paths per step of the CPU reference arm (0: the whole batch if it fits the time budget)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="paths in the cpu_baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-gather", action="store_true", help="N>1: leave each rank's tiles on its own GPU")
-    ap.add_argument("--gather", default="arena", choices=["arena", "nccl"],
-                    help="N>1: arena = the fused kernel stores its alpha tiles straight into GPU 0's memory over NVLink (CUDA IPC peer "
-                         "mapping; origins / spans / ranges follow by peer copy); nccl = send/recv of finished sub-batches")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--ordered", action="store_true", help="copy the results into path order (k_gather_paths) instead of leaving them in the fused kernel's arena")
-    ap.add_argument("--gather-chunks", type=int, default=4, help="N>1: sub-batches per step whose tiles travel to GPU 0 behind the kernels")
+    ap.add_argument("--workloads", default="all", help="'all', 'none' or a comma list of: c1x1M, svg64, glyphs100k, glyphs1M, rings5a, g4x10M")
+    ap.add_argument("--big-paths", type=int, default=10_000_000, help="paths of the g4x10M workload (config 5b), all ranks together")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -196,10 +270,12 @@ def main():
     import torch.distributed as dist
 
     import ochre_b200 as ob
+    from ochre_b200 import sharding
     from ochre_b200 import workloads as W
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- ochre_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa(local_rank, world) if world > 1 else {"node": None, "cpus": None}
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -209,19 +285,7 @@ def main():
         ctx.set_chunk(args.chunk)
     P = args.paths
     first = rank * P  # weak scaling: every rank owns its own range of the generator
-
-    # ---- workload into pinned host memory, then a resident device copy ----------------
-    n_cmds = W.blobs_count(P, first)
-    h_cmds_t = torch.empty(n_cmds * 28, dtype=torch.uint8, pin_memory=True)
-    h_xf_t = torch.empty(P * 6, dtype=torch.float32, pin_memory=True)
-    h_cmds = h_cmds_t.numpy().view(ob.CMD_DTYPE)
-    h_xf = h_xf_t.numpy().reshape(P, 6)
-    _, off, _ = W._gen(4, first, P, cmds_out=h_cmds, xf_out=h_xf)
-    h_off_t = torch.empty(P + 1, dtype=torch.int32, pin_memory=True)
-    h_off = h_off_t.numpy().view(np.uint32)
-    h_off[:] = off
-    d_cmds_t, d_off_t, d_xf_t = h_cmds_t.cuda(), h_off_t.cuda(), h_xf_t.cuda()
-    torch.cuda.synchronize()
+    n_host_threads = host_threads()
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,93 +307,71 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, warmup, steps):
+        """ms per step of fn(): CUDA events bracketing `steps` calls, barrier + synchronize on both sides, max over ranks."""
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, out
+
+    class Batch:
+        """A generated batch in pinned host memory plus its resident device copy."""
+
+        def __init__(self, kind, first, n):
+            self.n = n
+            self.h_off_t = torch.empty(n + 1, dtype=torch.int32, pin_memory=True)
+            self.h_xf_t = torch.empty(max(n, 1) * 6, dtype=torch.float32, pin_memory=True)
+            self.h_off = self.h_off_t.numpy().view(np.uint32)
+            self.h_xf = self.h_xf_t.numpy()[: n * 6].reshape(n, 6)
+            box = {}
+
+            def alloc(total):
+                box["t"] = torch.empty(max(total, 1) * 28, dtype=torch.uint8, pin_memory=True)
+                return box["t"].numpy()[: total * 28].view(ob.CMD_DTYPE)
+
+            self.n_cmds = W.gen_into(kind, first, n, alloc, self.h_off, self.h_xf)
+            self.h_cmds_t = box["t"]
+            self.h_cmds = self.h_cmds_t.numpy()[: self.n_cmds * 28].view(ob.CMD_DTYPE)
+            self.d_cmds_t, self.d_off_t, self.d_xf_t = self.h_cmds_t.cuda(), self.h_off_t.cuda(), self.h_xf_t.cuda()
+            torch.cuda.synchronize()
+
+        def device_call(self, c, a=0, b=None, unordered=True):
+            b = self.n if b is None else b
+            return c.rasterize_ptrs(self.d_cmds_t.data_ptr(), self.d_off_t.data_ptr() + 4 * a, self.d_xf_t.data_ptr() + 24 * a, b - a,
+                                    self.h_off[a:b + 1], in_device=True, out_device=True, unordered=unordered)
+
+        def host_call(self, c, unordered=True):
+            return c.rasterize_ptrs(self.h_cmds_t.data_ptr(), self.h_off_t.data_ptr(), self.h_xf_t.data_ptr(), self.n, self.h_off,
+                                    in_device=False, out_device=False, copy=False, unordered=unordered)
+
+    # ---- headline batch into pinned host memory, then a resident device copy -----------------------
+    g4 = Batch(4, first, P)
+    n_cmds = g4.n_cmds
+
     gather = world > 1 and not args.no_gather
-    use_arena = gather and args.gather == "arena"
-    gbuf = {}
     arena = None
     arena_info = {}
-
-    # N > 1: the gather is pipelined behind the kernels.  The rank's batch is cut into sub-batches that alternate
-    # between two contexts (each owns its result arenas); while sub-batch j + 1 is rasterised, sub-batch j's tiles
-    # travel to GPU 0.  Blocks land in arrival order (sub-batch major, rank minor); `gather_blocks` is the table.
-    K = max(1, args.gather_chunks)
-    subs = [(P * j // K, P * (j + 1) // K) for j in range(K)]
-    ctxs = [ctx]
-    gather_blocks = []
-    if gather and not use_arena:
-        # GPU 0 keeps its own sub-batches where they were produced (one context per sub-batch, no copy);
-        # the other ranks alternate between two contexts while the previous sub-batch is on the wire
-        for _ in range((K if rank == 0 else 2) - 1):
-            c2 = ob.Context(local_rank)
-            if args.chunk:
-                c2.set_chunk(args.chunk)
-            ctxs.append(c2)
-    NC = len(ctxs)
-
-    UNORD = not args.ordered
-
-    def raster_sub(c, a, b):
-        return c.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr() + 4 * a, d_xf_t.data_ptr() + 24 * a, b - a, h_off[a:b + 1],
-                                in_device=True, out_device=True, unordered=UNORD)
-
-    def step_pipelined():
-        from ochre_b200 import sharding
-
-        pending = [None] * NC
-        offs = {"alpha": 0, "xy": 0, "spans": 0}
-        agg = None
-        gather_blocks.clear()
-        for j, (a, b) in enumerate(subs):
-            c = ctxs[j % NC]
-            if pending[j % NC] is not None:  # the arenas of this context are still being read by the previous send
-                pending[j % NC].synchronize()
-                pending[j % NC] = None
-            res = raster_sub(c, a, b)
-            agg = res if agg is None else _merge_counts(agg, res)
-            ptrs = res.device_ptrs
-            mine = {
-                "alpha": torch.as_tensor(CudaArray(ptrs["alpha"], max(res.n_tiles * 64, 1)), device="cuda")[: res.n_tiles * 64],
-                "xy": torch.as_tensor(CudaArray(ptrs["tile_xy"], max(res.n_tiles * 4, 1)), device="cuda")[: res.n_tiles * 4],
-                "spans": torch.as_tensor(CudaArray(ptrs["spans"], max(res.n_spans * 8, 1)), device="cuda")[: res.n_spans * 8],
-            }
-            sizes = sharding.post_gather(mine, rank, world, gbuf, offs, own_in_place=True)
-            gather_blocks.append({n: sizes[n].tolist() for n in sizes})
-            ev = torch.cuda.Event()
-            ev.record()  # NCCL work of this sub-batch is ordered before the event on the current stream
-            pending[j % NC] = ev
-        torch.cuda.synchronize()
-        return agg
-
-    def _merge_counts(x, y):
-        x.n_tiles += y.n_tiles
-        x.n_spans += y.n_spans
-        x.n_cmds += y.n_cmds
-        x.n_chunks += y.n_chunks
-        x.kernel_launches += y.kernel_launches
-        x.device_ms += y.device_ms
-        x.stage_ms = tuple(p + q for p, q in zip(x.stage_ms, y.stage_ms))
-        x.used |= y.used
-        return x
-
-    def step_device():
-        if gather and not use_arena:
-            return step_pipelined()
-        return ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True,
-                                  out_device=True, unordered=UNORD)
-
-    if use_arena:
+    if gather:
         # One local run sizes the slices; GPU 0 allocates the arena and hands its IPC handle round; from then on every
         # rank's fused kernel stores its alpha tiles into its slice of GPU 0's memory while it rasterises.
-        r = ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True,
-                               unordered=True)
+        r = g4.device_call(ctx)
         local_sum = int(torch.as_tensor(CudaArray(r.device_ptrs["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64]
                         .sum(dtype=torch.int64).item())
         mine = torch.tensor([r.n_tiles, r.n_spans, P, local_sum], dtype=torch.int64, device="cuda")
         allc = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         allc = torch.stack(allc).cpu().numpy()
-        t_cap = [int(v) + 4096 for v in allc[:, 0]]
-        s_cap = [int(v) + 4096 for v in allc[:, 1]]
+        # (3 % of slack: the arena also takes the sub-batches of the 10 M-path workload, other ranges of the same generator)
+        t_cap = [int(v * 1.03) + 4096 for v in allc[:, 0]]
+        s_cap = [int(v * 1.03) + 4096 for v in allc[:, 1]]
         t_start = np.concatenate([[0], np.cumsum(t_cap)]).astype(np.int64)
         s_start = np.concatenate([[0], np.cumsum(s_cap)]).astype(np.int64)
         p_start = np.concatenate([[0], np.cumsum(allc[:, 2])]).astype(np.int64)
@@ -341,43 +383,28 @@ def main():
         dist.broadcast_object_list(box, src=0)
         if rank != 0:
             arena = ctx.arena_open(box[0], *caps)
-        ctx.set_output_arena(arena, int(t_start[rank]), t_cap[rank], int(s_start[rank]), s_cap[rank], int(p_start[rank]), P)
-        arena_info = {"allc": allc, "t_start": t_start, "s_start": s_start, "p_start": p_start, "bytes": int(arena.c.bytes)}
-        UNORD = True
-    elif gather:
-        # size every arena before anything is in flight: both contexts see every sub-batch once, and GPU 0's
-        # gather buffers are sized from the all-rank totals
-        nt = ns = 0
-        for j, (a, b) in enumerate(subs):
-            for c in (ctxs[j % NC:j % NC + 1] if rank == 0 else ctxs):
-                r = raster_sub(c, a, b)
-            nt += r.n_tiles
-            ns += r.n_spans
-        tot = torch.tensor([nt if rank else 0, ns if rank else 0], dtype=torch.int64, device="cuda")  # GPU 0's own tiles stay in place
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            gbuf["alpha"] = torch.empty(int(tot[0]) * 64 + 4096, dtype=torch.uint8, device="cuda")
-            gbuf["xy"] = torch.empty(int(tot[0]) * 4 + 4096, dtype=torch.uint8, device="cuda")
-            gbuf["spans"] = torch.empty(int(tot[1]) * 8 + 4096, dtype=torch.uint8, device="cuda")
+        arena_info = {"allc": allc, "t_start": t_start, "s_start": s_start, "p_start": p_start, "bytes": int(arena.c.bytes),
+                      "t_cap": t_cap, "s_cap": s_cap}
 
-    def step_e2e():
-        return ctx.rasterize_ptrs(h_cmds_t.data_ptr(), h_off_t.data_ptr(), h_xf_t.data_ptr(), P, h_off, in_device=False,
-                                  out_device=False, copy=False, unordered=UNORD)
+    def arena_on():
+        ctx.set_output_arena(arena, int(arena_info["t_start"][rank]), arena_info["t_cap"][rank], int(arena_info["s_start"][rank]),
+                             arena_info["s_cap"][rank], int(arena_info["p_start"][rank]), P)
 
     # ---- value: device-resident ---------------------------------------------------------
+    if gather:
+        arena_on()
     for _ in range(args.warmup):
-        res = step_device()
+        res = g4.device_call(ctx)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = np.zeros(8)
     launches = 0
     dev_ms = 0.0
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = step_device()
+        res = g4.device_call(ctx)
         stage_ms += np.array(res.stage_ms)
         launches += res.kernel_launches
         dev_ms += res.device_ms
@@ -396,7 +423,7 @@ def main():
 
     # the arena on GPU 0 must hold every rank's result: per-slice tile counts (from the ranges) and alpha byte sums
     gather_check = None
-    if use_arena:
+    if gather:
         barrier()
         if rank == 0:
             ok = True
@@ -412,27 +439,27 @@ def main():
         barrier()
         ctx.set_output_arena(None)
 
-    # ungathered figure for N > 1 (what a renderer that draws per GPU would see)
+    # the same step with the lists copied into path order (the reference's order across a batch of rasterisers), and for
+    # N > 1 without the gather (what a renderer that draws per GPU would see)
+    side_steps = max(2, min(args.steps, 5))
+    ord_ms, ord_res = timed(lambda: g4.device_call(ctx, unordered=False), 1, side_steps)
+    ordered = {"value": paths_total / (ord_ms * 1e-3), "unit": "paths/s", "ms_per_step": ord_ms, "steps": side_steps,
+               "layout": "path-ordered lists, tile_off / span_off (k_gather_paths behind k_path)" + (", not gathered" if world > 1 else "")}
     ungathered = None
     if gather:
-        ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True, unordered=UNORD)  # sizes the arenas
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            ctx.rasterize_ptrs(d_cmds_t.data_ptr(), d_off_t.data_ptr(), d_xf_t.data_ptr(), P, h_off, in_device=True, out_device=True, unordered=UNORD)
-        e1.record()
-        barrier()
-        ug_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-        ungathered = {"value": paths_total / (ug_ms * 1e-3), "unit": "paths/s", "ms_per_step": ug_ms}
+        ug_ms, _ = timed(lambda: g4.device_call(ctx), 1, side_steps)
+        ungathered = {"value": paths_total / (ug_ms * 1e-3), "unit": "paths/s", "ms_per_step": ug_ms, "steps": side_steps}
 
-    # ---- e2e: host buffers in, host buffers out ----------------------------------------
+    # ---- e2e: host buffers in, host buffers out, every tile and span through a TileBuilder on the host ------------------
     e2e = None
     e2e_ok = not args.no_e2e
+    sink_threads = max(1, n_host_threads if world == 1 else (numa.get("cpus") or max(1, n_host_threads // world)))
     if e2e_ok:
         # The first call allocates the pinned host mirrors of the result (11 GB per rank): if that fails on any rank
         # (host memory of a box shared by N ranks), every rank skips the end-to-end leg together.
+        ctx.set_host_sink(sink_threads)
         try:
-            r2 = step_e2e()
+            r2 = g4.host_call(ctx)
             ok = 1.0
         except Exception as exc:  # noqa: BLE001 -- reported, not swallowed
             print(f"bench.py: rank {rank}: end-to-end leg unavailable: {exc}", file=sys.stderr, flush=True)
@@ -440,30 +467,34 @@ def main():
         e2e_ok = sum_over_ranks(ok) == float(world)
         if not e2e_ok:
             e2e = {"unavailable": "pinned host buffers for the result could not be allocated on every rank"}
+    sink = None
     if e2e_ok:
-        for _ in range(max(1, min(args.warmup, 2)) - 1):
-            r2 = step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        n_e2e = max(2, min(args.steps, 3))
-        for _ in range(n_e2e):
-            r2 = step_e2e()
-        e1.record()
-        barrier()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / n_e2e
+        n_e2e = max(1, args.e2e_steps)
+        e2e_ms, r2 = timed(lambda: g4.host_call(ctx), 1, n_e2e)
+        sink = ctx.last_sink()
+        ctx.set_host_sink(0)
+        nosink_ms, _ = timed(lambda: g4.host_call(ctx), 0, max(2, min(n_e2e, 3)))
         h2d = n_cmds * 28 + (P + 1) * 4 + P * 24
-        d2h = r2.n_tiles * 68 + r2.n_spans * 8 + (16 * P if UNORD else 2 * (P + 1) * 4 + 16 * P)
+        d2h = r2.n_tiles * 68 + r2.n_spans * 8 + 16 * P
         e2e = {"value": paths_total / (e2e_ms * 1e-3), "unit": "paths/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": n_e2e,
-               "copy_ms_per_step": float(r2.stage_ms[7])}
+               "copy_ms_per_step": float(r2.stage_ms[7]),
+               "end_point": "the last TileBuilder call has returned: every chunk of the result is replayed into a counting / checksumming "
+                            "builder by host threads as soon as its download has finished (ochre_b200_set_host_sink)",
+               "sink": {"threads": sink_threads, "tiles": sink["tiles"], "spans": sink["spans"], "geom_sum": sink["geom_sum"],
+                        "alpha_sum": sink["alpha_sum"], "busy_ms_slowest_thread": sink["seconds"] * 1e3},
+               "without_sink": {"value": paths_total / (nosink_ms * 1e-3), "ms_per_step": nosink_ms,
+                                "note": "round 1's end point: result arrays in pinned host memory, nothing consumed"},
+               "host_GBps_aggregate": (h2d + d2h) * world / (e2e_ms * 1e-3) / 1e9, "numa": numa}
+        if sink["tiles"] != r2.n_tiles or sink["spans"] != r2.n_spans:
+            raise SystemExit("bench.py: the host sink did not see every tile and span of the result")
 
     # ---- roofline of the dominant kernel -------------------------------------------------
     peak, peak_src = peaks()
-    b_alg = 28 * res.n_cmds + 24 * P + 4 * (P + 1) + 68 * res.n_tiles + 8 * res.n_spans
+    alg = b_alg(res.n_cmds, P, res.n_tiles, res.n_spans)
     if res.used & 1 and not res.used & 2:
         # fused per-path kernel: commands in, tiles/spans out -- its algorithmic bytes ARE B_alg
-        sb = {"k_path": b_alg, "gather": 2 * (68 * res.n_tiles + 8 * res.n_spans) + 24 * P}
+        sb = {"k_path": alg, "gather": 2 * (68 * res.n_tiles + 8 * res.n_spans) + 24 * P}
         names = {0: "k_path", 6: "gather"}
         kern = {"k_path": "k_path (flatten + bin + coverage + backdrop + emission per path; two CTA shapes, pkl 91 % / pks 7.5 % of the step, + k_classify)",
                 "gather": "device_scan x2 + k_gather_paths (staging arena -> path order)"}
@@ -498,25 +529,188 @@ def main():
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
         "stage_ms": stage_report,
         "stage_alg_GB": {k: v / 1e9 for k, v in sb.items()},
-        "pipeline_b_alg_GB": b_alg / 1e9,
-        "pipeline_frac": b_alg / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-        "note": "the kernel is instruction-issue and barrier bound (per-pixel f32 DDA, many short phases per path), not HBM bound: 62 % of the issue slots busy in ncu; see DESIGN.md section 6",
+        "pipeline_b_alg_GB": alg / 1e9,
+        "pipeline_frac": alg / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+        "note": "the kernel is instruction-issue and barrier bound (per-pixel f32 DDA, many short phases per path), not HBM bound; see DESIGN.md section 6",
     }
+
+    # ---- the other BASELINE configs ---------------------------------------------------------------------------------
+    want = args.workloads.split(",") if args.workloads not in ("all", "none") else (
+        ["c1x1M", "svg64", "glyphs100k", "glyphs1M", "rings5a", "g4x10M"] if args.workloads == "all" else [])
+    wl_steps, wl_warm = 3, 2
+    workloads = {}
+
+    def report(name, n_paths, ms, r, note, n_ranks=world, tiles=None, spans=None, cmds=None, extra=None):
+        """One workload line: the rank-local result r scaled by the ranks that ran it."""
+        tiles = sum_over_ranks(float(r.n_tiles)) if tiles is None else tiles
+        spans = sum_over_ranks(float(r.n_spans)) if spans is None else spans
+        cmds = sum_over_ranks(float(r.n_cmds)) if cmds is None else cmds
+        alg_b = b_alg(cmds, n_paths, tiles, spans)
+        d = {"paths": int(n_paths), "ms_per_step": ms, "paths_per_s": n_paths / (ms * 1e-3), "tiles": int(tiles), "spans": int(spans),
+             "tiles_per_s": tiles / (ms * 1e-3), "alpha_MB_per_s": 64e-6 * tiles / (ms * 1e-3), "b_alg_GB": alg_b / 1e9,
+             "hbm_frac": alg_b / (ms * 1e-3) / 1e9 / (peak * n_ranks), "steps": wl_steps, "warmup": wl_warm,
+             "implementation": {1: "fused kernel", 2: "general pipeline", 3: "fused kernel + general pipeline for the paths over its budgets"}.get(r.used & 3, "?"),
+             "note": note}
+        if extra:
+            d.update(extra)
+        workloads[name] = d
+
+    def upload(cmds, off, xf):
+        return (torch.from_numpy(cmds.view(np.uint8).reshape(-1).copy()).cuda(), torch.from_numpy(off.astype(np.int32)).cuda(),
+                torch.from_numpy(np.ascontiguousarray(xf, np.float32).reshape(-1).copy()).cuda())
+
+    def replicate(cmds, off, xf, times, sw=None):
+        n = len(off) - 1
+        c = np.tile(cmds, times)
+        o = (np.arange(times, dtype=np.int64)[:, None] * int(off[-1]) + off[None, :-1].astype(np.int64)).reshape(-1)
+        o = np.concatenate([o, [times * int(off[-1])]]).astype(np.uint32)
+        x = np.tile(np.asarray(xf, np.float32).reshape(n, 6), (times, 1))
+        return (c, o, x) if sw is None else (c, o, x, np.tile(sw, times))
+
+    for name in want:
+        barrier()
+        if name == "c1x1M":
+            # config 1: the path of examples/basic.rs under Transform::id(), replicated as 1 M independent paths per GPU
+            c, o, x = replicate(*W.basic(), 1_000_000)
+            dc, do, dx = upload(c, o, x)
+            fn = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), len(o) - 1, o, in_device=True, out_device=True, unordered=True)  # noqa: E731
+            ms, r = timed(fn, wl_warm, wl_steps)
+            report(name, (len(o) - 1) * world, ms, r, "examples/basic.rs:26-31 (Move, Quadratic, Cubic, Close) x 1 M per GPU; device-resident in and out, unordered layout"
+                   + ("; not gathered" if world > 1 else ""))
+            del dc, do, dx
+        elif name == "svg64":
+            # config 2: every paint (fill or stroke) of the three bundled SVGs, at 1x and 4x, 64 copies of the document per GPU as one batch;
+            # stroke paints are flattened and offset on the device (ochre_b200_rasterize_paints)
+            for doc in ("tiger", "lorem_ipsum", "calabi_yau"):
+                for scale in (1.0, 4.0):
+                    c, o, x, sw = replicate(*W.svg_paint_batch(doc, scale)[:3], 64, sw=W.svg_paint_batch(doc, scale)[3])
+                    fn = lambda: ctx.rasterize_paints(c, o, x, sw, out_device=True, unordered=True)  # noqa: E731
+                    ms, r = timed(fn, wl_warm, wl_steps)
+                    report(f"svg64_{doc}_{int(scale)}x", (len(o) - 1) * world, ms, r,
+                           f"examples/res {doc} at {int(scale)}x: {(len(o) - 1) // 64} paints ({int((sw > 0).sum()) // 64} strokes, stroked on the device) x 64 per GPU; "
+                           f"host PathCmd arrays in ({c.nbytes / 1e6:.1f} MB uploaded inside the call), results left on the device"
+                           + ("; not gathered" if world > 1 else ""),
+                           extra={"stroker_ms": ctx.stroker_ms()})
+        elif name in ("glyphs100k", "glyphs1M"):
+            # config 3: G3 glyph outlines at 12-48 px, every glyph its own path
+            n = 100_000 if name == "glyphs100k" else 1_000_000
+            b = Batch(3, rank * n, n)
+            ms, r = timed(lambda: b.device_call(ctx), wl_warm, wl_steps)
+            report(name, n * world, ms, r, f"generator G3, {n} glyphs per GPU; device-resident in and out, unordered layout" + ("; not gathered" if world > 1 else ""))
+            del b
+        elif name == "rings5a":
+            # config 5a: ONE path of 511 concentric rings on a 16384^2 canvas.  N > 1: every rank flattens the whole path and
+            # rasterises its band of tile rows (bands balanced by the control polygons crossing each row); the bands are gathered
+            # to GPU 0 inside the timed region; concatenated in band order they are the 1-GPU result (checked below).
+            c, o, x = W.rings()
+            dc, do, dx = upload(c, o, x)
+            call = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), 1, o, in_device=True, out_device=True, unordered=False)  # noqa: E731
+            whole = call()
+            whole_sum = None
+            if world > 1:
+                whole_sum = int(torch.as_tensor(CudaArray(whole.device_ptrs["alpha"], max(whole.n_tiles * 64, 1)), device="cuda")[: whole.n_tiles * 64]
+                                .sum(dtype=torch.int64).item())
+                rows = (0, 16384 // 8)
+                bands = sharding.plan_row_bands(rows[0], rows[1], world, sharding.band_weights_from_bbox(c, x, rows[0], rows[1]))
+                lo, hi = bands[rank]
+                # the first and the last band also take whatever lies outside the canvas rows
+                ctx.set_row_band(-32768 if rank == 0 else lo, 32767 if rank == world - 1 else hi)
+                gbufs = {}
+                got = {}
+
+                def fn():
+                    r = call()
+                    p = r.device_ptrs
+                    mine = {"a_alpha": torch.as_tensor(CudaArray(p["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64],
+                            "b_xy": torch.as_tensor(CudaArray(p["tile_xy"], max(r.n_tiles * 4, 1)), device="cuda")[: r.n_tiles * 4],
+                            "c_spans": torch.as_tensor(CudaArray(p["spans"], max(r.n_spans * 8, 1)), device="cuda")[: r.n_spans * 8]}
+                    got["sizes"], got["g"] = sharding.gather_bytes(mine, rank, world, gbufs)
+                    return r
+
+                ms, r = timed(fn, wl_warm, wl_steps)
+                ctx.set_row_band(0, 0)
+                check = None
+                if rank == 0:
+                    g = got["g"]
+                    nt = int(g["a_alpha"].numel()) // 64
+                    check = {"bands": world, "tiles_gathered": nt, "tiles_one_gpu": int(whole.n_tiles),
+                             "spans_gathered": int(g["c_spans"].numel()) // 8, "spans_one_gpu": int(whole.n_spans),
+                             "alpha_sum_matches_one_gpu": int(g["a_alpha"].sum(dtype=torch.int64).item()) == whole_sum}
+                    same_xy = torch.equal(g["b_xy"], torch.as_tensor(CudaArray(whole.device_ptrs["tile_xy"], max(whole.n_tiles * 4, 1)), device="cuda")[: whole.n_tiles * 4]) if nt == whole.n_tiles else False
+                    same_alpha = torch.equal(g["a_alpha"], torch.as_tensor(CudaArray(whole.device_ptrs["alpha"], max(whole.n_tiles * 64, 1)), device="cuda")[: whole.n_tiles * 64]) if nt == whole.n_tiles else False
+                    check["byte_identical_to_one_gpu"] = bool(same_xy and same_alpha)
+                    if not check["byte_identical_to_one_gpu"]:
+                        raise SystemExit(f"bench.py: the gathered row bands differ from the one-GPU result: {check}")
+                report(name, 1, ms, r, f"generator G5a: one path, 511 rings, 131 k cubics on a 16384^2 canvas; sharded by canvas row bands over {world} GPUs "
+                       "(every rank flattens the whole path, rasterises its tile rows), bands gathered to GPU 0 over NCCL inside the timed region",
+                       tiles=float(whole.n_tiles), spans=float(whole.n_spans), cmds=float(whole.n_cmds), extra={"bands_check": check})
+            else:
+                ms, r = timed(call, wl_warm, wl_steps)
+                report(name, 1, ms, r, "generator G5a: one path, 511 rings, 131 k cubics on a 16384^2 canvas; one GPU, path-ordered result on the device")
+            del dc, do, dx
+        elif name == "g4x10M":
+            # config 5b: 10 M G4 paths sharded by path: every rank takes a contiguous tenth-of-a-batch share and rasterises it in
+            # sub-batches of <= 1 M paths (results of a sub-batch are consumed -- here: dropped -- before the next overwrites them);
+            # N > 1: gathered to GPU 0 through the arena like the headline
+            share = args.big_paths // world
+            b = Batch(4, 10_000_000_000 + rank * share, share)  # (a range of the generator the headline does not use)
+            sub = min(P, 1_000_000)
+            cuts = list(range(0, share, sub)) + [share]
+            if gather:
+                arena_on()
+            tot = {"t": 0, "s": 0, "c": 0, "used": 0}
+
+            def fn():
+                tot.update(t=0, s=0, c=0)
+                r = None
+                for a, z in zip(cuts[:-1], cuts[1:]):
+                    r = b.device_call(ctx, a, z)
+                    tot["t"] += r.n_tiles
+                    tot["s"] += r.n_spans
+                    tot["c"] += r.n_cmds
+                return r
+
+            ms, r = timed(fn, 1, wl_steps)
+            if gather:
+                barrier()
+                ctx.set_output_arena(None)
+            report(name, share * world, ms, r, f"generator G4, {share * world} paths sharded by path over {world} GPU(s), {len(cuts) - 1} sub-batch(es) of <= {sub} paths per rank; "
+                   "device-resident in and out, unordered layout" + ("; gathered to GPU 0 through the arena" if gather else ""),
+                   tiles=sum_over_ranks(float(tot["t"])), spans=sum_over_ranks(float(tot["s"])), cmds=sum_over_ranks(float(tot["c"])))
+            del b
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
         import oracle as O
 
-        threads = host_threads()
-        probe = 2000
-        r0 = O.rasterize_batch(h_cmds[: off[probe]], off[: probe + 1].astype(np.uint64), h_xf[:probe], threads=threads, count_only=True)
+        threads = n_host_threads
+        probe = min(P, 2000)
+        off = g4.h_off
+        r0 = O.rasterize_batch(g4.h_cmds[: off[probe]], off[: probe + 1].astype(np.uint64), g4.h_xf[:probe], threads=threads, count_only=True)
         rate = probe / max(r0.seconds, 1e-6)
         sample = args.cpu_sample or int(min(P, max(probe, rate * 15.0)))
-        rs = O.rasterize_batch(h_cmds[: off[sample]], off[: sample + 1].astype(np.uint64), h_xf[:sample], threads=threads, count_only=True)
+        rs = O.rasterize_batch(g4.h_cmds[: off[sample]], off[: sample + 1].astype(np.uint64), g4.h_xf[:sample], threads=threads, count_only=True)
         cpu = {"value": sample / rs.seconds, "unit": "paths/s", "cores": threads, "kind": "port",
                "sample": f"first {sample} paths of the same G4 batch, all host threads (OpenMP dynamic,64), checksum sink",
                "tiles_per_s": rs.n_tiles / rs.seconds, "seconds": rs.seconds}
+        if e2e_ok and e2e is not None:
+            # parity inside the bench run: the same sample through the GPU path's host sink must give the oracle's counts, its
+            # geometry checksum bit for bit, and an alpha byte sum that differs by no more than the +-1 bytes the contract allows
+            ctx.set_host_sink(sink_threads)
+            rg = ctx.rasterize_ptrs(g4.h_cmds_t.data_ptr(), g4.h_off_t.data_ptr(), g4.h_xf_t.data_ptr(), sample, off[: sample + 1],
+                                    in_device=False, out_device=False, copy=False, unordered=True)
+            sk = ctx.last_sink()
+            ctx.set_host_sink(0)
+            d_alpha = abs(sk["alpha_sum"] - rs.alpha_sum)
+            e2e["checksum_matches_cpu"] = bool(sk["tiles"] == rs.n_tiles and sk["spans"] == rs.n_spans and sk["geom_sum"] == rs.geom_sum
+                                               and d_alpha <= max(16, 64 * rs.n_tiles * 2e-5))
+            e2e["checksum_detail"] = {"sample_paths": sample, "tiles": [sk["tiles"], rs.n_tiles], "spans": [sk["spans"], rs.n_spans],
+                                      "geom_sum_equal": sk["geom_sum"] == rs.geom_sum, "alpha_sum_abs_diff": int(d_alpha),
+                                      "alpha_bytes": int(64 * rs.n_tiles), "mix_sum_equal": sk["mix_sum"] == rs.checksum}
+            if not e2e["checksum_matches_cpu"]:
+                raise SystemExit(f"bench.py: the GPU result of the cpu_baseline sample does not match the oracle: {e2e['checksum_detail']}")
 
     if rank == 0:
         tps = tiles_total / (ms_per_step * 1e-3)
@@ -529,13 +723,13 @@ def main():
                 "lines_per_gpu": int(res.n_lines), "bin_records_per_gpu": int(res.n_records), "tiles_total": int(tiles_total),
                 "spans_total": int(spans_total), "tiles_per_s": tps, "alpha_MB_per_s": tps * 64e-6, "chunks": int(res.n_chunks),
                 "parallelism": f"path-batch x{world}" + ((", tiles gathered to GPU 0 inside the kernel: alpha stores go to an arena in GPU 0's memory over NVLink (CUDA IPC peer "
-                                                              "mapping), origins / spans / ranges follow by peer copy behind the kernels") if use_arena else
-                                                             f", tiles gathered to GPU 0 (NCCL send/recv, pipelined in {K} sub-batches)" if gather else ""),
-                "layout": ("path-ordered lists (k_gather_paths)" if args.ordered else
-                           "per-path lists in completion order + per-path (start, count) ranges (OCHRE_OUT_UNORDERED)"),
+                                                              "mapping), origins / spans / ranges follow by peer copy behind the kernels") if gather else ""),
+                "layout": "per-path lists in completion order + per-path (start, count) ranges (OCHRE_OUT_UNORDERED); `ordered` = the same step with path-ordered lists",
+                "ordered": ordered,
                 "l2": "inputs (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (n_cmds * 28 / 1e9),
                 "timing": "CUDA events bracketing the K steps, max over ranks; library-reported device ms/step = %.3f, wall = %.3f"
                           % (dev_ms / args.steps, wall_ms / args.steps),
+                "workloads": workloads,
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

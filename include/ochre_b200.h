@@ -219,6 +219,24 @@ typedef struct OchreAtlas {
  * until the next call on the ctx. */
 int ochre_b200_build_atlas(ochre_b200_ctx* ctx, const uint8_t* colors, uint32_t flags, OchreAtlas* out);
 
+/* ---- host sink: the reference's TileBuilder consumer, inside the call ----------------------------------
+ * Rasterizer::finish hands every tile and span to a TileBuilder (src/rasterizer.rs:12-22, :241, :261-264); a caller of this
+ * library replays the result arrays into one.  With a host sink set, ochre_b200_rasterize does that replay itself for
+ * host-resident results: `threads` worker threads take every chunk of the result as soon as its download has finished --
+ * while later chunks are still being rasterised and downloaded -- and pass each tile and each span to a counting,
+ * checksumming builder (two indirect calls per tile / span, as a `&mut impl TileBuilder` costs).  This is the "last
+ * TileBuilder callback returned" end point of an end-to-end measurement.  The sums of the last call
+ * are read with ochre_b200_last_sink.  threads == 0 switches the sink off (default). */
+typedef struct OchreSinkSum {
+    uint64_t tiles, spans; /* TileBuilder::tile / ::span calls */
+    uint64_t geom_sum;     /* over tile origins and spans only: equals the reference's bit for bit */
+    uint64_t alpha_sum;    /* sum of every alpha byte (differs from the reference's by at most the count of +-1 bytes) */
+    uint64_t mix_sum;      /* per tile a hash of origin and all 64 alpha bytes, per span x << 32 ^ y << 16 ^ w, summed */
+    double seconds;        /* busy time of the slowest sink thread */
+} OchreSinkSum;
+int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads);
+int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out);
+
 /* Human-readable description of the last error on this ctx (never NULL). */
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);
 

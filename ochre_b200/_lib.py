@@ -25,6 +25,7 @@ SYMBOLS = [
     "ochre_b200_set_output_arena", "ochre_b200_copy_to_host", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_debug_stroker_ms", "ochre_b200_version",
+    "ochre_b200_set_host_sink", "ochre_b200_last_sink",
 ]
 
 
@@ -51,6 +52,13 @@ class OchreArena(C.Structure):
         ("base", C.c_void_p), ("bytes", C.c_uint64), ("cap_tiles", C.c_uint64), ("cap_spans", C.c_uint64),
         ("cap_paths", C.c_uint64), ("alpha", C.c_void_p), ("tile_xy", C.c_void_p), ("spans", C.c_void_p),
         ("ranges", C.c_void_p), ("ipc", C.c_ubyte * 64), ("owner", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class OchreSinkSum(C.Structure):
+    _fields_ = [
+        ("tiles", C.c_uint64), ("spans", C.c_uint64), ("geom_sum", C.c_uint64), ("alpha_sum", C.c_uint64),
+        ("mix_sum", C.c_uint64), ("seconds", C.c_double),
     ]
 
 
@@ -101,6 +109,8 @@ def load():
     L.ochre_b200_debug_stroker_ms.argtypes = [vp]
     L.ochre_b200_debug_stroker_ms.restype = C.c_float
     L.ochre_b200_version.restype = C.c_char_p
+    L.ochre_b200_set_host_sink.argtypes = [vp, u32]
+    L.ochre_b200_last_sink.argtypes = [vp, C.POINTER(OchreSinkSum)]
     for f in SYMBOLS:
         getattr(L, f)  # AttributeError here = the library does not export what the header declares
     _lib = L

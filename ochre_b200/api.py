@@ -172,6 +172,18 @@ class Context:
         """Rasterise only tile rows [lo, hi) (row-band sharding of one huge path); lo >= hi resets."""
         _check(self._h, _lib.load().ochre_b200_set_row_band(self._h, int(tile_row_lo), int(tile_row_hi)))
 
+    def set_host_sink(self, threads: int = 0):
+        """`threads` worker threads replay every host-resident result into a counting / checksumming TileBuilder inside
+        the call, chunk by chunk behind the downloads (`ochre_b200_set_host_sink`); 0 switches the sink off."""
+        _check(self._h, _lib.load().ochre_b200_set_host_sink(self._h, int(threads)))
+
+    def last_sink(self) -> dict:
+        """Sums of the host sink over the last call: TileBuilder calls, geometry / alpha / mixed checksums, busy seconds."""
+        s = _lib.OchreSinkSum()
+        _check(self._h, _lib.load().ochre_b200_last_sink(self._h, C.byref(s)))
+        return dict(tiles=int(s.tiles), spans=int(s.spans), geom_sum=int(s.geom_sum), alpha_sum=int(s.alpha_sum),
+                    mix_sum=int(s.mix_sum), seconds=float(s.seconds))
+
     def build_atlas(self, colors, out_device: bool = False, copy: bool = True) -> "AtlasResult":
         """Device-side atlas packer + quad builder (the reference's examples/svg.rs `Builder`, svg.rs:22-88)
         over the result of the last `rasterize` call.  colors: (n_paths, 4) uint8 rgba."""

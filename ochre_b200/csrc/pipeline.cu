@@ -22,7 +22,11 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ochre_b200.h"
@@ -697,8 +701,141 @@ constexpr int N_STAGE = 8;
 
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Host sink (ochre_b200_set_host_sink): the replay of a host-resident result into a TileBuilder, run by worker threads
+// chunk by chunk behind the downloads.  The builder is the counting / checksumming one the CPU baseline uses as its
+// timing sink (same sums, re-implemented here: the product links nothing from oracle/).
+// ---------------------------------------------------------------------------
+struct SinkBuilder {  // a `&mut impl TileBuilder`: two indirect calls
+    void (*tile)(SinkBuilder*, int16_t, int16_t, const uint8_t*);
+    void (*span)(SinkBuilder*, int16_t, int16_t, uint16_t);
+    OchreSinkSum sum;
+};
+static void sink_tile(SinkBuilder* b, int16_t x, int16_t y, const uint8_t* d) {
+    const uint64_t g = (uint64_t)(uint16_t)x * 0x9E3779B97F4A7C15ull + (uint16_t)y;
+    uint64_t s = g, a = 0;
+    uint64_t w[8];
+    memcpy(w, d, 64);
+    for (int i = 0; i < 8; ++i) {
+        s = (s ^ w[i]) * 0x100000001B3ull;
+        // byte sum of the word: pairwise widening adds
+        uint64_t v = w[i];
+        v = (v & 0x00ff00ff00ff00ffull) + ((v >> 8) & 0x00ff00ff00ff00ffull);
+        v = (v & 0x0000ffff0000ffffull) + ((v >> 16) & 0x0000ffff0000ffffull);
+        a += (v & 0xffffffffull) + (v >> 32);
+    }
+    b->sum.mix_sum += s;
+    b->sum.geom_sum += g;
+    b->sum.alpha_sum += a;
+    b->sum.tiles++;
+}
+static void sink_span(SinkBuilder* b, int16_t x, int16_t y, uint16_t w) {
+    const uint64_t v = ((uint64_t)(uint16_t)x << 32) ^ ((uint64_t)(uint16_t)y << 16) ^ w;
+    b->sum.mix_sum += v;
+    b->sum.geom_sum += v;
+    b->sum.spans++;
+}
+
+struct SinkTask {
+    size_t t0, nt, s0, ns;
+    cudaEvent_t ready;  // recorded behind the chunk's downloads
+};
+struct SinkRun {
+    int device = 0;
+    uint32_t n_threads = 0;
+    // the result arrays (pinned host memory; may be moved by a reallocation, only while the run is drained)
+    const int16_t* volatile tile_xy = nullptr;
+    const uint8_t* volatile alpha = nullptr;
+    const OchreSpan* volatile spans = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<SinkTask> tasks;
+    bool closed = false;
+    uint64_t done = 0;  // (task, thread) pairs finished
+    std::vector<std::thread> workers;
+    std::vector<SinkBuilder> partial;
+    std::vector<double> busy;
+
+    void worker(uint32_t t) {
+        cudaSetDevice(device);
+        alignas(128) SinkBuilder b = partial[t];  // (on the thread's own stack: neighbouring builders in the vector share cache lines)
+        size_t next = 0;
+        for (;;) {
+            SinkTask k;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next < tasks.size() || closed; });
+                if (next >= tasks.size()) {
+                    partial[t] = b;
+                    return;
+                }
+                k = tasks[next++];
+            }
+            cudaEventSynchronize(k.ready);
+            const auto t_a = std::chrono::steady_clock::now();
+            // this thread's slice of the chunk, in the result's order: tiles, then spans
+            const size_t a0 = k.t0 + k.nt * t / n_threads, a1 = k.t0 + k.nt * (t + 1) / n_threads;
+            const int16_t* xy = tile_xy;
+            const uint8_t* al = alpha;
+            for (size_t i = a0; i < a1; ++i) b.tile(&b, xy[2 * i], xy[2 * i + 1], al + 64 * i);
+            const size_t b0 = k.s0 + k.ns * t / n_threads, b1 = k.s0 + k.ns * (t + 1) / n_threads;
+            const OchreSpan* sp = spans;
+            for (size_t i = b0; i < b1; ++i) b.span(&b, sp[i].x, sp[i].y, sp[i].w);
+            busy[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_a).count();
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ++done;
+            }
+            cv.notify_all();
+        }
+    }
+    ~SinkRun() {
+        if (!workers.empty()) finish();  // (an error path left the call early)
+    }
+    void start(int dev, uint32_t n) {
+        device = dev;
+        n_threads = n;
+        partial.assign(n, SinkBuilder{sink_tile, sink_span, OchreSinkSum{}});
+        busy.assign(n, 0.0);
+        for (uint32_t t = 0; t < n; ++t) workers.emplace_back([this, t] { worker(t); });
+    }
+    void post(const SinkTask& k) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            tasks.push_back(k);
+        }
+        cv.notify_all();
+    }
+    void drain() {  // every posted task is finished by every thread
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done == (uint64_t)tasks.size() * n_threads; });
+    }
+    OchreSinkSum finish() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            closed = true;
+        }
+        cv.notify_all();
+        for (std::thread& w : workers) w.join();
+        workers.clear();
+        OchreSinkSum r{};
+        for (uint32_t t = 0; t < n_threads; ++t) {
+            r.tiles += partial[t].sum.tiles;
+            r.spans += partial[t].sum.spans;
+            r.geom_sum += partial[t].sum.geom_sum;
+            r.alpha_sum += partial[t].sum.alpha_sum;
+            r.mix_sum += partial[t].sum.mix_sum;
+            r.seconds = std::max(r.seconds, busy[t]);
+        }
+        return r;
+    }
+};
+
 struct ochre_b200_ctx {
     int device = 0;
+    uint32_t sink_threads = 0;  // host sink (ochre_b200_set_host_sink): 0 = off
+    OchreSinkSum sink_last = {};
+    std::vector<cudaEvent_t> ev_sink;
     cudaStream_t st = nullptr;       // kernels
     cudaStream_t st_in = nullptr;    // host -> device input upload, one event per chunk
     cudaStream_t st_out = nullptr;   // device -> host result download, chunk by chunk behind the kernels
@@ -1317,6 +1454,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
     if (ctx->st_in) cudaStreamSynchronize(ctx->st_in);
     if (ctx->st_out) cudaStreamSynchronize(ctx->st_out);
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_sink) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_out)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_g)
@@ -1373,6 +1511,18 @@ int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t ti
 }
 
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads) {
+    if (!ctx || threads > 1024) return OCHRE_E_INVALID_ARG;
+    ctx->sink_threads = threads;
+    return 0;
+}
+
+int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out) {
+    if (!ctx || !out) return OCHRE_E_INVALID_ARG;
+    *out = ctx->sink_last;
+    return 0;
+}
 
 static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
                           uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out) {
@@ -1497,6 +1647,14 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(cudaEventRecord(ctx->ev_out[0], ctx->st_out));
     }
 
+    // ---- host sink: worker threads replay every downloaded chunk into a TileBuilder ------------
+    std::unique_ptr<SinkRun> sink;
+    size_t sink_events = 0;  // events of ctx->ev_sink this call has used
+    if (ctx->sink_threads && !out_dev) {
+        sink.reset(new SinkRun);
+        sink->start(ctx->device, ctx->sink_threads);
+    }
+    ctx->sink_last = OchreSinkSum{};
     // ---- chunks ---------------------------------------------------------------
     const bool trace = getenv("OCHRE_B200_TRACE") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
@@ -1533,19 +1691,46 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             // the chunk is complete on the device (run_chunk* drained the kernel stream): its slice of the
             // result goes to the host while the next chunk is being rasterised
             const size_t t0 = tile_base, nt = co.n_tiles, s0 = span_base, ns = co.n_spans;
+            if (sink && ((t0 + nt) * 4 + 4 > ctx->h_tile_xy.cap || (t0 + nt) * 64 + 64 > ctx->h_alpha.cap ||
+                         (s0 + ns) * sizeof(OchreSpan) + 8 > ctx->h_spans.cap))
+                sink->drain();  // a host array is about to move: no sink thread may be reading it
             CK(ctx->h_tile_xy.ensure_keep((t0 + nt) * 4 + 4, t0 * 4, ctx->st_out));
             CK(ctx->h_alpha.ensure_keep((t0 + nt) * 64 + 64, t0 * 64, ctx->st_out));
             CK(ctx->h_spans.ensure_keep((s0 + ns) * sizeof(OchreSpan) + 8, s0 * sizeof(OchreSpan), ctx->st_out));
-            if (nt) {
-                CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + t0 * 4, r_tile_xy.as<uint8_t>() + t0 * 4, nt * 4, cudaMemcpyDeviceToHost, ctx->st_out));
-                CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + t0 * 64, r_alpha.as<uint8_t>() + t0 * 64, nt * 64, cudaMemcpyDeviceToHost, ctx->st_out));
+            // with a host sink the tiles travel in pieces of 32 MB, each handed to the sink threads as soon as it has landed
+            // (the replay of the call's last piece is all that is left when the download ends)
+            auto sink_post = [&](size_t ta, size_t tn, size_t sa, size_t sn) -> int {
+                if (sink_events == ctx->ev_sink.size()) {
+                    cudaEvent_t e;
+                    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    ctx->ev_sink.push_back(e);
+                }
+                cudaEvent_t e = ctx->ev_sink[sink_events++];
+                CK(cudaEventRecord(e, ctx->st_out));
+                sink->tile_xy = ctx->h_tile_xy.as<int16_t>();
+                sink->alpha = ctx->h_alpha.as<uint8_t>();
+                sink->spans = ctx->h_spans.as<OchreSpan>();
+                sink->post(SinkTask{ta, tn, sa, sn, e});
+                return 0;
+            };
+            const size_t piece = sink ? ((size_t)32 << 20) / 64 : (nt ? nt : 1);
+            for (size_t a = 0; a < nt; a += piece) {
+                const size_t n = std::min(piece, nt - a);
+                CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + (t0 + a) * 4, r_tile_xy.as<uint8_t>() + (t0 + a) * 4, n * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + (t0 + a) * 64, r_alpha.as<uint8_t>() + (t0 + a) * 64, n * 64, cudaMemcpyDeviceToHost, ctx->st_out));
+                if (sink)
+                    if (int rc2 = sink_post(t0 + a, n, 0, 0)) return rc2;
             }
-            if (ns)
+            if (ns) {
                 CK(cudaMemcpyAsync(ctx->h_spans.as<OchreSpan>() + s0, r_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToHost, ctx->st_out));
+                if (sink)
+                    if (int rc2 = sink_post(0, 0, s0, ns)) return rc2;
+            }
             if (!unordered) {
                 CK(cudaMemcpyAsync(ctx->h_tile_off.as<uint32_t>() + p0, ctx->o_tile_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
                 CK(cudaMemcpyAsync(ctx->h_span_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, ctx->st_out));
             }
+
         }
         if (ext) {
             // the chunk's alpha tiles are in the arena already (stored there by the kernel); its tile origins, spans and
@@ -1621,6 +1806,10 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         if (trace) fprintf(stderr, "[ochre_b200] kernels done at %.3f ms\n", now_ms());
         CK(cudaStreamSynchronize(ctx->st_out));
         if (trace) fprintf(stderr, "[ochre_b200] download done at %.3f ms\n", now_ms());
+        if (sink) {
+            ctx->sink_last = sink->finish();  // the last TileBuilder call has returned
+            if (trace) fprintf(stderr, "[ochre_b200] host sink done at %.3f ms (slowest thread busy %.3f ms)\n", now_ms(), ctx->sink_last.seconds * 1e3);
+        }
         CK(cudaEventElapsedTime(&copy_ms, ctx->ev_out[0], ctx->ev_out[1]));
         out->tile_off = unordered ? nullptr : ctx->h_tile_off.as<uint32_t>();
         out->span_off = unordered ? nullptr : ctx->h_span_off.as<uint32_t>();

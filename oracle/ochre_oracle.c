@@ -731,22 +731,28 @@ typedef struct orc_batch {
     uint64_t n_lines, n_increments, n_tile_increments;
     uint64_t checksum;
     double seconds;
+    uint64_t geom_sum;   /* mode 1: the checksum's terms that depend on tile origins and spans only (exact by contract) */
+    uint64_t alpha_sum;  /* mode 1: sum of every alpha byte */
 } orc_batch;
 
 typedef struct {
-    uint64_t tiles, spans, sum;
+    uint64_t tiles, spans, sum, geom, alpha;
 } CountSink;
 static void cnt_tile(void *ctx, int16_t x, int16_t y, const uint8_t d[64]) {
     CountSink *c = (CountSink *)ctx;
     uint64_t s = (uint64_t)(uint16_t)x * 0x9E3779B97F4A7C15ull + (uint16_t)y;
+    c->geom += s;
     const uint64_t *w = (const uint64_t *)d;
     for (int i = 0; i < 8; i++) s = (s ^ w[i]) * 0x100000001B3ull;
+    for (int i = 0; i < 64; i++) c->alpha += d[i];
     c->sum += s;
     c->tiles++;
 }
 static void cnt_span(void *ctx, int16_t x, int16_t y, uint16_t w) {
     CountSink *c = (CountSink *)ctx;
-    c->sum += ((uint64_t)(uint16_t)x << 32) ^ ((uint64_t)(uint16_t)y << 16) ^ w;
+    const uint64_t v = ((uint64_t)(uint16_t)x << 32) ^ ((uint64_t)(uint16_t)y << 16) ^ w;
+    c->sum += v;
+    c->geom += v;
     c->spans++;
 }
 
@@ -767,14 +773,14 @@ API orc_batch *orc_rasterize_batch(const OchreCmd *cmds, const uint64_t *cmd_off
     B->span_off = (uint64_t *)calloc((size_t)n_paths + 1, 8);
     Collector *cols = NULL;
     if (mode == 0) cols = (Collector *)calloc(n_paths ? n_paths : 1, sizeof(Collector));
-    uint64_t nl = 0, ni = 0, nti = 0, cs = 0;
+    uint64_t nl = 0, ni = 0, nti = 0, cs = 0, gs = 0, as = 0;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
 #else
     (void)threads;
 #endif
     double t0 = now_s();
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nl, ni, nti, cs)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nl, ni, nti, cs, gs, as)
     for (int64_t p = 0; p < (int64_t)n_paths; p++) {
         orc_rasterizer r;
         rast_init(&r);
@@ -788,12 +794,14 @@ API orc_batch *orc_rasterize_batch(const OchreCmd *cmds, const uint64_t *cmd_off
             B->tile_off[p + 1] = cols[p].tiles.n;
             B->span_off[p + 1] = cols[p].spans.n;
         } else {
-            CountSink s = {0, 0, 0};
+            CountSink s = {0, 0, 0, 0, 0};
             TileBuilder b = {cnt_tile, cnt_span, &s};
             rast_finish(&r, &b);
             B->tile_off[p + 1] = s.tiles;
             B->span_off[p + 1] = s.spans;
             cs += s.sum;
+            gs += s.geom;
+            as += s.alpha;
         }
         nl += r.n_lines;
         ni += r.increments.n;
@@ -811,6 +819,8 @@ API orc_batch *orc_rasterize_batch(const OchreCmd *cmds, const uint64_t *cmd_off
     B->n_increments = ni;
     B->n_tile_increments = nti;
     B->checksum = cs;
+    B->geom_sum = gs;
+    B->alpha_sum = as;
     if (mode == 0) {
         B->tile_xy = (int16_t *)malloc((B->n_tiles ? B->n_tiles : 1) * 4);
         B->alpha = (uint8_t *)malloc((B->n_tiles ? B->n_tiles : 1) * 64);

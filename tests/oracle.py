@@ -39,6 +39,8 @@ class _Batch(C.Structure):
         ("n_tile_increments", C.c_uint64),
         ("checksum", C.c_uint64),
         ("seconds", C.c_double),
+        ("geom_sum", C.c_uint64),
+        ("alpha_sum", C.c_uint64),
     ]
 
 
@@ -197,6 +199,8 @@ class BatchResult:
     n_tile_increments: int
     checksum: int
     seconds: float
+    geom_sum: int = 0   # count_only: checksum terms of tile origins and spans only
+    alpha_sum: int = 0  # count_only: sum of every alpha byte
 
     @property
     def n_tiles(self):
@@ -227,7 +231,7 @@ def rasterize_batch(cmds, cmd_off, xf, stroke_width=None, threads: int = 0, coun
         alpha = np.ctypeslib.as_array(bb.alpha, (max(nt, 1) * 64,))[: nt * 64].copy().reshape(nt, 64)
         spans = np.frombuffer(C.string_at(bb.spans, ns * 8), dtype=SPAN_DTYPE).copy() if ns else np.zeros(0, SPAN_DTYPE)
     out = BatchResult(tile_off, span_off, tile_xy, alpha, spans, int(bb.n_lines), int(bb.n_increments),
-                      int(bb.n_tile_increments), int(bb.checksum), float(bb.seconds))
+                      int(bb.n_tile_increments), int(bb.checksum), float(bb.seconds), int(bb.geom_sum), int(bb.alpha_sum))
     L.orc_batch_free(b)
     return out
 
