@@ -13,8 +13,12 @@ HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.j
 
 # -fmad=false: the reference never fuses multiply-add; tile membership depends on the rounded f32 DDA.
 # Defaults kept on purpose: -prec-div=true -prec-sqrt=true -ftz=false (IEEE division, sqrt, denormals).
+# (-DOC_PK_EVICT_LAST=1 -DOC_L2_SETASIDE_MB=64 gives the fused kernel's line scratch an L2 evict_last policy and a 64 MB set-aside:
+# DRAM traffic of k_path drops from 1.57x to 1.35x of its algorithmic bytes, but k_path gets 3 % slower and k_gather_paths loses half
+# of its bandwidth to the set-aside -- measured in round 2, profiles/r02_evict_last.txt; off by default.)
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "--extended-lambda", "-std=c++17",
+
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-fvisibility=default", "-shared",
 ]
 

@@ -1559,7 +1559,14 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     const bool out_dev = (flags & OCHRE_OUT_DEVICE) != 0;
     const bool banded_call = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;
     // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
-    const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && ctx->mode != OCHRE_MODE_GENERAL && !banded_call;
+    // Mode auto, a call of few but large paths (a document: tens to hundreds of paths, hundreds of commands each): one CTA per
+    // path leaves most of the GPU idle and the longest path sets the time, while the general pipeline spreads every stage over
+    // the whole device (calabi-yau 4x, 99 paths: 0.69 ms against 1.02 ms) -- such a call goes to the general pipeline as a whole.
+    int mode = ctx->mode;
+    if (mode == OCHRE_MODE_AUTO && !ctx->x_on && n_paths <= (uint32_t)ctx->sm_count * pkl::PK_CTAS_PER_SM && n_cmds >= 8192u &&
+        (uint64_t)n_cmds >= 64ull * n_paths)
+        mode = OCHRE_MODE_GENERAL;
+    const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && mode != OCHRE_MODE_GENERAL && !banded_call;
     const bool ext = ctx->x_on;
     if (ext && !(out_dev && unordered)) {
         ctx->err = "an output arena needs OCHRE_OUT_DEVICE | OCHRE_OUT_UNORDERED, mode auto or fused, and no row band";
@@ -1582,7 +1589,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk, and
     // with an output arena the origins / spans / ranges of a chunk travel behind the next chunk's kernels.
     const uint32_t chunk_vcmds = ctx->chunk_vcmds ? ctx->chunk_vcmds
-                                 : (out_dev && !ctx->x_on && ctx->mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
+                                 : (out_dev && !ctx->x_on && mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
     const bool ramp = !out_dev && chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
         uint32_t p1 = p0;
@@ -1667,11 +1674,11 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         ChunkOut co;
         int rc = RC_NEED_GENERAL;
         const bool banded = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;  // the row filter lives in the general pipeline
-        if (ctx->mode != OCHRE_MODE_GENERAL && !banded) {
+        if (mode != OCHRE_MODE_GENERAL && !banded) {
             rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, unordered,
                                  n_paths);
             if (rc == 0) ctx->used_paths |= 1u;
-            if (rc == RC_NEED_GENERAL && ctx->mode == OCHRE_MODE_FUSED) {
+            if (rc == RC_NEED_GENERAL && mode == OCHRE_MODE_FUSED) {
                 ctx->err = "a path exceeds the fused kernel's on-chip budgets (mode = fused only)";
                 return OCHRE_E_TOO_LARGE;
             }
