@@ -75,6 +75,12 @@ typedef struct OchreSpan {
                                   * tile_off / span_off are NULL.  Ignored (the result is ordered) in OCHRE_MODE_GENERAL and with
                                   * a row band. */
 
+#define OCHRE_SKIP_BAD_PATHS 0x10u /* a path with an invalid command (unknown tag, a transformed coordinate that is not finite or
+                                    * >= 32760 px in magnitude, a Conic weight <= -1) yields no tiles and no spans instead of failing
+                                    * the whole call with OCHRE_E_BAD_COORD / OCHRE_E_BAD_TAG; ochre_b200_path_status tells which
+                                    * paths were dropped and why.  Structural errors (null pointers, non-monotone offsets, index
+                                    * space) still fail the call. */
+
 /* Result of one call.  Tiles and spans of path p are tile_off[p]..tile_off[p+1]
  * and span_off[p]..span_off[p+1]; inside a path tiles ascend by (tile_y, tile_x)
  * -- the order of the reference's TileBuilder::tile calls -- and a span belongs
@@ -236,6 +242,11 @@ typedef struct OchreSinkSum {
 } OchreSinkSum;
 int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads);
 int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out);
+
+/* Per-path status of the last ochre_b200_rasterize* call made with OCHRE_SKIP_BAD_PATHS: *status points at n_paths bytes of
+ * ctx-owned host memory (0 = rasterised, else the OCHRE_E_* code the path was dropped for), *n_bad is the number of
+ * dropped paths.  Without the flag (or when no path was dropped) *status is NULL and *n_bad is 0. */
+int ochre_b200_path_status(ochre_b200_ctx* ctx, const int8_t** status, uint32_t* n_bad);
 
 /* Human-readable description of the last error on this ctx (never NULL). */
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx);

@@ -11,6 +11,7 @@ OCHRE_IN_DEVICE = 0x1
 OCHRE_OUT_DEVICE = 0x2
 OCHRE_KEEP_STAGES = 0x4
 OCHRE_OUT_UNORDERED = 0x8
+OCHRE_SKIP_BAD_PATHS = 0x10
 MODE_AUTO, MODE_GENERAL, MODE_FUSED = 0, 1, 2
 
 ERRORS = {
@@ -25,7 +26,7 @@ SYMBOLS = [
     "ochre_b200_set_output_arena", "ochre_b200_copy_to_host", "ochre_b200_build_atlas", "ochre_b200_last_error",
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_debug_stroker_ms", "ochre_b200_version",
-    "ochre_b200_set_host_sink", "ochre_b200_last_sink",
+    "ochre_b200_set_host_sink", "ochre_b200_last_sink", "ochre_b200_path_status",
 ]
 
 
@@ -111,6 +112,7 @@ def load():
     L.ochre_b200_version.restype = C.c_char_p
     L.ochre_b200_set_host_sink.argtypes = [vp, u32]
     L.ochre_b200_last_sink.argtypes = [vp, C.POINTER(OchreSinkSum)]
+    L.ochre_b200_path_status.argtypes = [vp, C.POINTER(vp), C.POINTER(u32)]
     for f in SYMBOLS:
         getattr(L, f)  # AttributeError here = the library does not export what the header declares
     _lib = L

@@ -207,12 +207,22 @@ class Context:
         return AtlasResult(view(res.vertices, nq * 48, VERTEX_DTYPE, (nq * 4,)), view(res.indices, nq * 24, np.uint32, (nq * 6,)),
                            view(res.atlas, npg * 4096 * 4096, np.uint8, (npg, 4096, 4096)), **common)
 
-    def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True, unordered: bool = False) -> BatchResult:
+    def path_status(self, n_paths: int):
+        """Per-path status of the last call made with skip_bad=True: (status int8 array or None, number of dropped paths)."""
+        p, n = C.c_void_p(), C.c_uint32(0)
+        _check(self._h, _lib.load().ochre_b200_path_status(self._h, C.byref(p), C.byref(n)))
+        if not p.value:
+            return None, int(n.value)
+        return np.frombuffer((C.c_int8 * n_paths).from_address(p.value), dtype=np.int8).copy(), int(n.value)
+
+    def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True, unordered: bool = False,
+                  skip_bad: bool = False) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.
 
         cmds: CMD_DTYPE array; cmd_off: uint32 offsets (n_paths+1); xf: (n_paths, 6) float32 rows
         (`OchreTransform`).  Host arrays in, host arrays out unless out_device.
         copy=False returns views of the ctx-owned pinned buffers (valid until the next call).
+        skip_bad: a path with an invalid command yields nothing instead of failing the call (`path_status`).
         """
         L = _lib.load()
         cmds = np.ascontiguousarray(cmds, dtype=CMD_DTYPE)
@@ -220,7 +230,8 @@ class Context:
         n_paths = len(cmd_off) - 1
         xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n_paths, 6) if n_paths else np.zeros((0, 6), np.float32)
         res = _lib.OchreResult()
-        flags = (_lib.OCHRE_OUT_DEVICE if out_device else 0) | (_lib.OCHRE_OUT_UNORDERED if unordered else 0)
+        flags = ((_lib.OCHRE_OUT_DEVICE if out_device else 0) | (_lib.OCHRE_OUT_UNORDERED if unordered else 0)
+                 | (_lib.OCHRE_SKIP_BAD_PATHS if skip_bad else 0))
         rc = L.ochre_b200_rasterize(self._h, cmds.ctypes.data, cmd_off.ctypes.data, xf.ctypes.data, n_paths, flags, None,
                                     C.byref(res))
         _check(self._h, rc)

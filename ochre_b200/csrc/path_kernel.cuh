@@ -561,6 +561,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
         // (a path with more commands than line slots is handed over at once, without flattening its first 16 k lines:
         // the next stage validates it)
         bool fallback = nv > (uint32_t)PK_LINECAP, bad_path = false;
+        int bad_code = 0;
         for (uint32_t jb = 0; jb < nv && !fallback; jb += PK_THREADS) {
             const uint32_t j = jb + tid;
             uint32_t my_n = 0, my_tag = TAG_CLOSE;
@@ -678,7 +679,10 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             }
             // one bad command poisons `last` of its successors: the path is not walked at all (the
             // call fails with the status code anyway)
-            if (__syncthreads_or(bad)) bad_path = true;
+            if (__syncthreads_or(bad)) {
+                bad_path = true;
+                bad_code = __syncthreads_or(bad == 2) ? OCHRE_E_BAD_TAG : OCHRE_E_BAD_COORD;
+            }
             if (bad_path || fallback) break;
             // thread per line: one curve evaluation each.  A line's start point is its predecessor's end point,
             // taken from the neighbouring lane: every warp pass covers 31 lines, lane 0 only evaluates the
@@ -721,7 +725,13 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             n_lines += total;
             __syncthreads();
         }
-        if (bad_path) continue;
+        if (bad_path) {  // no tiles, no spans: the status word fails the call, or (OCHRE_SKIP_BAD_PATHS) the path is reported as dropped
+            if (tid == 0) {
+                A.rec[p] = make_uint4(0u, 0u, 0u, 0u);
+                if (A.path_status) A.path_status[p] = (int8_t)bad_code;
+            }
+            continue;
+        }
         if (!fallback) {
             const int x0 = __reduce_min_sync(0xffffffffu, bb.x0), y0 = __reduce_min_sync(0xffffffffu, bb.y0);
             const int x1 = __reduce_max_sync(0xffffffffu, bb.x1), y1 = __reduce_max_sync(0xffffffffu, bb.y1);

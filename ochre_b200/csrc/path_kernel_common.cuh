@@ -41,6 +41,7 @@ struct PathKernelArgs {
     const uint32_t* path_list;  // null: paths 0 .. n_paths-1; else the n_paths chunk-local ids to rasterise
     const uint32_t* n_paths_dev;  // non-null: the number of list entries to take is read from device memory (classified lists)
     uint32_t list_rev;          // 1: the list is path_list[n_paths - 1], path_list[n_paths - 2], ... (the large end of a two-ended list)
+    int8_t* path_status;        // null, or per path (chunk-local id): the OCHRE_E_* code a path with an invalid command is dropped for
 };
 
 enum : uint32_t { CF_TOUCHED = 1, CF_WIND = 2, CF_SPAN = 4 };

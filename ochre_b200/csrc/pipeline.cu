@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t find_path_dev(const uint32_t* __restrict__ c
 __global__ void __launch_bounds__(TPB)
 k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base,
                 const float* __restrict__ xf, uint32_t n_paths, uint32_t n_v, uint32_t* __restrict__ vpath,
-                uint32_t* __restrict__ nlines, int* __restrict__ status) {
+                uint32_t* __restrict__ nlines, int* __restrict__ status, int8_t* __restrict__ path_status) {
     uint32_t v = blockIdx.x * TPB + threadIdx.x;
     if (v >= n_v) return;
     uint32_t p = find_path_dev(cmd_off, cmd_base, n_paths, v);
@@ -111,11 +111,17 @@ k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_o
     vpath[v] = p;
     if (j < c1 - c0) {
         uint32_t tag = pc[j].tag;
-        if (tag > TAG_CLOSE) atomicMax(status, (int)ST_BAD_TAG);
+        if (tag > TAG_CLOSE) {
+            atomicMax(status, (int)ST_BAD_TAG);
+            if (path_status) path_status[p] = (int8_t)OCHRE_E_BAD_TAG;
+        }
         int np = cmd_npts(tag);
         bool ok = true;
         for (int i = 0; i < np; ++i) ok = ok && coord_ok(cmd_point(pc[j], i, m));
-        if (!ok) atomicMax(status, (int)ST_BAD_COORD);
+        if (!ok) {
+            atomicMax(status, (int)ST_BAD_COORD);
+            if (path_status && tag <= TAG_CLOSE) path_status[p] = (int8_t)OCHRE_E_BAD_COORD;
+        }
         if (!ok || tag > TAG_CLOSE) {
             nlines[v] = 0;
             return;
@@ -125,13 +131,31 @@ k_flatten_count(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_o
     // `last` (and `first`, for the closing lines) are inherited from earlier commands: a curve that starts at a rejected
     // point gets a dt its t loop cannot advance with, so the command is dropped here, not only the one that owns the point
     uint32_t n = 0;
-    if (coord_ok(c.last) && coord_ok(c.a) && (c.tag != TAG_CONIC || conic_weight_ok(c.w))) n = vcmd_line_count(c);
-    else atomicMax(status, (int)ST_BAD_COORD);
+    bool okc = coord_ok(c.last) && coord_ok(c.a) && (c.tag != TAG_CONIC || conic_weight_ok(c.w));
+    if (okc) n = vcmd_line_count(c);
     if (n >= OC_CURVE_CAP) {  // a Conic point out of range
-        atomicMax(status, (int)ST_BAD_COORD);
+        okc = false;
         n = 0;
     }
+    if (!okc) {
+        atomicMax(status, (int)ST_BAD_COORD);
+        // (a path that also holds an unknown tag keeps that code: whichever thread writes last, both are errors of the path)
+        if (path_status && path_status[p] == 0) path_status[p] = (int8_t)OCHRE_E_BAD_COORD;
+    }
     nlines[v] = n;
+}
+
+// OCHRE_SKIP_BAD_PATHS: a path with an invalid command loses all its lines (and its empty-path tile, k_phantom_fix)
+__global__ void __launch_bounds__(TPB)
+k_drop_bad_paths(uint32_t n_v, const uint32_t* __restrict__ vpath, const int8_t* __restrict__ path_status, uint32_t* __restrict__ nlines) {
+    uint32_t v = blockIdx.x * TPB + threadIdx.x;
+    if (v < n_v && path_status[vpath[v]] != 0) nlines[v] = 0;
+}
+// hand-over side batch -> the call's status array
+__global__ void __launch_bounds__(TPB)
+k_fb_status(const uint32_t* __restrict__ fb, uint32_t n_fb, const int8_t* __restrict__ sub_status, int8_t* __restrict__ path_status) {
+    uint32_t q = blockIdx.x * TPB + threadIdx.x;
+    if (q < n_fb && sub_status[q] != 0) path_status[fb[q]] = sub_status[q];
 }
 
 // ---------------------------------------------------------------------------
@@ -181,9 +205,11 @@ k_flatten_emit(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_of
 // the path's FINISH command.
 __global__ void __launch_bounds__(TPB)
 k_phantom_fix(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_paths,
-              const uint32_t* __restrict__ path_has_inc, uint32_t* __restrict__ nrec, int band_lo, int band_hi) {
+              const uint32_t* __restrict__ path_has_inc, uint32_t* __restrict__ nrec, int band_lo, int band_hi,
+              const int8_t* __restrict__ path_status) {
     uint32_t p = blockIdx.x * TPB + threadIdx.x;
     if (p >= n_paths) return;
+    if (path_status && path_status[p] != 0) return;  // a dropped path yields nothing, not even the empty path's tile
     if (!path_has_inc[p] && band_lo <= 0 && 0 < band_hi) nrec[cmd_off[p + 1] - cmd_base + p] += 1u;
 }
 
@@ -833,6 +859,12 @@ struct SinkRun {
 
 struct ochre_b200_ctx {
     int device = 0;
+    // OCHRE_SKIP_BAD_PATHS: per-path status of the current / last call (device array, host mirror)
+    DevBuf d_pstatus, f_pstatus;
+    HostBuf h_pstatus;
+    int8_t* cur_pstatus = nullptr;  // device array of the running call, or null (a bad path fails the call)
+    uint32_t last_bad = 0;
+    bool pstatus_valid = false;
     uint32_t sink_threads = 0;  // host sink (ochre_b200_set_host_sink): 0 = off
     OchreSinkSum sink_last = {};
     std::vector<cudaEvent_t> ev_sink;
@@ -945,7 +977,7 @@ struct OutTarget {
 
 int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all, uint32_t p0,
               uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base, uint32_t span_base, ChunkOut* co,
-              const OutTarget& ot) {
+              const OutTarget& ot, int8_t* pstatus /* per path of [p0, p1), or null: a bad path fails the call */) {
     cudaStream_t st = ctx->st;
     const uint32_t n_paths = p1 - p0;
     const uint32_t n_cmds = cmd_hi - cmd_lo;
@@ -979,8 +1011,12 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     CK(cudaMemsetAsync(d_sc, 0, SC_COUNT * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(path_has_inc, 0, (size_t)n_paths * 4, st));
     k_flatten_count<<<nblk(n_v, TPB), TPB, 0, st>>>(cmds, cmd_off, cmd_lo, xf, n_paths, n_v, vpath, line_off,
-                                                      reinterpret_cast<int*>(d_sc + SC_STATUS));
+                                                      reinterpret_cast<int*>(d_sc + SC_STATUS), pstatus);
     launches += 1;
+    if (pstatus) {  // OCHRE_SKIP_BAD_PATHS: a path with a rejected command is dropped as a whole
+        k_drop_bad_paths<<<nblk(n_v, TPB), TPB, 0, st>>>(n_v, vpath, pstatus, line_off);
+        launches += 1;
+    }
     {
         uint32_t* lo_ = line_off;
         launches += device_scan(
@@ -989,7 +1025,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
             d_sc + SC_NLINES);
     }
     if (int rc = read_scalars(ctx)) return rc;
-    if (h_sc[SC_STATUS] != ST_OK) {
+    if (h_sc[SC_STATUS] != ST_OK && !pstatus) {
         switch (h_sc[SC_STATUS]) {
             case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
             default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
@@ -1001,7 +1037,7 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     float4* lines = ctx->d_lines.as<float4>();
     k_flatten_emit<<<nblk(n_v, TPB), TPB, 0, st>>>(cmds, cmd_off, cmd_lo, xf, n_v, vpath, line_off, lines, rec_off,
                                                      path_has_inc, ctx->band_lo, ctx->band_hi);
-    k_phantom_fix<<<nblk(n_paths, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_paths, path_has_inc, rec_off, ctx->band_lo, ctx->band_hi);
+    k_phantom_fix<<<nblk(n_paths, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_paths, path_has_inc, rec_off, ctx->band_lo, ctx->band_hi, pstatus);
     launches += 2;
     CK(cudaEventRecord(ctx->ev[1], st));
     // ---- stage 2: bin + sort ---------------------------------------------------
@@ -1141,7 +1177,7 @@ enum { PKC_TICKET = 0, PKC_CURSOR = 1, PKC_STATUS = 3, PKC_NSMALL = 8, PKC_NLARG
 
 int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_off_all, const float* d_xf_all,
                     const uint32_t* h_off, uint32_t p0, uint32_t p1, uint32_t cmd_lo, uint32_t cmd_hi, uint32_t tile_base,
-                    uint32_t span_base, ChunkOut* co, bool unordered, uint32_t n_paths_total) {
+                    uint32_t span_base, ChunkOut* co, bool unordered, uint32_t n_paths_total, int8_t* pstatus) {
     cudaStream_t st = ctx->st;
     const uint32_t n_paths = p1 - p0;
     // unordered: the arena the kernel fills IS the result (paths in completion order, one (start, count)
@@ -1215,6 +1251,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.n_paths_dev = nullptr;
         A.list_rev = 0;
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
+        A.path_status = pstatus;
         CK(cudaEventRecord(ctx->ev[0], st));
         if (route) {
             uint32_t* list = ctx->d_pk_list.as<uint32_t>();
@@ -1244,7 +1281,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         co->ms[0] += ms;
         co->launches += 1;
         const int* stt = reinterpret_cast<const int*>(h_ctl + PKC_STATUS);
-        if (stt[0] != ST_OK) {
+        if (stt[0] != ST_OK && !pstatus) {
             switch (stt[0]) {
                 case ST_BAD_COORD: ctx->err = "a transformed coordinate is not finite or its magnitude is >= 32760 px"; return OCHRE_E_BAD_COORD;
                 default: ctx->err = "unknown PathCmd tag"; return OCHRE_E_BAD_TAG;
@@ -1317,8 +1354,15 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             CK(cudaStreamSynchronize(st));  // fb / sub_off are host temporaries
             ChunkOut co2;
             OutTarget ot{&ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, ctx->f_tile_off.as<uint32_t>(), ctx->f_span_off.as<uint32_t>()};
-            int rc = run_chunk(ctx, ctx->f_cmds.as<Cmd>(), ctx->f_off.as<uint32_t>(), ctx->f_xf.as<float>(), 0, n_fb, 0, n_sub, 0, 0, &co2, ot);
+            int8_t* sub_status = nullptr;
+            if (pstatus) {
+                CK(ctx->f_pstatus.ensure((size_t)n_fb + 16));
+                CK(cudaMemsetAsync(ctx->f_pstatus.p, 0, n_fb, st));
+                sub_status = ctx->f_pstatus.as<int8_t>();
+            }
+            int rc = run_chunk(ctx, ctx->f_cmds.as<Cmd>(), ctx->f_off.as<uint32_t>(), ctx->f_xf.as<float>(), 0, n_fb, 0, n_sub, 0, 0, &co2, ot, sub_status);
             if (rc != 0) return rc;
+            if (pstatus) k_fb_status<<<nblk(n_fb, TPB), TPB, 0, st>>>(ctx->f_fb.as<uint32_t>(), n_fb, sub_status, pstatus);
             if ((uint64_t)tile_base + (nt - base_t) + co2.n_tiles >= 0xffffffffull ||
                 (uint64_t)span_base + (ns - base_s) + co2.n_spans >= 0xffffffffull) {
                 ctx->err = "more than 2^32 tiles or spans in one call";
@@ -1465,12 +1509,12 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
                     &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
                     &ctx->k_nout, &ctx->k_out_off, &ctx->k_out};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
+    HostBuf* hb[] = {&ctx->h_pstatus, &ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1511,6 +1555,13 @@ int ochre_b200_set_row_band(ochre_b200_ctx* ctx, int32_t tile_row_lo, int32_t ti
 }
 
 const char* ochre_b200_last_error(const ochre_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int ochre_b200_path_status(ochre_b200_ctx* ctx, const int8_t** status, uint32_t* n_bad) {
+    if (!ctx || !status || !n_bad) return OCHRE_E_INVALID_ARG;
+    *status = (ctx->pstatus_valid && ctx->last_bad) ? ctx->h_pstatus.as<int8_t>() : nullptr;
+    *n_bad = ctx->pstatus_valid ? ctx->last_bad : 0u;
+    return 0;
+}
 
 int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads) {
     if (!ctx || threads > 1024) return OCHRE_E_INVALID_ARG;
@@ -1557,6 +1608,15 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     out->n_cmds = n_cmds;
 
     const bool out_dev = (flags & OCHRE_OUT_DEVICE) != 0;
+    const bool skip_bad = (flags & OCHRE_SKIP_BAD_PATHS) != 0;
+    ctx->cur_pstatus = nullptr;
+    ctx->pstatus_valid = false;
+    ctx->last_bad = 0;
+    if (skip_bad && n_paths) {
+        CK(ctx->d_pstatus.ensure((size_t)n_paths + 16));
+        CK(cudaMemsetAsync(ctx->d_pstatus.p, 0, n_paths, st));
+        ctx->cur_pstatus = ctx->d_pstatus.as<int8_t>();
+    }
     const bool banded_call = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;
     // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
     // Mode auto, a call of few but large paths (a document: tens to hundreds of paths, hundreds of commands each): one CTA per
@@ -1676,7 +1736,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         const bool banded = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;  // the row filter lives in the general pipeline
         if (mode != OCHRE_MODE_GENERAL && !banded) {
             rc = run_chunk_fused(ctx, d_cmds, d_off, d_xf, h_off, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, unordered,
-                                 n_paths);
+                                 n_paths, ctx->cur_pstatus ? ctx->cur_pstatus + p0 : nullptr);
             if (rc == 0) ctx->used_paths |= 1u;
             if (rc == RC_NEED_GENERAL && mode == OCHRE_MODE_FUSED) {
                 ctx->err = "a path exceeds the fused kernel's on-chip budgets (mode = fused only)";
@@ -1685,7 +1745,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         }
         if (rc == RC_NEED_GENERAL) {
             OutTarget ot{&ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, ctx->o_tile_off.as<uint32_t>() + p0, ctx->o_span_off.as<uint32_t>() + p0};
-            rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, ot);
+            rc = run_chunk(ctx, d_cmds, d_off, d_xf, p0, p1, h_off[p0], h_off[p1], tile_base, span_base, &co, ot,
+                           ctx->cur_pstatus ? ctx->cur_pstatus + p0 : nullptr);
             if (rc == 0) ctx->used_paths |= 2u;
         }
         if (rc != 0) {
@@ -1779,6 +1840,18 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)span_base / ((double)n_cmds + n_paths));
     }
 
+    // ---- per-path status (OCHRE_SKIP_BAD_PATHS) ------------------------------------------
+    if (ctx->cur_pstatus) {
+        CK(ctx->h_pstatus.ensure((size_t)n_paths + 16));
+        CK(cudaMemcpyAsync(ctx->h_pstatus.p, ctx->d_pstatus.p, n_paths, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int8_t* hs = ctx->h_pstatus.as<int8_t>();
+        uint32_t nb = 0;
+        for (uint32_t p = 0; p < n_paths; ++p) nb += hs[p] != 0;
+        ctx->last_bad = nb;
+        ctx->pstatus_valid = true;
+        ctx->cur_pstatus = nullptr;
+    }
     // ---- per-path ranges (both layouts) ---------------------------------------------
     if (!unordered) {
         CK(ctx->d_pk_rec.ensure((size_t)n_paths * sizeof(uint4) + 16));
@@ -1842,7 +1915,7 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
         ctx->err = "null result pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED)) {
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS)) {
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }
@@ -1860,7 +1933,7 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
         ctx->err = "null result pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED)) {
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS)) {
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }

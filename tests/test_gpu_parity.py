@@ -567,3 +567,38 @@ def test_inputs_that_would_never_end_are_rejected_not_walked(ctx):
     # the host twins of the stroker reject the same inputs
     with pytest.raises(Exception):
         ob.stroke_to_fill(make_cmds([(MOVE, 0, 0), (QUADRATIC, float("inf"), 10.0, 20.0, 0.0)]), 2.0)
+
+
+def test_one_bad_path_does_not_fail_the_batch(ctx):
+    """OCHRE_SKIP_BAD_PATHS: a path with an invalid command yields no tiles and no spans and is reported per path; every
+    other path of the call is byte-identical to the same call without the bad paths."""
+    cmds, off, xf = W.blobs(3000, first=31)
+    paths = [cmds[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    bad = {
+        17: make_cmds([(MOVE, 0, 0), (LINE, float("nan"), 1.0), (LINE, 5.0, 9.0)]),                     # non-finite coordinate
+        1500: make_cmds([(MOVE, 0, 0), (LINE, 1e30, 0.0), (QUADRATIC, 10.0, 10.0, 20.0, 0.0)]),         # a curve that starts out of range
+        2999: make_cmds([(MOVE, 1, 1), (9, 0, 0), (LINE, 4.0, 4.0)]),                                    # unknown tag
+        2000: make_cmds([(MOVE, 0, 0), (CONIC, 10.0, 10.0, 20.0, 0.0, -1.0)]),                          # Conic weight <= -1
+    }
+    mixed = list(paths)
+    for k, c in bad.items():
+        mixed[k] = c
+    mc, mo, _ = pack(mixed)
+    with pytest.raises(ob._lib.OchreError):
+        ctx.rasterize(mc, mo, xf)
+    got = ctx.rasterize(mc, mo, xf, skip_bad=True)
+    status, n_bad = ctx.path_status(len(mo) - 1)
+    assert n_bad == len(bad) and sorted(np.nonzero(status)[0].tolist()) == sorted(bad)
+    assert status[17] == -2 and status[1500] == -2 and status[2000] == -2 and status[2999] == -3
+    good = [p for i, p in enumerate(paths) if i not in bad]
+    gc, go, _ = pack(good)
+    keep = np.array([i not in bad for i in range(len(paths))])
+    want = ctx.rasterize(gc, go, xf[keep])
+    nt = np.diff(got.tile_off.astype(np.int64))
+    ns = np.diff(got.span_off.astype(np.int64))
+    assert not nt[~keep].any() and not ns[~keep].any(), "a dropped path yields nothing, not even the empty path's tile"
+    assert np.array_equal(nt[keep], np.diff(want.tile_off.astype(np.int64))) and np.array_equal(ns[keep], np.diff(want.span_off.astype(np.int64)))
+    assert np.array_equal(got.tile_xy, want.tile_xy) and np.array_equal(got.alpha, want.alpha) and got.spans.tobytes() == want.spans.tobytes()
+    # without dropped paths the accessor reports none
+    ctx.rasterize(gc, go, xf[keep], skip_bad=True)
+    assert ctx.path_status(len(go) - 1) == (None, 0)
