@@ -9,8 +9,8 @@
 //   2 bin          scan -> k_bin_scatter -> radix sort by (path, tile_y, tile_x)
 //   3 tile heads   scan over sorted records -> group_start[]
 //   4 winding      k_group_info -> scans -> k_span_width -> scan (+ span emission)
-//   5 coverage     k_coverage: thread per tile, accumulators in shared memory, row carry
-//                  inside the CTA that owns the tile-row segment, 64-byte alpha rows out
+//   5 coverage     k_coverage: thread per (tile, line), 2^-22 fixed-point accumulators in shared memory, segmented
+//                  row carry (warp scan + look-back across CTAs), 8-byte alpha rows out
 //
 // No tensor cores: nothing here is a dense contraction.  The work is scans, a sort,
 // a sequential f32 DDA per line and byte-granular output -- HBM and issue bound.
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(TPB)
 k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t n_v, const uint32_t* __restrict__ vpath,
               const uint32_t* __restrict__ line_off, const float4* __restrict__ lines,
               const uint32_t* __restrict__ rec_off, const uint32_t* __restrict__ path_has_inc,
-              uint64_t* __restrict__ keys, uint64_t* __restrict__ vals, int band_lo, int band_hi) {
+              uint64_t* __restrict__ keys, uint64_t* __restrict__ vals, WalkEntry* __restrict__ entry, int band_lo, int band_hi) {
     uint32_t v = blockIdx.x * TPB + threadIdx.x;
     if (v >= n_v) return;
     uint32_t r0 = rec_off[v], r1 = rec_off[v + 1];
@@ -230,6 +230,7 @@ k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t 
     trk.init();
     trk.sink.keys = keys + r0;
     trk.sink.vals = vals + r0;
+    trk.sink.entry = entry + r0;
     trk.sink.path_local = p;
     trk.sink.n = 0;
     trk.sink.band_lo = band_lo;
@@ -241,7 +242,7 @@ k_bin_scatter(const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, uint32_t 
     }
     trk.finish();
     bool is_finish = (v == cmd_off[p + 1] - cmd_base + p);
-    if (is_finish && !path_has_inc[p]) trk.sink.emit(0, 0, 0u, 0u, 0, false);  // the empty path's zero tile (if row 0 is in the band)
+    if (is_finish && !path_has_inc[p]) trk.sink.emit(0, 0, 0u, 0u, 0, false, WalkEntry{0.0f, 0.0f, 0.0f, 0, 0});  // the empty path's zero tile (if row 0 is in the band)
 }
 
 // ---------------------------------------------------------------------------
@@ -355,144 +356,240 @@ k_path_offsets(uint32_t n_paths, const uint32_t* __restrict__ path_first, const 
 }
 
 // ---------------------------------------------------------------------------
-// Stage 5: coverage.  One thread per tile; its 64 area + 64 height accumulators
-// live in shared memory, interleaved so that lane i always hits bank i.  A CTA owns
-// every tile-row segment (path, tile_y) that STARTS inside its 128-group range and
-// follows the last one past the range end, so the left-to-right row carry
-// (`prev`/`next`, rasterizer.rs:233-250) never crosses CTAs.
+// Stage 5: coverage.  A CTA of 256 threads takes 32 consecutive tile groups of the sorted record list.
+//   accumulate  the lines of the CTA's tiles are enumerated (count per tile, warp scan) and handed out one per thread, so
+//               a tile with many lines does not serialise on one thread: every thread walks its line's DDA
+//               (rasterizer.rs:97-136) and adds the increments that land in its tile to the tile's 8x9 block of 64-bit
+//               accumulators with shared-memory integer atomics -- the fused kernel's 2^-22 fixed point (column x holds area,
+//               column x+1 receives height - area), so both implementations produce the same bytes, in any order
+//   row carry   `prev` / `next` of rasterizer.rs:233-250: per pixel row the exclusive sum of the row totals of the tiles on
+//               the left in the same (path, tile row) segment -- inside the CTA a segmented warp scan (warp = pixel row,
+//               lane = tile), across CTAs a decoupled look-back over the aggregates every CTA publishes for its last
+//               segment (exact integer sums: the order of the additions does not matter)
+//   emission    thread per (tile, pixel row): prefix, quantise, one 8-byte store per row (256 contiguous bytes per warp)
+// The first line of a record resumes from the DDA state the binning pass saved at the tile's entry (WalkEntry) instead of
+// walking the line again from its start.  CTAs take their index from a ticket, so a CTA only ever waits for CTAs that
+// started before it.
 // ---------------------------------------------------------------------------
-constexpr int CV_THREADS = 128;
-constexpr size_t CV_SMEM = (size_t)CV_THREADS * 128 * sizeof(float);
-
-struct SmemAcc {
-    float* base;  // &acc[tid]; element e of this thread lives at base[e * CV_THREADS]
-    __device__ __forceinline__ void add(int pix, float area, float height) {
-        base[(2 * pix) * CV_THREADS] += area;
-        base[(2 * pix + 1) * CV_THREADS] += height;
-    }
-};
-struct LineFetch {
-    const float4* lines;
-    __device__ __forceinline__ void operator()(uint32_t i, V2& a, V2& b) const {
-        float4 L = __ldg(&lines[i]);
-        a = mk(L.x, L.y);
-        b = mk(L.z, L.w);
-    }
-};
+#ifndef OC_CV_THREADS
+#define OC_CV_THREADS 128  /* config 5a rings: 0.96 ms with 64 or 128 threads, 1.45 ms with 256 (most of a CTA's time is fixed cost) */
+#endif
+constexpr int CV_THREADS = OC_CV_THREADS;
+constexpr int CV_TILES = 32;
+constexpr int CV_W = 73;  // words per tile: 8 rows x 9 columns (+ 1 pad: odd stride)
 
 __global__ void __launch_bounds__(CV_THREADS)
-k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, const uint32_t* __restrict__ group_start,
+k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals, const uint32_t* __restrict__ ridx,
+           const WalkEntry* __restrict__ entry, const uint32_t* __restrict__ group_start,
            uint32_t n_groups, uint32_t n_rec, const float4* __restrict__ lines, const uint32_t* __restrict__ g_real,
            const uint32_t* __restrict__ tile_idx, uint32_t tile_base, int16_t* __restrict__ tile_xy,
-           uint8_t* __restrict__ alpha) {
-    extern __shared__ float cv_acc[];
-    __shared__ float s_row[8][CV_THREADS];
-    __shared__ float s_carry[8];
-    __shared__ uint32_t s_flag[CV_THREADS];
-    __shared__ uint32_t s_first, s_stop;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lo = blockIdx.x * CV_THREADS;
-    const uint32_t hi = (lo + CV_THREADS < n_groups) ? lo + CV_THREADS : n_groups;
-
-    if (tid == 0) s_first = 0xffffffffu;
-    if (tid < 8) s_carry[tid] = 0.0f;
+           uint8_t* __restrict__ alpha, unsigned long long* __restrict__ pub /* per CTA: 8 aggregates, 8 inclusive prefixes */,
+           uint32_t* __restrict__ pub_flag /* per CTA: 0 nothing yet, 1 aggregate, 2 inclusive prefix */, uint32_t* __restrict__ ticket) {
+    __shared__ unsigned long long acc[CV_TILES * CV_W];
+    __shared__ long long s_tot[8][CV_TILES];    // row totals, then the carry into every tile
+    __shared__ uint32_t s_off[CV_TILES + 1], s_r0[CV_TILES], s_r1[CV_TILES], s_head[CV_TILES], s_real[CV_TILES];
+    __shared__ int s_tx[CV_TILES], s_ty[CV_TILES];
+    __shared__ uint32_t s_bid;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // ---- the CTA's tiles: records, position, segment heads, lines per tile -> item offsets (warp 0, while the others zero) -----
+    if (warp == 0) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(ticket, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (lane == 0) s_bid = b;
+        const uint32_t g = b * CV_TILES + lane;
+        uint32_t r0 = 0, r1 = 0, head = 0, real = 0, nl = 0;
+        int tx = 0, ty = 0;
+        if (g < n_groups) {
+            r0 = group_start[g];
+            r1 = group_end(group_start, g, n_groups, n_rec);
+            const uint64_t key = keys[r0];
+            tx = key_tx(key);
+            ty = key_ty(key);
+            head = (g == 0) || key_row(key) != key_row(keys[group_start[g - 1]]);
+            real = g_real[g];
+            for (uint32_t r = r0; r < r1; ++r) {
+                const uint64_t v = vals[r];
+                if (!val_wonly(v)) nl += val_nlines(v);
+            }
+        }
+        s_r0[lane] = r0;
+        s_r1[lane] = r1;
+        s_tx[lane] = tx;
+        s_ty[lane] = ty;
+        s_head[lane] = head;
+        s_real[lane] = real;
+        const uint32_t incl = warp_incl_scan(nl);
+        s_off[lane] = incl - nl;
+        if (lane == 31) s_off[CV_TILES] = incl;
+    }
+    for (uint32_t i = tid; i < CV_TILES * CV_W; i += CV_THREADS) acc[i] = 0ull;
     __syncthreads();
-    {
-        uint32_t g = lo + tid;
-        if (g < hi) {
-            bool start = (g == 0) || key_row(keys[group_start[g]]) != key_row(keys[group_start[g - 1]]);
-            if (start) atomicMin(&s_first, g);
+    const uint32_t bid = s_bid, base = bid * CV_TILES;
+
+    // ---- accumulate: one (tile, line) item per thread ------------------------------------------------------
+    const uint32_t n_items = s_off[CV_TILES];
+    for (uint32_t it = tid; it < n_items; it += CV_THREADS) {
+        uint32_t t = 0;  // the tile: largest t with s_off[t] <= it
+#pragma unroll
+        for (int d = CV_TILES / 2; d > 0; d >>= 1)
+            if (s_off[t + d] <= it) t += d;
+        uint32_t k = it - s_off[t], r = s_r0[t];
+        uint64_t v = vals[r];
+        for (;;) {  // the record that holds the tile's k-th line
+            if (!val_wonly(v)) {
+                const uint32_t n = val_nlines(v);
+                if (k < n) break;
+                k -= n;
+            }
+            v = vals[++r];
+        }
+        const float4 L = __ldg(&lines[val_line0(v) + k]);
+        if (L.x == L.z && L.y == L.w) continue;  // degenerate line slot (line_to skips it, rasterizer.rs:73)
+        const int tx = s_tx[t], ty = s_ty[t];
+        unsigned long long* const a = acc + t * CV_W;
+        LineWalk w;
+        w.init(L, tx * 8, ty * 8);  // pixel coordinates relative to the tile: inside <=> both in [0, 8)
+        float t0 = 0.0f;
+        if (k == 0) {
+            // the record's first line resumes where the binning walk entered the tile (the same rounded recurrences: the
+            // state is what a walk from the line's start reaches); the other lines of a run start inside the tile
+            const WalkEntry e = entry[ridx[r]];
+            w.row_t1 = e.row_t1;
+            w.col_t1 = e.col_t1;
+            w.x = e.x - tx * 8;
+            w.y = e.y - ty * 8;
+            t0 = e.t0;
+        }
+        float p0x = (1.0f - t0) * w.lx + t0 * w.px, p0y = (1.0f - t0) * w.ly + t0 * w.py;
+        float right = (float)(w.x + tx * 8 + 1);
+        const float right_step = (float)w.x_dir;
+        bool seen = false;
+        for (;;) {
+            const int x0 = w.x, y0 = w.y;
+            const float rt = right;
+            bool row;
+            const float t1 = w.advance(row);
+            right += row ? 0.0f : right_step;
+            const float omt = 1.0f - t1;
+            const float p1x = omt * w.lx + t1 * w.px, p1y = omt * w.ly + t1 * w.py;
+            const bool inside = ((unsigned)x0 | (unsigned)y0) < 8u;
+            if (inside) {
+                // area = 0.5 * height * ((right - p0.x) + (right - p1.x)), rasterizer.rs:108, in 2^-22 units (path_kernel.cuh)
+                const float hq = (p1y - p0y) * OC_FX_SCALE;
+                const float aq = (hq * 0.5f) * ((rt - p0x) + (rt - p1x));
+                const long long qa = (long long)__float2int_rn(aq), qh = (long long)__float2int_rn(hq);
+                atomicAdd(&a[y0 * 9 + x0], (unsigned long long)qa);
+                atomicAdd(&a[y0 * 9 + x0 + 1], (unsigned long long)(qh - qa));
+                seen = true;
+            } else if (seen) {
+                break;  // a line's increments inside one tile are contiguous (monotone walk)
+            }
+            if (t1 == 1.0f) break;
+            p0x = p1x;
+            p0y = p1y;
         }
     }
     __syncthreads();
-    const uint32_t first = s_first;
-    if (first == 0xffffffffu) return;  // every group of this range belongs to an earlier CTA's segment
 
-    float* my = cv_acc + tid;
-    SmemAcc acc{my};
-    LineFetch fetch{lines};
+    // ---- row totals: thread per (tile, pixel row) -------------------------------------------------------------
+    for (uint32_t q = tid; q < CV_TILES * 8; q += CV_THREADS) {
+        const unsigned long long* d = acc + (q >> 3) * CV_W + (q & 7u) * 9;
+        long long rs = 0;
+#pragma unroll
+        for (int x = 0; x < 9; ++x) rs += (long long)d[x];
+        s_tot[q & 7u][q >> 3] = rs;
+    }
+    __syncthreads();
 
-    for (uint32_t base = first;; base += CV_THREADS) {
-        if (tid == 0) s_stop = 0xffffffffu;
-        __syncthreads();
-        const uint32_t g = base + tid;
-        const bool in_range = g < n_groups;
-        uint64_t key = 0;
-        uint32_t r0 = 0, r1 = 0;
-        bool seg_start = false;
-        if (in_range) {
-            r0 = group_start[g];
-            r1 = group_end(group_start, g, n_groups, n_rec);
-            key = keys[r0];
-            seg_start = (g == 0) || key_row(key) != key_row(keys[group_start[g - 1]]);
-            if (g >= hi && seg_start) atomicMin(&s_stop, g);
-        }
-        s_flag[tid] = seg_start ? 1u : 0u;
-        __syncthreads();
-        const uint32_t stop = s_stop;  // first group owned by a later CTA (if it falls in this round)
-        const bool real = in_range && g < stop && g_real[g] != 0;
-        const int tx = key_tx(key), ty = key_ty(key);
-
-        if (real) {
-#pragma unroll 8
-            for (int e = 0; e < 128; ++e) my[e * CV_THREADS] = 0.0f;
-            for (uint32_t r = r0; r < r1; ++r) {
-                uint64_t v = vals[r];
-                if (!val_wonly(v)) cover_record(acc, fetch, val_line0(v), val_nlines(v), tx, ty);
+    // ---- row carry: a warp per pixel row (lane = tile): segmented scan, then the look-back across CTAs ----------------
+    constexpr int NW = CV_THREADS / 32, YPW = 8 / NW;  // pixel rows per warp
+    long long sc_v[YPW], sc_own[YPW];
+    uint32_t sc_f[YPW];
+    uint32_t has_head = 0;
+#pragma unroll
+    for (int k = 0; k < YPW; ++k) {
+        const uint32_t y = warp + (uint32_t)k * NW;
+        const long long own = s_tot[y][lane];
+        long long v = own;
+        uint32_t f = s_head[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long uv = __shfl_up_sync(0xffffffffu, v, d);
+            const uint32_t uf = __shfl_up_sync(0xffffffffu, f, d);
+            if (lane >= (uint32_t)d && !f) {
+                v += uv;
+                f |= uf;
             }
         }
-        // heights summed per pixel row: what this tile adds to the carry of the tiles on its right
+        // v: inclusive sum back to the segment head (or to the CTA's first tile), f: a head lies in that range
+        sc_v[k] = v;
+        sc_own[k] = own;
+        sc_f[k] = f;
+        has_head = __shfl_sync(0xffffffffu, f, 31);
+        // publish the last segment's sum: complete (it started in this CTA) or an aggregate still missing the CTAs before
+        if (lane == 31) pub[(size_t)bid * 16 + (has_head ? 8 : 0) + y] = (unsigned long long)v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(&pub_flag[bid], has_head ? 2u : 1u);
+#ifndef CV_NO_LOOKBACK
+#define CV_NO_LOOKBACK 0
+#endif
+    const bool continues = !CV_NO_LOOKBACK && !s_head[0] && bid > 0;  // the first tile continues a segment of earlier CTAs (uniform)
 #pragma unroll
-        for (int y = 0; y < 8; ++y) {
-            float s = 0.0f;
-            if (real) {
-#pragma unroll
-                for (int x = 0; x < 8; ++x) s += my[(2 * (y * 8 + x) + 1) * CV_THREADS];
-            }
-            s_row[y][tid] = s;
-        }
-        __syncthreads();
-        if (tid < 8) {  // exclusive, segment-restarting running sum along the row, left to right
-            float c = s_carry[tid];
-            for (int t = 0; t < CV_THREADS; ++t) {
-                if (s_flag[t]) c = 0.0f;
-                float rs = s_row[tid][t];
-                s_row[tid][t] = c;
-                c += rs;
-            }
-            s_carry[tid] = c;
-        }
-        __syncthreads();
-        if (real) {
-            const uint32_t ti = tile_base + tile_idx[g];
-            uint32_t xy = (uint32_t)(uint16_t)(int16_t)(tx * 8) | ((uint32_t)(uint16_t)(int16_t)(ty * 8) << 16);
-            reinterpret_cast<uint32_t*>(tile_xy)[ti] = xy;
-            uint4* out = reinterpret_cast<uint4*>(alpha + (size_t)ti * 64);
-#pragma unroll
-            for (int yy = 0; yy < 8; yy += 2) {
-                uint32_t w[4];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int y = yy + h;
-                    float a = s_row[y][tid];  // `prev[y]`
-                    uint32_t lo32 = 0, hi32 = 0;
-#pragma unroll
-                    for (int x = 0; x < 8; ++x) {
-                        const int pix = y * 8 + x;
-                        uint32_t q = alpha_u8(a + my[(2 * pix) * CV_THREADS]);
-                        a += my[(2 * pix + 1) * CV_THREADS];
-                        if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
-                    }
-                    w[2 * h] = lo32;
-                    w[2 * h + 1] = hi32;
+    for (int k = 0; k < YPW; ++k) {
+        const uint32_t y = warp + (uint32_t)k * NW;
+        long long cin = 0;
+        if (continues) {
+            // a window of 32 predecessors per round trip (lane i looks at CTA cur - 1 - i): the sums up to and including the
+            // nearest CTA that knows its inclusive prefix
+            for (int cur = (int)bid;; cur -= 32) {
+                const int j = cur - 1 - (int)lane;
+                uint32_t fl = 2u;  // (before the first CTA: "inclusive, nothing")
+                long long val = 0;
+                if (j >= 0) {
+                    while ((fl = *reinterpret_cast<volatile uint32_t*>(&pub_flag[j])) == 0u) __nanosleep(20);
+                    __threadfence();
+                    val = (long long)*reinterpret_cast<volatile unsigned long long*>(&pub[(size_t)j * 16 + (fl == 2u ? 8 : 0) + y]);
                 }
-                out[yy >> 1] = make_uint4(w[0], w[1], w[2], w[3]);
+                const uint32_t incl = __ballot_sync(0xffffffffu, fl == 2u);
+                const uint32_t upto = incl ? (uint32_t)__ffs((int)incl) - 1u : 31u;
+                long long part = lane <= upto ? val : 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                cin += part;
+                if (incl) break;
             }
+            // the whole CTA lies inside that segment: its inclusive prefix lets later CTAs stop here
+            if (!has_head && lane == 31) pub[(size_t)bid * 16 + 8 + y] = (unsigned long long)(cin + sc_v[k]);
         }
-        const bool last_round = (stop != 0xffffffffu) || (base + CV_THREADS >= n_groups);
-        __syncthreads();
-        if (last_round) break;
+        s_tot[y][lane] = sc_v[k] - sc_own[k] + (sc_f[k] ? 0 : cin);  // exclusive: what the tiles on the left add to this tile's rows
+    }
+    if (continues && !has_head) __threadfence();
+    __syncthreads();
+    if (tid == 0 && continues && !has_head) atomicExch(&pub_flag[bid], 2u);
+
+    // ---- quantise + emit: thread per (tile, pixel row) -> one 8-byte store ------------------------------
+    for (uint32_t q = tid; q < CV_TILES * 8; q += CV_THREADS) {
+        const uint32_t my_t = q >> 3, my_y = q & 7u, g = base + my_t;
+        if (g >= n_groups || !s_real[my_t]) continue;
+        const uint32_t ti = tile_base + tile_idx[g];
+        const unsigned long long* d = acc + my_t * CV_W + my_y * 9;
+        const float c = (float)s_tot[my_y][my_t] * OC_FX_TO_256;
+        long long run = 0;
+        uint32_t lo32 = 0, hi32 = 0;
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            run += (long long)d[x];
+            // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
+            uint32_t qv;
+            asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(qv) : "f"(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c))));
+            if (x < 4) lo32 |= qv << (8 * x); else hi32 |= qv << (8 * (x - 4));
+        }
+        reinterpret_cast<uint2*>(alpha + (size_t)ti * 64)[my_y] = make_uint2(lo32, hi32);
+        if (my_y == 0)
+            reinterpret_cast<uint32_t*>(tile_xy)[ti] = (uint32_t)(uint16_t)(int16_t)(s_tx[my_t] * 8) | ((uint32_t)(uint16_t)(int16_t)(s_ty[my_t] * 8) << 16);
     }
 }
 
@@ -881,9 +978,9 @@ struct ochre_b200_ctx {
     // per virtual command
     DevBuf d_vpath, d_line_off, d_rec_off, d_path_has_inc, d_scalars, d_scan_ws;
     // lines and records
-    DevBuf d_lines, d_keys[2], d_vals[2], d_hist;
+    DevBuf d_lines, d_keys[2], d_vals[2], d_hist, d_entry, d_ridx[2];
     // per group
-    DevBuf d_group_start, d_g_real, d_g_wd, d_tile_idx, d_span_w, d_span_idx, d_path_first;
+    DevBuf d_group_start, d_g_real, d_g_wd, d_tile_idx, d_span_w, d_span_idx, d_path_first, d_cv_pub;
     // outputs
     DevBuf o_tile_off, o_span_off, o_tile_xy, o_alpha, o_spans;
     HostBuf h_tile_off, h_span_off, h_tile_xy, h_alpha, h_spans, h_scalars;
@@ -1065,17 +1162,21 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
         CK(ctx->d_keys[b].ensure(((size_t)n_rec + 1) * 8));
         CK(ctx->d_vals[b].ensure(((size_t)n_rec + 1) * 8));
     }
+    CK(ctx->d_entry.ensure(((size_t)n_rec + 1) * sizeof(WalkEntry)));
+    for (int b = 0; b < 2; ++b) CK(ctx->d_ridx[b].ensure(((size_t)n_rec + 1) * 4));
     CK(ctx->d_hist.ensure((rp.hist_words + 1) * 4));
     CK(ctx->d_scan_ws.ensure((rp.scan_words + scan_ws_words(n_rec) + scan_ws_words(n_v)) * 4));
     uint64_t* keys2[2] = {ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>()};
     uint64_t* vals2[2] = {ctx->d_vals[0].as<uint64_t>(), ctx->d_vals[1].as<uint64_t>()};
     k_bin_scatter<<<nblk(n_v, TPB), TPB, 0, st>>>(cmd_off, cmd_lo, n_v, vpath, line_off, lines, rec_off, path_has_inc,
-                                                    keys2[0], vals2[0], ctx->band_lo, ctx->band_hi);
+                                                    keys2[0], vals2[0], ctx->d_entry.as<WalkEntry>(), ctx->band_lo, ctx->band_hi);
     launches += 1;
     CK(cudaEventRecord(ctx->ev[2], st));
     int lc = 0;
     const int sort_bits = OC_KEY_TILE_BITS + bits_for(n_paths);
-    int cur = radix_sort_pairs(st, keys2, vals2, n_rec, sort_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan_ws.as<uint32_t>(), &lc);
+    uint32_t* ridx2[2] = {ctx->d_ridx[0].as<uint32_t>(), ctx->d_ridx[1].as<uint32_t>()};
+    int cur = radix_sort_pairs(st, keys2, vals2, n_rec, sort_bits, ctx->d_hist.as<uint32_t>(), ctx->d_scan_ws.as<uint32_t>(), &lc, ridx2);
+    const uint32_t* ridx = ridx2[cur];  // sorted record -> its position before the sort (the walk entry states stay there)
     launches += lc;
     const uint64_t* keys = keys2[cur];
     const uint64_t* vals = vals2[cur];
@@ -1136,8 +1237,13 @@ int run_chunk(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* d_cmd_
     uint8_t* o_alpha = ot.alpha->as<uint8_t>();
     OchreSpan* o_spans = ot.spans->as<OchreSpan>();
     if (n_groups) {
-        k_coverage<<<nblk(n_groups, CV_THREADS), CV_THREADS, CV_SMEM, st>>>(keys, vals, group_start, n_groups, n_rec, lines,
-                                                                            g_real, tile_idx, tile_base, o_xy, o_alpha);
+        const uint32_t n_cta = nblk(n_groups, CV_TILES);
+        CK(ctx->d_cv_pub.ensure((size_t)n_cta * (16 * 8 + 4) + 64));
+        unsigned long long* pub = ctx->d_cv_pub.as<unsigned long long>();
+        uint32_t* pub_flag = reinterpret_cast<uint32_t*>(pub + (size_t)n_cta * 16);
+        CK(cudaMemsetAsync(pub_flag, 0, ((size_t)n_cta + 1) * 4, st));  // flags + the ticket behind them
+        k_coverage<<<n_cta, CV_THREADS, 0, st>>>(keys, vals, ridx, ctx->d_entry.as<WalkEntry>(), group_start, n_groups, n_rec, lines, g_real, tile_idx,
+                                                 tile_base, o_xy, o_alpha, pub, pub_flag, pub_flag + n_cta);
         launches += 1;
     }
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -1470,8 +1576,7 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
         e = cudaEventCreate(&ctx->ev[i]);
         if (e != cudaSuccess) { delete ctx; return (int)e; }
     }
-    e = cudaFuncSetAttribute(k_coverage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CV_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
+    e = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SCATTER_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pks::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pks::PK_SMEM);
@@ -1507,8 +1612,8 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
     if (ctx->st_out) cudaStreamDestroy(ctx->st_out);
     DevBuf* db[] = {&ctx->d_cmds, &ctx->d_cmd_off, &ctx->d_xf, &ctx->d_vpath, &ctx->d_line_off, &ctx->d_rec_off,
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
-                    &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
-                    &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->o_tile_off, &ctx->o_span_off,
+                    &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_entry, &ctx->d_ridx[0], &ctx->d_ridx[1], &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
+                    &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->d_cv_pub, &ctx->o_tile_off, &ctx->o_span_off,
                     &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
                     &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
@@ -1621,10 +1726,11 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
     // Mode auto, a call of few but large paths (a document: tens to hundreds of paths, hundreds of commands each): one CTA per
     // path leaves most of the GPU idle and the longest path sets the time, while the general pipeline spreads every stage over
-    // the whole device (calabi-yau 4x, 99 paths: 0.69 ms against 1.02 ms) -- such a call goes to the general pipeline as a whole.
+    // the whole device (calabi-yau 4x, 99 paths: 0.64 ms against 1.02 ms; Tiger 4x, 305 paints: 1.35 against 2.7 ms) -- such a call
+    // goes to the general pipeline as a whole.  Both implementations produce the same bytes.
     int mode = ctx->mode;
     if (mode == OCHRE_MODE_AUTO && !ctx->x_on && n_paths <= (uint32_t)ctx->sm_count * pkl::PK_CTAS_PER_SM && n_cmds >= 8192u &&
-        (uint64_t)n_cmds >= 64ull * n_paths)
+        (uint64_t)n_cmds >= 32ull * n_paths)
         mode = OCHRE_MODE_GENERAL;
     const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && mode != OCHRE_MODE_GENERAL && !banded_call;
     const bool ext = ctx->x_on;

@@ -9,7 +9,8 @@
 //                         k_radix_scatter (stable in-CTA ranking with warp match, staged
 //                                          through shared memory so each digit's run is
 //                                          written with consecutive threads)
-// HBM traffic per pass and record: 8 B (hist) + 16 B (read) + 16 B (write).
+// HBM traffic per pass and record: 8 B (hist) + 16 B (read) + 16 B (write), + 4 B each way for the optional
+// index payload (the record's position before the sort: side arrays such as the walk entry states are not moved).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,10 +45,12 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const uint64_t* __res
 __global__ void __launch_bounds__(RS_THREADS)
 k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict__ vals_in,
                 uint64_t* __restrict__ keys_out, uint64_t* __restrict__ vals_out, uint32_t n, int shift,
-                const uint32_t* __restrict__ gbase /* scanned hist */, uint32_t nblocks) {
+                const uint32_t* __restrict__ gbase /* scanned hist */, uint32_t nblocks,
+                const uint32_t* __restrict__ idx_in /* null: the identity */, uint32_t* __restrict__ idx_out /* null: no index payload */) {
     extern __shared__ unsigned char rs_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_smem);   // RS_TILE
     uint64_t* s_vals = s_keys + RS_TILE;                        // RS_TILE
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_vals + RS_TILE);  // RS_TILE: where the record was before the sort
     __shared__ uint32_t cnt[RS_WARPS][RS_RADIX];                // per-warp digit counters -> warp bases
     __shared__ uint32_t dstart[RS_RADIX];                       // CTA-local start of each digit run
     __shared__ uint32_t dglobal[RS_RADIX];                      // global base of each digit for this CTA
@@ -63,7 +66,7 @@ k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
     // warp `warp` owns items [warp*512, warp*512+512) of the tile, 32 consecutive items per round,
     // so (warp, round, lane) order == input order.
     uint64_t key[RS_ITEMS], val[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    uint32_t rank[RS_ITEMS], idx[RS_ITEMS];
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -71,6 +74,7 @@ k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
         bool ok = li < n_valid;
         key[r] = ok ? keys_in[base + li] : ~0ull;
         val[r] = ok ? vals_in[base + li] : 0ull;
+        idx[r] = (ok && idx_in) ? idx_in[base + li] : base + li;
     }
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r) {
@@ -108,6 +112,7 @@ k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
         uint32_t pos = dstart[d] + cnt[warp][d] + rank[r];
         s_keys[pos] = key[r];
         s_vals[pos] = val[r];
+        s_idx[pos] = idx[r];
     }
     __syncthreads();
 
@@ -122,6 +127,7 @@ k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint64_t* __restrict
             uint32_t dst = dglobal[d] + (pos - dstart[d]);
             keys_out[dst] = kk;
             vals_out[dst] = s_vals[pos];
+            if (idx_out) idx_out[dst] = s_idx[pos];
         }
     }
 }
@@ -138,12 +144,13 @@ inline RadixSortPlan radix_plan(uint32_t n) {
     p.scan_words = scan_ws_words(p.hist_words);
     return p;
 }
-constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * 16;
+constexpr size_t RS_SCATTER_SMEM = (size_t)RS_TILE * 20;
 
 // Sorts bits [0, nbits) of the keys.  Buffers ping-pong; returns the index (0/1) of the
 // buffer pair that holds the result.  *launches is incremented by the kernels launched.
+// idx (may be null): ping-pong buffers that receive, for every sorted record, its position before the sort.
 inline int radix_sort_pairs(cudaStream_t st, uint64_t* keys[2], uint64_t* vals[2], uint32_t n, int nbits,
-                            uint32_t* hist, uint32_t* scan_ws, int* launches) {
+                            uint32_t* hist, uint32_t* scan_ws, int* launches, uint32_t** idx = nullptr) {
     if (n == 0) return 0;
     RadixSortPlan p = radix_plan(n);
     int cur = 0;
@@ -155,7 +162,8 @@ inline int radix_sort_pairs(cudaStream_t st, uint64_t* keys[2], uint64_t* vals[2
             st, (uint32_t)p.hist_words, [hin] __device__(uint32_t i) { return hin[i]; },
             [hout] __device__(uint32_t i, uint32_t excl, uint32_t) { hout[i] = excl; }, scan_ws, nullptr);
         k_radix_scatter<<<p.nblocks, RS_THREADS, RS_SCATTER_SMEM, st>>>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1],
-                                                                         n, shift, hist, p.nblocks);
+                                                                         n, shift, hist, p.nblocks, (idx && shift > 0) ? idx[cur] : nullptr,
+                                                                         idx ? idx[cur ^ 1] : nullptr);
         *launches += 1;
         cur ^= 1;
     }

@@ -392,23 +392,32 @@ OC_HD bool val_wonly(uint64_t v) { return (v >> 63) != 0; }
 // tiles and spans depend only on the records of that row).
 #define OC_BAND_MIN (-32768)
 #define OC_BAND_MAX 32767
+// State of a line's DDA right before the first increment of a run: the coverage stage resumes the record's first line from
+// it instead of walking the line again from its start (a line of the 16384^2 rings crosses ten tiles, every one of which
+// would repeat the walk up to its own entry).  The other lines of a run start inside the run's tile.
+struct WalkEntry {
+    float row_t1, col_t1, t0;  // t0 = max(row_t0, col_t0): the t1 the previous trip consumed
+    int x, y;                  // pixel of the increment
+};
 struct CountSink {
     uint32_t n;
     int band_lo, band_hi;
-    OC_HD void emit(int, int ty, uint32_t, uint32_t, int, bool) {
+    OC_HD void emit(int, int ty, uint32_t, uint32_t, int, bool, const WalkEntry&) {
         if (ty >= band_lo && ty < band_hi) n++;
     }
 };
 struct StoreSink {
     uint64_t* keys;
     uint64_t* vals;
+    WalkEntry* entry;  // (20 bytes per record, not moved by the sort: the sorted records carry their original index)
     uint32_t path_local;
     uint32_t n;
     int band_lo, band_hi;
-    OC_HD void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly) {
+    OC_HD void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly, const WalkEntry& e) {
         if (ty < band_lo || ty >= band_hi) return;
         keys[n] = make_key(path_local, tx, ty);
         vals[n] = make_val(line0, nlines, wdelta, wonly);
+        entry[n] = e;
         n++;
     }
 };
@@ -420,6 +429,7 @@ struct RunTracker {
     int tx, ty, wdelta;
     int ptx, pty, psign;
     uint32_t line0, last_line;
+    WalkEntry ent;  // of the open run's first increment
 
     OC_HD void init() {
         have = false;
@@ -428,17 +438,22 @@ struct RunTracker {
         tx = ty = wdelta = 0;
         ptx = pty = psign = 0;
         line0 = last_line = 0;
+        ent.row_t1 = ent.col_t1 = ent.t0 = 0.0f;
+        ent.x = ent.y = 0;
     }
     OC_HD void close_run() {
-        if (have) sink.emit(tx, ty, line0, last_line - line0 + 1, wdelta, false);
+        if (have) sink.emit(tx, ty, line0, last_line - line0 + 1, wdelta, false, ent);
         have = false;
     }
     OC_HD void flush_pend() {
-        if (pend) sink.emit(ptx, pty, 0, 0, psign, true);
+        if (pend) {
+            WalkEntry none = {0.0f, 0.0f, 0.0f, 0, 0};
+            sink.emit(ptx, pty, 0, 0, psign, true, none);
+        }
         pend = false;
     }
-    // an increment of line `line` lands on pixel (x, y)
-    OC_HD void on_inc(uint32_t line, int x, int y) {
+    // an increment of line `line` lands on pixel (x, y); e = the walk's state right before it
+    OC_HD void on_inc(uint32_t line, int x, int y, const WalkEntry& e) {
         int ntx = x >> 3, nty = y >> 3;
         any_inc = true;
         if (!have || ntx != tx || nty != ty || line - line0 >= OC_MAX_RUN_LINES) {
@@ -447,6 +462,7 @@ struct RunTracker {
             tx = ntx;
             ty = nty;
             line0 = line;
+            ent = e;
             wdelta = 0;
             if (pend) {
                 if (ptx == tx && pty == ty) {
@@ -482,8 +498,14 @@ struct RunTracker {
         w.init(a, b);
         for (;;) {
             int ix, iy;
+            WalkEntry e;
+            e.row_t1 = w.row_t1;
+            e.col_t1 = w.col_t1;
+            e.t0 = fmaxf(w.row_t0, w.col_t0);
+            e.x = w.x;
+            e.y = w.y;
             bool done = w.step_cells(ix, iy);
-            on_inc(line, ix, iy);
+            on_inc(line, ix, iy, e);
             if (w.ti_sign != 0) on_tinc(w.ti_tx, w.ti_ty, w.ti_sign);
             if (done) break;
         }

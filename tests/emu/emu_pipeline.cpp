@@ -26,7 +26,7 @@ struct VecSink {
     std::vector<uint64_t>* vals;
     uint32_t path_local;
     int band_lo, band_hi;
-    void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly) {
+    void emit(int tx, int ty, uint32_t line0, uint32_t nlines, int wdelta, bool wonly, const WalkEntry&) {
         if (ty < band_lo || ty >= band_hi) return;
         keys->push_back(make_key(path_local, tx, ty));
         vals->push_back(make_val(line0, nlines, wdelta, wonly));
@@ -109,7 +109,7 @@ EmuResult* emu_rasterize_band(const OchreCmd* cmds_, const uint32_t* cmd_off, co
             vcmd_for_each_line(c, f);
             trk.finish();
             has_inc = has_inc || trk.any_inc;
-            if (j == nc && !has_inc) trk.sink.emit(0, 0, 0u, 0u, 0, false);
+            if (j == nc && !has_inc) trk.sink.emit(0, 0, 0u, 0u, 0, false, WalkEntry{0.0f, 0.0f, 0.0f, 0, 0});
         }
     }
     // sort (stable)
