@@ -1724,14 +1724,17 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
     const bool banded_call = ctx->band_lo != OC_BAND_MIN || ctx->band_hi != OC_BAND_MAX;
     // unordered results come straight out of the fused kernel's arena; the general pipeline always orders
-    // Mode auto, a call of few but large paths (a document: tens to hundreds of paths, hundreds of commands each): one CTA per
-    // path leaves most of the GPU idle and the longest path sets the time, while the general pipeline spreads every stage over
+    // Mode auto, a call of few paths (less than one wave of CTAs) with a large one among them (a document: tens to hundreds of
+    // paints, some of thousands of commands): one CTA per path leaves most of the GPU idle and the longest path sets the time --
+    // or is handed over anyway, after the fused kernel has run --, while the general pipeline spreads every stage over
     // the whole device (calabi-yau 4x, 99 paths: 0.64 ms against 1.02 ms; Tiger 4x, 305 paints: 1.35 against 2.7 ms) -- such a call
     // goes to the general pipeline as a whole.  Both implementations produce the same bytes.
     int mode = ctx->mode;
-    if (mode == OCHRE_MODE_AUTO && !ctx->x_on && n_paths <= (uint32_t)ctx->sm_count * pkl::PK_CTAS_PER_SM && n_cmds >= 8192u &&
-        (uint64_t)n_cmds >= 32ull * n_paths)
-        mode = OCHRE_MODE_GENERAL;
+    if (mode == OCHRE_MODE_AUTO && !ctx->x_on && n_paths <= (uint32_t)ctx->sm_count * pkl::PK_CTAS_PER_SM) {
+        uint32_t biggest = 0;  // (a batch of less than one wave of CTAs: the largest path decides)
+        for (uint32_t p = 0; p < n_paths; ++p) biggest = std::max(biggest, h_off[p + 1] - h_off[p]);
+        if (biggest >= 2048u) mode = OCHRE_MODE_GENERAL;
+    }
     const bool unordered = (flags & OCHRE_OUT_UNORDERED) != 0 && mode != OCHRE_MODE_GENERAL && !banded_call;
     const bool ext = ctx->x_on;
     if (ext && !(out_dev && unordered)) {
