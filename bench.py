@@ -234,6 +234,17 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def byte_sum(torch, ptr: int, nbytes: int) -> int:
+    """Sum of the bytes of ctx-owned device memory, in pieces: a one-shot `sum(dtype=int64)` over 10 GB lets torch cache an
+    80 GB temporary, which then starves the library's own cudaMalloc calls."""
+    total, piece = 0, 256 << 20
+    for o in range(0, nbytes, piece):
+        n = min(piece, nbytes - o)
+        total += int(torch.as_tensor(CudaArray(ptr + o, n), device="cuda").sum(dtype=torch.int64).item())
+    torch.cuda.empty_cache()
+    return total
+
+
 class CudaArray:
     """Minimal __cuda_array_interface__ holder so torch can view ctx-owned device memory."""
 
@@ -251,6 +262,8 @@ def main():
     ap.add_argument("--ref-paths", type=int, default=0, help="paths per step of the CPU reference arm (0: the whole batch if it fits the time budget)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="paths in the cpu_baseline sample (0 = auto, ~15 s)")
     ap.add_argument("--no-gather", action="store_true", help="N>1: leave each rank's tiles on its own GPU")
+    ap.add_argument("--compress", action="store_true", help="N>1: row-compressed gather (constant halves of the tiles stay at home, GPU 0 fills them in); "
+                    "measured in round 2: no gain at N = 8 (71.5 vs 71.1 M paths/s), a loss at N = 4 (60 vs 77 M) -- off by default, see DESIGN.md section 7")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
@@ -363,38 +376,72 @@ def main():
         # One local run sizes the slices; GPU 0 allocates the arena and hands its IPC handle round; from then on every
         # rank's fused kernel stores its alpha tiles into its slice of GPU 0's memory while it rasterises.
         r = g4.device_call(ctx)
-        local_sum = int(torch.as_tensor(CudaArray(r.device_ptrs["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64]
-                        .sum(dtype=torch.int64).item())
+        local_sum = byte_sum(torch, r.device_ptrs["alpha"], r.n_tiles * 64)
         mine = torch.tensor([r.n_tiles, r.n_spans, P, local_sum], dtype=torch.int64, device="cuda")
         allc = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
         allc = torch.stack(allc).cpu().numpy()
-        # (3 % of slack: the arena also takes the sub-batches of the 10 M-path workload, other ranges of the same generator)
-        t_cap = [int(v * 1.03) + 4096 for v in allc[:, 0]]
-        s_cap = [int(v * 1.03) + 4096 for v in allc[:, 1]]
-        t_start = np.concatenate([[0], np.cumsum(t_cap)]).astype(np.int64)
-        s_start = np.concatenate([[0], np.cumsum(s_cap)]).astype(np.int64)
-        p_start = np.concatenate([[0], np.cumsum(allc[:, 2])]).astype(np.int64)
-        caps = (int(t_start[-1]), int(s_start[-1]), int(p_start[-1]))
-        box = [None]
-        if rank == 0:
-            arena = ctx.arena_create(*caps)
-            box[0] = arena.handle
+        # (2 % of slack: the arena also takes the sub-batches of the 10 M-path workload, other ranges of the same generator)
+        box = [None, None]
+        for slack in (1.02, 1.002):
+            t_cap = [int(v * slack) + 4096 for v in allc[:, 0]]
+            s_cap = [int(v * slack) + 4096 for v in allc[:, 1]]
+            t_start = np.concatenate([[0], np.cumsum(t_cap)]).astype(np.int64)
+            s_start = np.concatenate([[0], np.cumsum(s_cap)]).astype(np.int64)
+            p_start = np.concatenate([[0], np.cumsum(allc[:, 2])]).astype(np.int64)
+            caps = (int(t_start[-1]), int(s_start[-1]), int(p_start[-1]))
+            if rank == 0:
+                torch.cuda.empty_cache()
+                try:
+                    arena = ctx.arena_create(*caps)
+                    box = [arena.handle, slack]
+                    break
+                except Exception as exc:  # noqa: BLE001
+                    free, total = torch.cuda.mem_get_info()
+                    print(f"bench.py: arena of {caps[0] * 70 / 1e9:.1f} GB refused ({exc}); device memory free {free / 1e9:.1f} of {total / 1e9:.1f} GB",
+                          file=sys.stderr, flush=True)
+            else:
+                break
         dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            raise SystemExit("bench.py: GPU 0 cannot hold the gather arena")
         if rank != 0:
+            slack = box[1]
+            t_cap = [int(v * slack) + 4096 for v in allc[:, 0]]
+            s_cap = [int(v * slack) + 4096 for v in allc[:, 1]]
+            t_start = np.concatenate([[0], np.cumsum(t_cap)]).astype(np.int64)
+            s_start = np.concatenate([[0], np.cumsum(s_cap)]).astype(np.int64)
+            caps = (int(t_start[-1]), int(s_start[-1]), int(p_start[-1]))
             arena = ctx.arena_open(box[0], *caps)
         arena_info = {"allc": allc, "t_start": t_start, "s_start": s_start, "p_start": p_start, "bytes": int(arena.c.bytes),
                       "t_cap": t_cap, "s_cap": s_cap}
 
+    compress = gather and args.compress
+
     def arena_on():
         ctx.set_output_arena(arena, int(arena_info["t_start"][rank]), arena_info["t_cap"][rank], int(arena_info["s_start"][rank]),
                              arena_info["s_cap"][rank], int(arena_info["p_start"][rank]), P)
+        ctx.arena_compress(compress and rank != 0)  # (GPU 0's own stores are local)
+
+    def gathered_call(fn):
+        """One gathered step: every rank rasterises into its slice of GPU 0's arena; with the row-compressed gather GPU 0 then
+        fills in the rows that did not travel -- after a barrier (the producers are done) and before another (nobody overwrites
+        a slice that is being expanded)."""
+        r = fn()
+        if compress:
+            dist.barrier()
+            if rank == 0:
+                for q in range(1, world):
+                    ctx.arena_expand(arena, int(arena_info["t_start"][q]), arena_info["t_cap"][q])
+            dist.barrier()
+        return r
 
     # ---- value: device-resident ---------------------------------------------------------
     if gather:
         arena_on()
+    step_fn = (lambda: gathered_call(lambda: g4.device_call(ctx))) if gather else (lambda: g4.device_call(ctx))
     for _ in range(args.warmup):
-        res = g4.device_call(ctx)
+        res = step_fn()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -404,7 +451,7 @@ def main():
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = g4.device_call(ctx)
+        res = step_fn()
         stage_ms += np.array(res.stage_ms)
         launches += res.kernel_launches
         dev_ms += res.device_ms
@@ -430,8 +477,7 @@ def main():
             for q in range(world):
                 rg = ctx.to_host(arena.ptrs["ranges"] + 16 * int(arena_info["p_start"][q]), 16 * P, np.uint32).reshape(P, 4)
                 nt_q = int(rg[:, 1].astype(np.int64).sum())
-                a = torch.as_tensor(CudaArray(arena.ptrs["alpha"] + 64 * int(arena_info["t_start"][q]), max(nt_q * 64, 1)), device="cuda")
-                sum_q = int(a[: nt_q * 64].sum(dtype=torch.int64).item())
+                sum_q = byte_sum(torch, arena.ptrs["alpha"] + 64 * int(arena_info["t_start"][q]), nt_q * 64)
                 ok = ok and nt_q == int(arena_info["allc"][q, 0]) and sum_q == int(arena_info["allc"][q, 3])
             gather_check = {"slices": world, "tile_counts_and_alpha_sums_match_local_runs": bool(ok), "arena_GB": arena_info["bytes"] / 1e9}
             if not ok:
@@ -608,8 +654,7 @@ def main():
             whole = call()
             whole_sum = None
             if world > 1:
-                whole_sum = int(torch.as_tensor(CudaArray(whole.device_ptrs["alpha"], max(whole.n_tiles * 64, 1)), device="cuda")[: whole.n_tiles * 64]
-                                .sum(dtype=torch.int64).item())
+                whole_sum = byte_sum(torch, whole.device_ptrs["alpha"], whole.n_tiles * 64)
                 rows = (0, 16384 // 8)
                 bands = sharding.plan_row_bands(rows[0], rows[1], world, sharding.band_weights_from_bbox(c, x, rows[0], rows[1]))
                 lo, hi = bands[rank]
@@ -664,7 +709,7 @@ def main():
                 tot.update(t=0, s=0, c=0)
                 r = None
                 for a, z in zip(cuts[:-1], cuts[1:]):
-                    r = b.device_call(ctx, a, z)
+                    r = gathered_call(lambda: b.device_call(ctx, a, z)) if gather else b.device_call(ctx, a, z)
                     tot["t"] += r.n_tiles
                     tot["s"] += r.n_spans
                     tot["c"] += r.n_cmds
@@ -723,7 +768,9 @@ def main():
                 "lines_per_gpu": int(res.n_lines), "bin_records_per_gpu": int(res.n_records), "tiles_total": int(tiles_total),
                 "spans_total": int(spans_total), "tiles_per_s": tps, "alpha_MB_per_s": tps * 64e-6, "chunks": int(res.n_chunks),
                 "parallelism": f"path-batch x{world}" + ((", tiles gathered to GPU 0 inside the kernel: alpha stores go to an arena in GPU 0's memory over NVLink (CUDA IPC peer "
-                                                              "mapping), origins / spans / ranges follow by peer copy behind the kernels") if gather else ""),
+                                                              "mapping), origins / spans / ranges follow by peer copy behind the kernels"
+                                                              + ("; row-compressed: constant pixel rows (all 0 / all 255) stay at home, 2 bytes of row classes per tile travel "
+                                                                 "instead, GPU 0 fills the rows in after a barrier (inside the timed region)" if compress else "")) if gather else ""),
                 "layout": "per-path lists in completion order + per-path (start, count) ranges (OCHRE_OUT_UNORDERED); `ordered` = the same step with path-ordered lists",
                 "ordered": ordered,
                 "l2": "inputs (%.2f GB) and every intermediate exceed the 126 MB L2; no flush needed" % (n_cmds * 28 / 1e9),

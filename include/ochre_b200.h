@@ -192,6 +192,16 @@ int ochre_b200_arena_close(ochre_b200_ctx* ctx, OchreArena* arena);
 int ochre_b200_set_output_arena(ochre_b200_ctx* ctx, const OchreArena* arena, uint64_t tile_start, uint64_t tile_cap,
                                 uint64_t span_start, uint64_t span_cap, uint64_t path_start, uint64_t path_cap);
 
+/* Row-compressed gather.  The NVLink ingress of the arena's owner is the wall of an 8-GPU gather, and
+ * 30 % of the 32-byte halves of a boundary tile are constant (4 pixel rows all 0 outside the shape, or all 255 inside).  With
+ * compression on, a producer's kernel stores only the other halves into the arena plus 2 bytes of row classes per tile (whole
+ * halves, so that the owner fills whole sectors in and never read-modify-writes); when the producers' calls
+ * have returned (and a barrier has passed), the owner calls ochre_b200_arena_expand on every compressed slice: a streaming pass
+ * over its own memory that fills the constant rows in.  After that the slice holds exactly the uncompressed bytes.
+ * (The owner's own slice needs neither: its stores are local.) */
+int ochre_b200_arena_compress(ochre_b200_ctx* ctx, int on);
+int ochre_b200_arena_expand(ochre_b200_ctx* ctx, const OchreArena* arena, uint64_t tile_start, uint64_t n_tiles);
+
 /* Synchronous device -> host copy of `bytes` bytes on the ctx's device (reading back an arena or an OCHRE_OUT_DEVICE result). */
 int ochre_b200_copy_to_host(ochre_b200_ctx* ctx, void* dst, const void* src_device, uint64_t bytes);
 

@@ -27,6 +27,7 @@ SYMBOLS = [
     "ochre_b200_stroke_path", "ochre_b200_flatten_path", "ochre_b200_free", "ochre_b200_debug_lines",
     "ochre_b200_debug_records", "ochre_b200_debug_stroked", "ochre_b200_debug_stroker_ms", "ochre_b200_version",
     "ochre_b200_set_host_sink", "ochre_b200_last_sink", "ochre_b200_path_status",
+    "ochre_b200_arena_compress", "ochre_b200_arena_expand",
 ]
 
 
@@ -113,6 +114,8 @@ def load():
     L.ochre_b200_set_host_sink.argtypes = [vp, u32]
     L.ochre_b200_last_sink.argtypes = [vp, C.POINTER(OchreSinkSum)]
     L.ochre_b200_path_status.argtypes = [vp, C.POINTER(vp), C.POINTER(u32)]
+    L.ochre_b200_arena_compress.argtypes = [vp, C.c_int]
+    L.ochre_b200_arena_expand.argtypes = [vp, C.POINTER(OchreArena), u64, u64]
     for f in SYMBOLS:
         getattr(L, f)  # AttributeError here = the library does not export what the header declares
     _lib = L

@@ -317,6 +317,14 @@ class Context:
             _check(self._h, L.ochre_b200_set_output_arena(self._h, C.byref(arena.c), tile_start, tile_cap, span_start, span_cap,
                                                           path_start, path_cap))
 
+    def arena_compress(self, on: bool):
+        """Row-compressed gather: this ctx's kernel stores only the non-constant rows of its tiles into the arena (+ 2 bytes of
+        row classes per tile); the arena's owner fills the rest in with `arena_expand` once the producers are done."""
+        _check(self._h, _lib.load().ochre_b200_arena_compress(self._h, 1 if on else 0))
+
+    def arena_expand(self, arena: "Arena", tile_start: int, n_tiles: int):
+        _check(self._h, _lib.load().ochre_b200_arena_expand(self._h, C.byref(arena.c), int(tile_start), int(n_tiles)))
+
     def to_host(self, dev_ptr: int, nbytes: int, dtype=np.uint8) -> np.ndarray:
         """Synchronous device -> host copy of raw device memory (arenas, out_device results)."""
         out = np.empty(nbytes, np.uint8)

@@ -985,7 +985,25 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                     }
                     const uint32_t ti = tile_at + rank0 + s;
-                    __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
+                    if (A.row_class) {
+                        // row-compressed gather: constant rows do not travel; the 8 lanes of a tile assemble its class word
+                        // (the lanes of a tile are 8 consecutive, aligned lanes: all in this trip or none)
+                        // A row stays at home only if the whole 32-byte half of the tile (4 rows) is the same constant: the owner
+                        // then fills whole sectors in (a lone constant row would cost it a read-modify-write of its sector, more
+                        // than the row saves on the wire).
+                        const uint32_t act = __activemask();
+                        uint32_t cls = (lo32 | hi32) == 0u ? 0u : ((lo32 & hi32) == 0xffffffffu ? 1u : 2u);
+                        const uint32_t c1 = __shfl_xor_sync(act, cls, 1), c2 = __shfl_xor_sync(act, cls, 2), c3 = __shfl_xor_sync(act, c1, 2);
+                        if (!(cls == c1 && cls == c2 && cls == c3)) cls = 2u;
+                        if (cls == 2u) __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
+                        uint32_t w = cls << (2u * y);
+                        w |= __shfl_xor_sync(act, w, 1);
+                        w |= __shfl_xor_sync(act, w, 2);
+                        w |= __shfl_xor_sync(act, w, 4);
+                        if (y == 0) A.row_class[ti] = (uint16_t)w;
+                    } else {
+                        __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)ti * 64) + y, make_uint2(lo32, hi32));
+                    }
                 }
             }
         };
@@ -1056,6 +1074,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             if (empty && !fallback && fits) {
                 if (tid < 16) reinterpret_cast<uint32_t*>(A.alpha + (size_t)tile_at * 64)[tid] = 0u;
                 if (tid == 0) reinterpret_cast<uint32_t*>(A.tile_xy)[tile_at] = 0u;
+                if (tid == 0 && A.row_class) A.row_class[tile_at] = (uint16_t)OC_ROWS_ALL_STORED;
             }
         }
     }

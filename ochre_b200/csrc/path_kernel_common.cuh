@@ -42,7 +42,11 @@ struct PathKernelArgs {
     const uint32_t* n_paths_dev;  // non-null: the number of list entries to take is read from device memory (classified lists)
     uint32_t list_rev;          // 1: the list is path_list[n_paths - 1], path_list[n_paths - 2], ... (the large end of a two-ended list)
     int8_t* path_status;        // null, or per path (chunk-local id): the OCHRE_E_* code a path with an invalid command is dropped for
+    uint16_t* row_class;        // null, or per tile (same index as alpha): 2 bits per pixel row -- 0: all 0, 1: all 255, 2: stored.  Rows of
+                                // class 0 / 1 are NOT stored: the arena's owner fills them in (k_arena_expand).  Whole 4-row halves only:
+                                // 30 % of the halves of a G4 batch are constant (46 % of its rows)
 };
+#define OC_ROWS_ALL_STORED 0xaaaau
 
 enum : uint32_t { CF_TOUCHED = 1, CF_WIND = 2, CF_SPAN = 4 };
 

@@ -721,6 +721,10 @@ __global__ void k_words_to_host(const uint32_t* __restrict__ src, volatile uint3
 __global__ void k_ctl_reset(uint32_t* __restrict__ ctl, uint32_t n, uint32_t cursor_at, uint32_t cur_t, uint32_t cur_s) {
     if (threadIdx.x < n) ctl[threadIdx.x] = threadIdx.x == cursor_at ? cur_t : threadIdx.x == cursor_at + 1 ? cur_s : 0u;
 }
+__global__ void __launch_bounds__(256) k_fill_u16(uint16_t* __restrict__ p, uint32_t n, uint16_t v) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 __global__ void k_set_words2(uint32_t* __restrict__ a, uint32_t va, uint32_t* __restrict__ b, uint32_t vb) {
     *a = va;
     *b = vb;
@@ -1007,6 +1011,7 @@ struct ochre_b200_ctx {
     long l2_setaside_mb = -1;
     uint64_t fb_paths = 0;  // paths the fused kernel left to the general pipeline in the last call  // ctl: ticket(1) cursor(2) status(3) words
     DevBuf s_tile_xy, s_alpha, s_spans;        // staging arena of the fused kernel (completion order)
+    DevBuf s_row_class;                         // row classes of a compressed gather: written at home, sent in bulk behind the kernels
     HostBuf h_pk_ctl;
     // device stroker (csrc/stroke_kernels.cuh): inputs, widths, flattened polygons, the batch handed to the rasteriser
     DevBuf k_cmds, k_off, k_xf, k_width, k_foff, k_flat_off, k_fpt, k_ftag, k_flags, k_closes, k_con_start, k_con_len, k_con_pc, k_item_off,
@@ -1021,6 +1026,8 @@ struct ochre_b200_ctx {
     int16_t* x_tile_xy = nullptr;
     OchreSpan* x_spans = nullptr;
     OchrePathRange* x_ranges = nullptr;
+    uint16_t* x_row_class = nullptr;  // row classes of the slice (row-compressed gather)
+    bool x_compress = false;          // ochre_b200_arena_compress: constant rows are not stored, the arena's owner fills them in
     uint64_t x_tile_cap = 0, x_span_cap = 0, x_path_cap = 0;
     uint32_t used_paths = 0;  // bit 0: fused kernel, bit 1: general pipeline
     double tiles_per_cmd = 4.0, spans_per_cmd = 0.75;  // arena growth estimates, refined every call
@@ -1358,6 +1365,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.list_rev = 0;
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
         A.path_status = pstatus;
+        if (ext && ctx->x_compress) CK(ctx->s_row_class.ensure(ctx->s_tile_xy.cap / 2, base_t > 0, st));
+        A.row_class = (ext && ctx->x_compress) ? ctx->s_row_class.as<uint16_t>() : nullptr;
         CK(cudaEventRecord(ctx->ev[0], st));
         if (route) {
             uint32_t* list = ctx->d_pk_list.as<uint32_t>();
@@ -1485,6 +1494,8 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             if (co2.n_tiles) {
                 CK(cudaMemcpyAsync(ctx->s_tile_xy.as<uint32_t>() + nt, ctx->f_tile_xy.p, (size_t)co2.n_tiles * 4, cudaMemcpyDeviceToDevice, st));
                 CK(cudaMemcpyAsync((ext ? ctx->x_alpha : ctx->s_alpha.as<uint8_t>()) + (size_t)nt * 64, ctx->f_alpha.p, (size_t)co2.n_tiles * 64, cudaMemcpyDeviceToDevice, st));
+                if (ext && ctx->x_compress)  // handed-over paths arrive as whole tiles
+                    k_fill_u16<<<nblk(co2.n_tiles, 256), 256, 0, st>>>(ctx->s_row_class.as<uint16_t>() + nt, co2.n_tiles, (uint16_t)OC_ROWS_ALL_STORED);
             }
             if (co2.n_spans)
                 CK(cudaMemcpyAsync(ctx->s_spans.as<OchreSpan>() + ns, ctx->f_spans.p, (size_t)co2.n_spans * sizeof(OchreSpan), cudaMemcpyDeviceToDevice, st));
@@ -1571,7 +1582,7 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_g[1]);
     if (e != cudaSuccess) { delete ctx; return (int)e; }
     ctx->o_tile_xy.guard = ctx->o_alpha.guard = ctx->o_spans.guard = ctx->o_tile_off.guard = ctx->o_span_off.guard = ctx->st_out;
-    ctx->s_tile_xy.guard = ctx->s_alpha.guard = ctx->s_spans.guard = ctx->d_pk_rec.guard = ctx->st_out;
+    ctx->s_tile_xy.guard = ctx->s_alpha.guard = ctx->s_spans.guard = ctx->s_row_class.guard = ctx->d_pk_rec.guard = ctx->st_out;
     for (int i = 0; i <= N_STAGE; ++i) {
         e = cudaEventCreate(&ctx->ev[i]);
         if (e != cudaSuccess) { delete ctx; return (int)e; }
@@ -1614,7 +1625,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_entry, &ctx->d_ridx[0], &ctx->d_ridx[1], &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->d_cv_pub, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans, &ctx->s_row_class,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
                     &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
                     &ctx->k_nout, &ctx->k_out_off, &ctx->k_out};
@@ -1914,6 +1925,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             // path ranges follow on the download stream while the next chunk is rasterised
             const size_t t0 = tile_base, nt = co.n_tiles, s0 = span_base, ns = co.n_spans;
             if (nt) CK(cudaMemcpyAsync(ctx->x_tile_xy + 2 * t0, ctx->s_tile_xy.as<int16_t>() + 2 * t0, nt * 4, cudaMemcpyDeviceToDevice, ctx->st_out));
+            if (nt && ctx->x_compress)
+                CK(cudaMemcpyAsync(ctx->x_row_class + t0, ctx->s_row_class.as<uint16_t>() + t0, nt * 2, cudaMemcpyDeviceToDevice, ctx->st_out));
             if (ns) CK(cudaMemcpyAsync(ctx->x_spans + s0, ctx->s_spans.as<OchreSpan>() + s0, ns * sizeof(OchreSpan), cudaMemcpyDeviceToDevice, ctx->st_out));
             CK(cudaMemcpyAsync(ctx->x_ranges + p0, ctx->d_pk_rec.as<OchrePathRange>() + p0, (size_t)(p1 - p0) * sizeof(OchrePathRange),
                                cudaMemcpyDeviceToDevice, ctx->st_out));
@@ -2250,7 +2263,9 @@ int ochre_b200_debug_stroked(ochre_b200_ctx* ctx, OchreCmd* cmds, uint64_t cap, 
 }
 
 // ---- output arenas: the gather to one GPU, fused into the kernel's stores ---------------------------
-static void arena_layout(OchreArena* a) {
+// Layout of an arena: alpha | tile origins | spans | ranges | row classes (2 bytes per tile, row-compressed gather).  Returns the
+// offset of the row classes (the struct has no field for them: it is part of the ABI).
+static uint64_t arena_layout(OchreArena* a) {
     unsigned char* b = static_cast<unsigned char*>(a->base);
     auto up = [](uint64_t v) { return (v + 255u) & ~(uint64_t)255u; };
     uint64_t o = 0;
@@ -2262,7 +2277,31 @@ static void arena_layout(OchreArena* a) {
     o = up(o + sizeof(OchreSpan) * a->cap_spans);
     a->ranges = reinterpret_cast<OchrePathRange*>(b + o);
     o = up(o + sizeof(OchrePathRange) * a->cap_paths);
+    const uint64_t cls = o;
+    o = up(o + 2 * a->cap_tiles);
     a->bytes = o + 256;
+    return cls;
+}
+static uint16_t* arena_row_class(const OchreArena* a) {
+    OchreArena t = *a;
+    const uint64_t off = arena_layout(&t);
+    return reinterpret_cast<uint16_t*>(static_cast<unsigned char*>(a->base) + off);
+}
+
+// Row-compressed gather, the owner's side: fills in the halves the producers did not send (4 rows of class 0: all 0, or of
+// class 1: all 255).  Thread per 32-byte half of a tile: two 16-byte stores, whole sectors.
+__global__ void __launch_bounds__(256)
+k_arena_expand(uint4* __restrict__ alpha /* 4 per tile */, const uint16_t* __restrict__ row_class, uint64_t n_halves) {
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n_halves; i += (uint64_t)gridDim.x * 256) {
+        const uint32_t c = ((uint32_t)__ldg(&row_class[i >> 1]) >> (8u * (uint32_t)(i & 1u))) & 0xffu;  // the half's four row classes
+        if (c == 0x00u) {
+            alpha[2 * i] = make_uint4(0u, 0u, 0u, 0u);
+            alpha[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+        } else if (c == 0x55u) {
+            alpha[2 * i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            alpha[2 * i + 1] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        }
+    }
 }
 
 int ochre_b200_arena_create(ochre_b200_ctx* ctx, uint64_t cap_tiles, uint64_t cap_spans, uint64_t cap_paths, OchreArena* out) {
@@ -2353,9 +2392,34 @@ int ochre_b200_set_output_arena(ochre_b200_ctx* ctx, const OchreArena* arena, ui
     ctx->x_tile_xy = arena->tile_xy + 2 * tile_start;
     ctx->x_spans = arena->spans + span_start;
     ctx->x_ranges = arena->ranges + path_start;
+    ctx->x_row_class = arena_row_class(arena) + tile_start;
     ctx->x_tile_cap = tile_cap;
     ctx->x_span_cap = span_cap;
     ctx->x_path_cap = path_cap;
+    return 0;
+}
+
+int ochre_b200_arena_compress(ochre_b200_ctx* ctx, int on) {
+    if (!ctx) return OCHRE_E_INVALID_ARG;
+    ctx->x_compress = on != 0;
+    return 0;
+}
+
+int ochre_b200_arena_expand(ochre_b200_ctx* ctx, const OchreArena* arena, uint64_t tile_start, uint64_t n_tiles) {
+    if (!ctx || !arena || !arena->base) return OCHRE_E_INVALID_ARG;
+    ctx->err.clear();
+    if (tile_start + n_tiles > arena->cap_tiles) {
+        ctx->err = "tile range outside the arena";
+        return OCHRE_E_INVALID_ARG;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (n_tiles) {
+        const uint64_t n_halves = n_tiles * 2;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_halves + 255) / 256, (uint64_t)ctx->sm_count * 64);
+        k_arena_expand<<<grid, 256, 0, ctx->st>>>(reinterpret_cast<uint4*>(arena->alpha + 64 * tile_start), arena_row_class(arena) + tile_start, n_halves);
+        CK(cudaStreamSynchronize(ctx->st));
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 

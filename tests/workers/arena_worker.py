@@ -19,6 +19,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     n_per = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    compress = len(sys.argv) > 3 and sys.argv[3] == "compress"  # row-compressed gather: constant rows stay at home, rank 0 fills them in
     dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only: counts and the 64-byte handle
     dev = rank % torch.cuda.device_count()
     ctx = ob.Context(dev)
@@ -55,6 +56,8 @@ def main():
         arena = ctx.arena_open(box[0], *caps)
     ctx.set_output_arena(arena, int(t_start[rank]), counts[rank][0] + 16, int(s_start[rank]), counts[rank][1] + 16,
                          int(p_start[rank]), n_paths)
+    if compress:
+        ctx.arena_compress(True)
     for _ in range(2):  # twice: the slice is simply overwritten
         r = ctx.rasterize(c, o, x, out_device=True, unordered=True)
     assert (r.n_tiles, r.n_spans) == (local.n_tiles, local.n_spans)
@@ -70,6 +73,9 @@ def main():
                          int(p_start[rank]), n_paths)
     r = ctx.rasterize(c, o, x, out_device=True, unordered=True)
     dist.barrier()
+    if compress and rank == 0:  # the producers are done: the owner fills in the rows that did not travel
+        for q in range(world):
+            ctx.arena_expand(arena, int(t_start[q]), counts[q][0])
     # every rank ships its expected result to rank 0 over the control plane
     exp = [None] * world
     dist.gather_object((local.tile_off, local.span_off, local.tile_xy, local.alpha, local.spans), exp if rank == 0 else None, dst=0)
@@ -81,7 +87,7 @@ def main():
             assert np.array_equal(got.tile_xy, xy), f"slice {q}: tile origins"
             assert np.array_equal(got.alpha, alpha), f"slice {q}: alpha"
             assert got.spans.tobytes() == spans.tobytes(), f"slice {q}: spans"
-        print(f"arena ok: {world} ranks on {torch.cuda.device_count()} GPU(s), {caps[0]} tile slots, used paths {r.used}")
+        print(f"arena ok: {world} ranks on {torch.cuda.device_count()} GPU(s), {caps[0]} tile slots, used paths {r.used}" + (", row-compressed" if compress else ""))
     dist.barrier()
     ctx.set_output_arena(None)
     arena.close()
