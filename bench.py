@@ -268,7 +268,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--workloads", default="all", help="'all', 'none' or a comma list of: c1x1M, svg64, glyphs100k, glyphs1M, rings5a, g4x10M")
+    ap.add_argument("--workloads", default="all", help="'all', 'none' or a comma list of: c1x1M, svg64, glyphs100k, glyphs1M, rings5a, rings5a_dense, g4x10M")
     ap.add_argument("--big-paths", type=int, default=10_000_000, help="paths of the g4x10M workload (config 5b), all ranks together")
     args = ap.parse_args()
 
@@ -496,6 +496,166 @@ def main():
         ug_ms, _ = timed(lambda: g4.device_call(ctx), 1, side_steps)
         ungathered = {"value": paths_total / (ug_ms * 1e-3), "unit": "paths/s", "ms_per_step": ug_ms, "steps": side_steps}
 
+    # ---- the other BASELINE configs ---------------------------------------------------------------------------------
+    peak, peak_src = peaks()
+    want = args.workloads.split(",") if args.workloads not in ("all", "none") else (
+        ["g4x10M", "c1x1M", "svg64", "glyphs100k", "glyphs1M", "rings5a", "rings5a_dense"] if args.workloads == "all" else [])
+    want = sorted(want, key=lambda n: n != "g4x10M")  # the 10 M-path workload goes first: it is the last user of the gather arena
+    wl_steps, wl_warm = 3, 2
+    workloads = {}
+
+    def report(name, n_paths, ms, r, note, n_ranks=world, tiles=None, spans=None, cmds=None, extra=None):
+        """One workload line: the rank-local result r scaled by the ranks that ran it."""
+        tiles = sum_over_ranks(float(r.n_tiles)) if tiles is None else tiles
+        spans = sum_over_ranks(float(r.n_spans)) if spans is None else spans
+        cmds = sum_over_ranks(float(r.n_cmds)) if cmds is None else cmds
+        alg_b = b_alg(cmds, n_paths, tiles, spans)
+        d = {"paths": int(n_paths), "ms_per_step": ms, "paths_per_s": n_paths / (ms * 1e-3), "tiles": int(tiles), "spans": int(spans),
+             "tiles_per_s": tiles / (ms * 1e-3), "alpha_MB_per_s": 64e-6 * tiles / (ms * 1e-3), "b_alg_GB": alg_b / 1e9,
+             "hbm_frac": alg_b / (ms * 1e-3) / 1e9 / (peak * n_ranks), "steps": wl_steps, "warmup": wl_warm,
+             "implementation": {1: "fused kernel", 2: "general pipeline", 3: "fused kernel + general pipeline for the paths over its budgets"}.get(r.used & 3, "?"),
+             "note": note}
+        if extra:
+            d.update(extra)
+        workloads[name] = d
+
+    def upload(cmds, off, xf):
+        return (torch.from_numpy(cmds.view(np.uint8).reshape(-1).copy()).cuda(), torch.from_numpy(off.astype(np.int32)).cuda(),
+                torch.from_numpy(np.ascontiguousarray(xf, np.float32).reshape(-1).copy()).cuda())
+
+    def replicate(cmds, off, xf, times, sw=None):
+        n = len(off) - 1
+        c = np.tile(cmds, times)
+        o = (np.arange(times, dtype=np.int64)[:, None] * int(off[-1]) + off[None, :-1].astype(np.int64)).reshape(-1)
+        o = np.concatenate([o, [times * int(off[-1])]]).astype(np.uint32)
+        x = np.tile(np.asarray(xf, np.float32).reshape(n, 6), (times, 1))
+        return (c, o, x) if sw is None else (c, o, x, np.tile(sw, times))
+
+    def close_arena():
+        nonlocal arena
+        if arena is not None:
+            barrier()
+            ctx.set_output_arena(None)
+            arena.close()
+            arena = None
+            torch.cuda.empty_cache()
+
+    for name in want:
+        if name != "g4x10M":
+            close_arena()  # GPU 0 gets the arena's memory back (91 GB at N = 8) before anything else allocates
+        barrier()
+        if name == "c1x1M":
+            # config 1: the path of examples/basic.rs under Transform::id(), replicated as 1 M independent paths per GPU
+            c, o, x = replicate(*W.basic(), 1_000_000)
+            dc, do, dx = upload(c, o, x)
+            fn = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), len(o) - 1, o, in_device=True, out_device=True, unordered=True)  # noqa: E731
+            ms, r = timed(fn, wl_warm, wl_steps)
+            report(name, (len(o) - 1) * world, ms, r, "examples/basic.rs:26-31 (Move, Quadratic, Cubic, Close) x 1 M per GPU; device-resident in and out, unordered layout"
+                   + ("; not gathered" if world > 1 else ""))
+            del dc, do, dx
+        elif name == "svg64":
+            # config 2: every paint (fill or stroke) of the three bundled SVGs, at 1x and 4x, 64 copies of the document per GPU as one batch;
+            # stroke paints are flattened and offset on the device (ochre_b200_rasterize_paints)
+            for doc in ("tiger", "lorem_ipsum", "calabi_yau"):
+                for scale in (1.0, 4.0):
+                    c, o, x, sw = replicate(*W.svg_paint_batch(doc, scale)[:3], 64, sw=W.svg_paint_batch(doc, scale)[3])
+                    fn = lambda: ctx.rasterize_paints(c, o, x, sw, out_device=True, unordered=True)  # noqa: E731
+                    ms, r = timed(fn, wl_warm, wl_steps)
+                    report(f"svg64_{doc}_{int(scale)}x", (len(o) - 1) * world, ms, r,
+                           f"examples/res {doc} at {int(scale)}x: {(len(o) - 1) // 64} paints ({int((sw > 0).sum()) // 64} strokes, stroked on the device) x 64 per GPU; "
+                           f"host PathCmd arrays in ({c.nbytes / 1e6:.1f} MB uploaded inside the call), results left on the device"
+                           + ("; not gathered" if world > 1 else ""),
+                           extra={"stroker_ms": ctx.stroker_ms()})
+        elif name in ("glyphs100k", "glyphs1M"):
+            # config 3: G3 glyph outlines at 12-48 px, every glyph its own path
+            n = 100_000 if name == "glyphs100k" else 1_000_000
+            b = Batch(3, rank * n, n)
+            ms, r = timed(lambda: b.device_call(ctx), wl_warm, wl_steps)
+            report(name, n * world, ms, r, f"generator G3, {n} glyphs per GPU; device-resident in and out, unordered layout" + ("; not gathered" if world > 1 else ""))
+            del b
+        elif name in ("rings5a", "rings5a_dense"):
+            # config 5a: ONE path of 511 concentric rings on a 16384^2 canvas.  N > 1: every rank flattens the whole path and
+            # rasterises its band of tile rows (bands balanced by the control polygons crossing each row); the bands are gathered
+            # to GPU 0 inside the timed region; concatenated in band order they are the 1-GPU result (checked below).
+            # (rings5a_dense: SURVEY.md's stress variant, 2047 rings 4 px apart: every tile of the canvas is a boundary tile)
+            c, o, x = W.rings() if name == "rings5a" else W.rings(2047, 4.0, 256)
+            dc, do, dx = upload(c, o, x)
+            call = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), 1, o, in_device=True, out_device=True, unordered=False)  # noqa: E731
+            whole = call()
+            whole_sum = None
+            if world > 1:
+                whole_sum = byte_sum(torch, whole.device_ptrs["alpha"], whole.n_tiles * 64)
+                rows = (0, 16384 // 8)
+                bands = sharding.plan_row_bands(rows[0], rows[1], world, sharding.band_weights_from_bbox(c, x, rows[0], rows[1]))
+                lo, hi = bands[rank]
+                # the first and the last band also take whatever lies outside the canvas rows
+                ctx.set_row_band(-32768 if rank == 0 else lo, 32767 if rank == world - 1 else hi)
+                gbufs = {}
+                got = {}
+
+                def fn():
+                    r = call()
+                    p = r.device_ptrs
+                    mine = {"a_alpha": torch.as_tensor(CudaArray(p["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64],
+                            "b_xy": torch.as_tensor(CudaArray(p["tile_xy"], max(r.n_tiles * 4, 1)), device="cuda")[: r.n_tiles * 4],
+                            "c_spans": torch.as_tensor(CudaArray(p["spans"], max(r.n_spans * 8, 1)), device="cuda")[: r.n_spans * 8]}
+                    got["sizes"], got["g"] = sharding.gather_bytes(mine, rank, world, gbufs)
+                    return r
+
+                ms, r = timed(fn, wl_warm, wl_steps)
+                ctx.set_row_band(0, 0)
+                check = None
+                if rank == 0:
+                    g = got["g"]
+                    nt = int(g["a_alpha"].numel()) // 64
+                    check = {"bands": world, "tiles_gathered": nt, "tiles_one_gpu": int(whole.n_tiles),
+                             "spans_gathered": int(g["c_spans"].numel()) // 8, "spans_one_gpu": int(whole.n_spans),
+                             "alpha_sum_matches_one_gpu": int(g["a_alpha"].sum(dtype=torch.int64).item()) == whole_sum}
+                    same_xy = torch.equal(g["b_xy"], torch.as_tensor(CudaArray(whole.device_ptrs["tile_xy"], max(whole.n_tiles * 4, 1)), device="cuda")[: whole.n_tiles * 4]) if nt == whole.n_tiles else False
+                    same_alpha = torch.equal(g["a_alpha"], torch.as_tensor(CudaArray(whole.device_ptrs["alpha"], max(whole.n_tiles * 64, 1)), device="cuda")[: whole.n_tiles * 64]) if nt == whole.n_tiles else False
+                    check["byte_identical_to_one_gpu"] = bool(same_xy and same_alpha)
+                    if not check["byte_identical_to_one_gpu"]:
+                        raise SystemExit(f"bench.py: the gathered row bands differ from the one-GPU result: {check}")
+                report(name, 1, ms, r, f"generator G5a: one path, {len(c) // 258} rings, {len(c) // 1000} k cubics on a 16384^2 canvas; sharded by canvas row bands over {world} GPUs "
+                       "(every rank flattens the whole path, rasterises its tile rows), bands gathered to GPU 0 over NCCL inside the timed region",
+                       tiles=float(whole.n_tiles), spans=float(whole.n_spans), cmds=float(whole.n_cmds), extra={"bands_check": check})
+            else:
+                ms, r = timed(call, wl_warm, wl_steps)
+                report(name, 1, ms, r, f"generator G5a: one path, {len(c) // 258} rings, {len(c) // 1000} k cubics on a 16384^2 canvas; one GPU, path-ordered result on the device")
+            del dc, do, dx
+        elif name == "g4x10M":
+            # config 5b: 10 M G4 paths sharded by path: every rank takes a contiguous tenth-of-a-batch share and rasterises it in
+            # sub-batches of <= 1 M paths (results of a sub-batch are consumed -- here: dropped -- before the next overwrites them);
+            # N > 1: gathered to GPU 0 through the arena like the headline
+            share = args.big_paths // world
+            b = Batch(4, 10_000_000_000 + rank * share, share)  # (a range of the generator the headline does not use)
+            sub = min(P, 1_000_000)
+            cuts = list(range(0, share, sub)) + [share]
+            if gather:
+                arena_on()
+            tot = {"t": 0, "s": 0, "c": 0, "used": 0}
+
+            def fn():
+                tot.update(t=0, s=0, c=0)
+                r = None
+                for a, z in zip(cuts[:-1], cuts[1:]):
+                    r = gathered_call(lambda: b.device_call(ctx, a, z)) if gather else b.device_call(ctx, a, z)
+                    tot["t"] += r.n_tiles
+                    tot["s"] += r.n_spans
+                    tot["c"] += r.n_cmds
+                return r
+
+            ms, r = timed(fn, 1, wl_steps)
+            if gather:
+                barrier()
+                ctx.set_output_arena(None)
+            report(name, share * world, ms, r, f"generator G4, {share * world} paths sharded by path over {world} GPU(s), {len(cuts) - 1} sub-batch(es) of <= {sub} paths per rank; "
+                   "device-resident in and out, unordered layout" + ("; gathered to GPU 0 through the arena" if gather else ""),
+                   tiles=sum_over_ranks(float(tot["t"])), spans=sum_over_ranks(float(tot["s"])), cmds=sum_over_ranks(float(tot["c"])))
+            del b
+        torch.cuda.empty_cache()
+    close_arena()
+
     # ---- e2e: host buffers in, host buffers out, every tile and span through a TileBuilder on the host ------------------
     e2e = None
     e2e_ok = not args.no_e2e
@@ -579,151 +739,6 @@ def main():
         "pipeline_frac": alg / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
         "note": "the kernel is instruction-issue and barrier bound (per-pixel f32 DDA, many short phases per path), not HBM bound; see DESIGN.md section 6",
     }
-
-    # ---- the other BASELINE configs ---------------------------------------------------------------------------------
-    want = args.workloads.split(",") if args.workloads not in ("all", "none") else (
-        ["c1x1M", "svg64", "glyphs100k", "glyphs1M", "rings5a", "g4x10M"] if args.workloads == "all" else [])
-    wl_steps, wl_warm = 3, 2
-    workloads = {}
-
-    def report(name, n_paths, ms, r, note, n_ranks=world, tiles=None, spans=None, cmds=None, extra=None):
-        """One workload line: the rank-local result r scaled by the ranks that ran it."""
-        tiles = sum_over_ranks(float(r.n_tiles)) if tiles is None else tiles
-        spans = sum_over_ranks(float(r.n_spans)) if spans is None else spans
-        cmds = sum_over_ranks(float(r.n_cmds)) if cmds is None else cmds
-        alg_b = b_alg(cmds, n_paths, tiles, spans)
-        d = {"paths": int(n_paths), "ms_per_step": ms, "paths_per_s": n_paths / (ms * 1e-3), "tiles": int(tiles), "spans": int(spans),
-             "tiles_per_s": tiles / (ms * 1e-3), "alpha_MB_per_s": 64e-6 * tiles / (ms * 1e-3), "b_alg_GB": alg_b / 1e9,
-             "hbm_frac": alg_b / (ms * 1e-3) / 1e9 / (peak * n_ranks), "steps": wl_steps, "warmup": wl_warm,
-             "implementation": {1: "fused kernel", 2: "general pipeline", 3: "fused kernel + general pipeline for the paths over its budgets"}.get(r.used & 3, "?"),
-             "note": note}
-        if extra:
-            d.update(extra)
-        workloads[name] = d
-
-    def upload(cmds, off, xf):
-        return (torch.from_numpy(cmds.view(np.uint8).reshape(-1).copy()).cuda(), torch.from_numpy(off.astype(np.int32)).cuda(),
-                torch.from_numpy(np.ascontiguousarray(xf, np.float32).reshape(-1).copy()).cuda())
-
-    def replicate(cmds, off, xf, times, sw=None):
-        n = len(off) - 1
-        c = np.tile(cmds, times)
-        o = (np.arange(times, dtype=np.int64)[:, None] * int(off[-1]) + off[None, :-1].astype(np.int64)).reshape(-1)
-        o = np.concatenate([o, [times * int(off[-1])]]).astype(np.uint32)
-        x = np.tile(np.asarray(xf, np.float32).reshape(n, 6), (times, 1))
-        return (c, o, x) if sw is None else (c, o, x, np.tile(sw, times))
-
-    for name in want:
-        barrier()
-        if name == "c1x1M":
-            # config 1: the path of examples/basic.rs under Transform::id(), replicated as 1 M independent paths per GPU
-            c, o, x = replicate(*W.basic(), 1_000_000)
-            dc, do, dx = upload(c, o, x)
-            fn = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), len(o) - 1, o, in_device=True, out_device=True, unordered=True)  # noqa: E731
-            ms, r = timed(fn, wl_warm, wl_steps)
-            report(name, (len(o) - 1) * world, ms, r, "examples/basic.rs:26-31 (Move, Quadratic, Cubic, Close) x 1 M per GPU; device-resident in and out, unordered layout"
-                   + ("; not gathered" if world > 1 else ""))
-            del dc, do, dx
-        elif name == "svg64":
-            # config 2: every paint (fill or stroke) of the three bundled SVGs, at 1x and 4x, 64 copies of the document per GPU as one batch;
-            # stroke paints are flattened and offset on the device (ochre_b200_rasterize_paints)
-            for doc in ("tiger", "lorem_ipsum", "calabi_yau"):
-                for scale in (1.0, 4.0):
-                    c, o, x, sw = replicate(*W.svg_paint_batch(doc, scale)[:3], 64, sw=W.svg_paint_batch(doc, scale)[3])
-                    fn = lambda: ctx.rasterize_paints(c, o, x, sw, out_device=True, unordered=True)  # noqa: E731
-                    ms, r = timed(fn, wl_warm, wl_steps)
-                    report(f"svg64_{doc}_{int(scale)}x", (len(o) - 1) * world, ms, r,
-                           f"examples/res {doc} at {int(scale)}x: {(len(o) - 1) // 64} paints ({int((sw > 0).sum()) // 64} strokes, stroked on the device) x 64 per GPU; "
-                           f"host PathCmd arrays in ({c.nbytes / 1e6:.1f} MB uploaded inside the call), results left on the device"
-                           + ("; not gathered" if world > 1 else ""),
-                           extra={"stroker_ms": ctx.stroker_ms()})
-        elif name in ("glyphs100k", "glyphs1M"):
-            # config 3: G3 glyph outlines at 12-48 px, every glyph its own path
-            n = 100_000 if name == "glyphs100k" else 1_000_000
-            b = Batch(3, rank * n, n)
-            ms, r = timed(lambda: b.device_call(ctx), wl_warm, wl_steps)
-            report(name, n * world, ms, r, f"generator G3, {n} glyphs per GPU; device-resident in and out, unordered layout" + ("; not gathered" if world > 1 else ""))
-            del b
-        elif name == "rings5a":
-            # config 5a: ONE path of 511 concentric rings on a 16384^2 canvas.  N > 1: every rank flattens the whole path and
-            # rasterises its band of tile rows (bands balanced by the control polygons crossing each row); the bands are gathered
-            # to GPU 0 inside the timed region; concatenated in band order they are the 1-GPU result (checked below).
-            c, o, x = W.rings()
-            dc, do, dx = upload(c, o, x)
-            call = lambda: ctx.rasterize_ptrs(dc.data_ptr(), do.data_ptr(), dx.data_ptr(), 1, o, in_device=True, out_device=True, unordered=False)  # noqa: E731
-            whole = call()
-            whole_sum = None
-            if world > 1:
-                whole_sum = byte_sum(torch, whole.device_ptrs["alpha"], whole.n_tiles * 64)
-                rows = (0, 16384 // 8)
-                bands = sharding.plan_row_bands(rows[0], rows[1], world, sharding.band_weights_from_bbox(c, x, rows[0], rows[1]))
-                lo, hi = bands[rank]
-                # the first and the last band also take whatever lies outside the canvas rows
-                ctx.set_row_band(-32768 if rank == 0 else lo, 32767 if rank == world - 1 else hi)
-                gbufs = {}
-                got = {}
-
-                def fn():
-                    r = call()
-                    p = r.device_ptrs
-                    mine = {"a_alpha": torch.as_tensor(CudaArray(p["alpha"], max(r.n_tiles * 64, 1)), device="cuda")[: r.n_tiles * 64],
-                            "b_xy": torch.as_tensor(CudaArray(p["tile_xy"], max(r.n_tiles * 4, 1)), device="cuda")[: r.n_tiles * 4],
-                            "c_spans": torch.as_tensor(CudaArray(p["spans"], max(r.n_spans * 8, 1)), device="cuda")[: r.n_spans * 8]}
-                    got["sizes"], got["g"] = sharding.gather_bytes(mine, rank, world, gbufs)
-                    return r
-
-                ms, r = timed(fn, wl_warm, wl_steps)
-                ctx.set_row_band(0, 0)
-                check = None
-                if rank == 0:
-                    g = got["g"]
-                    nt = int(g["a_alpha"].numel()) // 64
-                    check = {"bands": world, "tiles_gathered": nt, "tiles_one_gpu": int(whole.n_tiles),
-                             "spans_gathered": int(g["c_spans"].numel()) // 8, "spans_one_gpu": int(whole.n_spans),
-                             "alpha_sum_matches_one_gpu": int(g["a_alpha"].sum(dtype=torch.int64).item()) == whole_sum}
-                    same_xy = torch.equal(g["b_xy"], torch.as_tensor(CudaArray(whole.device_ptrs["tile_xy"], max(whole.n_tiles * 4, 1)), device="cuda")[: whole.n_tiles * 4]) if nt == whole.n_tiles else False
-                    same_alpha = torch.equal(g["a_alpha"], torch.as_tensor(CudaArray(whole.device_ptrs["alpha"], max(whole.n_tiles * 64, 1)), device="cuda")[: whole.n_tiles * 64]) if nt == whole.n_tiles else False
-                    check["byte_identical_to_one_gpu"] = bool(same_xy and same_alpha)
-                    if not check["byte_identical_to_one_gpu"]:
-                        raise SystemExit(f"bench.py: the gathered row bands differ from the one-GPU result: {check}")
-                report(name, 1, ms, r, f"generator G5a: one path, 511 rings, 131 k cubics on a 16384^2 canvas; sharded by canvas row bands over {world} GPUs "
-                       "(every rank flattens the whole path, rasterises its tile rows), bands gathered to GPU 0 over NCCL inside the timed region",
-                       tiles=float(whole.n_tiles), spans=float(whole.n_spans), cmds=float(whole.n_cmds), extra={"bands_check": check})
-            else:
-                ms, r = timed(call, wl_warm, wl_steps)
-                report(name, 1, ms, r, "generator G5a: one path, 511 rings, 131 k cubics on a 16384^2 canvas; one GPU, path-ordered result on the device")
-            del dc, do, dx
-        elif name == "g4x10M":
-            # config 5b: 10 M G4 paths sharded by path: every rank takes a contiguous tenth-of-a-batch share and rasterises it in
-            # sub-batches of <= 1 M paths (results of a sub-batch are consumed -- here: dropped -- before the next overwrites them);
-            # N > 1: gathered to GPU 0 through the arena like the headline
-            share = args.big_paths // world
-            b = Batch(4, 10_000_000_000 + rank * share, share)  # (a range of the generator the headline does not use)
-            sub = min(P, 1_000_000)
-            cuts = list(range(0, share, sub)) + [share]
-            if gather:
-                arena_on()
-            tot = {"t": 0, "s": 0, "c": 0, "used": 0}
-
-            def fn():
-                tot.update(t=0, s=0, c=0)
-                r = None
-                for a, z in zip(cuts[:-1], cuts[1:]):
-                    r = gathered_call(lambda: b.device_call(ctx, a, z)) if gather else b.device_call(ctx, a, z)
-                    tot["t"] += r.n_tiles
-                    tot["s"] += r.n_spans
-                    tot["c"] += r.n_cmds
-                return r
-
-            ms, r = timed(fn, 1, wl_steps)
-            if gather:
-                barrier()
-                ctx.set_output_arena(None)
-            report(name, share * world, ms, r, f"generator G4, {share * world} paths sharded by path over {world} GPU(s), {len(cuts) - 1} sub-batch(es) of <= {sub} paths per rank; "
-                   "device-resident in and out, unordered layout" + ("; gathered to GPU 0 through the arena" if gather else ""),
-                   tiles=sum_over_ranks(float(tot["t"])), spans=sum_over_ranks(float(tot["s"])), cmds=sum_over_ranks(float(tot["c"])))
-            del b
-        torch.cuda.empty_cache()
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------
     cpu = None
