@@ -603,3 +603,32 @@ def test_one_bad_path_does_not_fail_the_batch(ctx):
     # without dropped paths the accessor reports none
     ctx.rasterize(gc, go, xf[keep], skip_bad=True)
     assert ctx.path_status(len(go) - 1) == (None, 0)
+
+
+def test_host_sink_sees_every_tile_and_span(ctx):
+    """ochre_b200_set_host_sink: the replay of a host-resident result into a counting / checksumming TileBuilder inside the
+    call (chunk by chunk behind the downloads) -- its sums equal the ones computed from the returned arrays and the oracle's."""
+    cmds, off, xf = W.blobs(1500, first=900)
+    ctx.set_chunk(9000)  # several chunks, several 32 MB pieces would need a larger batch; several tasks either way
+    ctx.set_host_sink(3)
+    try:
+        g = ctx.rasterize(cmds, off, xf)
+        s = ctx.last_sink()
+    finally:
+        ctx.set_host_sink(0)
+        ctx.set_chunk(0)
+    assert s["tiles"] == g.n_tiles and s["spans"] == g.n_spans
+    assert s["alpha_sum"] == int(g.alpha.astype(np.uint64).sum())
+    M = (1 << 64) - 1
+    geom = 0
+    for x, y in g.tile_xy.astype(np.int64) & 0xffff:
+        geom = (geom + int(x) * 0x9E3779B97F4A7C15 + int(y)) & M
+    for sp in g.spans:
+        geom = (geom + ((int(sp["x"]) & 0xffff) << 32 ^ (int(sp["y"]) & 0xffff) << 16 ^ int(sp["w"]))) & M
+    assert s["geom_sum"] == geom
+    want = O.rasterize_batch(cmds, off.astype(np.uint64), xf, threads=0, count_only=True)
+    assert (want.n_tiles, want.n_spans, want.geom_sum) == (s["tiles"], s["spans"], s["geom_sum"])
+    assert abs(want.alpha_sum - s["alpha_sum"]) <= 64  # +-1 alpha bytes only
+    # a call without the sink reports nothing
+    ctx.rasterize(cmds, off, xf)
+    assert ctx.last_sink()["tiles"] == 0
