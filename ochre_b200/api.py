@@ -182,7 +182,7 @@ class Context:
         s = _lib.OchreSinkSum()
         _check(self._h, _lib.load().ochre_b200_last_sink(self._h, C.byref(s)))
         return dict(tiles=int(s.tiles), spans=int(s.spans), geom_sum=int(s.geom_sum), alpha_sum=int(s.alpha_sum),
-                    mix_sum=int(s.mix_sum), seconds=float(s.seconds))
+                    mix_sum=int(s.mix_sum), seconds=float(s.seconds), packed_alpha_bytes=int(s.packed_alpha_bytes))
 
     def build_atlas(self, colors, out_device: bool = False, copy: bool = True) -> "AtlasResult":
         """Device-side atlas packer + quad builder (the reference's examples/svg.rs `Builder`, svg.rs:22-88)
@@ -216,7 +216,7 @@ class Context:
         return np.frombuffer((C.c_int8 * n_paths).from_address(p.value), dtype=np.int8).copy(), int(n.value)
 
     def rasterize(self, cmds, cmd_off, xf, out_device: bool = False, copy: bool = True, unordered: bool = False,
-                  skip_bad: bool = False) -> BatchResult:
+                  skip_bad: bool = False, sink_packed: bool = False) -> BatchResult:
         """fill + finish of len(cmd_off)-1 independent paths.
 
         cmds: CMD_DTYPE array; cmd_off: uint32 offsets (n_paths+1); xf: (n_paths, 6) float32 rows
@@ -231,7 +231,7 @@ class Context:
         xf = np.ascontiguousarray(xf, dtype=np.float32).reshape(n_paths, 6) if n_paths else np.zeros((0, 6), np.float32)
         res = _lib.OchreResult()
         flags = ((_lib.OCHRE_OUT_DEVICE if out_device else 0) | (_lib.OCHRE_OUT_UNORDERED if unordered else 0)
-                 | (_lib.OCHRE_SKIP_BAD_PATHS if skip_bad else 0))
+                 | (_lib.OCHRE_SKIP_BAD_PATHS if skip_bad else 0) | (_lib.OCHRE_OUT_SINK_PACKED if sink_packed else 0))
         rc = L.ochre_b200_rasterize(self._h, cmds.ctypes.data, cmd_off.ctypes.data, xf.ctypes.data, n_paths, flags, None,
                                     C.byref(res))
         _check(self._h, rc)
@@ -257,12 +257,12 @@ class Context:
         return self._wrap(res, n_paths, out_device, copy)
 
     def rasterize_ptrs(self, cmds_ptr: int, cmd_off_ptr: int, xf_ptr: int, n_paths: int, cmd_off_host: np.ndarray,
-                       in_device: bool, out_device: bool, copy: bool = False, unordered: bool = False) -> BatchResult:
-        """Raw-pointer form (pinned host buffers or device buffers), used by bench.py."""
+                       in_device: bool, out_device: bool, copy: bool = False, unordered: bool = False, sink_packed: bool = False) -> BatchResult:
+        """Raw-pointer form (pinned host buffers or device buffers), used by bench.py.  sink_packed: OCHRE_OUT_SINK_PACKED."""
         L = _lib.load()
         res = _lib.OchreResult()
         flags = ((_lib.OCHRE_IN_DEVICE if in_device else 0) | (_lib.OCHRE_OUT_DEVICE if out_device else 0)
-                 | (_lib.OCHRE_OUT_UNORDERED if unordered else 0))
+                 | (_lib.OCHRE_OUT_UNORDERED if unordered else 0) | (_lib.OCHRE_OUT_SINK_PACKED if sink_packed else 0))
         cmd_off_host = np.ascontiguousarray(cmd_off_host, dtype=np.uint32)
         rc = L.ochre_b200_rasterize(self._h, cmds_ptr, cmd_off_ptr, xf_ptr, n_paths, flags, cmd_off_host.ctypes.data,
                                     C.byref(res))
@@ -291,7 +291,7 @@ class Context:
         span_off = None if unordered else view(res.span_off, (n_paths + 1) * 4, np.uint32, (n_paths + 1,))
         ranges = view(res.ranges, n_paths * 16, np.uint32, (n_paths, 4))
         tile_xy = view(res.tile_xy, nt * 4, np.int16, (nt, 2))
-        alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64))
+        alpha = view(res.alpha, nt * 64, np.uint8, (nt, 64)) if res.alpha else None  # (None: row-packed transport, tiles went to the host sink)
         spans = view(res.spans, ns * 8, SPAN_DTYPE, (ns,))
         return BatchResult(tile_off, span_off, tile_xy, alpha, spans, ranges=ranges, **common)
 

@@ -23,6 +23,9 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <memory>
 #include <mutex>
 #include <string>
@@ -725,6 +728,44 @@ __global__ void __launch_bounds__(256) k_fill_u16(uint16_t* __restrict__ p, uint
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// ---------------------------------------------------------------------------
+// Row-packed transport of a host-resident result (OCHRE_OUT_SINK_PACKED): 46 % of the pixel rows of a boundary tile are
+// constant (all 0 outside the shape, all 255 inside).  Per tile a 16-bit class word (2 bits per row: 0 all 0, 1 all 255,
+// 2 stored) and only the stored rows, packed back to back, cross PCIe; the host sink rebuilds every tile on the fly.
+// ---------------------------------------------------------------------------
+constexpr uint32_t PACK_BLOCK = 1024;  // tiles per block of the packed stream (the host gets the stream offset of every block)
+__device__ __forceinline__ uint32_t pack_stored_mask(uint32_t cls) { return (cls >> 1) & ~cls & 0x5555u; }  // bit 2y: row y is stored
+__global__ void __launch_bounds__(256)
+k_pack_classify(const uint2* __restrict__ rows, uint64_t n_rows, uint16_t* __restrict__ cls) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;  // row index; the 8 rows of a tile sit in 8 consecutive lanes
+    uint32_t c = 0;
+    if (i < n_rows) {
+        const uint2 v = rows[i];
+        c = (v.x | v.y) == 0u ? 0u : ((v.x & v.y) == 0xffffffffu ? 1u : 2u);
+    }
+    uint32_t w = c << (2u * (threadIdx.x & 7u));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if (i < n_rows && (threadIdx.x & 7u) == 0) cls[i >> 3] = (uint16_t)w;
+}
+__global__ void __launch_bounds__(256)
+k_pack_rows(const uint2* __restrict__ rows, uint64_t n_rows, const uint16_t* __restrict__ cls, const uint32_t* __restrict__ off,
+            uint2* __restrict__ packed) {
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_rows) return;
+    const uint32_t y = (uint32_t)(i & 7u), m = pack_stored_mask(cls[i >> 3]);
+    if (m & (1u << (2u * y))) packed[off[i >> 3] + (uint32_t)__popc(m & ((1u << (2u * y)) - 1u))] = rows[i];
+}
+// stream offset of every block of PACK_BLOCK tiles (+ the total), straight into mapped host memory
+__global__ void __launch_bounds__(256)
+k_pack_block_offsets(const uint32_t* __restrict__ off, uint32_t n_tiles, const uint32_t* __restrict__ total, volatile uint32_t* __restrict__ host) {
+    const uint32_t b = blockIdx.x * 256 + threadIdx.x, nb = (n_tiles + PACK_BLOCK - 1) / PACK_BLOCK;
+    if (b < nb) host[b] = off[b * PACK_BLOCK];
+    if (b == nb) host[nb] = *total;
+    __threadfence_system();
+}
+
 __global__ void k_set_words2(uint32_t* __restrict__ a, uint32_t va, uint32_t* __restrict__ b, uint32_t vb) {
     *a = va;
     *b = vb;
@@ -840,17 +881,29 @@ struct SinkBuilder {  // a `&mut impl TileBuilder`: two indirect calls
 };
 static void sink_tile(SinkBuilder* b, int16_t x, int16_t y, const uint8_t* d) {
     const uint64_t g = (uint64_t)(uint16_t)x * 0x9E3779B97F4A7C15ull + (uint16_t)y;
-    uint64_t s = g, a = 0;
     uint64_t w[8];
     memcpy(w, d, 64);
-    for (int i = 0; i < 8; ++i) {
-        s = (s ^ w[i]) * 0x100000001B3ull;
-        // byte sum of the word: pairwise widening adds
+    // mixed checksum: position-dependent, every byte counts, no serial chain between the eight multiplies (a consumer that
+    // reads a tile should not be bound by the latency of its own hash)
+    uint64_t s = g;
+    static const uint64_t K[8] = {0x100000001B3ull, 0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull,
+                                  0xD6E8FEB86659FD93ull, 0xFF51AFD7ED558CCDull, 0xC4CEB9FE1A85EC53ull, 0x2545F4914F6CDD1Dull};
+    for (int i = 0; i < 8; ++i) s += (w[i] ^ g) * K[i];
+    uint64_t a = 0;
+#if defined(__SSE2__)
+    for (int i = 0; i < 4; ++i) {  // byte sums: one psadbw per 16 bytes
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(d + 16 * i));
+        const __m128i sad = _mm_sad_epu8(v, _mm_setzero_si128());
+        a += (uint64_t)_mm_cvtsi128_si64(sad) + (uint64_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(sad, sad));
+    }
+#else
+    for (int i = 0; i < 8; ++i) {  // pairwise widening adds
         uint64_t v = w[i];
         v = (v & 0x00ff00ff00ff00ffull) + ((v >> 8) & 0x00ff00ff00ff00ffull);
         v = (v & 0x0000ffff0000ffffull) + ((v >> 16) & 0x0000ffff0000ffffull);
         a += (v & 0xffffffffull) + (v >> 32);
     }
+#endif
     b->sum.mix_sum += s;
     b->sum.geom_sum += g;
     b->sum.alpha_sum += a;
@@ -866,6 +919,10 @@ static void sink_span(SinkBuilder* b, int16_t x, int16_t y, uint16_t w) {
 struct SinkTask {
     size_t t0, nt, s0, ns;
     cudaEvent_t ready;  // recorded behind the chunk's downloads
+    // row-packed tiles (OCHRE_OUT_SINK_PACKED): blocks [b0, b1) of the chunk whose first tile is chunk_t0; boff[b] = offset of
+    // block b's stored rows in the chunk's stream, which starts at row_base of the host stream
+    std::shared_ptr<std::vector<uint32_t>> boff;
+    size_t chunk_t0 = 0, chunk_nt = 0, row_base = 0, b0 = 0, b1 = 0;
 };
 struct SinkRun {
     int device = 0;
@@ -874,6 +931,8 @@ struct SinkRun {
     const int16_t* volatile tile_xy = nullptr;
     const uint8_t* volatile alpha = nullptr;
     const OchreSpan* volatile spans = nullptr;
+    const uint16_t* volatile cls = nullptr;     // row-packed transport: class words per tile,
+    const uint64_t* volatile prow = nullptr;    // ... the stored rows back to back
     std::mutex mu;
     std::condition_variable cv;
     std::vector<SinkTask> tasks;
@@ -901,10 +960,35 @@ struct SinkRun {
             cudaEventSynchronize(k.ready);
             const auto t_a = std::chrono::steady_clock::now();
             // this thread's slice of the chunk, in the result's order: tiles, then spans
-            const size_t a0 = k.t0 + k.nt * t / n_threads, a1 = k.t0 + k.nt * (t + 1) / n_threads;
             const int16_t* xy = tile_xy;
-            const uint8_t* al = alpha;
-            for (size_t i = a0; i < a1; ++i) b.tile(&b, xy[2 * i], xy[2 * i + 1], al + 64 * i);
+            if (k.boff) {
+                // row-packed tiles: this thread's share of the blocks; every tile is rebuilt from its class word and its stored rows
+                const uint16_t* cw = cls;
+                const uint64_t* pr = prow;
+                const size_t nbk = k.b1 - k.b0;
+                for (size_t bk = k.b0 + nbk * t / n_threads; bk < k.b0 + nbk * (t + 1) / n_threads; ++bk) {
+                    const size_t ta = k.chunk_t0 + bk * PACK_BLOCK, tn = std::min<size_t>(PACK_BLOCK, k.chunk_t0 + k.chunk_nt - ta);
+                    const uint64_t* r = pr + k.row_base + (*k.boff)[bk];
+                    for (size_t i = ta; i < ta + tn; ++i) {
+                        const uint32_t c = cw[i];
+                        alignas(8) uint64_t tile[8];
+                        for (int y = 0; y < 8; ++y) {
+                            const uint32_t q = (c >> (2 * y)) & 3u;
+                            // branch-free (the classes of consecutive rows are as good as random to a branch predictor): the next
+                            // stored row is loaded whether it is this row's or not (the stream has 64 bytes of slack at its end)
+                            const uint64_t konst = 0ull - (uint64_t)(q & 1u);  // class 1: all ones, class 0: zero
+                            const uint64_t lit = 0ull - (uint64_t)(q >> 1);    // class 2: take the stored row
+                            tile[y] = (*r & lit) | (konst & ~lit);
+                            r += q >> 1;
+                        }
+                        b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(tile));
+                    }
+                }
+            } else {
+                const size_t a0 = k.t0 + k.nt * t / n_threads, a1 = k.t0 + k.nt * (t + 1) / n_threads;
+                const uint8_t* al = alpha;
+                for (size_t i = a0; i < a1; ++i) b.tile(&b, xy[2 * i], xy[2 * i + 1], al + 64 * i);
+            }
             const size_t b0 = k.s0 + k.ns * t / n_threads, b1 = k.s0 + k.ns * (t + 1) / n_threads;
             const OchreSpan* sp = spans;
             for (size_t i = b0; i < b1; ++i) b.span(&b, sp[i].x, sp[i].y, sp[i].w);
@@ -966,6 +1050,11 @@ struct ochre_b200_ctx {
     int8_t* cur_pstatus = nullptr;  // device array of the running call, or null (a bad path fails the call)
     uint32_t last_bad = 0;
     bool pstatus_valid = false;
+    // row-packed transport (OCHRE_OUT_SINK_PACKED)
+    DevBuf d_pack_cls[2], d_pack_off, d_pack_rows[2];  // (class words and stored rows are double-buffered: chunk c packs while chunk c - 1 is still on the wire)
+    HostBuf h_pack_cls, h_pack_rows, h_pack_boff;
+    cudaEvent_t ev_pack[2] = {};
+    uint64_t last_packed_bytes = 0;  // alpha bytes the last packed call moved over PCIe (stored rows + class words)
     uint32_t sink_threads = 0;  // host sink (ochre_b200_set_host_sink): 0 = off
     OchreSinkSum sink_last = {};
     std::vector<cudaEvent_t> ev_sink;
@@ -1578,10 +1667,13 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_out[1]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pack[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_pack[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_g[0]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_g[1]);
     if (e != cudaSuccess) { delete ctx; return (int)e; }
     ctx->o_tile_xy.guard = ctx->o_alpha.guard = ctx->o_spans.guard = ctx->o_tile_off.guard = ctx->o_span_off.guard = ctx->st_out;
+    ctx->d_pack_rows[0].guard = ctx->d_pack_rows[1].guard = ctx->d_pack_cls[0].guard = ctx->d_pack_cls[1].guard = ctx->st_out;
     ctx->s_tile_xy.guard = ctx->s_alpha.guard = ctx->s_spans.guard = ctx->s_row_class.guard = ctx->d_pk_rec.guard = ctx->st_out;
     for (int i = 0; i <= N_STAGE; ++i) {
         e = cudaEventCreate(&ctx->ev[i]);
@@ -1615,6 +1707,8 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
     if (ctx->st_out) cudaStreamSynchronize(ctx->st_out);
     for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_sink) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_pack)
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_out)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->ev_g)
@@ -1625,12 +1719,12 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_entry, &ctx->d_ridx[0], &ctx->d_ridx[1], &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->d_cv_pub, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans, &ctx->s_row_class,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pack_cls[0], &ctx->d_pack_cls[1], &ctx->d_pack_off, &ctx->d_pack_rows[0], &ctx->d_pack_rows[1], &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans, &ctx->s_row_class,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
                     &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
                     &ctx->k_nout, &ctx->k_out_off, &ctx->k_out};
     for (DevBuf* b : db) b->release();
-    HostBuf* hb[] = {&ctx->h_pstatus, &ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
+    HostBuf* hb[] = {&ctx->h_pack_cls, &ctx->h_pack_rows, &ctx->h_pack_boff, &ctx->h_pstatus, &ctx->h_ranges, &ctx->ha_vtx, &ctx->ha_idx, &ctx->ha_atlas, &ctx->ha_page, &ctx->h_tile_off, &ctx->h_span_off, &ctx->h_tile_xy, &ctx->h_alpha, &ctx->h_spans, &ctx->h_scalars, &ctx->h_pk_ctl, &ctx->hk_off};
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= N_STAGE; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1688,6 +1782,7 @@ int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads) {
 int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out) {
     if (!ctx || !out) return OCHRE_E_INVALID_ARG;
     *out = ctx->sink_last;
+    out->packed_alpha_bytes = ctx->last_packed_bytes;
     return 0;
 }
 
@@ -1826,7 +1921,13 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(ctx->h_tile_off.ensure(((size_t)n_paths + 1) * 4));
         CK(ctx->h_span_off.ensure(((size_t)n_paths + 1) * 4));
         CK(ctx->h_tile_xy.ensure_keep(est_t * 4, 0, ctx->st_out));
-        CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
+        const bool want_packed = (flags & OCHRE_OUT_SINK_PACKED) != 0 && ctx->sink_threads != 0;
+        if (want_packed) {  // row-packed transport: class words + (at most) every row, sized for 70 % stored rows up front
+            CK(ctx->h_pack_cls.ensure_keep(est_t * 2 + 64, 0, ctx->st_out));
+            CK(ctx->h_pack_rows.ensure_keep((size_t)(est_t * 64 * 0.7) + 64, 0, ctx->st_out));
+        } else {
+            CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
+        }
         CK(ctx->h_spans.ensure_keep(est_s * sizeof(OchreSpan), 0, ctx->st_out));
         CK(r_tile_xy.ensure(est_t * 4));
         CK(r_alpha.ensure(est_t * 64));
@@ -1842,6 +1943,9 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         sink->start(ctx->device, ctx->sink_threads);
     }
     ctx->sink_last = OchreSinkSum{};
+    const bool packed = (flags & OCHRE_OUT_SINK_PACKED) != 0 && sink != nullptr;
+    size_t pack_row_base = 0;  // stored rows of the chunks before this one (host stream)
+    ctx->last_packed_bytes = 0;
     // ---- chunks ---------------------------------------------------------------
     const bool trace = getenv("OCHRE_B200_TRACE") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
@@ -1879,11 +1983,11 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
             // the chunk is complete on the device (run_chunk* drained the kernel stream): its slice of the
             // result goes to the host while the next chunk is being rasterised
             const size_t t0 = tile_base, nt = co.n_tiles, s0 = span_base, ns = co.n_spans;
-            if (sink && ((t0 + nt) * 4 + 4 > ctx->h_tile_xy.cap || (t0 + nt) * 64 + 64 > ctx->h_alpha.cap ||
+            if (sink && ((t0 + nt) * 4 + 4 > ctx->h_tile_xy.cap || (!packed && (t0 + nt) * 64 + 64 > ctx->h_alpha.cap) ||
                          (s0 + ns) * sizeof(OchreSpan) + 8 > ctx->h_spans.cap))
                 sink->drain();  // a host array is about to move: no sink thread may be reading it
             CK(ctx->h_tile_xy.ensure_keep((t0 + nt) * 4 + 4, t0 * 4, ctx->st_out));
-            CK(ctx->h_alpha.ensure_keep((t0 + nt) * 64 + 64, t0 * 64, ctx->st_out));
+            if (!packed) CK(ctx->h_alpha.ensure_keep((t0 + nt) * 64 + 64, t0 * 64, ctx->st_out));
             CK(ctx->h_spans.ensure_keep((s0 + ns) * sizeof(OchreSpan) + 8, s0 * sizeof(OchreSpan), ctx->st_out));
             // with a host sink the tiles travel in pieces of 32 MB, each handed to the sink threads as soon as it has landed
             // (the replay of the call's last piece is all that is left when the download ends)
@@ -1901,8 +2005,71 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 sink->post(SinkTask{ta, tn, sa, sn, e});
                 return 0;
             };
+            if (packed && nt) {
+                // ---- row-packed transport: classify, scan, pack on the device; class words + stored rows over PCIe ----
+                const int pb = (int)(c & 1);
+                uint32_t* d_sc = ctx->d_scalars.as<uint32_t>();
+                CK(ctx->d_pack_off.ensure((nt + 2) * 4));
+                CK(ctx->d_scan_ws.ensure(scan_ws_words(nt) * 4));
+                if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->ev_pack[pb], 0));  // the downloads of chunk c - 2 read these buffers
+                CK(ctx->d_pack_cls[pb].ensure(nt * 2 + 64));
+                CK(ctx->d_pack_rows[pb].ensure(nt * 64 + 64));
+                const uint2* rows = reinterpret_cast<const uint2*>(r_alpha.as<uint8_t>() + t0 * 64);
+                const uint64_t n_rows = (uint64_t)nt * 8;
+                uint16_t* cls = ctx->d_pack_cls[pb].as<uint16_t>();
+                uint32_t* off = ctx->d_pack_off.as<uint32_t>();
+                k_pack_classify<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls);
+                total.launches += 1 + device_scan(
+                    st, (uint32_t)nt, [cls] __device__(uint32_t i) { return (uint32_t)__popc(pack_stored_mask(cls[i])); },
+                    [off] __device__(uint32_t i, uint32_t excl, uint32_t) { off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(), d_sc + 6);
+                k_pack_rows<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls, off, ctx->d_pack_rows[pb].as<uint2>());
+                const uint32_t nb = nblk(nt, PACK_BLOCK);
+                CK(ctx->h_pack_boff.ensure_mapped(((size_t)1 << 22) * 4 + 64));
+                k_pack_block_offsets<<<nblk((uint64_t)nb + 1, 256), 256, 0, st>>>(off, (uint32_t)nt, d_sc + 6, static_cast<uint32_t*>(ctx->h_pack_boff.dev));
+                total.launches += 2;
+                CK(cudaStreamSynchronize(st));
+                CK(cudaGetLastError());
+                auto boff = std::make_shared<std::vector<uint32_t>>(ctx->h_pack_boff.as<uint32_t>(), ctx->h_pack_boff.as<uint32_t>() + nb + 1);
+                const size_t chunk_rows = (*boff)[nb];
+                if ((pack_row_base + chunk_rows) * 8 + 64 > ctx->h_pack_rows.cap || (t0 + nt) * 2 + 64 > ctx->h_pack_cls.cap) sink->drain();
+                CK(ctx->h_pack_rows.ensure_keep((pack_row_base + chunk_rows) * 8 + 64, pack_row_base * 8, ctx->st_out));
+                CK(ctx->h_pack_cls.ensure_keep((t0 + nt) * 2 + 64, t0 * 2, ctx->st_out));
+                constexpr uint32_t PIECE_BLOCKS = 512;  // ~ 18 MB of stored rows per piece
+                for (uint32_t b0 = 0; b0 < nb; b0 += PIECE_BLOCKS) {
+                    const uint32_t b1 = std::min(nb, b0 + PIECE_BLOCKS);
+                    const size_t ta = t0 + (size_t)b0 * PACK_BLOCK, tn = std::min<size_t>(nt - (size_t)b0 * PACK_BLOCK, (size_t)(b1 - b0) * PACK_BLOCK);
+                    const size_t r0 = (*boff)[b0], r1 = (*boff)[b1];
+                    CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + ta * 4, r_tile_xy.as<uint8_t>() + ta * 4, tn * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                    CK(cudaMemcpyAsync(ctx->h_pack_cls.as<uint16_t>() + ta, cls + (size_t)b0 * PACK_BLOCK, tn * 2, cudaMemcpyDeviceToHost, ctx->st_out));
+                    if (r1 > r0)
+                        CK(cudaMemcpyAsync(ctx->h_pack_rows.as<uint64_t>() + pack_row_base + r0, ctx->d_pack_rows[pb].as<uint64_t>() + r0, (r1 - r0) * 8,
+                                           cudaMemcpyDeviceToHost, ctx->st_out));
+                    if (sink_events == ctx->ev_sink.size()) {
+                        cudaEvent_t e;
+                        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        ctx->ev_sink.push_back(e);
+                    }
+                    cudaEvent_t e = ctx->ev_sink[sink_events++];
+                    CK(cudaEventRecord(e, ctx->st_out));
+                    sink->tile_xy = ctx->h_tile_xy.as<int16_t>();
+                    sink->cls = ctx->h_pack_cls.as<uint16_t>();
+                    sink->prow = ctx->h_pack_rows.as<uint64_t>();
+                    SinkTask k{};
+                    k.ready = e;
+                    k.boff = boff;
+                    k.chunk_t0 = t0;
+                    k.chunk_nt = nt;
+                    k.row_base = pack_row_base;
+                    k.b0 = b0;
+                    k.b1 = b1;
+                    sink->post(k);
+                }
+                CK(cudaEventRecord(ctx->ev_pack[pb], ctx->st_out));
+                pack_row_base += chunk_rows;
+                ctx->last_packed_bytes += chunk_rows * 8 + nt * 2;
+            }
             const size_t piece = sink ? ((size_t)32 << 20) / 64 : (nt ? nt : 1);
-            for (size_t a = 0; a < nt; a += piece) {
+            for (size_t a = 0; a < nt && !packed; a += piece) {
                 const size_t n = std::min(piece, nt - a);
                 CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + (t0 + a) * 4, r_tile_xy.as<uint8_t>() + (t0 + a) * 4, n * 4, cudaMemcpyDeviceToHost, ctx->st_out));
                 CK(cudaMemcpyAsync(ctx->h_alpha.as<uint8_t>() + (t0 + a) * 64, r_alpha.as<uint8_t>() + (t0 + a) * 64, n * 64, cudaMemcpyDeviceToHost, ctx->st_out));
@@ -1957,9 +2124,12 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         dev_ms += total.ms[s];
     }
     out->device_ms = dev_ms;
-    if (n_cmds + n_paths) {  // refine the arena estimates
-        ctx->tiles_per_cmd = std::max(ctx->tiles_per_cmd, (double)tile_base / ((double)n_cmds + n_paths));
-        ctx->spans_per_cmd = std::max(ctx->spans_per_cmd, (double)span_base / ((double)n_cmds + n_paths));
+    if (n_cmds + n_paths) {
+        // The arena estimates follow the LAST call, not the densest call the ctx has ever seen: buffers only grow, so a ctx that
+        // alternates between workloads does not reallocate, but a call is not sized (11 GB of pinned host memory per million G4
+        // paths) by a tile-dense batch that happened to run before it.
+        ctx->tiles_per_cmd = std::max(1.0, (double)tile_base / ((double)n_cmds + n_paths));
+        ctx->spans_per_cmd = std::max(0.1, (double)span_base / ((double)n_cmds + n_paths));
     }
 
     // ---- per-path status (OCHRE_SKIP_BAD_PATHS) ------------------------------------------
@@ -2016,7 +2186,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         out->tile_off = unordered ? nullptr : ctx->h_tile_off.as<uint32_t>();
         out->span_off = unordered ? nullptr : ctx->h_span_off.as<uint32_t>();
         out->tile_xy = ctx->h_tile_xy.as<int16_t>();
-        out->alpha = ctx->h_alpha.as<uint8_t>();
+        out->alpha = packed ? nullptr : ctx->h_alpha.as<uint8_t>();  // (row-packed transport: the tiles went to the host sink only)
         out->spans = ctx->h_spans.as<OchreSpan>();
         out->ranges = ctx->h_ranges.as<OchrePathRange>();
     }
@@ -2037,7 +2207,7 @@ int ochre_b200_rasterize(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32
         ctx->err = "null result pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS)) {
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS | OCHRE_OUT_SINK_PACKED)) {
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }
@@ -2055,7 +2225,7 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
         ctx->err = "null result pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS)) {
+    if (flags & ~(OCHRE_IN_DEVICE | OCHRE_OUT_DEVICE | OCHRE_KEEP_STAGES | OCHRE_OUT_UNORDERED | OCHRE_SKIP_BAD_PATHS | OCHRE_OUT_SINK_PACKED)) {
         ctx->err = "unknown flag bits";
         return OCHRE_E_INVALID_ARG;
     }

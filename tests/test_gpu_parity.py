@@ -632,3 +632,18 @@ def test_host_sink_sees_every_tile_and_span(ctx):
     # a call without the sink reports nothing
     ctx.rasterize(cmds, off, xf)
     assert ctx.last_sink()["tiles"] == 0
+    # row-packed transport (OCHRE_OUT_SINK_PACKED): class words + stored rows cross PCIe, the sink threads rebuild every tile --
+    # the builder must see exactly the same tiles (every sum equal), over several chunks and blocks, in both layouts
+    for unordered in (False, True):
+        ctx.set_chunk(20000)
+        ctx.set_host_sink(4)
+        try:
+            gp = ctx.rasterize(cmds, off, xf, unordered=unordered, sink_packed=True, copy=False)
+            sp = ctx.last_sink()
+        finally:
+            ctx.set_host_sink(0)
+            ctx.set_chunk(0)
+        assert gp.alpha is None and gp.n_tiles == g.n_tiles
+        for k in ("tiles", "spans", "geom_sum", "alpha_sum", "mix_sum"):
+            assert sp[k] == s[k], k
+        assert 0 < sp["packed_alpha_bytes"] < 64 * g.n_tiles * 0.75
