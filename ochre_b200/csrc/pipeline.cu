@@ -969,8 +969,20 @@ struct SinkRun {
                 for (size_t bk = k.b0 + nbk * t / n_threads; bk < k.b0 + nbk * (t + 1) / n_threads; ++bk) {
                     const size_t ta = k.chunk_t0 + bk * PACK_BLOCK, tn = std::min<size_t>(PACK_BLOCK, k.chunk_t0 + k.chunk_nt - ta);
                     const uint64_t* r = pr + k.row_base + (*k.boff)[bk];
+                    static const uint64_t k_full[8] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
+                    static const uint64_t k_zero[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
                     for (size_t i = ta; i < ta + tn; ++i) {
                         const uint32_t c = cw[i];
+                        // tiles that need no rebuilding: all eight rows stored (they are contiguous in the stream), or a constant tile
+                        if (c == 0xaaaau) {
+                            b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(r));
+                            r += 8;
+                            continue;
+                        }
+                        if (c == 0x5555u || c == 0u) {
+                            b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(c ? k_full : k_zero));
+                            continue;
+                        }
                         alignas(8) uint64_t tile[8];
                         for (int y = 0; y < 8; ++y) {
                             const uint32_t q = (c >> (2 * y)) & 3u;

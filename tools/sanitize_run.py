@@ -1,5 +1,5 @@
 """Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
-  python tools/sanitize_run.py [case ...]      cases: pkl striped pks general banded stroker atlas conic
+  python tools/sanitize_run.py [case ...]      cases: pkl striped pks general banded stroker atlas conic sink status
 Each case checks its result against the CPU oracle, so a sanitizer-clean run is also a correct one."""
 import os
 import sys
@@ -15,7 +15,7 @@ from ochre_b200 import workloads as W
 from ochre_b200.geom import CLOSE, CONIC, CUBIC, LINE, MOVE, make_cmds
 from parity import assert_batch_parity
 
-cases = sys.argv[1:] or ["pkl", "striped", "pks", "general", "banded", "stroker", "atlas", "conic"]
+cases = sys.argv[1:] or ["pkl", "striped", "pks", "general", "banded", "stroker", "atlas", "conic", "sink", "status"]
 ctx = ob.Context(0)
 
 
@@ -83,5 +83,25 @@ for case in cases:
         for mode in ("auto", "general"):
             ctx.set_mode(mode)
             check(ctx.rasterize(c, o, O.IDENTITY[None]), c, o, O.IDENTITY[None], f"conic ({mode})")
+    elif case == "sink":  # host sink, whole tiles and row-packed transport (k_pack_*), several chunks
+        c, o, x = W.blobs(300, first=41)
+        ctx.set_chunk(4000)
+        ctx.set_host_sink(3)
+        a = ctx.rasterize(c, o, x); sa = ctx.last_sink()
+        ctx.rasterize(c, o, x, unordered=True, sink_packed=True, copy=False); sb = ctx.last_sink()
+        ctx.set_host_sink(0); ctx.set_chunk(0)
+        assert all(sa[k] == sb[k] for k in ("tiles", "spans", "geom_sum", "alpha_sum", "mix_sum")) and sa["tiles"] == a.n_tiles
+        print(f"sink: ok, {sa['tiles']} tiles through the builder, {sb['packed_alpha_bytes'] / max(1, sa['tiles']):.1f} alpha bytes per tile over PCIe", flush=True)
+    elif case == "status":  # per-path status: a bad path among good ones, both implementations
+        c, o, x = W.blobs(60, first=51)
+        bad = make_cmds([(MOVE, 0, 0), (LINE, float("nan"), 1.0)])
+        cc = np.concatenate([c[:o[30]], bad, c[o[30]:]]); oo = np.concatenate([o[:31], o[30:] + len(bad)]).astype(np.uint32)
+        xx = np.concatenate([x[:30], O.IDENTITY[None], x[30:]])
+        for mode in ("auto", "general"):
+            ctx.set_mode(mode)
+            g = ctx.rasterize(cc, oo, xx, skip_bad=True)
+            st, nb = ctx.path_status(len(oo) - 1)
+            assert nb == 1 and st[30] == -2 and g.tile_off[31] == g.tile_off[30]
+        print("status: ok", flush=True)
 ctx.close()
 print("all cases done")
