@@ -42,6 +42,7 @@ struct PathKernelArgs {
     const uint32_t* n_paths_dev;  // non-null: the number of list entries to take is read from device memory (classified lists)
     uint32_t list_rev;          // 1: the list is path_list[n_paths - 1], path_list[n_paths - 2], ... (the large end of a two-ended list)
     int8_t* path_status;        // null, or per path (chunk-local id): the OCHRE_E_* code a path with an invalid command is dropped for
+    const uint2* box;           // glyph_kernel.cuh only: per list entry, the bounding grid k_classify computed (origin, W | H << 16)
     uint16_t* row_class;        // null, or per tile (same index as alpha): 2 bits per pixel row -- 0: all 0, 1: all 255, 2: stored.  Rows of
                                 // class 0 / 1 are NOT stored: the arena's owner fills them in (k_arena_expand).  Whole 4-row halves only:
                                 // 30 % of the halves of a G4 batch are constant (46 % of its rows)
@@ -221,9 +222,23 @@ __device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return 7u - ((f >>
 
 // Shared-memory reductions on a 32-bit shared-window address (computed once per pass): the generic-pointer
 // form makes the compiler rebuild the window base (S2UR + ULEA) at every atomic of the DDA loops.
+#if defined(OC_CUDA_ON_CPU)  // tests/emu/cuda_on_cpu.h: the "window address" is the offset into the CTA's shared memory
+inline uint32_t pk_saddr(const void* p) { return (uint32_t)((const unsigned char*)p - cemu::smem()); }
+inline void pk_red_add(uint32_t saddr, uint32_t v) { *reinterpret_cast<uint32_t*>(cemu::smem() + saddr) += v; }
+inline void pk_st_shared(uint32_t saddr, uint32_t v) { *reinterpret_cast<uint32_t*>(cemu::smem() + saddr) = v; }
+inline uint2 pk_ld_shared2(uint32_t saddr) { return *reinterpret_cast<const uint2*>(cemu::smem() + saddr); }
+inline uint32_t pk_below(uint32_t n) { return (1u << (n & 31u)) - 1u; }
+inline uint32_t pk_quant_u8(float v) { return v >= 255.0f ? 255u : (uint32_t)(int)v; }  // v >= 0, finite
+#else
 __device__ __forceinline__ uint32_t pk_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pk_red_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void pk_st_shared(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint2 pk_ld_shared2(uint32_t saddr) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
+    return r;
 }
 
 // (1 << n) - 1 for n in [0, 32)
@@ -232,5 +247,12 @@ __device__ __forceinline__ uint32_t pk_below(uint32_t n) {
     asm("bmsk.wrap.b32 %0, 0, %1;" : "=r"(m) : "r"(n));
     return m;
 }
+// trunc(min(v, 255)) for v >= 0: the conversion truncates and saturates
+__device__ __forceinline__ uint32_t pk_quant_u8(float v) {
+    uint32_t q;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(v));
+    return q;
+}
+#endif
 
 }  // namespace oc

@@ -74,6 +74,7 @@
 #define OC_PK_MAXB OC_PKS_MAXB
 #define OC_PK_NS pks
 #include "path_kernel.cuh"
+#include "glyph_kernel.cuh"
 #include "radix_sort.cuh"
 #include "raster_core.cuh"
 #include "scan.cuh"
@@ -667,53 +668,6 @@ k_fb_records(const uint32_t* __restrict__ fb, uint32_t n_fb, const uint32_t* __r
     rec[fb[q]] = make_uint4(tile_at + t0, t1 - t0, span_at + s0, s1 - s0);
 }
 
-// ---------------------------------------------------------------------------
-// Routing of a chunk's paths to the two instantiations of the fused kernel: a warp per path takes the bounding box
-// of the transformed control points (curves stay inside the hull of their control points; Conics with a negative
-// weight do not, they count as large).  Small paths fill `list` from the front, the others from the back.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TPB)
-k_classify(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, const float* __restrict__ xf,
-           uint32_t n_paths, int max_cells, uint32_t max_cmds, uint32_t* __restrict__ counts /* [0] small, [1] large */,
-           uint32_t* __restrict__ list) {
-    const uint32_t p = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (p >= n_paths) return;
-    const uint32_t c0 = cmd_off[p] - cmd_base, nc = cmd_off[p + 1] - cmd_off[p];
-    const float* m = xf + 6 * (size_t)p;
-    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff, odd = 0;
-    if (nc <= max_cmds) {
-        for (uint32_t j = lane; j < nc; j += 32) {
-            const Cmd& c = cmds[c0 + j];
-            const int np = cmd_npts(c.tag);
-            if (c.tag > TAG_CLOSE || (c.tag == TAG_CONIC && !(c.v[4] >= 0.0f))) odd = 1;
-            for (int i = 0; i < np; ++i) {
-                const V2 q = cmd_point(c, i, m);
-                if (!coord_ok(q)) odd = 1;
-                else {
-                    const int tx = floor_px(q.x) >> 3, ty = floor_px(q.y) >> 3;
-                    x0 = min(x0, tx); x1 = max(x1, tx);
-                    y0 = min(y0, ty); y1 = max(y1, ty);
-                }
-            }
-        }
-    } else {
-        odd = 1;
-    }
-    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
-    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
-    odd = __reduce_or_sync(0xffffffffu, (unsigned)odd);
-    if (lane == 0) {
-        // the path starts at (0, 0) unless it opens with a Move (rasterizer.rs:54-55): a first line from the origin counts
-        bool small = !odd;
-        if (small && x0 <= x1) {
-            if (nc && cmds[c0].tag != TAG_MOVE) { x0 = min(x0, 0); y0 = min(y0, 0); x1 = max(x1, 0); y1 = max(y1, 0); }
-            small = (long long)(x1 - x0 + 3) * (y1 - y0 + 3) <= max_cells;
-        }
-        if (small) list[atomicAdd(&counts[0], 1u)] = p;
-        else list[n_paths - 1u - atomicAdd(&counts[1], 1u)] = p;
-    }
-}
-
 // Control words travel between host and device in kernels, never through a copy engine: a few bytes queued on a
 // copy engine wait behind whatever bulk transfer another stream has put there (the result download, the input
 // upload) and would serialise the chunks of a call with those transfers.
@@ -858,6 +812,9 @@ struct HostBuf {  // pinned
 
 #ifndef OC_L2_SETASIDE_MB
 #define OC_L2_SETASIDE_MB 0
+#endif
+#ifndef OC_SMALL_KERNEL
+#define OC_SMALL_KERNEL 1
 #endif
 #ifndef OC_ROUTE_CELLS
 #define OC_ROUTE_CELLS 64
@@ -1099,8 +1056,9 @@ struct ochre_b200_ctx {
     int mode = OCHRE_MODE_AUTO;
     int band_lo = OC_BAND_MIN, band_hi = OC_BAND_MAX;  // tile rows rasterised (row-band sharding)
     int sm_count = 148;
-    DevBuf d_pk_scratch, d_pk_scratch_s, d_pk_list, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2, d_big;
+    DevBuf d_pk_scratch, d_pk_scratch_s, d_pk_list, d_pk_box, d_pk_rec, d_pk_ctl, d_pk_fb, d_pk_fb2, d_big;
     uint32_t route_min_paths = 8192;
+    int small_kernel = OC_SMALL_KERNEL;  // 1: glyph_kernel.cuh (a round of small paths per CTA), 0: path_kernel.cuh's warp-per-path shape
     int route_cells = OC_ROUTE_CELLS;  // paths whose control points span at most this many tiles (bounding grid incl. margins) take the small-path kernel
     DevBuf f_cmds, f_off, f_xf, f_fb, f_tile_off, f_span_off, f_tile_xy, f_alpha, f_spans;  // hand-over side batch
     // atlas / quad builder (csrc/atlas.cuh)
@@ -1411,6 +1369,7 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         if (route) {
             CK(ctx->d_pk_scratch_s.ensure((size_t)ctx->sm_count * pks::PK_CTAS_PER_SM * pks::PK_SCR_BYTES));
             CK(ctx->d_pk_list.ensure((size_t)n_paths * 4 + 4));
+            CK(ctx->d_pk_box.ensure((size_t)n_paths * 8 + 8));
         }
         // L2 set-aside for the kernel's evict_last accesses to its line scratch (path_kernel.cuh)
         const char* env = getenv("OCHRE_B200_L2_PERSIST_MB");
@@ -1466,18 +1425,28 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
         A.list_rev = 0;
         A.status = reinterpret_cast<int*>(ctl + PKC_STATUS);
         A.path_status = pstatus;
+        A.box = nullptr;
         if (ext && ctx->x_compress) CK(ctx->s_row_class.ensure(ctx->s_tile_xy.cap / 2, base_t > 0, st));
         A.row_class = (ext && ctx->x_compress) ? ctx->s_row_class.as<uint16_t>() : nullptr;
         CK(cudaEventRecord(ctx->ev[0], st));
         if (route) {
             uint32_t* list = ctx->d_pk_list.as<uint32_t>();
-            k_classify<<<nblk((uint64_t)n_paths * 32, TPB), TPB, 0, st>>>(A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, route_cells, 256u,
-                                                                         ctl + PKC_NSMALL, list);
+            // (the row-compressed arena emission exists in path_kernel.cuh only)
+            const bool glyphs = ctx->small_kernel == 1 && !A.row_class;
+            k_classify<<<nblk((uint64_t)n_paths * 32, CLS_THREADS), CLS_THREADS, 0, st>>>(
+                A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, glyphs ? std::min(route_cells, pkg::GK_GCELLS) : route_cells,
+                glyphs ? (uint32_t)pkg::GK_MAXCMDS : 256u, glyphs ? 1 : 0, ctl + PKC_NSMALL, list, ctx->d_pk_box.as<uint2>());
             PathKernelArgs S = A;  // small paths: list[0 .. n_small)
             S.path_list = list;
             S.n_paths_dev = ctl + PKC_NSMALL;
+            S.box = ctx->d_pk_box.as<uint2>();
             S.scratch = ctx->d_pk_scratch_s.as<unsigned char>();
-            pks::k_path<false><<<grid_s, pks::PK_THREADS, pks::PK_SMEM, st>>>(S);
+            if (glyphs) {
+                const uint32_t grid_g = (uint32_t)std::min<uint64_t>((n_paths + pkg::GK_FETCH - 1) / pkg::GK_FETCH, (uint64_t)ctx->sm_count * pkg::GK_CTAS_PER_SM);
+                pkg::k_glyphs<<<grid_g, pkg::GK_THREADS, pkg::GK_SMEM, st>>>(S);
+            } else {
+                pks::k_path<false><<<grid_s, pks::PK_THREADS, pks::PK_SMEM, st>>>(S);
+            }
             PathKernelArgs Lg = A;  // the others: list[n_paths - 1], list[n_paths - 2], ...
             Lg.path_list = list;
             Lg.n_paths_dev = ctl + PKC_NLARGE;
@@ -1695,9 +1664,12 @@ int ochre_b200_create(int device, ochre_b200_ctx** out) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pkl::k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkl::PK_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(pks::k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pks::PK_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pkg::k_glyphs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pkg::GK_SMEM);
     {
         const char* env = getenv("OCHRE_B200_ROUTE_CELLS");  // tuning / tests: 0 switches the small-path instantiation off
         if (env) ctx->route_cells = atoi(env);
+        env = getenv("OCHRE_B200_SMALL_KERNEL");  // "pks": path_kernel.cuh's warp-per-path shape instead of glyph_kernel.cuh
+        if (env) ctx->small_kernel = strcmp(env, "pks") == 0 ? 0 : 1;
         env = getenv("OCHRE_B200_ROUTE_MIN_PATHS");
         if (env) ctx->route_min_paths = (uint32_t)atol(env);
     }
@@ -1731,7 +1703,7 @@ int ochre_b200_destroy(ochre_b200_ctx* ctx) {
                     &ctx->d_path_has_inc, &ctx->d_scalars, &ctx->d_scan_ws, &ctx->d_lines, &ctx->d_keys[0], &ctx->d_keys[1],
                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_entry, &ctx->d_ridx[0], &ctx->d_ridx[1], &ctx->d_group_start, &ctx->d_g_real, &ctx->d_g_wd,
                     &ctx->d_tile_idx, &ctx->d_span_w, &ctx->d_span_idx, &ctx->d_path_first, &ctx->d_cv_pub, &ctx->o_tile_off, &ctx->o_span_off,
-                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pack_cls[0], &ctx->d_pack_cls[1], &ctx->d_pack_off, &ctx->d_pack_rows[0], &ctx->d_pack_rows[1], &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans, &ctx->s_row_class,
+                    &ctx->o_tile_xy, &ctx->o_alpha, &ctx->o_spans, &ctx->a_vtx, &ctx->a_idx, &ctx->a_atlas, &ctx->a_span_tile, &ctx->a_flag, &ctx->a_sb, &ctx->a_colors, &ctx->d_pstatus, &ctx->f_pstatus, &ctx->d_pack_cls[0], &ctx->d_pack_cls[1], &ctx->d_pack_off, &ctx->d_pack_rows[0], &ctx->d_pack_rows[1], &ctx->d_pk_scratch, &ctx->d_pk_scratch_s, &ctx->d_pk_list, &ctx->d_pk_box, &ctx->d_pk_rec, &ctx->d_pk_ctl, &ctx->d_pk_fb, &ctx->d_pk_fb2, &ctx->d_big, &ctx->f_cmds, &ctx->f_off, &ctx->f_xf, &ctx->f_fb, &ctx->f_tile_off, &ctx->f_span_off, &ctx->f_tile_xy, &ctx->f_alpha, &ctx->f_spans, &ctx->s_tile_xy, &ctx->s_alpha, &ctx->s_spans, &ctx->s_row_class,
                     &ctx->k_cmds, &ctx->k_off, &ctx->k_xf, &ctx->k_width, &ctx->k_foff, &ctx->k_flat_off, &ctx->k_fpt, &ctx->k_ftag, &ctx->k_flags,
                     &ctx->k_closes, &ctx->k_con_start, &ctx->k_con_len, &ctx->k_con_pc, &ctx->k_item_off, &ctx->k_item_out, &ctx->k_item0,
                     &ctx->k_nout, &ctx->k_out_off, &ctx->k_out};

@@ -48,6 +48,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* ws, ui
     return excl;
 }
 
+#if defined(__CUDACC__)  // (the block-level helpers above also compile under tests/emu/cuda_on_cpu.h)
 template <class In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(In in, uint32_t n, uint32_t* __restrict__ block_sums) {
     __shared__ uint32_t ws[33];
@@ -115,6 +116,8 @@ int device_scan(cudaStream_t st, uint32_t n, In in, Out out, uint32_t* block_sum
     k_scan_apply<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, block_sums);
     return 3;
 }
+
+#endif  // __CUDACC__
 
 inline size_t scan_ws_words(uint64_t n) { return (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 1; }
 

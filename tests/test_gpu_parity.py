@@ -23,17 +23,28 @@ pytestmark = pytest.mark.gpu
 ID = O.IDENTITY
 
 
-@pytest.fixture(scope="module", params=["general", "auto", "routed"])
+@pytest.fixture(scope="module", params=["general", "auto", "routed", "routed_pks"])
 def ctx(request):
     """The implementations behind ochre_b200_rasterize: the general global-memory pipeline; (mode auto) the fused
-    per-path kernel with the general pipeline as its fallback; and the same with small paths routed to the
-    warp-per-path shape of the fused kernel even in these small batches (by default only batches of >= 8192 paths
-    are routed)."""
-    c = ob.Context(0)  # raises loudly without a device / without the built extension
-    c.set_mode("auto" if request.param == "routed" else request.param)
-    if request.param == "routed":
-        c.set_routing(1024, 0)   # everything whose control points fit the small shape's grid
-    c.mode_name = "auto" if request.param == "routed" else request.param
+    per-path kernel with the general pipeline as its fallback; the same with small paths routed to the glyph kernel
+    (a round of small paths per CTA, csrc/glyph_kernel.cuh) even in these small batches (by default only batches of
+    >= 8192 paths are routed); and with small paths routed to the warp-per-path shape of the fused kernel instead."""
+    import os
+
+    routed = request.param.startswith("routed")
+    old = os.environ.get("OCHRE_B200_SMALL_KERNEL")
+    os.environ["OCHRE_B200_SMALL_KERNEL"] = "pks" if request.param == "routed_pks" else "pkg"  # (read when the context is created)
+    try:
+        c = ob.Context(0)  # raises loudly without a device / without the built extension
+    finally:
+        if old is None:
+            del os.environ["OCHRE_B200_SMALL_KERNEL"]
+        else:
+            os.environ["OCHRE_B200_SMALL_KERNEL"] = old
+    c.set_mode("auto" if routed else request.param)
+    if routed:
+        c.set_routing(1024, 0)   # everything whose control points fit the small kernel's grid
+    c.mode_name = "auto" if routed else request.param
     yield c
     c.close()
 

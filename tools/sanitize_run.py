@@ -1,5 +1,5 @@
 """Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
-  python tools/sanitize_run.py [case ...]      cases: pkl striped pks general banded stroker atlas conic sink status
+  python tools/sanitize_run.py [case ...]      cases: pkl striped pkg pks general banded stroker atlas conic sink status
 Each case checks its result against the CPU oracle, so a sanitizer-clean run is also a correct one."""
 import os
 import sys
@@ -15,7 +15,7 @@ from ochre_b200 import workloads as W
 from ochre_b200.geom import CLOSE, CONIC, CUBIC, LINE, MOVE, make_cmds
 from parity import assert_batch_parity
 
-cases = sys.argv[1:] or ["pkl", "striped", "pks", "general", "banded", "stroker", "atlas", "conic", "sink", "status"]
+cases = sys.argv[1:] or ["pkl", "striped", "pkg", "pks", "general", "banded", "stroker", "atlas", "conic", "sink", "status"]
 ctx = ob.Context(0)
 
 
@@ -46,10 +46,22 @@ for case in cases:
         o = np.concatenate([[0], [len(big)], len(big) + o2[1:], [len(big) + o2[-1] + len(wide)]]).astype(np.uint32)
         x = np.concatenate([O.IDENTITY[None], x2, O.IDENTITY[None]])
         check(ctx.rasterize(c, o, x), c, o, x, "striped + hand-over")
-    elif case == "pks":  # the warp-per-path shape, routed
+    elif case == "pkg":  # the glyph kernel (a round of small paths per CTA), routed; with paths it hands over (empty, no tile)
         ctx.set_routing(64, 0)
         c, o, x = W.glyphs(256, first=9)
-        check(ctx.rasterize(c, o, x), c, o, x, "pks: 256 routed glyphs")
+        empty = make_cmds([(MOVE, 5.0, 5.0), (CLOSE,)])
+        c = np.concatenate([c, empty]); o = np.concatenate([o, [o[-1] + len(empty), o[-1] + len(empty)]]).astype(np.uint32)
+        x = np.concatenate([x, O.IDENTITY[None], O.IDENTITY[None]])
+        check(ctx.rasterize(c, o, x), c, o, x, "pkg: 256 routed glyphs + 2 paths without a tile")
+    elif case == "pks":  # the warp-per-path shape, routed
+        os.environ["OCHRE_B200_SMALL_KERNEL"] = "pks"
+        c2 = ob.Context(0)
+        del os.environ["OCHRE_B200_SMALL_KERNEL"]
+        c2.set_mode("auto")
+        c2.set_routing(64, 0)
+        c, o, x = W.glyphs(256, first=9)
+        check(c2.rasterize(c, o, x), c, o, x, "pks: 256 routed glyphs")
+        c2.close()
     elif case == "general":  # global-memory pipeline: flatten, bin, radix sort, scans, coverage
         ctx.set_mode("general")
         c, o, x = W.rings(15, 16.0, 64)
