@@ -32,11 +32,23 @@
 #ifndef OC_DYN_SMEM
 #define OC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
+// (measured on 1 M glyphs, B200: 64 slots / 8 CTAs per SM / 384 lines 4.64 ms; 88 / 6 / 512: 4.79 ms; 56 / 9 and 48 / 10 lose the
+// paths of more than 56 / 48 grid cells to the per-path kernel and are slower)
 #ifndef OC_GK_SLOTS
-#define OC_GK_SLOTS 88
+#define OC_GK_SLOTS 64
 #endif
 #ifndef OC_GK_CTAS
-#define OC_GK_CTAS 6
+#define OC_GK_CTAS 8
+#endif
+#ifndef OC_GK_LCAP
+#define OC_GK_LCAP 384
+#endif
+
+#ifndef OC_GK_SERPENTINE
+#define OC_GK_SERPENTINE 1
+#endif
+#ifndef OC_GK_TILE_EST
+#define OC_GK_TILE_EST 0
 #endif
 
 namespace oc {
@@ -49,17 +61,25 @@ namespace oc {
 // int16), y = W | H << 16 (0 | 0: a path without a point).
 // ---------------------------------------------------------------------------
 constexpr int CLS_THREADS = 256;
+// LANES lanes per path (a power of two): 32 for paths of a hundred commands, 4 for glyphs -- a warp then has eight paths in
+// flight and a lane three to eight commands (1 M glyphs: 0.76 ms with a warp per path).
+template <int LANES>
 __global__ void __launch_bounds__(CLS_THREADS)
 k_classify(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, uint32_t cmd_base, const float* __restrict__ xf,
            uint32_t n_paths, int max_cells, uint32_t max_cmds, int conic_is_large, uint32_t* __restrict__ counts /* [0] small, [1] large */,
            uint32_t* __restrict__ list, uint2* __restrict__ box) {
-    const uint32_t p = (blockIdx.x * CLS_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (p >= n_paths) return;
-    const uint32_t c0 = cmd_off[p] - cmd_base, nc = cmd_off[p + 1] - cmd_off[p];
-    const float* m = xf + 6 * (size_t)p;
+    const uint32_t gt = blockIdx.x * CLS_THREADS + threadIdx.x;
+    const uint32_t p = gt / LANES, sub = gt % LANES;
+    const bool live = p < n_paths;  // (whole warps stay for the shuffles: n_paths need not be a multiple of the paths per warp)
+    uint32_t c0 = 0, nc = 0;
+    if (live) {
+        c0 = cmd_off[p] - cmd_base;
+        nc = cmd_off[p + 1] - cmd_off[p];
+    }
+    const float* m = xf + 6 * (size_t)(live ? p : 0u);
     int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff, odd = 0;
     if (nc <= max_cmds) {
-        for (uint32_t j = lane; j < nc; j += 32) {
+        for (uint32_t j = sub; j < nc; j += LANES) {
             const Cmd& c = cmds[c0 + j];
             const int np = cmd_npts(c.tag);
             if (c.tag > TAG_CLOSE || (c.tag == TAG_CONIC && (conic_is_large || !(c.v[4] >= 0.0f)))) odd = 1;
@@ -76,10 +96,13 @@ k_classify(const Cmd* __restrict__ cmds, const uint32_t* __restrict__ cmd_off, u
     } else {
         odd = 1;
     }
-    x0 = __reduce_min_sync(0xffffffffu, x0); y0 = __reduce_min_sync(0xffffffffu, y0);
-    x1 = __reduce_max_sync(0xffffffffu, x1); y1 = __reduce_max_sync(0xffffffffu, y1);
-    odd = (int)__reduce_or_sync(0xffffffffu, (unsigned)odd);
-    if (lane == 0) {
+#pragma unroll
+    for (int d = 1; d < LANES; d <<= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, d)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, d));
+        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, d)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, d));
+        odd |= __shfl_xor_sync(0xffffffffu, odd, d);
+    }
+    if (live && sub == 0) {
         // the path starts at (0, 0) unless it opens with a Move (rasterizer.rs:54-55): a first line from the origin counts
         bool small = !odd;
         uint2 bx = make_uint2(0u, 0u);
@@ -105,10 +128,10 @@ constexpr int GK_WARPS = GK_THREADS / 32;
 constexpr int GK_GMAX = 16;                 // paths per round
 constexpr int GK_FETCH = 16;                // list entries per ticket
 constexpr int GK_QCAP = 32;                 // fetched, not yet rasterised entries
-constexpr int GK_LCAP = 512;                // lines per round
+constexpr int GK_LCAP = OC_GK_LCAP;              // lines per round
 constexpr int GK_CCAP = 4 * GK_THREADS;     // grid cells per round (a thread scans 4)
-constexpr int GK_GCELLS = 64;               // grid cells per path (<= OC_GK_SLOTS: a path's tiles are resident together)
 constexpr int GK_SLOTS = OC_GK_SLOTS;       // resident accumulator blocks
+constexpr int GK_GCELLS = GK_SLOTS < 64 ? GK_SLOTS : 64;  // grid cells per path: its tiles (<= cells) are resident together
 constexpr int GK_ROWCAP = GK_CCAP / 3 + 2;  // tile rows per round (a grid row has >= 3 cells: one tile + the margins)
 constexpr int GK_CTAS_PER_SM = OC_GK_CTAS;
 constexpr int GK_MAXCMDS = GK_THREADS - 1;  // commands per path (+ FINISH = one chunk)
@@ -126,19 +149,21 @@ struct GkShared {
         } f;
     } u;
     float4 lines[GK_LCAP];
-    uint8_t lg[GK_LCAP];              // the line's path (slot of the round), 0xff: skipped (degenerate, rasterizer.rs:73)
+    uint8_t lg[GK_LCAP];              // the line's path (slot of the round) | step-count class << 4; 0xff: skipped (degenerate, rasterizer.rs:73)
+    uint16_t sidx[GK_LCAP];           // the lines that are walked, longest step-count class first: the lanes of a warp walk lines of (nearly) equal length
+    uint32_t ccnt[PK_NCLS], ccur[PK_NCLS];
     uint2 rk[GK_CCAP / 32 + 2];       // per 32 cells: x = bitmask of touched cells, y = touched cells before the word
-    uint32_t q_path[GK_QCAP], q_nv[GK_QCAP];
+    uint32_t q_path[GK_QCAP], q_nv[GK_QCAP], q_c0[GK_QCAP];
     uint2 q_box[GK_QCAP];
-    uint32_t g_path[GK_GMAX], g_c0[GK_GMAX], g_flag[GK_GMAX], g_wbase[GK_GMAX];
+    uint32_t g_path[GK_GMAX], g_c0[GK_GMAX], g_flag[GK_GMAX];
     uint32_t g_vs[GK_GMAX + 1], g_cell[GK_GMAX + 1], g_line[GK_GMAX + 1], g_rank[GK_GMAX + 1], g_span[GK_GMAX + 1], g_row[GK_GMAX + 1];
     int g_x0[GK_GMAX], g_y0[GK_GMAX];
     uint32_t g_W[GK_GMAX], g_H[GK_GMAX];
     uint16_t rowc[GK_ROWCAP];         // first cell of every tile row of the round
     uint8_t roww[GK_ROWCAP];          // its width
-    uint32_t ws[72];
+    uint32_t ws[3][2 * GK_WARPS];     // warp totals of the round's three CTA scans (one buffer each: a scan costs one barrier)
     uint32_t cw[2 * GK_WARPS];
-    uint32_t qn, pop, exhausted, keep, lpv16, base_tiles, base_spans;
+    uint32_t qn, pop, exhausted, keep, lpv16, tpc256, base_tiles, base_spans;
 };
 constexpr size_t GK_SMEM = sizeof(GkShared);
 static_assert(GK_GCELLS <= GK_SLOTS, "a path's tiles must fit the resident slots");
@@ -166,6 +191,44 @@ __device__ __forceinline__ uint32_t gk_warp_incl(uint32_t v, unsigned lane) {
     return v;
 }
 
+// Exclusive scan of (a, b) across the CTA with ONE barrier: every thread adds up the totals of the warps before its own.
+// `buf` (2 * GK_WARPS words) must not be the buffer of the previous scan (its readers may still be at work).
+__device__ __forceinline__ void gk_scan_pair(uint32_t a, uint32_t b, uint32_t* buf, unsigned lane, unsigned warp, uint32_t& ex_a, uint32_t& ex_b,
+                                             uint32_t& tot_a, uint32_t& tot_b) {
+    const uint32_t ia = gk_warp_incl(a, lane), ib = gk_warp_incl(b, lane);
+    if (lane == 31) {
+        buf[warp] = ia;
+        buf[GK_WARPS + warp] = ib;
+    }
+    __syncthreads();
+    uint32_t oa = 0, ob = 0;
+    tot_a = tot_b = 0;
+#pragma unroll
+    for (unsigned w = 0; w < (unsigned)GK_WARPS; ++w) {
+        const uint32_t va = buf[w], vb = buf[GK_WARPS + w];
+        oa += w < warp ? va : 0u;
+        ob += w < warp ? vb : 0u;
+        tot_a += va;
+        tot_b += vb;
+    }
+    ex_a = ia - a + oa;
+    ex_b = ib - b + ob;
+}
+__device__ __forceinline__ uint32_t gk_scan(uint32_t a, uint32_t* buf, unsigned lane, unsigned warp, uint32_t& tot) {
+    const uint32_t ia = gk_warp_incl(a, lane);
+    if (lane == 31) buf[warp] = ia;
+    __syncthreads();
+    uint32_t oa = 0;
+    tot = 0;
+#pragma unroll
+    for (unsigned w = 0; w < (unsigned)GK_WARPS; ++w) {
+        const uint32_t va = buf[w];
+        oa += w < warp ? va : 0u;
+        tot += va;
+    }
+    return ia - a + oa;
+}
+
 __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKernelArgs A) {
     OC_DYN_SMEM(gk_smem_raw);
     GkShared& S = *reinterpret_cast<GkShared*>(gk_smem_raw);
@@ -176,7 +239,8 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
         S.qn = 0;
         S.pop = 0;
         S.exhausted = 0;
-        S.lpv16 = 48;  // lines per command (x16) the next round is planned with: follows the previous round
+        S.lpv16 = 48;    // lines per command (x16) the next round is planned with: follows the previous round
+        S.tpc256 = 112;  // tiles per grid cell (x256), likewise
     }
     uint32_t ex_t = 0, span_excl = 0;
     for (;;) {
@@ -188,12 +252,13 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             uint32_t exhausted = S.exhausted;
             {
                 const bool mv = lane + pop < qn;
-                const uint32_t a = mv ? S.q_path[lane + pop] : 0u, b = mv ? S.q_nv[lane + pop] : 0u;
+                const uint32_t a = mv ? S.q_path[lane + pop] : 0u, b = mv ? S.q_nv[lane + pop] : 0u, d = mv ? S.q_c0[lane + pop] : 0u;
                 const uint2 c = mv ? S.q_box[lane + pop] : make_uint2(0u, 0u);
                 __syncwarp();
                 if (mv) {
                     S.q_path[lane] = a;
                     S.q_nv[lane] = b;
+                    S.q_c0[lane] = d;
                     S.q_box[lane] = c;
                 }
                 qn -= pop;
@@ -207,8 +272,10 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                 if (lane < take) {
                     const uint32_t idx = t + lane;
                     const uint32_t p = A.path_list ? A.path_list[idx] : idx;
+                    const uint32_t o0 = A.cmd_off[p];
                     S.q_path[qn + lane] = p;
-                    S.q_nv[qn + lane] = A.cmd_off[p + 1] - A.cmd_off[p] + 1u;
+                    S.q_nv[qn + lane] = A.cmd_off[p + 1] - o0 + 1u;
+                    S.q_c0[qn + lane] = o0 - A.cmd_base;
                     S.q_box[qn + lane] = A.box[idx];
                 }
                 qn += take;
@@ -223,8 +290,10 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             const bool solo_bad = nv > (uint32_t)GK_THREADS || cells > (uint32_t)GK_GCELLS || cells == 0u;
             const uint32_t cum_nv = gk_warp_incl(nv, lane), cum_c = gk_warp_incl(cells4, lane), cum_h = gk_warp_incl(H, lane);
             // (the first path of a round is taken whatever the line estimate says)
+            // (lines and tiles are estimates from the previous round: a round over the line budget defers its last paths, a round
+            // over the slots walks its lines once per band of paths)
             const bool fit = cand && !solo_bad && cum_nv <= (uint32_t)GK_THREADS && cum_c <= (uint32_t)GK_CCAP &&
-                             (lane == 0 || (cum_nv * S.lpv16) / 16u <= (uint32_t)GK_LCAP);
+                             (lane == 0 || ((cum_nv * S.lpv16) / 16u <= (uint32_t)GK_LCAP && (!OC_GK_TILE_EST || (cum_c * S.tpc256) / 256u <= (uint32_t)GK_SLOTS)));
             const uint32_t fm = __ballot_sync(0xffffffffu, fit);
             const uint32_t keep = (uint32_t)__ffs((int)~fm) - 1u;  // leading run of fitting entries (lane 31 never fits: GK_GMAX < 32)
             uint32_t popn = 0;
@@ -237,7 +306,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             if (lane < keep) {
                 const uint32_t p = S.q_path[lane];
                 S.g_path[lane] = p;
-                S.g_c0[lane] = A.cmd_off[p] - A.cmd_base;
+                S.g_c0[lane] = S.q_c0[lane];
                 S.g_flag[lane] = 0;
                 S.g_vs[lane] = cum_nv - nv;
                 S.g_cell[lane] = cum_c - cells4;
@@ -282,6 +351,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             S.cw[warp] = bm;
             S.cw[GK_WARPS + warp] = bp;
         }
+        if (tid < (uint32_t)PK_NCLS) S.ccnt[tid] = S.ccur[tid] = 0;
         __syncthreads();
         uint32_t my_n = 0, my_tag = TAG_CLOSE;
         float my_dt = 0.0f;
@@ -330,17 +400,11 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             if (bad) atomicOr(&S.g_flag[g], (uint32_t)GF_CMD);
         }
         uint32_t total;
-        const uint32_t first = block_excl_scan(my_n, S.ws, total);
+        const uint32_t first = gk_scan(my_n, S.ws[0], lane, warp, total);
         if (act && k == 0) S.g_line[g] = first;
         if (tid == 0) S.g_line[keep0] = total;
-        __syncthreads();
-        // paths whose lines fit the round; the others stay in the queue (a first path that does not fit alone is handed over)
-        uint32_t keep = 0;
-        while (keep < keep0 && S.g_line[keep + 1] <= (uint32_t)GK_LCAP) ++keep;
-        const bool head_over = keep == 0;
-        if (head_over) keep = 1;
-        const uint32_t nl = head_over ? 0u : S.g_line[keep];
-        if (act && g < keep && my_n && !head_over) {
+        // (written before the round knows which of its paths fit the line budget: what lies beyond it is never read)
+        if (act && my_n && first + my_n <= (uint32_t)GK_LCAP) {
             S.u.f.last[tid] = c_last;
             S.u.f.a[tid] = c_a;
             S.u.f.b[tid] = c_b;
@@ -354,12 +418,18 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                 S.u.f.lrec[first + q] = make_uint2(__float_as_uint(t), tid);
             }
         }
+        __syncthreads();
+        // paths whose lines fit the round; the others stay in the queue (a first path that does not fit alone is handed over)
+        uint32_t keep = 0;
+        while (keep < keep0 && S.g_line[keep + 1] <= (uint32_t)GK_LCAP) ++keep;
+        const bool head_over = keep == 0;
+        if (head_over) keep = 1;
+        const uint32_t nl = head_over ? 0u : S.g_line[keep];
         if (tid == 0) {
             if (head_over) S.g_flag[0] = GF_CMD;
             S.pop = keep;
             S.lpv16 = min(64u * 16u, (total * 16u) / nvt + 8u);
         }
-        __syncthreads();
 
         // ---- lines: end points, then start points (the predecessor's end point) --------------------------------
         for (uint32_t i = tid; i < nl; i += GK_THREADS) {
@@ -382,7 +452,15 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             }
             const uint32_t gg = S.u.f.g[o];
             reinterpret_cast<float2*>(&S.lines[i])[0] = make_float2(a.x, a.y);
-            S.lg[i] = (same(a, mk(bb.x, bb.y)) || S.g_flag[gg]) ? (uint8_t)0xff : (uint8_t)gg;
+            uint32_t rec = 0xffu;
+            if (!(same(a, mk(bb.x, bb.y)) || S.g_flag[gg])) {
+                // DDA trips of the line, up to rounding overshoot -> step-count class, longest first (path_kernel_common.cuh)
+                const int n = abs(floor_px(bb.x) - floor_px(a.x)) + abs(floor_px(bb.y) - floor_px(a.y)) + 1;
+                const uint32_t cls = 7u - (uint32_t)(n <= 4 ? n - 1 : 4 + (n > 6) + (n > 9) + (n > 15));
+                atomicAdd(&S.ccnt[cls], 1u);
+                rec = gg | (cls << 4);
+            }
+            S.lg[i] = (uint8_t)rec;
         }
         __syncthreads();  // the command table is dead
 
@@ -397,21 +475,44 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                 S.roww[r0 + r] = (uint8_t)W;
             }
         }
+        uint32_t n_walk = 0;  // lines with two distinct end points
+        {
+            uint32_t cbase[PK_NCLS];
+#pragma unroll
+            for (int q = 0; q < PK_NCLS; ++q) {
+                cbase[q] = n_walk;
+                n_walk += S.ccnt[q];
+            }
+            for (uint32_t i = tid; i < nl; i += GK_THREADS) {
+                const uint32_t rec = S.lg[i];
+                if (rec == 0xffu) continue;
+                const uint32_t cls = rec >> 4;
+                uint32_t base = 0;
+#pragma unroll
+                for (int q = 0; q < PK_NCLS; ++q) base = (cls == (uint32_t)q) ? cbase[q] : base;
+                S.sidx[base + atomicAdd(&S.ccur[cls], 1u)] = (uint16_t)i;
+            }
+        }
         __syncthreads();
         {
             const uint32_t cell_s = smem_s + (uint32_t)offsetof(GkShared, u);
-            for (uint32_t i = tid; i < nl; i += GK_THREADS) {
-                const uint32_t gg = S.lg[i];
-                if (gg == 0xffu) continue;
+            // (the sorted lines go to the warps in serpentine order -- warps 0 1 2 3, then 3 2 1 0, ... -- so that no warp is left
+            // with the longest lines of every trip)
+            for (uint32_t trip = 0; trip * GK_THREADS < n_walk; ++trip) {
+                const uint32_t pos = (trip * GK_WARPS + (((trip & 1u) && OC_GK_SERPENTINE) ? (uint32_t)GK_WARPS - 1u - warp : warp)) * 32u + lane;
+                if (pos >= n_walk) continue;
+                const uint32_t i = S.sidx[pos];
+                const uint32_t gg = S.lg[i] & 15u;
                 const int W = (int)S.g_W[gg], H = (int)S.g_H[gg];
                 const uint32_t cb = cell_s + 4u * S.g_cell[gg];
                 LineWalk w;
                 w.init(S.lines[i], S.g_x0[gg] * 8, S.g_y0[gg] * 8);
                 int prev_ty = w.y >> 3;
-                bool done, out = false;
+                bool done, out = false, over = false;
                 do {
                     const int cx = w.x >> 3, cy = w.y >> 3;
-                    if ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) pk_red_add(cb + 4u * (uint32_t)(cy * W + cx), 1u);
+                    // (a 512th increment on a tile would take the fixed-point sums out of int32: the path is handed over)
+                    if ((unsigned)cx < (unsigned)W && (unsigned)cy < (unsigned)H) over |= (pk_atom_add(cb + 4u * (uint32_t)(cy * W + cx), 1u) & 0xffffu) >= (uint32_t)PK_MAXCNT;
                     else out = true;
                     bool row;
                     done = w.advance(row) == 1.0f;
@@ -425,6 +526,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                     }
                 } while (!done);
                 if (out) atomicOr(&S.g_flag[gg], (uint32_t)GF_GRID);  // (never, by construction: curves stay inside the hull of their control points)
+                if (over) atomicOr(&S.g_flag[gg], (uint32_t)GF_COUNT);
             }
         }
         __syncthreads();
@@ -436,11 +538,6 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
         for (uint32_t i = 1; i < keep; ++i) cg += (S.g_cell[i] <= c0) ? 1u : 0u;
         uint4 cw4 = make_uint4(PK_CELL_INIT, PK_CELL_INIT, PK_CELL_INIT, PK_CELL_INIT);
         if (own) cw4 = *reinterpret_cast<const uint4*>(&S.u.cell[c0]);
-        {
-            const uint32_t mx = max(max(cw4.x & 0xffffu, cw4.y & 0xffffu), max(cw4.z & 0xffffu, cw4.w & 0xffffu));
-            if (mx > (uint32_t)PK_MAXCNT) atomicOr(&S.g_flag[cg], (uint32_t)GF_COUNT);  // keeps the fixed-point sums inside int32
-        }
-        __syncthreads();
         if (own && S.g_flag[cg]) cw4 = make_uint4(PK_CELL_INIT, PK_CELL_INIT, PK_CELL_INIT, PK_CELL_INIT);  // a path that is handed over has no tiles here
         const uint32_t wv[4] = {cw4.x, cw4.y, cw4.z, cw4.w};
         uint32_t lt = 0, lw = 0;
@@ -450,16 +547,27 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             lw += (wv[q] >> 16) - 0x8000u;
         }
         uint32_t ex_w, tot_t, tot_w;
-        block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
-        if (own && c0 == S.g_cell[cg]) {
-            S.g_rank[cg] = ex_t;
-            S.g_wbase[cg] = ex_w;
+        gk_scan_pair(lt, lw, S.ws[1], lane, warp, ex_t, ex_w, tot_t, tot_w);
+        if (own && c0 == S.g_cell[cg]) S.g_rank[cg] = ex_t;
+        if (tid == 0) {
+            S.g_rank[keep] = tot_t;
+            S.tpc256 = (tot_t * 256u) / max(ncell, 1u) + 4u;
         }
-        if (tid == 0) S.g_rank[keep] = tot_t;
-        __syncthreads();
+        // (c) the cell words are in registers: the accumulators that share their memory are zeroed for the first band
+        {
+            uint4* z = reinterpret_cast<uint4*>(S.u.acc);
+            for (uint32_t i = tid; i < (uint32_t)(GK_SLOTS * (PK_ACCW / 4)); i += GK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         uint32_t fl[4] = {0u, 0u, 0u, 0u};
         if (own) {
-            int wp = (int)(ex_w - S.g_wbase[cg]);  // the reference's never-reset `winding` starts at 0 for every path (rasterizer.rs:219, :253-260)
+            // The reference's never-reset `winding` (rasterizer.rs:219, :253-260) starts at 0 for every path, and the scan
+            // carries nothing from one path's cells into the next: a line adds floor(end.y) / 8 - floor(start.y) / 8 in all,
+            // every line starts where its predecessor ends, and every subpath is closed (by Move or FINISH), so the deltas
+            // of a path add up to zero.
+            int wp = (int)ex_w;
+#if defined(OC_CUDA_ON_CPU)
+            if (c0 == S.g_cell[cg] && ex_w != 0) { fprintf(stderr, "glyph kernel: winding carried across paths\n"); abort(); }
+#endif
             uint32_t nib = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -491,46 +599,53 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             }
         }
         uint32_t tot_s;
-        span_excl = block_excl_scan(ls, S.ws, tot_s);
+        span_excl = gk_scan(ls, S.ws[2], lane, warp, tot_s);
         if (own && c0 == gcell0) S.g_span[cg] = span_excl;
+        // ---- reserve: one pair of atomics for the round.  Their results stay in thread 0's registers until the first band's
+        // lines are walked: nobody waits for the round trip to L2.
+        uint32_t res_t = 0, res_s = 0;
         if (tid == 0) {
             S.g_span[keep] = tot_s;
-            // ---- reserve: one pair of atomics for the round ----
-            S.base_tiles = atomicAdd(A.cursor, tot_t);
-            S.base_spans = atomicAdd(A.cursor + 1, tot_s);
+            res_t = atomicAdd(A.cursor, tot_t);
+            res_s = atomicAdd(A.cursor + 1, tot_s);
         }
-        __syncthreads();
-        const uint32_t tile_at = S.base_tiles, span_at = S.base_spans;
-        const bool fits = (uint64_t)tile_at + tot_t <= A.cap_tiles && (uint64_t)span_at + tot_s <= A.cap_spans;
-        if (tid < keep) {
-            const uint32_t p = S.g_path[tid];
-            const uint32_t nt = S.g_rank[tid + 1] - S.g_rank[tid], ns = S.g_span[tid + 1] - S.g_span[tid];
-            A.rec[p] = make_uint4(tile_at + S.g_rank[tid], nt, span_at + S.g_span[tid], ns);
-            if (nt == 0) A.fb_list[atomicAdd(A.status + 1, 1)] = p;  // handed over (or no tile at all: the striped form emits the empty path's tile)
-        }
-        if (!fits) {
-            if (tid == 0) atomicMax(A.status + 2, 1);
-            continue;
-        }
-        // ---- tile origins and spans ------------------------------------------------------------------------------
-        if (own) {
-            const int gx0 = S.g_x0[cg], gy0 = S.g_y0[cg];
-            uint32_t r = tile_at + ex_t, si = span_at + span_excl;
+        uint32_t tile_at = 0, span_at = 0;
+        bool fits = true, published = false;
+        // After the barrier that follows S.base_*: per-path records, tile origins, spans.
+        auto publish = [&]() {
+            tile_at = S.base_tiles;
+            span_at = S.base_spans;
+            fits = (uint64_t)tile_at + tot_t <= A.cap_tiles && (uint64_t)span_at + tot_s <= A.cap_spans;
+            published = true;
+            if (tid < keep) {
+                const uint32_t p = S.g_path[tid];
+                const uint32_t nt = S.g_rank[tid + 1] - S.g_rank[tid], ns = S.g_span[tid + 1] - S.g_span[tid];
+                A.rec[p] = make_uint4(tile_at + S.g_rank[tid], nt, span_at + S.g_span[tid], ns);
+                if (nt == 0) A.fb_list[atomicAdd(A.status + 1, 1)] = p;  // handed over (or no tile at all: the striped form emits the empty path's tile)
+            }
+            if (!fits) {
+                if (tid == 0) atomicMax(A.status + 2, 1);
+                return;
+            }
+            if (own) {  // tile origins and spans
+                const int gx0 = S.g_x0[cg], gy0 = S.g_y0[cg];
+                uint32_t r = tile_at + ex_t, si = span_at + span_excl;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (!(fl[q] & CF_TOUCHED)) continue;
-                const uint32_t c = c0 + (uint32_t)q, lc = c - gcell0;
-                const uint32_t cy = lc / gW, cx = lc - cy * gW;
-                const int px = (gx0 + (int)cx) * 8, py = (gy0 + (int)cy) * 8;
-                __stcs(reinterpret_cast<uint32_t*>(A.tile_xy) + r, (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16));
-                ++r;
-                if (fl[q] & CF_SPAN) {
-                    const uint32_t nx = gk_next_touched(S, c + 1u, gcell0 + (cy + 1u) * gW);
-                    __stcs(reinterpret_cast<uint2*>(A.spans) + si, make_uint2((uint32_t)(uint16_t)(int16_t)(px + 8) | ((uint32_t)(uint16_t)(int16_t)py << 16), (nx - c - 1u) * 8u));
-                    ++si;
+                for (int q = 0; q < 4; ++q) {
+                    if (!(fl[q] & CF_TOUCHED)) continue;
+                    const uint32_t c = c0 + (uint32_t)q, lc = c - gcell0;
+                    const uint32_t cy = lc / gW, cx = lc - cy * gW;
+                    const int px = (gx0 + (int)cx) * 8, py = (gy0 + (int)cy) * 8;
+                    __stcs(reinterpret_cast<uint32_t*>(A.tile_xy) + r, (uint32_t)(uint16_t)(int16_t)px | ((uint32_t)(uint16_t)(int16_t)py << 16));
+                    ++r;
+                    if (fl[q] & CF_SPAN) {
+                        const uint32_t nx = gk_next_touched(S, c + 1u, gcell0 + (cy + 1u) * gW);
+                        __stcs(reinterpret_cast<uint2*>(A.spans) + si, make_uint2((uint32_t)(uint16_t)(int16_t)(px + 8) | ((uint32_t)(uint16_t)(int16_t)py << 16), (nx - c - 1u) * 8u));
+                        ++si;
+                    }
                 }
             }
-        }
+        };
 
         // ---- coverage: bands of whole paths whose tiles fit the resident slots -----------------------------------
         const uint32_t acc_s = smem_s + (uint32_t)offsetof(GkShared, u);
@@ -539,20 +654,24 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             uint32_t gb = ga + 1;
             while (gb < keep && S.g_rank[gb + 1] - S.g_rank[ga] <= (uint32_t)GK_SLOTS) ++gb;
             const uint32_t rank0 = S.g_rank[ga], nslots = S.g_rank[gb] - rank0;
-            const uint32_t l0 = S.g_line[ga], l1 = S.g_line[gb], row0 = S.g_row[ga], row1 = S.g_row[gb];
+            const uint32_t band_lo = ga, band_hi = gb, row0 = S.g_row[ga], row1 = S.g_row[gb];
             ga = gb;
             if (nslots == 0) continue;
-            __syncthreads();  // the cell words (first band) / the previous band's accumulators are dead
-            {
+            if (band_lo != 0) {  // (the first band's accumulators were zeroed during the scan)
+                __syncthreads();  // the previous band's accumulators are dead
                 uint4* z = reinterpret_cast<uint4*>(S.u.acc);
                 for (uint32_t i = tid; i < nslots * (PK_ACCW / 4); i += GK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
             }
-            __syncthreads();
             {
                 const uint32_t slot0_s = acc_s - rank0 * (uint32_t)(4 * PK_ACCW);
-                for (uint32_t i = l0 + tid; i < l1; i += GK_THREADS) {
-                    const uint32_t gg = S.lg[i];
-                    if (gg == 0xffu || S.g_flag[gg]) continue;
+                const bool all = band_lo == 0 && band_hi == keep;
+                for (uint32_t trip = 0; trip * GK_THREADS < n_walk; ++trip) {
+                    const uint32_t pos = (trip * GK_WARPS + (((trip & 1u) && OC_GK_SERPENTINE) ? (uint32_t)GK_WARPS - 1u - warp : warp)) * 32u + lane;
+                    if (pos >= n_walk) continue;
+                    const uint32_t i = S.sidx[pos];
+                    const uint32_t gg = S.lg[i] & 15u;
+                    if ((!all && (gg < band_lo || gg >= band_hi)) || S.g_flag[gg]) continue;
                     const int W = (int)S.g_W[gg];
                     const uint32_t cb = S.g_cell[gg];
                     const int ox = S.g_x0[gg] * 8;
@@ -587,26 +706,26 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                     } while (t1 != 1.0f);
                 }
             }
-            __syncthreads();
-            // row sums: thread per (tile, pixel row); the sum of the 9 columns is the row's total height
-            for (uint32_t it = tid; it < nslots * 8u; it += GK_THREADS) {
-                int* d = &S.u.acc[(it >> 3) * PK_ACCW + (it & 7u) * 9u];
-                int rs = 0;
-#pragma unroll
-                for (int x = 0; x < 9; ++x) rs += d[x];
-                d[8] = rs;
+            if (!published && tid == 0) {
+                S.base_tiles = res_t;
+                S.base_spans = res_s;
             }
             __syncthreads();
-            // row carry: thread per (tile row, pixel row), left to right over the row's tiles, exact integer sum
+            if (!published) publish();
+            if (!fits) break;
+            // row carry: thread per (tile row, pixel row), left to right over the row's tiles, exact integer sum of the tiles' row
+            // totals (the 9 columns of a row add up to its total height)
             for (uint32_t it = tid; it < (row1 - row0) * 8u; it += GK_THREADS) {
                 const uint32_t rr = row0 + (it >> 3), y = it & 7u;
                 const uint32_t rc = S.rowc[rr];
                 const uint32_t s0 = gk_rank(S, rc) - rank0, s1 = gk_rank(S, rc + S.roww[rr]) - rank0;
                 long long c = 0;
                 for (uint32_t s = s0; s < s1; ++s) {
-                    int* d = &S.u.acc[s * PK_ACCW + y * 9u + 8u];
-                    const int rs = *d;
-                    *d = __float_as_int((float)c * OC_FX_TO_256);
+                    int* d = &S.u.acc[s * PK_ACCW + y * 9u];
+                    int rs = 0;
+#pragma unroll
+                    for (int x = 0; x < 9; ++x) rs += d[x];
+                    d[8] = __float_as_int((float)c * OC_FX_TO_256);
                     c += rs;
                 }
             }
@@ -627,6 +746,14 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
                 }
                 __stcs(reinterpret_cast<uint2*>(A.alpha + (size_t)(tile_at + rank0 + s) * 64) + y, make_uint2(lo32, hi32));
             }
+        }
+        if (!published) {  // a round without a single tile: its paths are handed over all the same
+            if (tid == 0) {
+                S.base_tiles = res_t;
+                S.base_spans = res_s;
+            }
+            __syncthreads();
+            publish();
         }
     }
 }

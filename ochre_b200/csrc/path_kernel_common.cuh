@@ -226,6 +226,7 @@ __device__ __forceinline__ uint32_t pk_info_cls(uint32_t f) { return 7u - ((f >>
 inline uint32_t pk_saddr(const void* p) { return (uint32_t)((const unsigned char*)p - cemu::smem()); }
 inline void pk_red_add(uint32_t saddr, uint32_t v) { *reinterpret_cast<uint32_t*>(cemu::smem() + saddr) += v; }
 inline void pk_st_shared(uint32_t saddr, uint32_t v) { *reinterpret_cast<uint32_t*>(cemu::smem() + saddr) = v; }
+inline uint32_t pk_atom_add(uint32_t saddr, uint32_t v) { uint32_t* p = reinterpret_cast<uint32_t*>(cemu::smem() + saddr); const uint32_t o = *p; *p = o + v; return o; }
 inline uint2 pk_ld_shared2(uint32_t saddr) { return *reinterpret_cast<const uint2*>(cemu::smem() + saddr); }
 inline uint32_t pk_below(uint32_t n) { return (1u << (n & 31u)) - 1u; }
 inline uint32_t pk_quant_u8(float v) { return v >= 255.0f ? 255u : (uint32_t)(int)v; }  // v >= 0, finite
@@ -233,6 +234,11 @@ inline uint32_t pk_quant_u8(float v) { return v >= 255.0f ? 255u : (uint32_t)(in
 __device__ __forceinline__ uint32_t pk_saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pk_red_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t pk_atom_add(uint32_t saddr, uint32_t v) {
+    uint32_t o;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(saddr), "r"(v) : "memory");
+    return o;
 }
 __device__ __forceinline__ void pk_st_shared(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint2 pk_ld_shared2(uint32_t saddr) {

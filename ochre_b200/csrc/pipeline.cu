@@ -30,6 +30,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <atomic>
 #include <vector>
 
 #include "../../include/ochre_b200.h"
@@ -1433,9 +1434,15 @@ int run_chunk_fused(ochre_b200_ctx* ctx, const Cmd* d_cmds_all, const uint32_t* 
             uint32_t* list = ctx->d_pk_list.as<uint32_t>();
             // (the row-compressed arena emission exists in path_kernel.cuh only)
             const bool glyphs = ctx->small_kernel == 1 && !A.row_class;
-            k_classify<<<nblk((uint64_t)n_paths * 32, CLS_THREADS), CLS_THREADS, 0, st>>>(
-                A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, glyphs ? std::min(route_cells, pkg::GK_GCELLS) : route_cells,
-                glyphs ? (uint32_t)pkg::GK_MAXCMDS : 256u, glyphs ? 1 : 0, ctl + PKC_NSMALL, list, ctx->d_pk_box.as<uint2>());
+            // (lanes per path from the batch's mean path length: a warp per path leaves most lanes idle on glyphs)
+            const int cls_cells = glyphs ? std::min(route_cells, pkg::GK_GCELLS) : route_cells;
+            const uint32_t cls_cmds = glyphs ? (uint32_t)pkg::GK_MAXCMDS : 256u;
+            if ((uint64_t)n_cmds <= 32ull * n_paths)
+                k_classify<4><<<nblk((uint64_t)n_paths * 4, CLS_THREADS), CLS_THREADS, 0, st>>>(A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, cls_cells, cls_cmds, glyphs ? 1 : 0,
+                                                                                            ctl + PKC_NSMALL, list, ctx->d_pk_box.as<uint2>());
+            else
+                k_classify<32><<<nblk((uint64_t)n_paths * 32, CLS_THREADS), CLS_THREADS, 0, st>>>(A.cmds, A.cmd_off, A.cmd_base, A.xf, n_paths, cls_cells, cls_cmds, glyphs ? 1 : 0,
+                                                                                              ctl + PKC_NSMALL, list, ctx->d_pk_box.as<uint2>());
             PathKernelArgs S = A;  // small paths: list[0 .. n_small)
             S.path_list = list;
             S.n_paths_dev = ctl + PKC_NSMALL;
@@ -1770,6 +1777,30 @@ int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out) {
     return 0;
 }
 
+// cmd_off monotone?  A walk over the offsets of a million paths costs 0.3-0.5 ms of host time (memory bound).  For device-resident
+// input the kernels read the caller's device array, the host array is its mirror (chunk planning and buffer sizes only, both
+// robust against a bad mirror: the cuts are checked where they are made): the mirror is checked BESIDE the kernels, by a helper
+// thread, and the call fails with the same code when it ends.
+struct OffsetCheck {
+    std::thread th;
+    std::atomic<uint32_t> bad{0};
+    static uint32_t scan(const uint32_t* h, uint32_t n) {
+        uint32_t b = 0;
+        for (uint32_t p = 0; p < n; ++p) b |= (uint32_t)(h[p + 1] < h[p]);
+        return b;
+    }
+    void start(const uint32_t* h, uint32_t n) {
+        th = std::thread([this, h, n] { bad.store(scan(h, n)); });
+    }
+    bool failed() {
+        if (th.joinable()) th.join();
+        return bad.load() != 0;
+    }
+    ~OffsetCheck() {
+        if (th.joinable()) th.join();
+    }
+};
+
 static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint32_t* cmd_off, const OchreTransform* xf,
                           uint32_t n_paths, uint32_t flags, const uint32_t* cmd_off_host, OchreResult* out) {
     ctx->err.clear();
@@ -1789,11 +1820,16 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     }
     static const uint32_t zero_off[1] = {0};
     if (n_paths == 0) h_off = zero_off;
-    for (uint32_t p = 0; p < n_paths; ++p) {
-        if (h_off[p + 1] < h_off[p]) {
-            ctx->err = "cmd_off is not monotone";
-            return OCHRE_E_INVALID_ARG;
-        }
+    OffsetCheck off_check;
+    if (in_dev && n_paths >= (1u << 16)) {
+        off_check.start(h_off, n_paths);
+    } else if (OffsetCheck::scan(h_off, n_paths)) {
+        ctx->err = "cmd_off is not monotone";
+        return OCHRE_E_INVALID_ARG;
+    }
+    if (h_off[n_paths] < h_off[0]) {
+        ctx->err = "cmd_off is not monotone";
+        return OCHRE_E_INVALID_ARG;
     }
     const uint32_t n_cmds = h_off[n_paths] - h_off[0];
     if (n_cmds && !cmds) {
@@ -1851,17 +1887,25 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                                  : (out_dev && !ctx->x_on && mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
     const bool ramp = !out_dev && chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
-        uint32_t p1 = p0;
-        uint64_t nv = 0;
         const uint64_t limit = ramp ? std::min<uint64_t>(chunk_vcmds, (uint64_t)RAMP_FIRST_VCMDS << std::min<size_t>(cuts.size() - 1, 16)) : chunk_vcmds;
-        while (p1 < n_paths) {
-            uint64_t add = (uint64_t)(h_off[p1 + 1] - h_off[p1]) + 1;
-            if (p1 > p0 && nv + add > limit) break;
-            nv += add;
-            ++p1;
+        // the longest run of paths [p0, p1) with (commands + paths) <= limit, at least one path: cmd_off is monotone, so the
+        // cut is found by bisection (a walk over a million paths costs a millisecond before the first launch)
+        auto vcmds = [&](uint32_t p) { return (uint64_t)(h_off[p] - h_off[p0]) + (p - p0); };
+        uint32_t lo = p0 + 1, hi = n_paths;  // answer in [lo, hi]
+        if (vcmds(hi) > limit) {
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo + 1) / 2;
+                if (vcmds(mid) <= limit) lo = mid; else hi = mid - 1;
+            }
+        } else {
+            lo = hi;
         }
-        cuts.push_back(p1);
-        p0 = p1;
+        if (h_off[lo] < h_off[p0]) {  // (a mirror that is still being checked: no chunk may have a negative command count)
+            ctx->err = "cmd_off is not monotone";
+            return OCHRE_E_INVALID_ARG;
+        }
+        cuts.push_back(lo);
+        p0 = lo;
     }
     const size_t n_chunks = cuts.size() - 1;
     // ---- inputs: uploaded chunk by chunk on their own stream, ahead of the kernels ---------------
@@ -2181,6 +2225,11 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     ctx->last_n_spans = span_base;
     ctx->last_valid = !ext;  // (the atlas builder reads the ctx's own result buffers)
     ctx->last_unordered = unordered;
+    if (off_check.failed()) {
+        ctx->err = "cmd_off is not monotone";
+        ctx->last_valid = false;
+        return OCHRE_E_INVALID_ARG;
+    }
     return 0;
 }
 
@@ -2224,8 +2273,11 @@ int ochre_b200_rasterize_paints(ochre_b200_ctx* ctx, const OchreCmd* cmds, const
         ctx->err = "null input pointer";
         return OCHRE_E_INVALID_ARG;
     }
-    for (uint32_t p = 0; p < n_paths; ++p) {
-        if (h_off[p + 1] < h_off[p]) {
+    {
+        // (branch-free so that it vectorises: a batch of a million glyphs spends no visible time here)
+        uint32_t bad = 0;
+        for (uint32_t p = 0; p < n_paths; ++p) bad |= (uint32_t)(h_off[p + 1] < h_off[p]);
+        if (bad) {
             ctx->err = "cmd_off is not monotone";
             return OCHRE_E_INVALID_ARG;
         }

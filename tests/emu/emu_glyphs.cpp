@@ -16,9 +16,12 @@ extern "C" int emu_glyphs_run(const Cmd* cmds, const uint32_t* cmd_off, const fl
     counts[0] = counts[1] = counts[2] = counts[3] = 0;
     status[0] = status[1] = status[2] = 0;
     uint2* boxp = box.data();
-    const unsigned cls_grid = (unsigned)(((uint64_t)n_paths * 32 + CLS_THREADS - 1) / CLS_THREADS);
+    // (the lanes-per-path form follows the fiber order's parity, so that the tests run both)
+    const int lanes = (order & 1) ? 32 : 4;
+    const unsigned cls_grid = (unsigned)(((uint64_t)n_paths * lanes + CLS_THREADS - 1) / CLS_THREADS);
     cemu::launch(cls_grid, CLS_THREADS, 0, order, [&]() {
-        k_classify(cmds, cmd_off, cmd_off[0], xf, n_paths, max_cells, (uint32_t)pkg::GK_MAXCMDS, 1, counts, list, boxp);
+        if (lanes == 4) k_classify<4>(cmds, cmd_off, cmd_off[0], xf, n_paths, max_cells, (uint32_t)pkg::GK_MAXCMDS, 1, counts, list, boxp);
+        else k_classify<32>(cmds, cmd_off, cmd_off[0], xf, n_paths, max_cells, (uint32_t)pkg::GK_MAXCMDS, 1, counts, list, boxp);
     });
     uint32_t ticket = 0;
     PathKernelArgs A;

@@ -93,6 +93,9 @@ def test_edge_paths():
         mkpath((MOVE, 1.0, 1.0), *[(LINE, 1.0 + (i % 7), 2.0 + (i % 5)) for i in range(140)]),  # more commands than a round takes
         mkpath((MOVE, 4.0, 4.0), (LINE, 4.0, 4.0), (LINE, 12.5, 4.0), (LINE, 12.5, 4.0), (LINE, 7.0, 13.0)),  # degenerate lines inside
         tri(40.0, 40.0, 6.0),
+        mkpath((MOVE, 1.25, 1.5), (LINE, 46.5, 45.75), (LINE, 44.0, 2.0)),  # 90-trip diagonals in a 64-cell grid: walked in 8 pieces
+        mkpath((MOVE, 2.0, 3.0), (LINE, 45.0, 3.0), (LINE, 45.0, 4.5), (LINE, 2.0, 4.5)),  # long horizontal lines: column steps only
+        mkpath((MOVE, 3.0, 2.0), (LINE, 3.0, 45.0), (LINE, 4.5, 45.0), (LINE, 4.5, 2.0)),  # long vertical lines: row steps only
     ]
     cmds, off, xf = batch(paths)
     r = check(cmds, off, xf)
@@ -142,3 +145,12 @@ def test_arena_overflow_is_reported_not_written():
     r = emu_glyphs.run(cmds, off, xf, cap_tiles=100, cap_spans=4)
     assert r.status[2] == 1
     assert np.all(r.alpha[100:] == 0x5a) if len(r.alpha) > 100 else True
+
+
+def test_a_tile_with_more_than_511_increments_is_handed_over():
+    # 120 diagonals through one tile: ~15 increments each; the fixed-point sums of that tile would leave int32
+    zig = [(MOVE, 0.1, 0.1)] + [(LINE, 7.9, 7.8) if i % 2 == 0 else (LINE, 0.1, 0.2) for i in range(120)]
+    tri = mkpath((MOVE, 3.5, 2.25), (LINE, 14.5, 2.25), (LINE, 3.5, 13.25), (CLOSE,))
+    cmds, off, xf = batch([tri, mkpath(*zig), tri])
+    r = check(cmds, off, xf)
+    assert [int(p) for p in r.handed_over] == [1]

@@ -38,6 +38,22 @@ MARKS = {
         ("quantise + emit: one thread per", "quantise + alpha rows out"),
         ("---- 4. count, reserve, emit", "reservation, stripe loop"),
     ],
+    "glyph_kernel.cuh": [
+        ("k_classify(const Cmd*", "classifier"),
+        ("uint32_t gk_rank(", "rank / next-touched lookups"),
+        ("k_glyphs(PathKernelArgs A)", "kernel entry"),
+        ("---- plan the round", "plan the round (warp 0)"),
+        ("---- commands: thread per command", "commands (ballots, last/first, dt, counts, scan, t sequence)"),
+        ("---- lines: end points", "lines (curve evaluation, start points)"),
+        ("---- mark ----", "mark (cell init, DDA control flow, cell counts)"),
+        ("---- one ordered scan", "grid scan (ranks, winding, spans, reservation, records)"),
+        ("---- tile origins and spans", "tile origins and spans out"),
+        ("---- coverage: bands", "coverage: band loop, zero accumulators"),
+        ("const uint32_t slot0_s = acc_s", "coverage: accumulate (DDA, areas, reductions)"),
+        ("row sums: thread per", "row sums"),
+        ("row carry: thread per", "row carry"),
+        ("quantise + emit: thread per", "quantise + alpha rows out"),
+    ],
     "path_kernel_common.cuh": [
         ("block_excl_scan_pair(", "scan helpers"),
         ("struct LineWalk", "DDA state: init (2 divisions) and step"),
