@@ -44,6 +44,7 @@ namespace oc {
 namespace OC_PK_NS {
 
 constexpr int PK_THREADS = OC_PK_THREADS;
+constexpr int PK_NW = (OC_PK_THREADS + 31) / 32;  // warps per CTA
 constexpr int PK_SLOTS = OC_PK_SLOTS;   // tiles whose accumulators are resident at once
 constexpr int PK_CELLS = OC_PK_CELLS;   // cells of the path's bounding grid (tiles)
 constexpr int PK_CTAS_PER_SM = OC_PK_CTAS;
@@ -330,7 +331,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         lw += (w >> 16) - 0x8000u;
     });
     uint32_t ex_t, ex_w, tot_t, tot_w;
-    block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
+    pk_scan_pair1<PK_NW>(lt, lw, S.ws + 32, ex_t, ex_w, tot_t, tot_w);
     {
         uint32_t r = ex_t;
         int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
@@ -371,7 +372,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         });
     }
     uint32_t tot_s;
-    sc.span_excl = block_excl_scan(ls, S.ws, tot_s);
+    sc.span_excl = pk_scan1<PK_NW>(ls, S.ws + 48, tot_s);
     n_spans = tot_s;
     bad = __syncthreads_or((int)err);
 }
@@ -426,7 +427,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         lw += (w >> 16) - 0x8000u;
     }
     uint32_t ex_t, ex_w, tot_t, tot_w;
-    block_excl_scan_pair(lt, lw, S.ws, ex_t, ex_w, tot_t, tot_w);
+    pk_scan_pair1<PK_NW>(lt, lw, S.ws + 32, ex_t, ex_w, tot_t, tot_w);
     {
         uint32_t r = ex_t, word = 0;
         int wp = wcarry + (int)ex_w;  // the reference's never-reset `winding` (rasterizer.rs:219, :253-260)
@@ -469,7 +470,7 @@ __device__ __forceinline__ void pk_grid_scan(PkShared& S, int W, int H, uint32_t
         }
     }
     uint32_t tot_s;
-    sc.span_excl = block_excl_scan(ls, S.ws, tot_s);
+    sc.span_excl = pk_scan1<PK_NW>(ls, S.ws + 48, tot_s);
     n_spans = tot_s;
     bad = __syncthreads_or((int)err);
 }
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 if (bad) atomicMax(A.status, bad);
             }
             uint32_t total;
-            const uint32_t first = n_lines + block_excl_scan(my_n, S.ws, total);
+            const uint32_t first = n_lines + pk_scan1<PK_NW>(my_n, S.ws + ((jb / PK_THREADS) & 1u) * 8u, total);  // (buffers alternate: one barrier per scan)
             if (tid == 0) {  // the carry for the next chunk (everybody has read this chunk's: the scan has barriers)
                 for (int w = (int)NW - 1; w >= 0; --w)
                     if (S.cw[NW + w]) {
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                     const uint32_t k = kb + tid;
                     const uint32_t v = (k < nkeys) ? S.bcur[k] : 0u;
                     uint32_t part;
-                    const uint32_t ex = total + block_excl_scan(v, S.ws, part);
+                    const uint32_t ex = total + pk_scan1<PK_NW>(v, S.ws + 16 + ((kb / PK_THREADS) & 1u) * 8u, part);
                     if (k < nkeys) {
                         S.boff[k] = ex;
                         S.bcur[k] = 0;

@@ -99,6 +99,55 @@ __device__ __forceinline__ void block_excl_scan_pair(uint32_t a, uint32_t b, uin
     __syncthreads();
 }
 
+// The same scans with ONE barrier each: every thread adds up the totals of the warps before its own (NW <= 8 warps).  `buf`
+// (NW words, 2 * NW for the pair) must not be the buffer of the CTA's previous scan: its readers may still be at work.
+template <int NW>
+__device__ __forceinline__ uint32_t pk_scan1(uint32_t v, uint32_t* buf, uint32_t& total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t inc = warp_incl_scan(v);
+    if (lane == 31) buf[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+    total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < (unsigned)NW; ++w) {
+        const uint32_t t = buf[w];
+        before += w < warp ? t : 0u;
+        total += t;
+    }
+    return inc - v + before;
+}
+template <int NW>
+__device__ __forceinline__ void pk_scan_pair1(uint32_t a, uint32_t b, uint32_t* buf, uint32_t& ex_a, uint32_t& ex_b, uint32_t& tot_a, uint32_t& tot_b) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t na = __shfl_up_sync(0xffffffffu, ia, d), nb = __shfl_up_sync(0xffffffffu, ib, d);
+        if (lane >= (unsigned)d) {
+            ia += na;
+            ib += nb;
+        }
+    }
+    if (lane == 31) {
+        buf[warp] = ia;
+        buf[NW + warp] = ib;
+    }
+    __syncthreads();
+    uint32_t oa = 0, ob = 0;
+    tot_a = tot_b = 0;
+#pragma unroll
+    for (unsigned w = 0; w < (unsigned)NW; ++w) {
+        const uint32_t ta = buf[w], tb = buf[NW + w];
+        oa += w < warp ? ta : 0u;
+        ob += w < warp ? tb : 0u;
+        tot_a += ta;
+        tot_b += tb;
+    }
+    ex_a = ia - a + oa;
+    ex_b = ib - b + ob;
+}
+
 // The DDA of Rasterizer::line_to (rasterizer.rs:74-136), device form.  Same operations in the
 // same order as raster_core.cuh's Walker; the loop exit `row_t0 == 1 || col_t0 == 1` is tested
 // as `t1 == 1`: the t0 a trip stores is the t1 it consumed, and an earlier one would have ended

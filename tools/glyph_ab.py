@@ -36,6 +36,8 @@ def main():
     batches = []
     for n in (100_000, 1_000_000):
         batches.append((f"glyphs {n}", W.glyphs(n)))
+    if only and "blobs 400000" in only:
+        batches.append(("blobs 400000", W.blobs(400_000)))  # (the headline's generator: every path goes to the 128-thread kernel)
     for doc, sc in (("lorem_ipsum", 1.0), ("lorem_ipsum", 4.0)):
         pc, po, px, sw = W.svg_paint_batch(doc, sc)
         assert not (sw > 0).any()
