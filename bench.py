@@ -571,7 +571,7 @@ def main():
             n = 100_000 if name == "glyphs100k" else 1_000_000
             b = Batch(3, rank * n, n)
             ms, r = timed(lambda: b.device_call(ctx), wl_warm, wl_steps)
-            report(name, n * world, ms, r, f"generator G3, {n} glyphs per GPU; device-resident in and out, unordered layout" + ("; not gathered" if world > 1 else ""))
+            report(name, n * world, ms, r, f"generator G3, {n} glyphs per GPU, through the glyph kernel (a round of small paths per CTA); device-resident in and out, unordered layout" + ("; not gathered" if world > 1 else ""))
             del b
         elif name in ("rings5a", "rings5a_dense"):
             # config 5a: ONE path of 511 concentric rings on a 16384^2 canvas.  N > 1: every rank flattens the whole path and
@@ -709,7 +709,7 @@ def main():
         # fused per-path kernel: commands in, tiles/spans out -- its algorithmic bytes ARE B_alg
         sb = {"k_path": alg, "gather": 2 * (68 * res.n_tiles + 8 * res.n_spans) + 24 * P}
         names = {0: "k_path", 6: "gather"}
-        kern = {"k_path": "k_path (flatten + bin + coverage + backdrop + emission per path; two CTA shapes, pkl 91 % / pks 7.5 % of the step, + k_classify)",
+        kern = {"k_path": "k_path (flatten + bin + coverage + backdrop + emission per path; the 128-thread shape pkl is > 95 % of the step, beside k_classify and the glyph kernel for the batch's few tiny paths)",
                 "gather": "device_scan x2 + k_gather_paths (staging arena -> path order)"}
         dom = max(names, key=lambda i: stage_ms[i])
         dom_name = names[dom]
