@@ -1790,7 +1790,11 @@ struct OffsetCheck {
         return b;
     }
     void start(const uint32_t* h, uint32_t n) {
-        th = std::thread([this, h, n] { bad.store(scan(h, n)); });
+        try {
+            th = std::thread([this, h, n] { bad.store(scan(h, n)); });
+        } catch (...) {  // no thread to be had: check here and now (nothing may be thrown across the C ABI)
+            bad.store(scan(h, n));
+        }
     }
     bool failed() {
         if (th.joinable()) th.join();
