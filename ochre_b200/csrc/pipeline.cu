@@ -392,7 +392,7 @@ k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals,
            uint32_t* __restrict__ pub_flag /* per CTA: 0 nothing yet, 1 aggregate, 2 inclusive prefix */, uint32_t* __restrict__ ticket) {
     __shared__ unsigned long long acc[CV_TILES * CV_W];
     __shared__ long long s_tot[8][CV_TILES];    // row totals, then the carry into every tile
-    __shared__ uint32_t s_off[CV_TILES + 1], s_r0[CV_TILES], s_r1[CV_TILES], s_head[CV_TILES], s_real[CV_TILES];
+    __shared__ uint32_t s_off[CV_TILES + 1], s_r0[CV_TILES], s_head[CV_TILES], s_real[CV_TILES];
     __shared__ int s_tx[CV_TILES], s_ty[CV_TILES];
     __shared__ uint32_t s_bid;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -419,7 +419,6 @@ k_coverage(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ vals,
             }
         }
         s_r0[lane] = r0;
-        s_r1[lane] = r1;
         s_tx[lane] = tx;
         s_ty[lane] = ty;
         s_head[lane] = head;
