@@ -29,9 +29,6 @@
 #pragma once
 #include "path_kernel_common.cuh"
 
-#ifndef OC_DYN_SMEM
-#define OC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
-#endif
 // (measured on 1 M glyphs, B200: 64 slots / 8 CTAs per SM / 384 lines 4.64 ms; 88 / 6 / 512: 4.79 ms; 56 / 9 and 48 / 10 lose the
 // paths of more than 56 / 48 grid cells to the per-path kernel and are slower)
 #ifndef OC_GK_SLOTS

@@ -163,7 +163,7 @@ __device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t 
 __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address of the cells */, uint32_t merr_s /* ... of PkShared::merr */, const float4* __restrict__ lines,
                                         const uint16_t* __restrict__ sidx, uint32_t n, int gx0, int gy0, int W, int H, bool striped, uint64_t pk_pol) {
     uint32_t pos = threadIdx.x;
-    asm volatile("" : "+r"(cell_s));  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
+    OC_KEEP_IN_REG(cell_s);  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
     // two-deep prefetch: the index of the line after next, the end points of the next line
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t inn = 0;
@@ -184,7 +184,7 @@ __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address
             const int cx = w.x >> 3, cy = w.y >> 3;
             const bool inx = (unsigned)cx < (unsigned)W, iny = (unsigned)cy < (unsigned)H;
             if (inx && iny) pk_red_add(cell_s + 4u * (uint32_t)(cy * W + cx), 1u);
-            else if (!inx || !striped) asm volatile("st.shared.u32 [%0], %1;" ::"r"(merr_s), "r"(1u) : "memory");  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
+            else if (!inx || !striped) pk_st_shared(merr_s, 1u);  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
             bool row;
             done = w.advance(row) == 1.0f;
             if (done) w.snap();
@@ -193,7 +193,7 @@ __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address
                 const int tiy = min(ty, prev_ty), tix = w.x >> 3;
                 const bool jnx = (unsigned)tix < (unsigned)W, jny = (unsigned)tiy < (unsigned)H;
                 if (jnx && jny) pk_red_add(cell_s + 4u * (uint32_t)(tiy * W + tix), (uint32_t)(ty - prev_ty) << 16);
-                else if (!jnx || !striped) asm volatile("st.shared.u32 [%0], %1;" ::"r"(merr_s), "r"(1u) : "memory");
+                else if (!jnx || !striped) pk_st_shared(merr_s, 1u);
                 prev_ty = ty;
             }
         } while (!done);
@@ -210,7 +210,8 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
     uint32_t slot0_s = acc_s - rank0 * (uint32_t)(4 * PK_ACCW);  // accumulator block of rank 0 (slot = rank - rank0)
     const int r0 = R0 - gy0;                       // the band's rows relative to the grid
     const uint32_t nrows = (uint32_t)(R1 - R0);
-    asm volatile("" : "+r"(slot0_s), "+r"(rk_s));
+    OC_KEEP_IN_REG(slot0_s);
+    OC_KEEP_IN_REG(rk_s);
     float4 Ln = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t inn = 0;
     if (pos < p1) Ln = pk_ld(&lines[pk_ld(&sidx[pos], pk_pol)], pk_pol);
@@ -248,8 +249,8 @@ __device__ __forceinline__ void pk_accumulate(uint32_t acc_s /* shared-window ad
             if ((uint32_t)(ry - r0) < nrows) {
                 // slot = rank(cell) - rank0, the rank structure read through its shared-window address
                 const uint32_t cidx = (uint32_t)(ry * W + (x0 >> 3));
-                uint32_t wbits, wb;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wbits), "=r"(wb) : "r"(rk_s + 8u * (cidx >> 5)));
+                const uint2 rkw = pk_ld_shared2(rk_s + 8u * (cidx >> 5));
+                const uint32_t wbits = rkw.x, wb = rkw.y;
                 const uint32_t rank = wb + (uint32_t)__popc(wbits & pk_below(cidx));
                 const uint32_t d = slot0_s + rank * (uint32_t)(4 * PK_ACCW) + 4u * (uint32_t)((y0 & 7) * 9 + (x0 & 7));
                 // (|height| exceeds 1 by a few ulps of the lerp: no mantissa trick for the rounding, F2I it is)
@@ -521,7 +522,7 @@ __device__ __forceinline__ int pk_band_of(const PkShared& S, int nb, int r) {
 // over that list (A.path_list); what it cannot take either goes to the general pipeline.
 template <bool STRIPED>
 __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelArgs A) {
-    extern __shared__ __align__(16) unsigned char pk_smem_raw[];
+    OC_DYN_SMEM(pk_smem_raw);
     PkShared& S = *reinterpret_cast<PkShared*>(pk_smem_raw);
     const uint32_t smem_s = pk_saddr(pk_smem_raw);  // shared-window address of S (for the DDA loops' reductions)
     const uint32_t tid = threadIdx.x;
@@ -981,8 +982,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                         run += d[x];
                         // rasterizer.rs:235 with both terms scaled by 256 (exact): trunc(min(|accum + area| * 256, 255))
                         // (exact product: the fma equals mul, add; the conversion truncates and saturates at 255: min(|v|, 255) as u8)
-                        uint32_t q;
-                        asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(q) : "f"(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c))));
+                        const uint32_t q = pk_quant_u8(fabsf(__fmaf_rn((float)run, OC_FX_TO_256, c)));
                         if (x < 4) lo32 |= q << (8 * x); else hi32 |= q << (8 * (x - 4));
                     }
                     const uint32_t ti = tile_at + rank0 + s;

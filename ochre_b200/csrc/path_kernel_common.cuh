@@ -10,6 +10,15 @@
 #include "raster_core.cuh"
 #include "scan.cuh"
 
+#ifndef OC_DYN_SMEM  // (tests/emu/cuda_on_cpu.h defines its own)
+#define OC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#if defined(OC_CUDA_ON_CPU)
+#define OC_KEEP_IN_REG(x) ((void)0)
+#else
+#define OC_KEEP_IN_REG(x) asm volatile("" : "+r"(x))
+#endif
+
 namespace oc {
 
 constexpr int PK_MAXSTRIPES = 8;    // stripes of tile rows for paths whose bounding grid or line count exceeds one pass

@@ -199,6 +199,8 @@ inline T exchange(T v, unsigned src_lane) {
 #define OC_DYN_SMEM(name) unsigned char* name = cemu::smem()
 #undef __launch_bounds__
 #define __launch_bounds__(...)
+#undef __noinline__
+#define __noinline__ __attribute__((noinline))
 
 inline void __syncthreads() { cemu::park(cemu::WAIT_CTA); }
 inline int __syncthreads_or(int v) {
@@ -209,6 +211,7 @@ inline int __syncthreads_or(int v) {
     return r;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { cemu::park(cemu::WAIT_WARP); }
+inline unsigned __activemask() { return 0xffffffffu; }  // (only meaningful where every lane is active: a collective under divergence deadlocks and is reported)
 #define OC_FULL_MASK_ONLY(m) do { if ((m) != 0xffffffffu) { fprintf(stderr, "cuda_on_cpu: partial-mask collective\n"); abort(); } } while (0)
 template <class T> inline T __shfl_sync(unsigned m, T v, int src) { OC_FULL_MASK_ONLY(m); return cemu::exchange(v, (unsigned)src); }
 template <class T> inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
