@@ -8,8 +8,8 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libochre_b200.so")
-SOURCES = ["pipeline.cu", "host_path.cpp"]
-HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join("..", "..", "include", "ochre_b200.h")]
+SOURCES = ["pipeline.cu", "host_path.cpp", "host_sink.cpp"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "ochre_b200.h")]
 
 # -fmad=false: the reference never fuses multiply-add; tile membership depends on the rounded f32 DDA.
 # Defaults kept on purpose: -prec-div=true -prec-sqrt=true -ftz=false (IEEE division, sqrt, denormals).

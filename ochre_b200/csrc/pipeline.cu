@@ -35,6 +35,7 @@
 
 #include "../../include/ochre_b200.h"
 #include "atlas.cuh"
+#include "host_sink.h"
 // the fused per-path kernel, twice: ordinary / large paths, and small paths (a warp per path)
 #ifndef OC_PK_THREADS
 #define OC_PK_THREADS 128
@@ -831,48 +832,6 @@ constexpr int N_STAGE = 8;
 // chunk by chunk behind the downloads.  The builder is the counting / checksumming one the CPU baseline uses as its
 // timing sink (same sums, re-implemented here: the product links nothing from oracle/).
 // ---------------------------------------------------------------------------
-struct SinkBuilder {  // a `&mut impl TileBuilder`: two indirect calls
-    void (*tile)(SinkBuilder*, int16_t, int16_t, const uint8_t*);
-    void (*span)(SinkBuilder*, int16_t, int16_t, uint16_t);
-    OchreSinkSum sum;
-};
-static void sink_tile(SinkBuilder* b, int16_t x, int16_t y, const uint8_t* d) {
-    const uint64_t g = (uint64_t)(uint16_t)x * 0x9E3779B97F4A7C15ull + (uint16_t)y;
-    uint64_t w[8];
-    memcpy(w, d, 64);
-    // mixed checksum: position-dependent, every byte counts, no serial chain between the eight multiplies (a consumer that
-    // reads a tile should not be bound by the latency of its own hash)
-    uint64_t s = g;
-    static const uint64_t K[8] = {0x100000001B3ull, 0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull,
-                                  0xD6E8FEB86659FD93ull, 0xFF51AFD7ED558CCDull, 0xC4CEB9FE1A85EC53ull, 0x2545F4914F6CDD1Dull};
-    for (int i = 0; i < 8; ++i) s += (w[i] ^ g) * K[i];
-    uint64_t a = 0;
-#if defined(__SSE2__)
-    for (int i = 0; i < 4; ++i) {  // byte sums: one psadbw per 16 bytes
-        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(d + 16 * i));
-        const __m128i sad = _mm_sad_epu8(v, _mm_setzero_si128());
-        a += (uint64_t)_mm_cvtsi128_si64(sad) + (uint64_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(sad, sad));
-    }
-#else
-    for (int i = 0; i < 8; ++i) {  // pairwise widening adds
-        uint64_t v = w[i];
-        v = (v & 0x00ff00ff00ff00ffull) + ((v >> 8) & 0x00ff00ff00ff00ffull);
-        v = (v & 0x0000ffff0000ffffull) + ((v >> 16) & 0x0000ffff0000ffffull);
-        a += (v & 0xffffffffull) + (v >> 32);
-    }
-#endif
-    b->sum.mix_sum += s;
-    b->sum.geom_sum += g;
-    b->sum.alpha_sum += a;
-    b->sum.tiles++;
-}
-static void sink_span(SinkBuilder* b, int16_t x, int16_t y, uint16_t w) {
-    const uint64_t v = ((uint64_t)(uint16_t)x << 32) ^ ((uint64_t)(uint16_t)y << 16) ^ w;
-    b->sum.mix_sum += v;
-    b->sum.geom_sum += v;
-    b->sum.spans++;
-}
-
 struct SinkTask {
     size_t t0, nt, s0, ns;
     cudaEvent_t ready;  // recorded behind the chunk's downloads
@@ -898,6 +857,7 @@ struct SinkRun {
     std::vector<std::thread> workers;
     std::vector<SinkBuilder> partial;
     std::vector<double> busy;
+    UnpackFn unpack = nullptr;
 
     void worker(uint32_t t) {
         cudaSetDevice(device);
@@ -925,33 +885,7 @@ struct SinkRun {
                 const size_t nbk = k.b1 - k.b0;
                 for (size_t bk = k.b0 + nbk * t / n_threads; bk < k.b0 + nbk * (t + 1) / n_threads; ++bk) {
                     const size_t ta = k.chunk_t0 + bk * PACK_BLOCK, tn = std::min<size_t>(PACK_BLOCK, k.chunk_t0 + k.chunk_nt - ta);
-                    const uint64_t* r = pr + k.row_base + (*k.boff)[bk];
-                    static const uint64_t k_full[8] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
-                    static const uint64_t k_zero[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
-                    for (size_t i = ta; i < ta + tn; ++i) {
-                        const uint32_t c = cw[i];
-                        // tiles that need no rebuilding: all eight rows stored (they are contiguous in the stream), or a constant tile
-                        if (c == 0xaaaau) {
-                            b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(r));
-                            r += 8;
-                            continue;
-                        }
-                        if (c == 0x5555u || c == 0u) {
-                            b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(c ? k_full : k_zero));
-                            continue;
-                        }
-                        alignas(8) uint64_t tile[8];
-                        for (int y = 0; y < 8; ++y) {
-                            const uint32_t q = (c >> (2 * y)) & 3u;
-                            // branch-free (the classes of consecutive rows are as good as random to a branch predictor): the next
-                            // stored row is loaded whether it is this row's or not (the stream has 64 bytes of slack at its end)
-                            const uint64_t konst = 0ull - (uint64_t)(q & 1u);  // class 1: all ones, class 0: zero
-                            const uint64_t lit = 0ull - (uint64_t)(q >> 1);    // class 2: take the stored row
-                            tile[y] = (*r & lit) | (konst & ~lit);
-                            r += q >> 1;
-                        }
-                        b.tile(&b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(tile));
-                    }
+                    unpack(&b, cw + ta, xy + 2 * ta, pr + k.row_base + (*k.boff)[bk], tn);
                 }
             } else {
                 const size_t a0 = k.t0 + k.nt * t / n_threads, a1 = k.t0 + k.nt * (t + 1) / n_threads;
@@ -975,7 +909,10 @@ struct SinkRun {
     void start(int dev, uint32_t n) {
         device = dev;
         n_threads = n;
-        partial.assign(n, SinkBuilder{sink_tile, sink_span, OchreSinkSum{}});
+        const char* env = getenv("OCHRE_B200_SINK_SIMD");  // "0": the portable builder and unpacking loop even where AVX-512 is there
+        const bool simd = !(env && env[0] == '0');
+        unpack = sink_unpack_fn(simd);
+        partial.assign(n, make_sink_builder(simd));
         busy.assign(n, 0.0);
         for (uint32_t t = 0; t < n; ++t) workers.emplace_back([this, t] { worker(t); });
     }
