@@ -658,3 +658,31 @@ def test_host_sink_sees_every_tile_and_span(ctx):
         for k in ("tiles", "spans", "geom_sum", "alpha_sum", "mix_sum"):
             assert sp[k] == s[k], k
         assert 0 < sp["packed_alpha_bytes"] < 64 * g.n_tiles * 0.75
+
+
+def test_large_device_resident_batch_with_a_bad_offset_mirror_fails_when_the_call_ends():
+    """Device-resident input of >= 65 536 paths: the host mirror of cmd_off is checked by a helper thread beside the kernels
+    (DESIGN.md section 3.2); a mirror that is not monotone still fails the call with OCHRE_E_INVALID_ARG, and the same call
+    with a good mirror equals the host-input call."""
+    import torch
+
+    c = ob.Context(0)
+    try:
+        cmds, off, xf = W.glyphs(70_000)
+        d_cmds = torch.from_numpy(cmds.view(np.uint8).reshape(-1).copy()).cuda()
+        d_off = torch.from_numpy(off.view(np.int32).copy()).cuda()
+        d_xf = torch.from_numpy(np.ascontiguousarray(xf, np.float32).reshape(-1).copy()).cuda()
+        n = len(off) - 1
+        r = c.rasterize_ptrs(d_cmds.data_ptr(), d_off.data_ptr(), d_xf.data_ptr(), n, off, in_device=True, out_device=False, copy=True)
+        g = c.rasterize(cmds, off, xf)
+        assert np.array_equal(r.tile_off, g.tile_off) and np.array_equal(r.alpha, g.alpha) and r.spans.tobytes() == g.spans.tobytes()
+        bad = off.copy()
+        bad[40_000] = bad[39_999] - 1
+        with pytest.raises(ob._lib.OchreError) as e:
+            c.rasterize_ptrs(d_cmds.data_ptr(), d_off.data_ptr(), d_xf.data_ptr(), n, bad, in_device=True, out_device=False, copy=True)
+        assert e.value.code == -1
+        # the context is still usable
+        r = c.rasterize_ptrs(d_cmds.data_ptr(), d_off.data_ptr(), d_xf.data_ptr(), n, off, in_device=True, out_device=False, copy=True)
+        assert np.array_equal(r.tile_off, g.tile_off)
+    finally:
+        c.close()
