@@ -137,7 +137,7 @@ enum : uint32_t { GF_CMD = 1, GF_GRID = 2, GF_COUNT = 4 };  // why a path is han
 struct GkShared {
     union {
         int acc[GK_SLOTS * PK_ACCW];
-        uint32_t cell[GK_CCAP];  // mark: [15:0] increments, [31:16] winding delta + 0x8000; after the scan: CF_* flags
+        uint32_t cell[GK_CCAP];  // mark: [15:0] increments, [31:16] winding delta + 0x8000 (the scan keeps its CF_* flags in registers)
         struct {                 // commands of the round (slot = thread id) and the (t, owner) of every line
             V2 last[GK_THREADS], a[GK_THREADS], b[GK_THREADS], c[GK_THREADS];
             uint32_t loff[GK_THREADS];
@@ -186,44 +186,6 @@ __device__ __forceinline__ uint32_t gk_warp_incl(uint32_t v, unsigned lane) {
         if (lane >= (unsigned)d) v += n;
     }
     return v;
-}
-
-// Exclusive scan of (a, b) across the CTA with ONE barrier: every thread adds up the totals of the warps before its own.
-// `buf` (2 * GK_WARPS words) must not be the buffer of the previous scan (its readers may still be at work).
-__device__ __forceinline__ void gk_scan_pair(uint32_t a, uint32_t b, uint32_t* buf, unsigned lane, unsigned warp, uint32_t& ex_a, uint32_t& ex_b,
-                                             uint32_t& tot_a, uint32_t& tot_b) {
-    const uint32_t ia = gk_warp_incl(a, lane), ib = gk_warp_incl(b, lane);
-    if (lane == 31) {
-        buf[warp] = ia;
-        buf[GK_WARPS + warp] = ib;
-    }
-    __syncthreads();
-    uint32_t oa = 0, ob = 0;
-    tot_a = tot_b = 0;
-#pragma unroll
-    for (unsigned w = 0; w < (unsigned)GK_WARPS; ++w) {
-        const uint32_t va = buf[w], vb = buf[GK_WARPS + w];
-        oa += w < warp ? va : 0u;
-        ob += w < warp ? vb : 0u;
-        tot_a += va;
-        tot_b += vb;
-    }
-    ex_a = ia - a + oa;
-    ex_b = ib - b + ob;
-}
-__device__ __forceinline__ uint32_t gk_scan(uint32_t a, uint32_t* buf, unsigned lane, unsigned warp, uint32_t& tot) {
-    const uint32_t ia = gk_warp_incl(a, lane);
-    if (lane == 31) buf[warp] = ia;
-    __syncthreads();
-    uint32_t oa = 0;
-    tot = 0;
-#pragma unroll
-    for (unsigned w = 0; w < (unsigned)GK_WARPS; ++w) {
-        const uint32_t va = buf[w];
-        oa += w < warp ? va : 0u;
-        tot += va;
-    }
-    return ia - a + oa;
 }
 
 __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKernelArgs A) {
@@ -397,7 +359,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             if (bad) atomicOr(&S.g_flag[g], (uint32_t)GF_CMD);
         }
         uint32_t total;
-        const uint32_t first = gk_scan(my_n, S.ws[0], lane, warp, total);
+        const uint32_t first = pk_scan1<GK_WARPS>(my_n, S.ws[0], total);  // (one barrier per scan: every scan of a round has its own buffer)
         if (act && k == 0) S.g_line[g] = first;
         if (tid == 0) S.g_line[keep0] = total;
         // (written before the round knows which of its paths fit the line budget: what lies beyond it is never read)
@@ -544,7 +506,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             lw += (wv[q] >> 16) - 0x8000u;
         }
         uint32_t ex_w, tot_t, tot_w;
-        gk_scan_pair(lt, lw, S.ws[1], lane, warp, ex_t, ex_w, tot_t, tot_w);
+        pk_scan_pair1<GK_WARPS>(lt, lw, S.ws[1], ex_t, ex_w, tot_t, tot_w);
         if (own && c0 == S.g_cell[cg]) S.g_rank[cg] = ex_t;
         if (tid == 0) {
             S.g_rank[keep] = tot_t;
@@ -596,7 +558,7 @@ __global__ void __launch_bounds__(GK_THREADS, GK_CTAS_PER_SM) k_glyphs(PathKerne
             }
         }
         uint32_t tot_s;
-        span_excl = gk_scan(ls, S.ws[2], lane, warp, tot_s);
+        span_excl = pk_scan1<GK_WARPS>(ls, S.ws[2], tot_s);
         if (own && c0 == gcell0) S.g_span[cg] = span_excl;
         // ---- reserve: one pair of atomics for the round.  Their results stay in thread 0's registers until the first band's
         // lines are walked: nobody waits for the round trip to L2.
