@@ -133,6 +133,7 @@ struct PkShared {
     uint2 rk[PK_WORDS + 2];  // per 32-cell word: x = bitmask of its touched cells, y = touched cells before the word (one 8-byte read)
     uint32_t boff[PK_MAXB * PK_NCLS + 1];   // bucket offsets into the sorted lines: (slot band, class)
     uint32_t bcur[PK_MAXB * PK_NCLS];       // bucket counters / cursors while bucketing
+    uint32_t ccur[PK_NCLS];                 // cursors of the first bucketing (by step-count class; its counts stay in bcur[0 .. PK_NCLS))
     uint16_t brow[PK_MAXB + 2];             // first row of every slot band (relative to the stripe)
     uint16_t srow[PK_MAXSTRIPES + 2];       // first grid row of every stripe
     uint32_t ws[72];
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             S.bbox[2] = S.bbox[3] = -0x7fffffff;
             S.carry[0] = S.carry[1] = S.carry[2] = S.carry[3] = 0.0f;  // last = first = (0, 0), rasterizer.rs:54-55
         }
-        if (tid < PK_NCLS) S.bcur[tid] = 0;  // lines per step-count class
+        if (tid < PK_NCLS) S.bcur[tid] = S.ccur[tid] = 0;  // lines per step-count class; the cursors of their bucketing
         __syncthreads();
         if (S.path >= n_take) return;
         const uint32_t p = A.path_list ? A.path_list[A.list_rev ? A.n_paths - 1u - S.path : S.path] : S.path;
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             const int Hs = R1 - R0, y0s = gy0 + R0;  // the stripe's rows as absolute tile rows [y0s, y0s + Hs)
             if (!whole) {  // (for the whole grid the class counts come from the flattening pass)
                 __syncthreads();
-                if (tid < PK_NCLS) S.bcur[tid] = 0;
+                if (tid < PK_NCLS) S.bcur[tid] = S.ccur[tid] = 0;
                 __syncthreads();
                 for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
                     const uint32_t info = pk_ld(&G.info[i], pk_pol);
@@ -824,7 +825,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 cbase[k] = n_sorted;
                 n_sorted += S.bcur[k];
             }
-            __syncthreads();  // everybody has read the class counts
+            // (the class counts stay where they are: the bucketing below has its own cursors, so nothing separates this
+            // set-up from it but the one barrier in front of the mark pass)
             if (tid <= PK_NCLS) {
                 uint32_t o = 0;
                 for (uint32_t k = 0; k < tid; ++k) o += S.bcur[k];
@@ -833,9 +835,6 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
             for (uint32_t i = tid; i < (uint32_t)(W * Hs); i += PK_THREADS) S.u.cell[i] = PK_CELL_INIT;
             for (uint32_t i = tid; i <= (uint32_t)(W * Hs) >> 5; i += PK_THREADS) S.rk[i].x = 0;
             if (tid == 0) S.merr = 0;
-            __syncthreads();
-            if (tid < PK_NCLS) S.bcur[tid] = 0;
-            __syncthreads();
             if (n_sorted > PK_MAXLINES) return false;
             uint32_t info_n = tid < n_lines ? pk_ld(&G.info[tid], pk_pol) : PK_INFO_NONE;  // (one trip ahead: the L2 round trip overlaps the trip's work)
             for (uint32_t i = tid; i < n_lines; i += PK_THREADS) {
@@ -847,7 +846,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 uint32_t base = 0;
 #pragma unroll
                 for (int q = 0; q < PK_NCLS; ++q) base = (k == (uint32_t)q) ? cbase[q] : base;
-                const uint32_t pos = base + atomicAdd(&S.bcur[k], 1u);
+                const uint32_t pos = base + atomicAdd(&S.ccur[k], 1u);
                 pk_st(&G.sidx[pos], (uint16_t)i, pk_pol);
             }
             __syncthreads();
