@@ -684,33 +684,42 @@ __global__ void __launch_bounds__(256) k_fill_u16(uint16_t* __restrict__ p, uint
     if (i < n) p[i] = v;
 }
 // ---------------------------------------------------------------------------
-// Row-packed transport of a host-resident result (OCHRE_OUT_SINK_PACKED): 46 % of the pixel rows of a boundary tile are
-// constant (all 0 outside the shape, all 255 inside).  Per tile a 16-bit class word (2 bits per row: 0 all 0, 1 all 255,
-// 2 stored) and only the stored rows, packed back to back, cross PCIe; the host sink rebuilds every tile on the fly.
+// Row-packed transport of a host-resident result (OCHRE_OUT_SINK_PACKED): most of a boundary tile is constant -- all 0 outside
+// the shape, all 255 inside: 46 % of its pixel rows, 67 % of its half rows (4 pixels).  Per tile a 32-bit class word (2 bits per
+// half row, index 2 * row + half: 0 all 0, 1 all 255, 2 stored) and only the stored half rows, packed back to back as 32-bit
+// words, cross PCIe: 24.8 instead of 64 bytes per tile (whole rows: 36.7).  The host sink rebuilds every tile on the fly -- with
+// AVX-512 by one expand-load (csrc/host_sink.cpp).
 // ---------------------------------------------------------------------------
 constexpr uint32_t PACK_BLOCK = 1024;  // tiles per block of the packed stream (the host gets the stream offset of every block)
-__device__ __forceinline__ uint32_t pack_stored_mask(uint32_t cls) { return (cls >> 1) & ~cls & 0x5555u; }  // bit 2y: row y is stored
+__device__ __forceinline__ uint32_t pack_stored_mask(uint32_t cls) { return (cls >> 1) & ~cls & 0x55555555u; }  // bit 2u: unit u (half row) is stored
+__device__ __forceinline__ uint32_t pack_class(uint32_t v) { return v == 0u ? 0u : (v == 0xffffffffu ? 1u : 2u); }
 __global__ void __launch_bounds__(256)
-k_pack_classify(const uint2* __restrict__ rows, uint64_t n_rows, uint16_t* __restrict__ cls) {
+k_pack_classify(const uint2* __restrict__ rows, uint64_t n_rows, uint32_t* __restrict__ cls) {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;  // row index; the 8 rows of a tile sit in 8 consecutive lanes
     uint32_t c = 0;
     if (i < n_rows) {
         const uint2 v = rows[i];
-        c = (v.x | v.y) == 0u ? 0u : ((v.x & v.y) == 0xffffffffu ? 1u : 2u);
+        c = pack_class(v.x) | (pack_class(v.y) << 2);
     }
-    uint32_t w = c << (2u * (threadIdx.x & 7u));
+    uint32_t w = c << (4u * (threadIdx.x & 7u));
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if (i < n_rows && (threadIdx.x & 7u) == 0) cls[i >> 3] = (uint16_t)w;
+    if (i < n_rows && (threadIdx.x & 7u) == 0) cls[i >> 3] = w;
 }
 __global__ void __launch_bounds__(256)
-k_pack_rows(const uint2* __restrict__ rows, uint64_t n_rows, const uint16_t* __restrict__ cls, const uint32_t* __restrict__ off,
-            uint2* __restrict__ packed) {
+k_pack_rows(const uint2* __restrict__ rows, uint64_t n_rows, const uint32_t* __restrict__ cls, const uint32_t* __restrict__ off,
+            uint32_t* __restrict__ packed) {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_rows) return;
     const uint32_t y = (uint32_t)(i & 7u), m = pack_stored_mask(cls[i >> 3]);
-    if (m & (1u << (2u * y))) packed[off[i >> 3] + (uint32_t)__popc(m & ((1u << (2u * y)) - 1u))] = rows[i];
+    const uint32_t b0 = 1u << (4u * y), b1 = b0 << 2;  // the row's two half rows in the mask
+    if (m & (b0 | b1)) {
+        const uint2 v = rows[i];
+        const uint32_t at = off[i >> 3] + (uint32_t)__popc(m & (b0 - 1u));
+        if (m & b0) packed[at] = v.x;
+        if (m & b1) packed[at + ((m & b0) ? 1u : 0u)] = v.y;
+    }
 }
 // stream offset of every block of PACK_BLOCK tiles (+ the total), straight into mapped host memory
 __global__ void __launch_bounds__(256)
@@ -847,8 +856,8 @@ struct SinkRun {
     const int16_t* volatile tile_xy = nullptr;
     const uint8_t* volatile alpha = nullptr;
     const OchreSpan* volatile spans = nullptr;
-    const uint16_t* volatile cls = nullptr;     // row-packed transport: class words per tile,
-    const uint64_t* volatile prow = nullptr;    // ... the stored rows back to back
+    const uint32_t* volatile cls = nullptr;     // row-packed transport: class words per tile,
+    const uint32_t* volatile prow = nullptr;    // ... the stored half rows back to back
     std::mutex mu;
     std::condition_variable cv;
     std::vector<SinkTask> tasks;
@@ -880,8 +889,8 @@ struct SinkRun {
             const int16_t* xy = tile_xy;
             if (k.boff) {
                 // row-packed tiles: this thread's share of the blocks; every tile is rebuilt from its class word and its stored rows
-                const uint16_t* cw = cls;
-                const uint64_t* pr = prow;
+                const uint32_t* cw = cls;
+                const uint32_t* pr = prow;
                 const size_t nbk = k.b1 - k.b0;
                 for (size_t bk = k.b0 + nbk * t / n_threads; bk < k.b0 + nbk * (t + 1) / n_threads; ++bk) {
                     const size_t ta = k.chunk_t0 + bk * PACK_BLOCK, tn = std::min<size_t>(PACK_BLOCK, k.chunk_t0 + k.chunk_nt - ta);
@@ -1891,8 +1900,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(ctx->h_tile_xy.ensure_keep(est_t * 4, 0, ctx->st_out));
         const bool want_packed = (flags & OCHRE_OUT_SINK_PACKED) != 0 && ctx->sink_threads != 0;
         if (want_packed) {  // row-packed transport: class words + (at most) every row, sized for 70 % stored rows up front
-            CK(ctx->h_pack_cls.ensure_keep(est_t * 2 + 64, 0, ctx->st_out));
-            CK(ctx->h_pack_rows.ensure_keep((size_t)(est_t * 64 * 0.7) + 64, 0, ctx->st_out));
+            CK(ctx->h_pack_cls.ensure_keep(est_t * 4 + 64, 0, ctx->st_out));
+            CK(ctx->h_pack_rows.ensure_keep((size_t)(est_t * 64 * 0.5) + 64, 0, ctx->st_out));
         } else {
             CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
         }
@@ -1980,17 +1989,17 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 CK(ctx->d_pack_off.ensure((nt + 2) * 4));
                 CK(ctx->d_scan_ws.ensure(scan_ws_words(nt) * 4));
                 if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->ev_pack[pb], 0));  // the downloads of chunk c - 2 read these buffers
-                CK(ctx->d_pack_cls[pb].ensure(nt * 2 + 64));
+                CK(ctx->d_pack_cls[pb].ensure(nt * 4 + 64));
                 CK(ctx->d_pack_rows[pb].ensure(nt * 64 + 64));
                 const uint2* rows = reinterpret_cast<const uint2*>(r_alpha.as<uint8_t>() + t0 * 64);
                 const uint64_t n_rows = (uint64_t)nt * 8;
-                uint16_t* cls = ctx->d_pack_cls[pb].as<uint16_t>();
+                uint32_t* cls = ctx->d_pack_cls[pb].as<uint32_t>();
                 uint32_t* off = ctx->d_pack_off.as<uint32_t>();
                 k_pack_classify<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls);
                 total.launches += 1 + device_scan(
                     st, (uint32_t)nt, [cls] __device__(uint32_t i) { return (uint32_t)__popc(pack_stored_mask(cls[i])); },
                     [off] __device__(uint32_t i, uint32_t excl, uint32_t) { off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(), d_sc + 6);
-                k_pack_rows<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls, off, ctx->d_pack_rows[pb].as<uint2>());
+                k_pack_rows<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls, off, ctx->d_pack_rows[pb].as<uint32_t>());
                 const uint32_t nb = nblk(nt, PACK_BLOCK);
                 CK(ctx->h_pack_boff.ensure_mapped(((size_t)1 << 22) * 4 + 64));
                 k_pack_block_offsets<<<nblk((uint64_t)nb + 1, 256), 256, 0, st>>>(off, (uint32_t)nt, d_sc + 6, static_cast<uint32_t*>(ctx->h_pack_boff.dev));
@@ -1999,18 +2008,19 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 CK(cudaGetLastError());
                 auto boff = std::make_shared<std::vector<uint32_t>>(ctx->h_pack_boff.as<uint32_t>(), ctx->h_pack_boff.as<uint32_t>() + nb + 1);
                 const size_t chunk_rows = (*boff)[nb];
-                if ((pack_row_base + chunk_rows) * 8 + 64 > ctx->h_pack_rows.cap || (t0 + nt) * 2 + 64 > ctx->h_pack_cls.cap) sink->drain();
-                CK(ctx->h_pack_rows.ensure_keep((pack_row_base + chunk_rows) * 8 + 64, pack_row_base * 8, ctx->st_out));
-                CK(ctx->h_pack_cls.ensure_keep((t0 + nt) * 2 + 64, t0 * 2, ctx->st_out));
-                constexpr uint32_t PIECE_BLOCKS = 512;  // ~ 18 MB of stored rows per piece
+                // (chunk_rows, pack_row_base, boff[]: in stored units of 4 bytes)
+                if ((pack_row_base + chunk_rows) * 4 + 64 > ctx->h_pack_rows.cap || (t0 + nt) * 4 + 64 > ctx->h_pack_cls.cap) sink->drain();
+                CK(ctx->h_pack_rows.ensure_keep((pack_row_base + chunk_rows) * 4 + 64, pack_row_base * 4, ctx->st_out));
+                CK(ctx->h_pack_cls.ensure_keep((t0 + nt) * 4 + 64, t0 * 4, ctx->st_out));
+                constexpr uint32_t PIECE_BLOCKS = 2048;  // ~ 44 MB of stored half rows per piece (three copies per piece: at 11 MB their fixed costs took 12 % of the link)
                 for (uint32_t b0 = 0; b0 < nb; b0 += PIECE_BLOCKS) {
                     const uint32_t b1 = std::min(nb, b0 + PIECE_BLOCKS);
                     const size_t ta = t0 + (size_t)b0 * PACK_BLOCK, tn = std::min<size_t>(nt - (size_t)b0 * PACK_BLOCK, (size_t)(b1 - b0) * PACK_BLOCK);
                     const size_t r0 = (*boff)[b0], r1 = (*boff)[b1];
                     CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + ta * 4, r_tile_xy.as<uint8_t>() + ta * 4, tn * 4, cudaMemcpyDeviceToHost, ctx->st_out));
-                    CK(cudaMemcpyAsync(ctx->h_pack_cls.as<uint16_t>() + ta, cls + (size_t)b0 * PACK_BLOCK, tn * 2, cudaMemcpyDeviceToHost, ctx->st_out));
+                    CK(cudaMemcpyAsync(ctx->h_pack_cls.as<uint32_t>() + ta, cls + (size_t)b0 * PACK_BLOCK, tn * 4, cudaMemcpyDeviceToHost, ctx->st_out));
                     if (r1 > r0)
-                        CK(cudaMemcpyAsync(ctx->h_pack_rows.as<uint64_t>() + pack_row_base + r0, ctx->d_pack_rows[pb].as<uint64_t>() + r0, (r1 - r0) * 8,
+                        CK(cudaMemcpyAsync(ctx->h_pack_rows.as<uint32_t>() + pack_row_base + r0, ctx->d_pack_rows[pb].as<uint32_t>() + r0, (r1 - r0) * 4,
                                            cudaMemcpyDeviceToHost, ctx->st_out));
                     if (sink_events == ctx->ev_sink.size()) {
                         cudaEvent_t e;
@@ -2020,8 +2030,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                     cudaEvent_t e = ctx->ev_sink[sink_events++];
                     CK(cudaEventRecord(e, ctx->st_out));
                     sink->tile_xy = ctx->h_tile_xy.as<int16_t>();
-                    sink->cls = ctx->h_pack_cls.as<uint16_t>();
-                    sink->prow = ctx->h_pack_rows.as<uint64_t>();
+                    sink->cls = ctx->h_pack_cls.as<uint32_t>();
+                    sink->prow = ctx->h_pack_rows.as<uint32_t>();
                     SinkTask k{};
                     k.ready = e;
                     k.boff = boff;
@@ -2034,7 +2044,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 }
                 CK(cudaEventRecord(ctx->ev_pack[pb], ctx->st_out));
                 pack_row_base += chunk_rows;
-                ctx->last_packed_bytes += chunk_rows * 8 + nt * 2;
+                ctx->last_packed_bytes += chunk_rows * 4 + nt * 4;
             }
             const size_t piece = sink ? ((size_t)32 << 20) / 64 : (nt ? nt : 1);
             for (size_t a = 0; a < nt && !packed; a += piece) {

@@ -2,7 +2,7 @@
 #include "../../ochre_b200/csrc/host_sink.cpp"
 
 extern "C" int hs_simd_available() { return oc::sink_simd_available() ? 1 : 0; }
-// Feeds n row-packed tiles through the unpacking loop into the checksumming builder; sums: tiles, geom, alpha, mix, rows consumed.
+// Feeds n row-packed tiles through the unpacking loop into the checksumming builder; sums: tiles, geom, alpha, mix, stored words consumed.
 // tiles_out (may be null): the rebuilt 64-byte tiles, captured by a recording builder instead.
 static uint8_t* g_out = nullptr;
 static void rec_tile(oc::SinkBuilder* b, int16_t, int16_t, const uint8_t* d) {
@@ -10,7 +10,7 @@ static void rec_tile(oc::SinkBuilder* b, int16_t, int16_t, const uint8_t* d) {
     b->sum.tiles++;
 }
 static void rec_span(oc::SinkBuilder*, int16_t, int16_t, uint16_t) {}
-extern "C" void hs_run(int simd, const uint16_t* cw, const int16_t* xy, const uint64_t* rows, size_t n, uint64_t* sums, uint8_t* tiles_out) {
+extern "C" void hs_run(int simd, const uint32_t* cw, const int16_t* xy, const uint32_t* rows, size_t n, uint64_t* sums, uint8_t* tiles_out) {
     oc::SinkBuilder b = oc::make_sink_builder(simd != 0);
     if (tiles_out) {
         g_out = tiles_out;
