@@ -54,28 +54,28 @@ static void sink_span(SinkBuilder* b, int16_t x, int16_t y, uint16_t w) {
 static const uint64_t K_FULL[8] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull};
 static const uint64_t K_ZERO[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
 
-static size_t unpack_portable(SinkBuilder* b, const uint32_t* cw, const int16_t* xy, const uint32_t* r, size_t n) {
-    const uint32_t* const r0 = r;
+static size_t unpack_portable(SinkBuilder* b, const uint64_t* cw, const int16_t* xy, const uint16_t* r, size_t n) {
+    const uint16_t* const r0 = r;
     for (size_t i = 0; i < n; ++i) {
-        const uint32_t c = cw[i];
-        // tiles that need no rebuilding: every half row stored (they are contiguous in the stream), or a constant tile
-        if (c == 0xaaaaaaaau) {
+        const uint64_t c = cw[i];
+        // tiles that need no rebuilding: every pixel pair stored (they are contiguous in the stream), or a constant tile
+        if (c == 0xaaaaaaaaaaaaaaaaull) {
             b->tile(b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(r));
-            r += 16;
+            r += 32;
             continue;
         }
-        if (c == 0x55555555u || c == 0u) {
+        if (c == 0x5555555555555555ull || c == 0ull) {
             b->tile(b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(c ? K_FULL : K_ZERO));
             continue;
         }
-        alignas(8) uint32_t tile[16];
-        for (int u = 0; u < 16; ++u) {
-            const uint32_t q = (c >> (2 * u)) & 3u;
+        alignas(8) uint16_t tile[32];
+        for (int u = 0; u < 32; ++u) {
+            const uint32_t q = (uint32_t)(c >> (2 * u)) & 3u;
             // branch-free (the classes of consecutive units are as good as random to a branch predictor): the next stored word is
             // loaded whether it is this unit's or not (the stream has 64 bytes of slack at its end)
             const uint32_t konst = 0u - (q & 1u);  // class 1: all ones, class 0: zero
             const uint32_t lit = 0u - (q >> 1);    // class 2: take the stored word
-            tile[u] = (*r & lit) | (konst & ~lit);
+            tile[u] = (uint16_t)((*r & lit) | (konst & ~lit));
             r += q >> 1;
         }
         b->tile(b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(tile));
@@ -84,7 +84,7 @@ static size_t unpack_portable(SinkBuilder* b, const uint32_t* cw, const int16_t*
 }
 
 #if OC_X86
-#define OC_T512 __attribute__((target("avx512f,avx512bw,avx512dq,bmi2,popcnt")))
+#define OC_T512 __attribute__((target("avx512f,avx512bw,avx512dq,avx512vbmi2,bmi2,popcnt")))
 // The same builder with 512-bit registers: one load, one multiply, one psadbw per tile.
 OC_T512 static void sink_tile_512(SinkBuilder* b, int16_t x, int16_t y, const uint8_t* d) {
     const uint64_t g = (uint64_t)(uint16_t)x * 0x9E3779B97F4A7C15ull + (uint16_t)y;
@@ -95,22 +95,22 @@ OC_T512 static void sink_tile_512(SinkBuilder* b, int16_t x, int16_t y, const ui
     b->sum.alpha_sum += (uint64_t)_mm512_reduce_add_epi64(_mm512_sad_epu8(w, _mm512_setzero_si512()));
     b->sum.tiles++;
 }
-// Rebuilding a tile is ONE expand-load: the stored half rows, contiguous in the stream, go to the lanes of their places in
-// the tile (vpexpandd under the mask of the class-2 units); the class-1 units are then set to all ones.
-OC_T512 static size_t unpack_512(SinkBuilder* b, const uint32_t* cw, const int16_t* xy, const uint32_t* r, size_t n) {
-    const uint32_t* const r0 = r;
+// Rebuilding a tile is ONE expand-load: the stored pixel pairs, contiguous in the stream, go to the lanes of their places in
+// the tile (vpexpandw under the mask of the class-2 units); the class-1 units are then set to all ones.
+OC_T512 static size_t unpack_512(SinkBuilder* b, const uint64_t* cw, const int16_t* xy, const uint16_t* r, size_t n) {
+    const uint16_t* const r0 = r;
     const __m512i ones = _mm512_set1_epi32(-1);
     for (size_t i = 0; i < n; ++i) {
-        const uint32_t c = cw[i];
-        if (c == 0xaaaaaaaau) {
+        const uint64_t c = cw[i];
+        if (c == 0xaaaaaaaaaaaaaaaaull) {
             b->tile(b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(r));
-            r += 16;
+            r += 32;
             continue;
         }
-        const uint32_t stored = _pext_u32(c, 0xaaaaaaaau), full = _pext_u32(c, 0x55555555u);  // bit u: unit u is class 2 / class 1
-        __m512i t = _mm512_maskz_expandloadu_epi32((__mmask16)stored, r);
-        t = _mm512_mask_mov_epi32(t, (__mmask16)full, ones);
-        alignas(64) uint32_t tile[16];
+        const uint32_t stored = (uint32_t)_pext_u64(c, 0xaaaaaaaaaaaaaaaaull), full = (uint32_t)_pext_u64(c, 0x5555555555555555ull);  // bit u: unit u is class 2 / class 1
+        __m512i t = _mm512_maskz_expandloadu_epi16((__mmask32)stored, r);
+        t = _mm512_mask_mov_epi16(t, (__mmask32)full, ones);
+        alignas(64) uint16_t tile[32];
         _mm512_store_si512(tile, t);
         b->tile(b, xy[2 * i], xy[2 * i + 1], reinterpret_cast<const uint8_t*>(tile));
         r += (uint32_t)_mm_popcnt_u32(stored);
@@ -122,7 +122,7 @@ OC_T512 static size_t unpack_512(SinkBuilder* b, const uint32_t* cw, const int16
 bool sink_simd_available() {
 #if OC_X86
     return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512dq") &&
-           __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt");
+           __builtin_cpu_supports("avx512vbmi2") && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt");
 #else
     return false;
 #endif

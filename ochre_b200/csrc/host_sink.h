@@ -20,10 +20,10 @@ struct SinkBuilder {  // a `&mut impl TileBuilder`: two indirect calls (trait Ti
 SinkBuilder make_sink_builder(bool simd);
 bool sink_simd_available();
 
-// Row-packed tiles: n tiles with 32-bit class words cw[] (2 bits per half row of 4 pixels, index 2 * row + half: 0 all 0,
-// 1 all 255, 2 stored) and origins xy[], their stored half rows back to back at r as 32-bit words (with >= 64 readable bytes
-// behind the last one).  Every tile is rebuilt and handed to b->tile.  Returns the number of stored words consumed.
-typedef size_t (*UnpackFn)(SinkBuilder* b, const uint32_t* cw, const int16_t* xy, const uint32_t* r, size_t n);
+// Row-packed tiles: n tiles with 64-bit class words cw[] (2 bits per pixel pair, index 4 * row + pair: 0 all 0, 1 all 255,
+// 2 stored) and origins xy[], their stored pairs back to back at r as 16-bit words (with >= 64 readable bytes behind the last
+// one).  Every tile is rebuilt and handed to b->tile.  Returns the number of stored words consumed.
+typedef size_t (*UnpackFn)(SinkBuilder* b, const uint64_t* cw, const int16_t* xy, const uint16_t* r, size_t n);
 UnpackFn sink_unpack_fn(bool simd);
 
 }  // namespace oc

@@ -685,40 +685,43 @@ __global__ void __launch_bounds__(256) k_fill_u16(uint16_t* __restrict__ p, uint
 }
 // ---------------------------------------------------------------------------
 // Row-packed transport of a host-resident result (OCHRE_OUT_SINK_PACKED): most of a boundary tile is constant -- all 0 outside
-// the shape, all 255 inside: 46 % of its pixel rows, 67 % of its half rows (4 pixels).  Per tile a 32-bit class word (2 bits per
-// half row, index 2 * row + half: 0 all 0, 1 all 255, 2 stored) and only the stored half rows, packed back to back as 32-bit
-// words, cross PCIe: 24.8 instead of 64 bytes per tile (whole rows: 36.7).  The host sink rebuilds every tile on the fly -- with
-// AVX-512 by one expand-load (csrc/host_sink.cpp).
+// the shape, all 255 inside: 46 % of its pixel rows, 67 % of its half rows, 80 % of its pixel pairs.  Per tile a 64-bit class
+// word (2 bits per pixel pair, index 4 * row + pair: 0 all 0, 1 all 255, 2 stored) and only the stored pairs, packed back to
+// back as 16-bit words, cross PCIe: 20.9 instead of 64 bytes per tile (whole rows: 36.7, half rows: 24.8).  The host sink
+// rebuilds every tile on the fly -- with AVX-512 by one expand-load (csrc/host_sink.cpp).
 // ---------------------------------------------------------------------------
 constexpr uint32_t PACK_BLOCK = 1024;  // tiles per block of the packed stream (the host gets the stream offset of every block)
-__device__ __forceinline__ uint32_t pack_stored_mask(uint32_t cls) { return (cls >> 1) & ~cls & 0x55555555u; }  // bit 2u: unit u (half row) is stored
-__device__ __forceinline__ uint32_t pack_class(uint32_t v) { return v == 0u ? 0u : (v == 0xffffffffu ? 1u : 2u); }
+__device__ __forceinline__ uint64_t pack_stored_mask(uint64_t cls) { return (cls >> 1) & ~cls & 0x5555555555555555ull; }  // bit 2u: unit u (pixel pair) is stored
+__device__ __forceinline__ uint32_t pack_class(uint32_t v16) { return v16 == 0u ? 0u : (v16 == 0xffffu ? 1u : 2u); }
 __global__ void __launch_bounds__(256)
-k_pack_classify(const uint2* __restrict__ rows, uint64_t n_rows, uint32_t* __restrict__ cls) {
+k_pack_classify(const uint2* __restrict__ rows, uint64_t n_rows, uint64_t* __restrict__ cls) {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;  // row index; the 8 rows of a tile sit in 8 consecutive lanes
     uint32_t c = 0;
     if (i < n_rows) {
         const uint2 v = rows[i];
-        c = pack_class(v.x) | (pack_class(v.y) << 2);
+        c = pack_class(v.x & 0xffffu) | (pack_class(v.x >> 16) << 2) | (pack_class(v.y & 0xffffu) << 4) | (pack_class(v.y >> 16) << 6);
     }
-    uint32_t w = c << (4u * (threadIdx.x & 7u));
+    unsigned long long w = (unsigned long long)c << (8u * (threadIdx.x & 7u));
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     w |= __shfl_xor_sync(0xffffffffu, w, 4);
     if (i < n_rows && (threadIdx.x & 7u) == 0) cls[i >> 3] = w;
 }
 __global__ void __launch_bounds__(256)
-k_pack_rows(const uint2* __restrict__ rows, uint64_t n_rows, const uint32_t* __restrict__ cls, const uint32_t* __restrict__ off,
-            uint32_t* __restrict__ packed) {
+k_pack_rows(const uint2* __restrict__ rows, uint64_t n_rows, const uint64_t* __restrict__ cls, const uint32_t* __restrict__ off,
+            uint16_t* __restrict__ packed) {
     const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_rows) return;
-    const uint32_t y = (uint32_t)(i & 7u), m = pack_stored_mask(cls[i >> 3]);
-    const uint32_t b0 = 1u << (4u * y), b1 = b0 << 2;  // the row's two half rows in the mask
-    if (m & (b0 | b1)) {
+    const uint32_t y = (uint32_t)(i & 7u);
+    const uint64_t m = pack_stored_mask(cls[i >> 3]);
+    const uint32_t mine = (uint32_t)(m >> (8u * y)) & 0x55u;  // the row's four pixel pairs in the mask (bits 0, 2, 4, 6)
+    if (mine) {
         const uint2 v = rows[i];
-        const uint32_t at = off[i >> 3] + (uint32_t)__popc(m & (b0 - 1u));
-        if (m & b0) packed[at] = v.x;
-        if (m & b1) packed[at + ((m & b0) ? 1u : 0u)] = v.y;
+        uint32_t at = off[i >> 3] + (uint32_t)__popcll(m & ((1ull << (8u * y)) - 1ull));
+        if (mine & 0x01u) packed[at++] = (uint16_t)(v.x & 0xffffu);
+        if (mine & 0x04u) packed[at++] = (uint16_t)(v.x >> 16);
+        if (mine & 0x10u) packed[at++] = (uint16_t)(v.y & 0xffffu);
+        if (mine & 0x40u) packed[at++] = (uint16_t)(v.y >> 16);
     }
 }
 // stream offset of every block of PACK_BLOCK tiles (+ the total), straight into mapped host memory
@@ -832,6 +835,7 @@ struct HostBuf {  // pinned
 constexpr uint32_t DEFAULT_CHUNK_VCMDS = 16u << 20;
 constexpr uint32_t RAMP_FIRST_VCMDS = 1u << 18;
 constexpr uint32_t DEVICE_CHUNK_VCMDS = 64u << 20;
+constexpr uint32_t PACKED_CHUNK_VCMDS = 4u << 20;  // host results in the row-packed transport
 constexpr int N_STAGE = 8;
 
 }  // namespace
@@ -856,8 +860,8 @@ struct SinkRun {
     const int16_t* volatile tile_xy = nullptr;
     const uint8_t* volatile alpha = nullptr;
     const OchreSpan* volatile spans = nullptr;
-    const uint32_t* volatile cls = nullptr;     // row-packed transport: class words per tile,
-    const uint32_t* volatile prow = nullptr;    // ... the stored half rows back to back
+    const uint64_t* volatile cls = nullptr;     // row-packed transport: class words per tile,
+    const uint16_t* volatile prow = nullptr;    // ... the stored pixel pairs back to back
     std::mutex mu;
     std::condition_variable cv;
     std::vector<SinkTask> tasks;
@@ -889,8 +893,8 @@ struct SinkRun {
             const int16_t* xy = tile_xy;
             if (k.boff) {
                 // row-packed tiles: this thread's share of the blocks; every tile is rebuilt from its class word and its stored rows
-                const uint32_t* cw = cls;
-                const uint32_t* pr = prow;
+                const uint64_t* cw = cls;
+                const uint16_t* pr = prow;
                 const size_t nbk = k.b1 - k.b0;
                 for (size_t bk = k.b0 + nbk * t / n_threads; bk < k.b0 + nbk * (t + 1) / n_threads; ++bk) {
                     const size_t ta = k.chunk_t0 + bk * PACK_BLOCK, tn = std::min<size_t>(PACK_BLOCK, k.chunk_t0 + k.chunk_nt - ta);
@@ -1832,8 +1836,16 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
     // Device-resident results of the fused kernel: nothing is pipelined behind the chunks, fewer and larger launches win
     // (1 M G4 paths: 50.1 ms in three chunks, 49.4 ms in one); the general pipeline's intermediates scale with the chunk, and
     // with an output arena the origins / spans / ranges of a chunk travel behind the next chunk's kernels.
+    // Row-packed host results: the link carries a third of the bytes, so the kernels (53 ms per 1 M G4 paths) are no longer
+    // short against the download (77 ms at the link's rate) and the chunks behind the ramp decide how much of the download waits
+    // for kernels: with 16 Mi virtual commands the last two chunks' copies start when 85 % of the kernels are done; a quarter
+    // of that keeps the link busy from the first millisecond to the end (OCHRE_B200_PACKED_CHUNK_VCMDS overrides it).
+    uint32_t packed_chunk = PACKED_CHUNK_VCMDS;
+    if (const char* env = getenv("OCHRE_B200_PACKED_CHUNK_VCMDS")) packed_chunk = (uint32_t)std::max(1l, atol(env));
+    const bool packed_host = !out_dev && (flags & OCHRE_OUT_SINK_PACKED) != 0 && ctx->sink_threads != 0;
     const uint32_t chunk_vcmds = ctx->chunk_vcmds ? ctx->chunk_vcmds
-                                 : (out_dev && !ctx->x_on && mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS : DEFAULT_CHUNK_VCMDS;
+                                 : (out_dev && !ctx->x_on && mode != OCHRE_MODE_GENERAL && !banded_call) ? DEVICE_CHUNK_VCMDS
+                                 : packed_host ? packed_chunk : DEFAULT_CHUNK_VCMDS;
     const bool ramp = !out_dev && chunk_vcmds > RAMP_FIRST_VCMDS;
     for (uint32_t p0 = 0; p0 < n_paths;) {
         const uint64_t limit = ramp ? std::min<uint64_t>(chunk_vcmds, (uint64_t)RAMP_FIRST_VCMDS << std::min<size_t>(cuts.size() - 1, 16)) : chunk_vcmds;
@@ -1900,8 +1912,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
         CK(ctx->h_tile_xy.ensure_keep(est_t * 4, 0, ctx->st_out));
         const bool want_packed = (flags & OCHRE_OUT_SINK_PACKED) != 0 && ctx->sink_threads != 0;
         if (want_packed) {  // row-packed transport: class words + (at most) every row, sized for 70 % stored rows up front
-            CK(ctx->h_pack_cls.ensure_keep(est_t * 4 + 64, 0, ctx->st_out));
-            CK(ctx->h_pack_rows.ensure_keep((size_t)(est_t * 64 * 0.5) + 64, 0, ctx->st_out));
+            CK(ctx->h_pack_cls.ensure_keep(est_t * 8 + 64, 0, ctx->st_out));
+            CK(ctx->h_pack_rows.ensure_keep((size_t)(est_t * 64 * 0.35) + 64, 0, ctx->st_out));
         } else {
             CK(ctx->h_alpha.ensure_keep(est_t * 64, 0, ctx->st_out));
         }
@@ -1989,17 +2001,17 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 CK(ctx->d_pack_off.ensure((nt + 2) * 4));
                 CK(ctx->d_scan_ws.ensure(scan_ws_words(nt) * 4));
                 if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->ev_pack[pb], 0));  // the downloads of chunk c - 2 read these buffers
-                CK(ctx->d_pack_cls[pb].ensure(nt * 4 + 64));
+                CK(ctx->d_pack_cls[pb].ensure(nt * 8 + 64));
                 CK(ctx->d_pack_rows[pb].ensure(nt * 64 + 64));
                 const uint2* rows = reinterpret_cast<const uint2*>(r_alpha.as<uint8_t>() + t0 * 64);
                 const uint64_t n_rows = (uint64_t)nt * 8;
-                uint32_t* cls = ctx->d_pack_cls[pb].as<uint32_t>();
+                uint64_t* cls = ctx->d_pack_cls[pb].as<uint64_t>();
                 uint32_t* off = ctx->d_pack_off.as<uint32_t>();
                 k_pack_classify<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls);
                 total.launches += 1 + device_scan(
-                    st, (uint32_t)nt, [cls] __device__(uint32_t i) { return (uint32_t)__popc(pack_stored_mask(cls[i])); },
+                    st, (uint32_t)nt, [cls] __device__(uint32_t i) { return (uint32_t)__popcll(pack_stored_mask(cls[i])); },
                     [off] __device__(uint32_t i, uint32_t excl, uint32_t) { off[i] = excl; }, ctx->d_scan_ws.as<uint32_t>(), d_sc + 6);
-                k_pack_rows<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls, off, ctx->d_pack_rows[pb].as<uint32_t>());
+                k_pack_rows<<<nblk(n_rows, 256), 256, 0, st>>>(rows, n_rows, cls, off, ctx->d_pack_rows[pb].as<uint16_t>());
                 const uint32_t nb = nblk(nt, PACK_BLOCK);
                 CK(ctx->h_pack_boff.ensure_mapped(((size_t)1 << 22) * 4 + 64));
                 k_pack_block_offsets<<<nblk((uint64_t)nb + 1, 256), 256, 0, st>>>(off, (uint32_t)nt, d_sc + 6, static_cast<uint32_t*>(ctx->h_pack_boff.dev));
@@ -2008,19 +2020,19 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 CK(cudaGetLastError());
                 auto boff = std::make_shared<std::vector<uint32_t>>(ctx->h_pack_boff.as<uint32_t>(), ctx->h_pack_boff.as<uint32_t>() + nb + 1);
                 const size_t chunk_rows = (*boff)[nb];
-                // (chunk_rows, pack_row_base, boff[]: in stored units of 4 bytes)
-                if ((pack_row_base + chunk_rows) * 4 + 64 > ctx->h_pack_rows.cap || (t0 + nt) * 4 + 64 > ctx->h_pack_cls.cap) sink->drain();
-                CK(ctx->h_pack_rows.ensure_keep((pack_row_base + chunk_rows) * 4 + 64, pack_row_base * 4, ctx->st_out));
-                CK(ctx->h_pack_cls.ensure_keep((t0 + nt) * 4 + 64, t0 * 4, ctx->st_out));
-                constexpr uint32_t PIECE_BLOCKS = 2048;  // ~ 44 MB of stored half rows per piece (three copies per piece: at 11 MB their fixed costs took 12 % of the link)
+                // (chunk_rows, pack_row_base, boff[]: in stored units of 2 bytes)
+                if ((pack_row_base + chunk_rows) * 2 + 64 > ctx->h_pack_rows.cap || (t0 + nt) * 8 + 64 > ctx->h_pack_cls.cap) sink->drain();
+                CK(ctx->h_pack_rows.ensure_keep((pack_row_base + chunk_rows) * 2 + 64, pack_row_base * 2, ctx->st_out));
+                CK(ctx->h_pack_cls.ensure_keep((t0 + nt) * 8 + 64, t0 * 8, ctx->st_out));
+                constexpr uint32_t PIECE_BLOCKS = 2048;  // ~ 27 MB of stored pixel pairs + 17 MB of class words per piece (three copies per piece: at a quarter of this their fixed costs took 12 % of the link)
                 for (uint32_t b0 = 0; b0 < nb; b0 += PIECE_BLOCKS) {
                     const uint32_t b1 = std::min(nb, b0 + PIECE_BLOCKS);
                     const size_t ta = t0 + (size_t)b0 * PACK_BLOCK, tn = std::min<size_t>(nt - (size_t)b0 * PACK_BLOCK, (size_t)(b1 - b0) * PACK_BLOCK);
                     const size_t r0 = (*boff)[b0], r1 = (*boff)[b1];
                     CK(cudaMemcpyAsync(ctx->h_tile_xy.as<uint8_t>() + ta * 4, r_tile_xy.as<uint8_t>() + ta * 4, tn * 4, cudaMemcpyDeviceToHost, ctx->st_out));
-                    CK(cudaMemcpyAsync(ctx->h_pack_cls.as<uint32_t>() + ta, cls + (size_t)b0 * PACK_BLOCK, tn * 4, cudaMemcpyDeviceToHost, ctx->st_out));
+                    CK(cudaMemcpyAsync(ctx->h_pack_cls.as<uint64_t>() + ta, cls + (size_t)b0 * PACK_BLOCK, tn * 8, cudaMemcpyDeviceToHost, ctx->st_out));
                     if (r1 > r0)
-                        CK(cudaMemcpyAsync(ctx->h_pack_rows.as<uint32_t>() + pack_row_base + r0, ctx->d_pack_rows[pb].as<uint32_t>() + r0, (r1 - r0) * 4,
+                        CK(cudaMemcpyAsync(ctx->h_pack_rows.as<uint16_t>() + pack_row_base + r0, ctx->d_pack_rows[pb].as<uint16_t>() + r0, (r1 - r0) * 2,
                                            cudaMemcpyDeviceToHost, ctx->st_out));
                     if (sink_events == ctx->ev_sink.size()) {
                         cudaEvent_t e;
@@ -2030,8 +2042,8 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                     cudaEvent_t e = ctx->ev_sink[sink_events++];
                     CK(cudaEventRecord(e, ctx->st_out));
                     sink->tile_xy = ctx->h_tile_xy.as<int16_t>();
-                    sink->cls = ctx->h_pack_cls.as<uint32_t>();
-                    sink->prow = ctx->h_pack_rows.as<uint32_t>();
+                    sink->cls = ctx->h_pack_cls.as<uint64_t>();
+                    sink->prow = ctx->h_pack_rows.as<uint16_t>();
                     SinkTask k{};
                     k.ready = e;
                     k.boff = boff;
@@ -2044,7 +2056,7 @@ static int rasterize_impl(ochre_b200_ctx* ctx, const OchreCmd* cmds, const uint3
                 }
                 CK(cudaEventRecord(ctx->ev_pack[pb], ctx->st_out));
                 pack_row_base += chunk_rows;
-                ctx->last_packed_bytes += chunk_rows * 4 + nt * 4;
+                ctx->last_packed_bytes += chunk_rows * 2 + nt * 8;
             }
             const size_t piece = sink ? ((size_t)32 << 20) / 64 : (nt ? nt : 1);
             for (size_t a = 0; a < nt && !packed; a += piece) {

@@ -10,7 +10,7 @@ static void rec_tile(oc::SinkBuilder* b, int16_t, int16_t, const uint8_t* d) {
     b->sum.tiles++;
 }
 static void rec_span(oc::SinkBuilder*, int16_t, int16_t, uint16_t) {}
-extern "C" void hs_run(int simd, const uint32_t* cw, const int16_t* xy, const uint32_t* rows, size_t n, uint64_t* sums, uint8_t* tiles_out) {
+extern "C" void hs_run(int simd, const uint64_t* cw, const int16_t* xy, const uint16_t* rows, size_t n, uint64_t* sums, uint8_t* tiles_out) {
     oc::SinkBuilder b = oc::make_sink_builder(simd != 0);
     if (tiles_out) {
         g_out = tiles_out;

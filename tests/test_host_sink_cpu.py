@@ -24,14 +24,14 @@ def lib():
 
 
 def pack(tiles):
-    """32-bit class words (2 bits per half row of 4 pixels, index 2 * row + half: 0 all 0, 1 all 255, 2 stored) + the stored half
-    rows back to back as 32-bit words (+ 64 bytes of slack)"""
-    units = tiles.reshape(-1, 16, 4)
-    cls = np.where((units == 0).all(2), 0, np.where((units == 255).all(2), 1, 2)).astype(np.uint32)
-    cw = (cls << (2 * np.arange(16, dtype=np.uint32))[None, :]).sum(1).astype(np.uint32)
-    stored = units[cls == 2].reshape(-1, 4)
+    """64-bit class words (2 bits per pixel pair, index 4 * row + pair: 0 all 0, 1 all 255, 2 stored) + the stored pairs back to
+    back as 16-bit words (+ 64 bytes of slack)"""
+    units = tiles.reshape(-1, 32, 2)
+    cls = np.where((units == 0).all(2), 0, np.where((units == 255).all(2), 1, 2)).astype(np.uint64)
+    cw = (cls << (2 * np.arange(32, dtype=np.uint64))[None, :]).sum(1).astype(np.uint64)
+    stored = units[cls == 2].reshape(-1, 2)
     stream = np.concatenate([stored.reshape(-1), np.full(64, 0xEE, np.uint8)])
-    return cw, np.ascontiguousarray(stream).view(np.uint32), int((cls == 2).sum())
+    return cw, np.ascontiguousarray(stream).view(np.uint16), int((cls == 2).sum())
 
 
 def random_tiles(n, seed):
@@ -44,6 +44,8 @@ def random_tiles(n, seed):
     t[half == 0, :4] = 0
     t[half == 1, 4:] = 255
     t[half == 2, :4] = 255
+    t[half == 3, 2:4] = 0
+    t[half == 3, 6:] = 255
     whole = rng.integers(0, 8, n)              # some tiles entirely stored / constant
     t[whole == 0] = rng.integers(1, 255, (int((whole == 0).sum()), 8, 8), dtype=np.uint8)
     t[whole == 1] = 0
