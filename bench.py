@@ -689,8 +689,8 @@ def main():
                "copy_ms_per_step": float(r2.stage_ms[7]),
                "end_point": "the last TileBuilder call has returned: every piece of the result is replayed into a counting / checksumming "
                             "builder by host threads as soon as its download has finished (ochre_b200_set_host_sink)",
-               "transport": "row-packed (OCHRE_OUT_SINK_PACKED): per tile a 16-bit class word and only the pixel rows that are neither all 0 nor all 255; "
-                            "the sink threads rebuild every 64-byte tile for the builder",
+               "transport": "packed (OCHRE_OUT_SINK_PACKED): per tile a 64-bit class word and only the pixel pairs that are neither all 0 nor all 255; "
+                            "the sink threads rebuild every 64-byte tile for the builder (one AVX-512 expand-load per tile where the host has it)",
                "alpha_bytes_per_tile_over_pcie": sink["packed_alpha_bytes"] / max(1, r2.n_tiles),
                "whole_tiles": {"value": paths_total / (whole_ms * 1e-3), "ms_per_step": whole_ms, "d2h_bytes_per_step": int(r2.n_tiles * 68 + r2.n_spans * 8 + 16 * P),
                                "note": "the same end point with 64-byte tiles over PCIe"},

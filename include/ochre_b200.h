@@ -82,8 +82,8 @@ typedef struct OchreSpan {
                                     * space) still fail the call. */
 
 #define OCHRE_OUT_SINK_PACKED 0x20u /* host-resident results with a host sink set (ochre_b200_set_host_sink): the alpha tiles reach the
-                                     * host row-packed -- per tile a 16-bit class word (2 bits per pixel row: all 0 / all 255 / stored) and
-                                     * only the stored rows, 46 % fewer bytes over PCIe on the G4 workload -- and are rebuilt on the fly by the
+                                     * host packed -- per tile a 64-bit class word (2 bits per pixel pair: all 0 / all 255 / stored) and
+                                     * only the stored pairs, 20.8 instead of 64 bytes per tile on the G4 workload -- and are rebuilt on the fly by the
                                      * sink threads for the TileBuilder; OchreResult.alpha is NULL (tile origins, spans, ranges as usual).
                                      * Ignored without a host sink or with OCHRE_OUT_DEVICE. */
 
@@ -255,7 +255,7 @@ typedef struct OchreSinkSum {
     uint64_t alpha_sum;    /* sum of every alpha byte (differs from the reference's by at most the count of +-1 bytes) */
     uint64_t mix_sum;      /* per tile a hash of origin and all 64 alpha bytes, per span x << 32 ^ y << 16 ^ w, summed */
     double seconds;        /* busy time of the slowest sink thread */
-    uint64_t packed_alpha_bytes; /* OCHRE_OUT_SINK_PACKED: bytes of class words + stored rows that crossed PCIe instead of 64 per tile */
+    uint64_t packed_alpha_bytes; /* OCHRE_OUT_SINK_PACKED: bytes of class words + stored pixel pairs that crossed PCIe instead of 64 per tile */
 } OchreSinkSum;
 int ochre_b200_set_host_sink(ochre_b200_ctx* ctx, uint32_t threads);
 int ochre_b200_last_sink(const ochre_b200_ctx* ctx, OchreSinkSum* out);
