@@ -83,23 +83,34 @@ inline void park(int state) {
     swapcontext(&f->ctx, &sched_ctx());
 }
 
-// order: 0 ascending thread ids, 1 descending, >= 2: shuffled with that seed (a new permutation every interval)
-inline void launch(unsigned grid, unsigned block, size_t smem_bytes, int order, const std::function<void()>& kernel_body) {
+// order: 0 ascending thread ids, 1 descending, >= 2: shuffled with that seed (a new permutation every interval).
+// resident: CTAs in flight at once (0: the whole grid, as persistent kernels that hand work to each other need it; kernels
+// whose CTAs are independent run in waves of a few CTAs, which keeps the fibers' stacks small in total).
+inline void launch_wave(unsigned grid, unsigned first, unsigned count, unsigned block, size_t smem_bytes, int order);
+inline void launch(unsigned grid, unsigned block, size_t smem_bytes, int order, const std::function<void()>& kernel_body, unsigned resident = 0) {
     block_dim() = Dim{block, 1, 1};
     grid_dim() = Dim{grid, 1, 1};
     body() = kernel_body;
-    std::vector<Cta> ctas(grid);
+    if (resident == 0 || resident >= grid) {
+        launch_wave(grid, 0, grid, block, smem_bytes, order);
+        return;
+    }
+    for (unsigned first = 0; first < grid; first += resident) launch_wave(grid, first, std::min(resident, grid - first), block, smem_bytes, order);
+}
+inline void launch_wave(unsigned grid, unsigned first, unsigned count, unsigned block, size_t smem_bytes, int order) {
+    (void)grid;
+    std::vector<Cta> ctas(count);
     std::vector<Fiber*> all;
-    for (unsigned b = 0; b < grid; ++b) {
+    for (unsigned b = 0; b < count; ++b) {
         Cta& c = ctas[b];
         c.fibers.resize(block);
         c.warps.resize((block + 31) / 32);
         c.smem.assign(smem_bytes + 64, 0xcd);  // poisoned: reads of never-written shared memory show up
         for (unsigned t = 0; t < block; ++t) {
             Fiber& f = c.fibers[t];
-            f.stack.resize(256 * 1024);
+            f.stack.resize(64 * 1024);
             f.tid = Dim{t, 0, 0};
-            f.bid = Dim{b, 0, 0};
+            f.bid = Dim{first + b, 0, 0};
             f.cta = &c;
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = f.stack.data();
@@ -271,6 +282,9 @@ template <class T> inline T atomicMax(T* p, T v) { T o = *p; *p = v > o ? v : o;
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline void __threadfence_system() {}
+inline void __threadfence() {}
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __float2int_rn(float f) { return (int)lrintf(f); }  // (round-to-nearest-even is the host's default mode)

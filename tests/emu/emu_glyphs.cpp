@@ -22,7 +22,7 @@ extern "C" int emu_glyphs_run(const Cmd* cmds, const uint32_t* cmd_off, const fl
     cemu::launch(cls_grid, CLS_THREADS, 0, order, [&]() {
         if (lanes == 4) k_classify<4>(cmds, cmd_off, cmd_off[0], xf, n_paths, max_cells, (uint32_t)pkg::GK_MAXCMDS, 1, counts, list, boxp);
         else k_classify<32>(cmds, cmd_off, cmd_off[0], xf, n_paths, max_cells, (uint32_t)pkg::GK_MAXCMDS, 1, counts, list, boxp);
-    });
+    }, 4);
     uint32_t ticket = 0;
     PathKernelArgs A;
     memset(&A, 0, sizeof(A));
