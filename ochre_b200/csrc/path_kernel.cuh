@@ -162,7 +162,8 @@ __device__ __forceinline__ uint32_t pk_next_touched(const PkShared& S, uint32_t 
 // Mark pass (rasterizer.rs:97-136, control flow only) over the bucketed lines [0, n): counts the
 // increments per cell of the W x H grid and adds the TileIncrement signs.
 __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address of the cells */, uint32_t merr_s /* ... of PkShared::merr */, const float4* __restrict__ lines,
-                                        const uint16_t* __restrict__ sidx, uint32_t n, int gx0, int gy0, int W, int H, bool striped, uint64_t pk_pol) {
+                                        const uint16_t* __restrict__ sidx, uint32_t n, int gx0, int gy0, int W, int H, bool striped, int grid_r0, int grid_h,
+                                        uint64_t pk_pol) {
     uint32_t pos = threadIdx.x;
     OC_KEEP_IN_REG(cell_s);  // keep the window address in a register (else it is rebuilt, S2UR + ULEA, at every atomic)
     // two-deep prefetch: the index of the line after next, the end points of the next line
@@ -185,7 +186,9 @@ __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address
             const int cx = w.x >> 3, cy = w.y >> 3;
             const bool inx = (unsigned)cx < (unsigned)W, iny = (unsigned)cy < (unsigned)H;
             if (inx && iny) pk_red_add(cell_s + 4u * (uint32_t)(cy * W + cx), 1u);
-            else if (!inx || !striped) pk_st_shared(merr_s, 1u);  // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes)
+            // (with stripes, rows outside [gy0, gy0 + H) belong to other stripes -- as long as they are rows of the path's grid: a
+            // long line's overshoot past the grid's first or last row is nobody's, and the path goes to the general pipeline)
+            else if (!inx || !striped || (unsigned)(cy + grid_r0) >= (unsigned)grid_h) pk_st_shared(merr_s, 1u);
             bool row;
             done = w.advance(row) == 1.0f;
             if (done) w.snap();
@@ -194,7 +197,7 @@ __device__ __forceinline__ void pk_mark(uint32_t cell_s /* shared-window address
                 const int tiy = min(ty, prev_ty), tix = w.x >> 3;
                 const bool jnx = (unsigned)tix < (unsigned)W, jny = (unsigned)tiy < (unsigned)H;
                 if (jnx && jny) pk_red_add(cell_s + 4u * (uint32_t)(tiy * W + tix), (uint32_t)(ty - prev_ty) << 16);
-                else if (!jnx || !striped) pk_st_shared(merr_s, 1u);
+                else if (!jnx || !striped || (unsigned)(tiy + grid_r0) >= (unsigned)grid_h) pk_st_shared(merr_s, 1u);
                 prev_ty = ty;
             }
         } while (!done);
@@ -850,7 +853,7 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
                 pk_st(&G.sidx[pos], (uint16_t)i, pk_pol);
             }
             __syncthreads();
-            pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), smem_s + (uint32_t)offsetof(PkShared, merr), G.lines, G.sidx, n_sorted, gx0, y0s, W, Hs, !whole, pk_pol);
+            pk_mark(smem_s + (uint32_t)offsetof(PkShared, u), smem_s + (uint32_t)offsetof(PkShared, merr), G.lines, G.sidx, n_sorted, gx0, y0s, W, Hs, !whole, R0, H, pk_pol);
             __syncthreads();
             const uint32_t err = S.merr;
             uint32_t bad;

@@ -259,16 +259,29 @@ struct PkBBox {
     int x0, y0, x1, y1;
 };
 
+// Pixels the DDA of a line may run past its end pixel before the end snap (rasterizer.rs:118-121), per axis.  The walk stops
+// when its rounded recurrence t += step reaches 1, not at a pixel count: over n steps along an axis the rounding of the step
+// itself (2^-24 relative) and of every addition (2^-24 of t <= 1 each) lets it arrive up to n^2 * 2^-23 steps late, and every
+// late step is one more increment past the end pixel.  Less than one step for lines of up to 2896 pixels -- one pixel of
+// overshoot, what the grid's one-tile margin and the row ranges below have always allowed for -- but 9 pixels observed, 115 by
+// this bound, for a line of 31 000 (the coordinate range allows 65 520).
+__device__ __forceinline__ int pk_overshoot(int n_steps) {
+    const int late = (int)(((long long)n_steps * n_steps + ((1 << 23) - 1)) >> 23);
+    return late > 1 ? late : 1;
+}
+
 // Per-line record for bucketing: [12:0] first tile row + 4096, [25:13] last tile row + 4096 (both
-// padded by one pixel for the DDA's overshoot before the end snap), [28:26] step-count class.
-// Also grows the bounding box (tile units).  Only called for lines with two distinct end points.
+// padded by the rows the DDA may overshoot before the end snap), [28:26] step-count class.
+// Also grows the bounding box (tile units; a line long enough to overshoot by more than a pixel pads it by that much: the
+// grid's margin of one tile covers the rest).  Only called for lines with two distinct end points.
 __device__ __forceinline__ uint32_t pk_line_info(V2 a, V2 b, PkBBox& bb) {
     const int ax = floor_px(a.x), ay = floor_px(a.y), ex = floor_px(b.x), ey = floor_px(b.y);
-    bb.x0 = min(bb.x0, min(ax, ex) >> 3);
-    bb.x1 = max(bb.x1, max(ax, ex) >> 3);
-    bb.y0 = min(bb.y0, min(ay, ey) >> 3);
-    bb.y1 = max(bb.y1, max(ay, ey) >> 3);
-    const int lo = ((min(ay, ey) - 1) >> 3) + 4096, hi = ((max(ay, ey) + 1) >> 3) + 4096;
+    const int pad_x = pk_overshoot(abs(ex - ax)), pad = pk_overshoot(abs(ey - ay));
+    bb.x0 = min(bb.x0, (min(ax, ex) - (pad_x - 1)) >> 3);
+    bb.x1 = max(bb.x1, (max(ax, ex) + (pad_x - 1)) >> 3);
+    bb.y0 = min(bb.y0, (min(ay, ey) - (pad - 1)) >> 3);
+    bb.y1 = max(bb.y1, (max(ay, ey) + (pad - 1)) >> 3);
+    const int lo = max(((min(ay, ey) - pad) >> 3) + 4096, 0), hi = min(((max(ay, ey) + pad) >> 3) + 4096, 8191);
     const int n = abs(ex - ax) + abs(ey - ay) + 1;  // DDA trips of the line, up to rounding overshoot
     const int cls = n <= 4 ? n - 1 : 4 + (n > 6) + (n > 9) + (n > 15);
     return (uint32_t)lo | ((uint32_t)hi << 13) | ((uint32_t)cls << 26);

@@ -686,3 +686,17 @@ def test_large_device_resident_batch_with_a_bad_offset_mirror_fails_when_the_cal
         assert np.array_equal(r.tile_off, g.tile_off)
     finally:
         c.close()
+
+
+def test_a_line_of_31000_pixels_overshoots_its_end_by_several_pixels(ctx):
+    """rasterizer.rs:97-136 stops a walk when its rounded recurrence t += step reaches 1: a line of 31 000 pixel rows arrives
+    several steps late and leaves increments up to 9 pixels past its end point (tile rows -1 and -2 above the origin here).
+    Every implementation -- the general pipeline, the fused kernel's striped form the tall grid needs -- has those tiles."""
+    tall = make_cmds([(MOVE, 8.2823124, 31000.049), (LINE, 8.327194, 31000.088), (LINE, 0.0, 0.0), (LINE, 8.361395, 31000.043)])
+    tri = make_cmds([(MOVE, 3.5, 2.25), (LINE, 94.5, 2.25), (LINE, 3.5, 93.25), (CLOSE,)])
+    cmds, off, xf = pack([tri, tall, tri])
+    o = oracle_batch(cmds, off, xf)
+    a, b = int(o.tile_off[1]), int(o.tile_off[2])
+    assert o.tile_xy[a:b, 1].min() <= -16
+    g = ctx.rasterize(cmds, off, xf)
+    assert_batch_parity(g, o, what="a 31 000-pixel line")

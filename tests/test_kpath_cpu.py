@@ -93,3 +93,21 @@ def test_a_bad_path_is_reported_and_dropped():
     assert r.rec[1][1] == 0 and r.rec[1][3] == 0
     ref = emu.rasterize(*batch([good, good]), fixed=True)
     assert r.rec[0][1] == ref.tile_off[1] and r.rec[2][1] == ref.tile_off[1]
+
+
+def test_long_lines_overshoot_their_end_pixel_by_more_than_one():
+    """The DDA stops when its rounded recurrence t += step reaches 1, not at a pixel count (rasterizer.rs:97-136): a line of
+    31 000 pixels arrives several steps late and leaves increments up to 9 pixels past its end point, here above the origin in
+    tile rows -1 and -2.  The per-line row ranges and the bounding grid allow for it (pk_overshoot); before they did, the
+    striped form dropped those tiles."""
+    tall = mkpath((MOVE, 8.2823124, 31000.049), (LINE, 8.327194, 31000.088), (LINE, 0.0, 0.0), (LINE, 8.361395, 31000.043))
+    tri = mkpath((MOVE, 3.5, 2.25), (LINE, 94.5, 2.25), (LINE, 3.5, 93.25), (CLOSE,))
+    cmds, off, xf = batch([tri, tall, tri])
+    ref = emu.rasterize(cmds, off, xf, fixed=True)
+    a, b = int(ref.tile_off[1]), int(ref.tile_off[2])
+    assert ref.tile_xy[a:b, 1].min() <= -16, "the reference's walk no longer overshoots: the case has lost its point"
+    r1 = EK.run_kpath(cmds, off, xf, shape="pkl", order=0, grid=2)
+    assert [int(p) for p in r1.handed_over] == [1]       # the grid is too tall for one pass
+    r2 = EK.run_kpath(cmds, off, xf, shape="pkl", striped=True, paths=r1.handed_over, order=1, grid=2, prev=r1)
+    assert len(r2.handed_over) == 0
+    compare(r2, ref, [0, 1, 2])
