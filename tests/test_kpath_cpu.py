@@ -111,3 +111,16 @@ def test_long_lines_overshoot_their_end_pixel_by_more_than_one():
     r2 = EK.run_kpath(cmds, off, xf, shape="pkl", striped=True, paths=r1.handed_over, order=1, grid=2, prev=r1)
     assert len(r2.handed_over) == 0
     compare(r2, ref, [0, 1, 2])
+
+
+@pytest.mark.parametrize("gen,seeds", [("mixed", (1, 2, 3)), ("tall", (4, 5, 6, 7))])
+def test_a_few_seeds_of_the_kernel_fuzzer(gen, seeds):
+    """tools/fuzz_kernels_cpu.py: random batches through the classifier + glyph kernel, both shapes of k_path and its striped form."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("fuzz_kernels_cpu", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_kernels_cpu.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    for s in seeds:
+        assert fz.one(s, gen) > 0
