@@ -752,7 +752,8 @@ __global__ void __launch_bounds__(PK_THREADS, PK_CTAS_PER_SM) k_path(PathKernelA
 
         // ---- 2. the bounding grid and its stripes ---------------------------------------------------------
         const bool empty = !fallback && (S.bbox[0] > S.bbox[2]);  // no line with two distinct end points
-        // one tile of margin: the DDA may overshoot its end pixel by one before the end snap
+        // one tile of margin: the DDA may overshoot its end pixel by one before the end snap (longer overshoots of very long
+        // lines are part of the bounding box already: pk_overshoot)
         const int gx0 = S.bbox[0] - 1, gy0 = S.bbox[1] - 1;
         const int W = empty ? 1 : S.bbox[2] - S.bbox[0] + 3, H = empty ? 1 : S.bbox[3] - S.bbox[1] + 3;
         const bool walk = !fallback && !empty;
