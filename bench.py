@@ -10,9 +10,11 @@ config 4: random closed cubic paths, 3-64 segments, 4096x4096 canvas (generator 
              same run with the lists copied into path order).  N > 1: weak scaling, every rank rasterises its own
              path range and the compacted tile / span lists are gathered to GPU 0 inside the timed region (the
              fused kernel stores its tiles straight into an arena in GPU 0's memory over NVLink).
-  e2e        paths/s through the public host API: pinned host PathCmd arrays in, pinned host tile / span arrays
-             out AND replayed into a counting TileBuilder by host threads (the reference's end point: the last
-             TileBuilder call returned); H2D, D2H and the replay inside the timed region.
+  e2e        paths/s through the public host API: pinned host PathCmd arrays in, every tile and span replayed into a
+             counting TileBuilder by host threads (the reference's end point: the last TileBuilder call returned);
+             H2D, D2H and the replay inside the timed region.  The tiles cross PCIe packed (OCHRE_OUT_SINK_PACKED: a
+             class word per tile + its non-constant pixel pairs) and are rebuilt for the builder by the host threads;
+             e2e.whole_tiles is the same end point with 64-byte tiles on the wire.
   config.workloads   the other BASELINE configs (1: examples/basic.rs x 1 M, 2: the bundled SVGs x 64 at 1x and
              4x, 3: 100 k glyphs, 5a: one 16384^2 path sharded by canvas row bands, 5b: 10 M paths sharded by
              path), each with paths/s, tiles/s, algorithmic bytes and their fraction of the HBM roofline.
