@@ -81,7 +81,7 @@ def rasterize(cmds, cmd_off, xf, fixed: bool = False, band=None) -> EmuResult:
     L = lib()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     lo, hi = band if band is not None else (-32768, 32767)
-    r = L.emu_rasterize_band(p(cmds), p(cmd_off), p(xf), n, 1 if fixed else 0, int(lo), int(hi))
+    r = L.emu_rasterize_band(p(cmds), p(cmd_off), p(xf), n, int(fixed), int(lo), int(hi))  # (2: the error-feedback experiment)
     st = L.emu_status(r)
     if st != 0:
         L.emu_free(r)

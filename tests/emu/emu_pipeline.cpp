@@ -54,6 +54,38 @@ struct FxAcc {
         h[pix] += (int)lrintf(height * 4194304.0f);
     }
 };
+// Experiment (test infrastructure only; DESIGN.md section 2, "known limit of the alpha bar"): the same 2^-22 sums with ERROR
+// FEEDBACK along a line -- the rounding residual of one increment's height is carried into the next increment of the same walk, so
+// a line's heights are off by less than one unit in total instead of up to half a unit per increment.  fixed == 2 selects it.
+template <class LineFetch>
+static void cover_record_feedback(FxAcc& acc, const LineFetch& fetch, uint32_t line0, uint32_t nlines, int tx, int ty) {
+    for (uint32_t k = 0; k < nlines; ++k) {
+        V2 a, b;
+        fetch(line0 + k, a, b);
+        if (same(a, b)) continue;
+        Walker w;
+        w.init(a, b);
+        float res = 0.0f;  // what the increments so far have rounded away, in 2^-22 units
+        bool inside_seen = false;
+        for (;;) {
+            int ix, iy;
+            float area, height;
+            bool done = w.step(ix, iy, area, height);
+            const float hq = height * 4194304.0f + res;
+            const int qh = (int)lrintf(hq);
+            res = hq - (float)qh;
+            if ((ix >> 3) == tx && (iy >> 3) == ty) {
+                const int pix = ((iy & 7) << 3) | (ix & 7);
+                acc.a[pix] += (int)lrintf(area * 4194304.0f);
+                acc.h[pix] += qh;
+                inside_seen = true;
+            } else if (inside_seen) {
+                break;
+            }
+            if (done) break;
+        }
+    }
+}
 struct Fetch {
     const float* lines;
     void operator()(uint32_t i, V2& a, V2& b) const {
@@ -189,7 +221,10 @@ EmuResult* emu_rasterize_band(const OchreCmd* cmds_, const uint32_t* cmd_off, co
             FxAcc fx;
             memset(&fx, 0, sizeof fx);
             for (uint32_t i = gs[g]; i < gend(g); ++i)
-                if (!val_wonly(V[i])) cover_record(fx, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
+                if (!val_wonly(V[i])) {
+                    if (fixed == 2) cover_record_feedback(fx, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
+                    else cover_record(fx, fetch, val_line0(V[i]), val_nlines(V[i]), tx, ty);
+                }
             // csrc/path_kernel.cuh: exact integer row carry, both terms of rasterizer.rs:235 scaled by 256
             const float k256 = 1.0f / 16384.0f;  // 2^-22 * 256
             for (int y = 0; y < 8; ++y) {
